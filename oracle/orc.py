@@ -1,0 +1,277 @@
+"""TEST INFRASTRUCTURE — ctypes binding of the CPU oracle (oracle/_build/liborc.so).
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this module.
+PARITY UNPINNED: the reference has no tests or golden vectors; see orc_pipeline.hpp.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "_build", "liborc.so")
+_REF = os.path.join(_HERE, "_ref", "libref_nanoflann.so")
+
+
+def build(force: bool = False) -> None:
+    """Compile the oracle (and oracle/_ref when /root/reference is present)."""
+    if force or not os.path.exists(_LIB) or any(
+        os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB) for f in ("orc_capi.cpp", "orc_pipeline.hpp", "orc_math.hpp")
+    ):
+        subprocess.run(["make", "-C", _HERE, "_build/liborc.so"], check=True, capture_output=True)
+    if os.path.isdir("/root/reference") and (force or not os.path.exists(_REF)):
+        subprocess.run(["make", "-C", _HERE, "ref"], check=True, capture_output=True)
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("n_scan", C.c_int), ("n_rings", C.c_int),
+        ("lidar_min", C.c_double), ("lidar_max", C.c_double), ("edge_threshold", C.c_double),
+        ("edge_leaf", C.c_double), ("surf_leaf", C.c_double), ("crop_half", C.c_double),
+        ("knn_gate", C.c_double), ("huber", C.c_double),
+        ("outer_iters", C.c_int), ("lm_max_iters", C.c_int), ("voxel_order", C.c_int), ("_pad", C.c_int),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB)
+        _lib.orc_odom_create.restype = C.c_void_p
+        _lib.orc_odom_cloud_size.restype = C.c_int
+        _lib.orc_odom_get_solves.restype = C.c_int
+        _lib.orc_solve.restype = C.c_int
+        _lib.orc_voxel_grid.restype = C.c_int
+    return _lib
+
+
+def ref_lib():
+    """The reference's own vendored nanoflann kd-tree (None if oracle/_ref was never built)."""
+    if not os.path.exists(_REF):
+        return None
+    return C.CDLL(_REF)
+
+
+def config(**kw) -> Config:
+    c = Config()
+    lib().orc_default_config(C.byref(c))
+    for k, v in kw.items():
+        if not hasattr(c, k):
+            raise AttributeError(k)
+        setattr(c, k, v)
+    return c
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def extract(cfg: Config, xyzi, ring=None):
+    """Stage 1 -> (edge [ne,4], edge_src [ne], surf [ns,4], surf_src [ns])."""
+    xyzi = _f32(xyzi)
+    n = xyzi.shape[0]
+    edge = np.empty((max(n, 1), 4), np.float32); surf = np.empty((max(n, 1), 4), np.float32)
+    es = np.empty(max(n, 1), np.int32); ss = np.empty(max(n, 1), np.int32)
+    ne = C.c_int(); ns = C.c_int()
+    rp = None
+    if ring is not None:
+        ring = np.ascontiguousarray(ring, dtype=np.uint16)
+        rp = _p(ring, C.c_uint16)
+    lib().orc_extract(C.byref(cfg), _p(xyzi, C.c_float), n, rp, _p(edge, C.c_float), _p(es, C.c_int), C.byref(ne),
+                      _p(surf, C.c_float), _p(ss, C.c_int), C.byref(ns))
+    return edge[:ne.value].copy(), es[:ne.value].copy(), surf[:ns.value].copy(), ss[:ns.value].copy()
+
+
+def voxel_grid(pts, leaf: float, order_mode: int = 0):
+    pts = _f32(pts)
+    n = pts.shape[0]
+    out = np.empty((max(n, 1), 4), np.float32)
+    no = C.c_int()
+    ok = lib().orc_voxel_grid(_p(pts, C.c_float), n, C.c_float(leaf), order_mode, _p(out, C.c_float), C.byref(no))
+    return out[:no.value].copy(), bool(ok)
+
+
+def crop_box(pts, mn, mx):
+    pts = _f32(pts)
+    n = pts.shape[0]
+    out = np.empty((max(n, 1), 4), np.float32)
+    no = C.c_int()
+    mn = _f64(mn); mx = _f64(mx)
+    lib().orc_crop_box(_p(pts, C.c_float), n, _p(mn, C.c_double), _p(mx, C.c_double), _p(out, C.c_float), C.byref(no))
+    return out[:no.value].copy()
+
+
+def _knn(fn, mp, q, k):
+    mp = _f32(mp); q = _f32(q)
+    nq = q.shape[0]
+    idx = np.empty((nq, k), np.int32); d2 = np.empty((nq, k), np.float32)
+    fn(_p(mp, C.c_float), mp.shape[0], _p(q, C.c_float), nq, k, _p(idx, C.c_int), _p(d2, C.c_float))
+    return idx, d2
+
+
+def knn(mp, q, k: int = 5):
+    """Oracle kd-tree (restated FLANN single index): exact k-NN, ascending squared fp32 distances."""
+    return _knn(lib().orc_knn, mp, q, k)
+
+
+def ref_knn(mp, q, k: int = 5):
+    """The reference's vendored nanoflann 1.3.2 on the same inputs (oracle/_ref)."""
+    r = ref_lib()
+    if r is None:
+        raise RuntimeError("oracle/_ref/libref_nanoflann.so not built")
+    return _knn(r.ref_nanoflann_knn, mp, q, k)
+
+
+def factors(cfg: Config, pose, edge, surf, map_e, map_s):
+    """Data association at `pose` -> dict of per-point outputs for edge and surf features."""
+    pose = _f64(pose); edge = _f32(edge); surf = _f32(surf); map_e = _f32(map_e); map_s = _f32(map_s)
+    ne, ns = edge.shape[0], surf.shape[0]
+    ev = np.zeros(max(ne, 1), np.uint8); eab = np.zeros((max(ne, 1), 6)); enn = np.zeros((max(ne, 1), 5), np.int32); ed2 = np.zeros((max(ne, 1), 5), np.float32)
+    sv = np.zeros(max(ns, 1), np.uint8); snd = np.zeros((max(ns, 1), 4)); snn = np.zeros((max(ns, 1), 5), np.int32); sd2 = np.zeros((max(ns, 1), 5), np.float32)
+    lib().orc_factors(C.byref(cfg), _p(pose, C.c_double), _p(edge, C.c_float), ne, _p(surf, C.c_float), ns,
+                      _p(map_e, C.c_float), map_e.shape[0], _p(map_s, C.c_float), map_s.shape[0],
+                      _p(ev, C.c_uint8), _p(eab, C.c_double), _p(enn, C.c_int), _p(ed2, C.c_float),
+                      _p(sv, C.c_uint8), _p(snd, C.c_double), _p(snn, C.c_int), _p(sd2, C.c_float))
+    return dict(edge_valid=ev[:ne], edge_ab=eab[:ne], edge_nn=enn[:ne], edge_d2=ed2[:ne],
+                surf_valid=sv[:ns], surf_nd=snd[:ns], surf_nn=snn[:ns], surf_d2=sd2[:ns])
+
+
+def pack_factors(edge, surf, f):
+    """(edge_pab [ke,9], surf_pnd [ks,7]) of the accepted factors, in residual-block order."""
+    ev = f["edge_valid"].astype(bool); sv = f["surf_valid"].astype(bool)
+    pab = np.concatenate([np.asarray(edge, np.float32)[ev, :3].astype(np.float64), f["edge_ab"][ev]], axis=1)
+    pnd = np.concatenate([np.asarray(surf, np.float32)[sv, :3].astype(np.float64), f["surf_nd"][sv]], axis=1)
+    return np.ascontiguousarray(pab), np.ascontiguousarray(pnd)
+
+
+def normal_eq(huber: float, pose, pab, pnd):
+    pose = _f64(pose); pab = _f64(pab); pnd = _f64(pnd)
+    H = np.zeros(21); g = np.zeros(6); cost = C.c_double()
+    lib().orc_normal_eq(C.c_double(huber), _p(pose, C.c_double), _p(pab, C.c_double), pab.shape[0], _p(pnd, C.c_double), pnd.shape[0],
+                        _p(H, C.c_double), _p(g, C.c_double), C.byref(cost))
+    return H, g, cost.value
+
+
+def solve(huber: float, max_iters: int, pose, pab, pnd):
+    """ceres::Solve restated -> (pose_out [7], trace [rows,16], termination)."""
+    pose = _f64(pose).copy(); pab = _f64(pab); pnd = _f64(pnd)
+    tr = np.zeros((max_iters + 2, 16)); nr = C.c_int()
+    term = lib().orc_solve(C.c_double(huber), max_iters, _p(pose, C.c_double), _p(pab, C.c_double), pab.shape[0], _p(pnd, C.c_double), pnd.shape[0],
+                           _p(tr, C.c_double), tr.shape[0], C.byref(nr))
+    return pose, tr[:nr.value].copy(), term
+
+
+def se3_plus(x, delta):
+    x = _f64(x); delta = _f64(delta); out = np.zeros(7)
+    lib().orc_se3_plus(_p(x, C.c_double), _p(delta, C.c_double), _p(out, C.c_double))
+    return out
+
+
+def edge_eval(pose, pab):
+    pose = _f64(pose); pab = _f64(pab); r = np.zeros(3); J = np.zeros((3, 6))
+    lib().orc_edge_eval(_p(pose, C.c_double), _p(pab, C.c_double), _p(r, C.c_double), _p(J, C.c_double))
+    return r, J
+
+
+def surf_eval(pose, pnd):
+    pose = _f64(pose); pnd = _f64(pnd); r = np.zeros(1); J = np.zeros((1, 6))
+    lib().orc_surf_eval(_p(pose, C.c_double), _p(pnd, C.c_double), _p(r, C.c_double), _p(J, C.c_double))
+    return r, J
+
+
+def eig3(Cm):
+    Cm = _f64(Cm); w = np.zeros(3); V = np.zeros((3, 3))
+    lib().orc_eig3(_p(Cm, C.c_double), _p(w, C.c_double), _p(V, C.c_double))
+    return w, V
+
+
+def lstsq5x3(A, b):
+    A = _f64(A); b = _f64(b); n = np.zeros(3)
+    lib().orc_lstsq5x3(_p(A, C.c_double), _p(b, C.c_double), _p(n, C.c_double))
+    return n
+
+
+MAP_EDGE, MAP_SURF, DS_EDGE, DS_SURF, REGISTERED, NO_REGISTERED = range(6)
+
+
+class Odometry:
+    """EstimationMapping (+ featureExtraction via process_scan) on the CPU."""
+
+    def __init__(self, cfg: Config):
+        self.cfg = cfg
+        self._h = C.c_void_p(lib().orc_odom_create(C.byref(cfg)))
+        self.frames = 0
+
+    def close(self):
+        if self._h:
+            lib().orc_odom_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def init_map(self, edge, surf):
+        edge = _f32(edge); surf = _f32(surf)
+        lib().orc_odom_init_map(self._h, _p(edge, C.c_float), edge.shape[0], _p(surf, C.c_float), surf.shape[0])
+
+    def update(self, edge, surf):
+        edge = _f32(edge); surf = _f32(surf); pose = np.zeros(7)
+        lib().orc_odom_update(self._h, _p(edge, C.c_float), edge.shape[0], _p(surf, C.c_float), surf.shape[0], _p(pose, C.c_double))
+        return pose
+
+    def process_scan(self, xyzi, ring=None):
+        xyzi = _f32(xyzi); pose = np.zeros(7); ne = C.c_int(); ns = C.c_int()
+        rp = None
+        if ring is not None:
+            ring = np.ascontiguousarray(ring, dtype=np.uint16)
+            rp = _p(ring, C.c_uint16)
+        lib().orc_odom_process_scan(self._h, _p(xyzi, C.c_float), xyzi.shape[0], rp, int(self.frames == 0), _p(pose, C.c_double), C.byref(ne), C.byref(ns))
+        self.frames += 1
+        return pose, ne.value, ns.value
+
+    def cloud(self, which: int):
+        n = lib().orc_odom_cloud_size(self._h, which)
+        out = np.empty((max(n, 1), 4), np.float32)
+        lib().orc_odom_get_cloud(self._h, which, _p(out, C.c_float))
+        return out[:n].copy()
+
+    def set_cloud(self, which: int, pts):
+        pts = _f32(pts)
+        lib().orc_odom_set_cloud(self._h, which, _p(pts, C.c_float), pts.shape[0])
+
+    def state(self):
+        s = np.zeros(31)
+        lib().orc_odom_get_state(self._h, _p(s, C.c_double))
+        return s
+
+    def set_state(self, s):
+        s = _f64(s)
+        lib().orc_odom_set_state(self._h, _p(s, C.c_double))
+
+    def solves(self):
+        out = np.zeros((8, 8))
+        n = lib().orc_odom_get_solves(self._h, _p(out, C.c_double), 8)
+        return out[:n].copy()
+
+    def timing(self):
+        t = np.zeros(7)
+        lib().orc_odom_get_timing(self._h, _p(t, C.c_double))
+        return dict(extract=t[0], scan_ds=t[1], kd_build=t[2], assoc=t[3], solve=t[4], map_update=t[5], frames=int(t[6]))
