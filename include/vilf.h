@@ -1,0 +1,162 @@
+/*
+ * vilf.h — C ABI of libvilf_cuda.so: the B200-native (sm_100a) lidar-odometry front end that replaces
+ * the CPU hot path of RichExplor/VIL_Fusion (F-LOAM-derived).
+ *
+ * The reference has no FFI layer: the path is two header-only C++ classes instantiated in the ROS node
+ * (src/visual_inertial_lidar/feature_tracker/feature_tracker_node.cpp:13-19).  Every entry point below
+ * cites the reference member it stands in for.  Abbreviations (all under
+ * src/visual_inertial_lidar/feature_tracker/include/):
+ *   FE = featureExtraction.hpp   EM = EstimationMapping.hpp   LF = lidarFactor.hpp   CM = common.h
+ *   NODE = ../feature_tracker_node.cpp
+ *
+ * Conventions: plain pointers and sizes only; every function returns a vilf_status (0 = OK); point
+ * clouds are packed float[n][4] = x, y, z, intensity (the payload of pcl::PointXYZI, CM:25); poses are
+ * double[7] = qx, qy, qz, qw, tx, ty, tz (parameter_opti, EM:383).  All buffers passed in are HOST
+ * memory unless a name ends in _dev.  One handle == one lidar sequence (one EstimationMapping +
+ * featureExtraction pair); handles created together by vilf_create_batch share a device context and can
+ * be stepped in lock-step by the *_batch calls (independent sequences, no data exchanged between them).
+ * There is no CPU fallback: every call needs a CUDA device and fails with VILF_ERR_CUDA otherwise.
+ */
+#ifndef VILF_H_
+#define VILF_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vilf_handle vilf_handle;
+
+typedef enum vilf_status {
+  VILF_OK = 0,
+  VILF_ERR_INVALID = 1,     /* bad argument */
+  VILF_ERR_CUDA = 2,        /* CUDA runtime error (see vilf_last_error) */
+  VILF_ERR_CAPACITY = 3,    /* an input or the local map exceeds the configured capacity */
+  VILF_ERR_UNSUPPORTED = 4, /* e.g. a ring with more than 6*2048+10 returns */
+  VILF_ERR_STATE = 5        /* call sequence error (e.g. update before map init) */
+} vilf_status;
+
+/* Parameters.  Defaults (vilf_default_config) are the reference's KITTI YAML values
+ * (config/kitti/velodyne_param_64.yaml:9-23) and its hard-coded constants. */
+typedef struct vilf_config {
+  int32_t n_scan;          /* FE:45  /N_SCAN: 16, 32 or 64 use the reference's vertical-angle formulas
+                              (FE:75-102); any other non-zero value bins everything into ring 0 like
+                              FE:103-106; 0 = explicit ring ids supplied with every scan */
+  int32_t n_rings;         /* number of rings when n_scan == 0 (<= 128) */
+  double lidar_min;        /* FE:46  /lidarMinRange, XY range */
+  double lidar_max;        /* FE:47  /lidarMaxRange */
+  double edge_threshold;   /* FE:48  /edgeThreshold */
+  double edge_leaf;        /* EM:82  /EdgeLeafSize */
+  double surf_leaf;        /* EM:83  /SurfLeafSize */
+  double crop_half;        /* EM:327-332 (100 m) */
+  double knn_gate;         /* EM:129, :189 squared-distance gate on the 5th neighbour (1.0) */
+  double huber;            /* EM:263 HuberLoss(0.1) */
+  int32_t outer_iters;     /* EM:260 (2) */
+  int32_t lm_max_iters;    /* EM:277 max_num_iterations (4) */
+  int32_t max_scan_points; /* capacity: points per scan */
+  int32_t max_map_points;  /* capacity: points per local map (edge and surf each) */
+} vilf_config;
+
+int vilf_default_config(vilf_config* cfg);
+
+/* ---- lifetime (EM:75-103 constructor/initParameter/allocateMemory, FE:43-52 initParam) ---- */
+int vilf_create(const vilf_config* cfg, int device, vilf_handle** out);
+/* `count` sequences sharing one device context; out[i] is sequence i. */
+int vilf_create_batch(const vilf_config* cfg, int device, int count, vilf_handle** out);
+int vilf_destroy(vilf_handle* h); /* destroying any handle of a batch destroys the whole batch */
+const char* vilf_last_error(const vilf_handle* h);
+/* Pinned host memory for scan buffers (optional; makes the H2D copy asynchronous). */
+int vilf_host_alloc(void** p, uint64_t bytes);
+int vilf_host_free(void* p);
+
+/* ---- the per-frame path, as the node drives it (NODE:339-389) ---- */
+/* extractFeature (FE:223-232) + first frame ? localMapInited (EM:105-115) : optimation_processing
+ * (EM:235-296), all on the device; only the pose (7 doubles) comes back.  ring may be NULL unless
+ * cfg.n_scan == 0.  Blocking. */
+int vilf_process_scan(vilf_handle* h, const float* xyzi, int n, const uint16_t* ring, double pose_out[7]);
+/* Asynchronous pair: submit enqueues H2D + the frame's kernels + D2H of the pose and returns a ticket;
+ * wait blocks until that frame is done.  Up to 8 frames may be in flight; the scan buffer must stay
+ * valid until its ticket has been waited for. */
+int vilf_submit_scan(vilf_handle* h, const float* xyzi, int n, const uint16_t* ring, int64_t* ticket);
+int vilf_wait(vilf_handle* h, int64_t ticket, double pose_out[7]);
+/* Lock-step over all sequences of a batch (hs = the array vilf_create_batch filled). */
+int vilf_submit_scan_batch(vilf_handle* const* hs, int count, const float* const* xyzi, const int* n,
+                           const uint16_t* const* ring, int64_t* ticket);
+int vilf_wait_batch(vilf_handle* const* hs, int count, int64_t ticket, double* poses_out /* [count][7] */);
+/* Same step, but the scans are already resident in device memory (bench: inputs in HBM). */
+int vilf_submit_scan_batch_dev(vilf_handle* const* hs, int count, const float* const* xyzi_dev, const int* n,
+                               const uint16_t* const* ring_dev, int64_t* ticket);
+
+/* ---- the reference's method surface, one call each ---- */
+/* featureExtraction::extractFeature (FE:223-232).  Results stay on the device (and become the input of
+ * vilf_map_init / vilf_update); counts are returned. */
+int vilf_feature_extract(vilf_handle* h, const float* xyzi, int n, const uint16_t* ring, int* n_edge, int* n_surf);
+/* which: 0 = edge, 1 = surf.  pts [cap][4] and src [cap] (index of each feature in the input scan) may be NULL. */
+int vilf_get_features(vilf_handle* h, int which, float* pts, int32_t* src, int cap, int* n);
+/* EstimationMapping::localMapInited (EM:105-115) on the last extracted features / on explicit clouds. */
+int vilf_map_init(vilf_handle* h);
+int vilf_map_init_points(vilf_handle* h, const float* edge, int n_edge, const float* surf, int n_surf);
+/* EstimationMapping::optimation_processing (EM:235-296) on the last extracted features / on explicit clouds. */
+int vilf_update(vilf_handle* h, double pose_out[7]);
+int vilf_update_points(vilf_handle* h, const float* edge, int n_edge, const float* surf, int n_surf, double pose_out[7]);
+/* globalOdom (EM:387): pose as quaternion + translation, and optionally the 3x3 rotation (row-major) + t. */
+int vilf_get_pose(vilf_handle* h, double pose_out[7], double* rt12_or_null);
+/* Clouds owned by the object. which: 0 localMapEdge, 1 localMapSurf (EM:394-395), 2/3 the voxel-filtered
+ * scan edge/surf features (EM:246-251), 4 cloudRegistered, 5 cloudNoRegistered (EM:391-392; getMapCloud
+ * EM:365-375 returns 4+5 or 5). */
+int vilf_get_cloud(vilf_handle* h, int which, float* out, int cap, int* n);
+
+/* ---- stage-level entry points (unit parity against the oracle; they clobber per-frame scratch only) ---- */
+/* pcl::VoxelGrid<PointXYZI>::filter (EM:248-251, :347-350). Returns n_out; *guard = 1 when PCL's
+ * "leaf size too small" int32 guard fired and the output is the input. */
+int vilf_voxel_downsample(vilf_handle* h, const float* pts, int n, float leaf, float* out, int cap, int* n_out, int* guard);
+/* pcl::CropBox (EM:335-344) followed by VoxelGrid, i.e. one map maintenance step on an explicit cloud. */
+int vilf_crop_voxel_downsample(vilf_handle* h, const float* pts, int n, const double center[3], double half, float leaf,
+                               float* out, int cap, int* n_out);
+/* pcl::CropBox::filter alone (closed AABB, order preserving). */
+int vilf_crop_box(vilf_handle* h, const float* pts, int n, const double mn[3], const double mx[3], float* out, int cap, int* n_out);
+/* pcl::KdTreeFLANN::nearestKSearch(k=5) (EM:128, :185) of nq queries against an explicit map.  Exact for
+ * every rank whose squared distance is < cfg.knn_gate (all the reference ever uses, EM:129/:189); ranks
+ * beyond the gate radius may be inexact or missing (idx -1, d2 FLT_MAX). */
+int vilf_knn5(vilf_handle* h, const float* map, int m, const float* q, int nq, int32_t* idx, float* d2);
+/* EdgeCostFactor / SurfCostFactor (EM:117-232) at `pose` against the CURRENT local maps: per input point
+ * validity, line end points a,b (6 doubles) / plane n,d (4 doubles), and the 5 neighbours. Output arrays may be NULL. */
+int vilf_factors(vilf_handle* h, const double pose[7], const float* edge, int n_edge, const float* surf, int n_surf,
+                 uint8_t* edge_valid, double* edge_ab, int32_t* edge_nn, float* edge_d2,
+                 uint8_t* surf_valid, double* surf_nd, int32_t* surf_nn, float* surf_d2);
+/* Robustified normal equations of explicit factors at `pose`: H = J^T J (upper triangle, row-major, 21),
+ * g = J^T r (6), cost = 1/2 sum rho (LF:21-52, :79-102 + HuberLoss).  edge_pab: 9 doubles per factor
+ * (p, a, b); surf_pnd: 7 doubles per factor (p, n, d). */
+int vilf_normal_equations(vilf_handle* h, const double pose[7], const double* edge_pab, int n_edge, const double* surf_pnd,
+                          int n_surf, double H21[21], double g6[6], double* cost);
+/* ceres::Solve (EM:263-283) on explicit factors.  trace rows: 16 doubles = iteration, step_valid,
+ * step_successful, cost, candidate_cost, model_cost_change, relative_decrease, radius, step_norm, x[7]. */
+int vilf_solve(vilf_handle* h, double pose_inout[7], const double* edge_pab, int n_edge, const double* surf_pnd, int n_surf,
+               int max_iters, double* trace, int max_rows, int* n_rows, int* termination);
+/* Per-solve summary of the last update: rows of 8 doubles = n_edge_factors, n_surf_factors, termination,
+ * n_iterations, initial cost, final cost, 0, 0. */
+int vilf_get_solves(vilf_handle* h, double* out, int max_rows, int* n_rows);
+
+/* ---- state export / import (teacher-forced parity tests, checkpoint/resume) ---- */
+/* state = x[7], globalOdom (R row-major 9 + t 3), globalOdom_last (12): 31 doubles. */
+int vilf_state_export(vilf_handle* h, double state31[31]);
+int vilf_state_import(vilf_handle* h, const double state31[31], const float* map_edge, int n_edge, const float* map_surf, int n_surf);
+
+/* ---- measurement ---- */
+/* Per-stage device time (CUDA events on the handle's stream) accumulated since the last reset.
+ * stage: 0 extract, 1 scan downsample, 2 grid build, 3 kNN + fit, 4 solve, 5 map update, 6 whole frame.
+ * Profiling adds event records between stages; enable only for roofline runs. */
+int vilf_profile_enable(vilf_handle* h, int on);
+int vilf_profile_read(vilf_handle* h, double ms_out[7], int64_t* frames, int reset);
+/* Number of kernels this library has launched on the handle's context since creation. */
+int vilf_launch_count(vilf_handle* h, int64_t* launches);
+/* The CUDA stream all work of this handle is issued on (for external cudaEvent timing). */
+int vilf_get_stream(vilf_handle* h, void** cuda_stream);
+/* Counts on the device after the last frame: n_edge, n_surf, n_ds_edge, n_ds_surf, n_map_edge, n_map_surf, status bits, frames. */
+int vilf_get_counts(vilf_handle* h, int32_t out8[8]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VILF_H_ */

@@ -1,0 +1,346 @@
+"""ctypes binding of libvilf_cuda.so (include/vilf.h) — the test / bench harness side of the C ABI.
+
+The shared library is the product; this module only marshals numpy arrays into it.  There is no CPU
+fallback: importing works without a GPU (so that the symbol table can be checked), every call needs one.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvilf_cuda.so")
+
+STATUS = {0: "OK", 1: "INVALID", 2: "CUDA", 3: "CAPACITY", 4: "UNSUPPORTED", 5: "STATE"}
+
+
+class VilfError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"vilf status {code} ({STATUS.get(code, '?')}): {msg}")
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("n_scan", C.c_int32), ("n_rings", C.c_int32),
+        ("lidar_min", C.c_double), ("lidar_max", C.c_double), ("edge_threshold", C.c_double),
+        ("edge_leaf", C.c_double), ("surf_leaf", C.c_double), ("crop_half", C.c_double),
+        ("knn_gate", C.c_double), ("huber", C.c_double),
+        ("outer_iters", C.c_int32), ("lm_max_iters", C.c_int32),
+        ("max_scan_points", C.c_int32), ("max_map_points", C.c_int32),
+    ]
+
+
+# every symbol include/vilf.h declares (tests/test_abi.py checks the .so exports all of them)
+SYMBOLS = [
+    "vilf_default_config", "vilf_create", "vilf_create_batch", "vilf_destroy", "vilf_last_error", "vilf_host_alloc", "vilf_host_free",
+    "vilf_process_scan", "vilf_submit_scan", "vilf_wait", "vilf_submit_scan_batch", "vilf_wait_batch", "vilf_submit_scan_batch_dev",
+    "vilf_feature_extract", "vilf_get_features", "vilf_map_init", "vilf_map_init_points", "vilf_update", "vilf_update_points",
+    "vilf_get_pose", "vilf_get_cloud", "vilf_voxel_downsample", "vilf_crop_voxel_downsample", "vilf_crop_box", "vilf_knn5",
+    "vilf_factors", "vilf_normal_equations", "vilf_solve", "vilf_get_solves", "vilf_state_export", "vilf_state_import",
+    "vilf_profile_enable", "vilf_profile_read", "vilf_launch_count", "vilf_get_stream", "vilf_get_counts",
+]
+
+_lib = None
+
+
+def lib():
+    """Load the shared library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.vilf_last_error.restype = C.c_char_p
+        _lib.vilf_last_error.argtypes = [C.c_void_p]
+    return _lib
+
+
+def default_config(**kw) -> Config:
+    c = Config()
+    lib().vilf_default_config(C.byref(c))
+    for k, v in kw.items():
+        if not hasattr(c, k):
+            raise AttributeError(k)
+        setattr(c, k, v)
+    return c
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a, t):
+    return None if a is None else a.ctypes.data_as(C.POINTER(t))
+
+
+MAP_EDGE, MAP_SURF, DS_EDGE, DS_SURF, REGISTERED, NO_REGISTERED = range(6)
+
+
+class Odometry:
+    """One lidar sequence: featureExtraction + EstimationMapping of the reference, on the GPU."""
+
+    def __init__(self, cfg: Config | None = None, device: int = 0, _handle=None, _owner=True):
+        self.cfg = cfg if cfg is not None else default_config()
+        self._owner = _owner
+        if _handle is None:
+            h = C.c_void_p()
+            rc = lib().vilf_create(C.byref(self.cfg), device, C.byref(h))
+            if rc:
+                raise VilfError(rc, "vilf_create failed (is a CUDA device visible?)")
+            self._h = h
+        else:
+            self._h = _handle
+
+    def _ck(self, rc):
+        if rc:
+            raise VilfError(rc, lib().vilf_last_error(self._h).decode())
+
+    def close(self):
+        if self._h and self._owner:
+            lib().vilf_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- per-frame path ----
+    def process_scan(self, xyzi, ring=None):
+        xyzi = _f32(xyzi)
+        pose = np.zeros(7)
+        r = None if ring is None else np.ascontiguousarray(ring, dtype=np.uint16)
+        self._ck(lib().vilf_process_scan(self._h, _p(xyzi, C.c_float), xyzi.shape[0], _p(r, C.c_uint16), _p(pose, C.c_double)))
+        return pose
+
+    def submit_scan(self, xyzi, ring=None) -> int:
+        """xyzi / ring must stay alive (and unmodified) until wait() of the returned ticket."""
+        t = C.c_int64()
+        self._ck(lib().vilf_submit_scan(self._h, _p(xyzi, C.c_float), xyzi.shape[0], _p(ring, C.c_uint16), C.byref(t)))
+        return t.value
+
+    def wait(self, ticket: int):
+        pose = np.zeros(7)
+        self._ck(lib().vilf_wait(self._h, C.c_int64(ticket), _p(pose, C.c_double)))
+        return pose
+
+    # ---- reference method surface ----
+    def feature_extract(self, xyzi, ring=None):
+        xyzi = _f32(xyzi)
+        r = None if ring is None else np.ascontiguousarray(ring, dtype=np.uint16)
+        ne, ns = C.c_int(), C.c_int()
+        self._ck(lib().vilf_feature_extract(self._h, _p(xyzi, C.c_float), xyzi.shape[0], _p(r, C.c_uint16), C.byref(ne), C.byref(ns)))
+        return ne.value, ns.value
+
+    def features(self, which: int):
+        n = C.c_int()
+        self._ck(lib().vilf_get_features(self._h, which, None, None, 0, C.byref(n)))
+        pts = np.empty((max(n.value, 1), 4), np.float32)
+        src = np.empty(max(n.value, 1), np.int32)
+        self._ck(lib().vilf_get_features(self._h, which, _p(pts, C.c_float), _p(src, C.c_int32), pts.shape[0], C.byref(n)))
+        return pts[:n.value].copy(), src[:n.value].copy()
+
+    def map_init(self, edge=None, surf=None):
+        if edge is None:
+            self._ck(lib().vilf_map_init(self._h))
+        else:
+            edge, surf = _f32(edge), _f32(surf)
+            self._ck(lib().vilf_map_init_points(self._h, _p(edge, C.c_float), edge.shape[0], _p(surf, C.c_float), surf.shape[0]))
+
+    def update(self, edge=None, surf=None):
+        pose = np.zeros(7)
+        if edge is None:
+            self._ck(lib().vilf_update(self._h, _p(pose, C.c_double)))
+        else:
+            edge, surf = _f32(edge), _f32(surf)
+            self._ck(lib().vilf_update_points(self._h, _p(edge, C.c_float), edge.shape[0], _p(surf, C.c_float), surf.shape[0], _p(pose, C.c_double)))
+        return pose
+
+    def pose(self):
+        pose = np.zeros(7)
+        rt = np.zeros(12)
+        self._ck(lib().vilf_get_pose(self._h, _p(pose, C.c_double), _p(rt, C.c_double)))
+        return pose, rt
+
+    def cloud(self, which: int):
+        n = C.c_int()
+        self._ck(lib().vilf_get_cloud(self._h, which, None, 0, C.byref(n)))
+        out = np.empty((max(n.value, 1), 4), np.float32)
+        self._ck(lib().vilf_get_cloud(self._h, which, _p(out, C.c_float), out.shape[0], C.byref(n)))
+        return out[:n.value].copy()
+
+    # ---- stage-level entry points ----
+    def voxel_downsample(self, pts, leaf: float):
+        pts = _f32(pts)
+        out = np.empty((max(pts.shape[0], 1), 4), np.float32)
+        n, g = C.c_int(), C.c_int()
+        self._ck(lib().vilf_voxel_downsample(self._h, _p(pts, C.c_float), pts.shape[0], C.c_float(leaf), _p(out, C.c_float), out.shape[0], C.byref(n), C.byref(g)))
+        return out[:n.value].copy(), bool(g.value)
+
+    def crop_voxel_downsample(self, pts, center, half: float, leaf: float):
+        pts = _f32(pts)
+        center = _f64(center)
+        out = np.empty((max(pts.shape[0], 1), 4), np.float32)
+        n = C.c_int()
+        self._ck(lib().vilf_crop_voxel_downsample(self._h, _p(pts, C.c_float), pts.shape[0], _p(center, C.c_double), C.c_double(half), C.c_float(leaf),
+                                                  _p(out, C.c_float), out.shape[0], C.byref(n)))
+        return out[:n.value].copy()
+
+    def crop_box(self, pts, mn, mx):
+        pts = _f32(pts)
+        mn, mx = _f64(mn), _f64(mx)
+        out = np.empty((max(pts.shape[0], 1), 4), np.float32)
+        n = C.c_int()
+        self._ck(lib().vilf_crop_box(self._h, _p(pts, C.c_float), pts.shape[0], _p(mn, C.c_double), _p(mx, C.c_double), _p(out, C.c_float), out.shape[0], C.byref(n)))
+        return out[:n.value].copy()
+
+    def knn5(self, mp, q):
+        mp, q = _f32(mp), _f32(q)
+        nq = q.shape[0]
+        idx = np.empty((max(nq, 1), 5), np.int32)
+        d2 = np.empty((max(nq, 1), 5), np.float32)
+        self._ck(lib().vilf_knn5(self._h, _p(mp, C.c_float), mp.shape[0], _p(q, C.c_float), nq, _p(idx, C.c_int32), _p(d2, C.c_float)))
+        return idx[:nq], d2[:nq]
+
+    def factors(self, pose, edge, surf):
+        pose, edge, surf = _f64(pose), _f32(edge), _f32(surf)
+        ne, ns = edge.shape[0], surf.shape[0]
+        ev = np.zeros(max(ne, 1), np.uint8); eab = np.zeros((max(ne, 1), 6)); enn = np.zeros((max(ne, 1), 5), np.int32); ed2 = np.zeros((max(ne, 1), 5), np.float32)
+        sv = np.zeros(max(ns, 1), np.uint8); snd = np.zeros((max(ns, 1), 4)); snn = np.zeros((max(ns, 1), 5), np.int32); sd2 = np.zeros((max(ns, 1), 5), np.float32)
+        self._ck(lib().vilf_factors(self._h, _p(pose, C.c_double), _p(edge, C.c_float), ne, _p(surf, C.c_float), ns,
+                                    _p(ev, C.c_uint8), _p(eab, C.c_double), _p(enn, C.c_int32), _p(ed2, C.c_float),
+                                    _p(sv, C.c_uint8), _p(snd, C.c_double), _p(snn, C.c_int32), _p(sd2, C.c_float)))
+        return dict(edge_valid=ev[:ne], edge_ab=eab[:ne], edge_nn=enn[:ne], edge_d2=ed2[:ne],
+                    surf_valid=sv[:ns], surf_nd=snd[:ns], surf_nn=snn[:ns], surf_d2=sd2[:ns])
+
+    def normal_equations(self, pose, pab, pnd):
+        pose, pab, pnd = _f64(pose), _f64(pab), _f64(pnd)
+        H = np.zeros(21); g = np.zeros(6); cost = C.c_double()
+        self._ck(lib().vilf_normal_equations(self._h, _p(pose, C.c_double), _p(pab, C.c_double), pab.shape[0], _p(pnd, C.c_double), pnd.shape[0],
+                                             _p(H, C.c_double), _p(g, C.c_double), C.byref(cost)))
+        return H, g, cost.value
+
+    def solve(self, pose, pab, pnd, max_iters: int = 4):
+        pose = _f64(pose).copy(); pab, pnd = _f64(pab), _f64(pnd)
+        tr = np.zeros((10, 16)); nr = C.c_int(); term = C.c_int()
+        self._ck(lib().vilf_solve(self._h, _p(pose, C.c_double), _p(pab, C.c_double), pab.shape[0], _p(pnd, C.c_double), pnd.shape[0], max_iters,
+                                  _p(tr, C.c_double), tr.shape[0], C.byref(nr), C.byref(term)))
+        return pose, tr[:nr.value].copy(), term.value
+
+    def solves(self):
+        out = np.zeros((8, 8)); n = C.c_int()
+        self._ck(lib().vilf_get_solves(self._h, _p(out, C.c_double), 8, C.byref(n)))
+        return out[:n.value].copy()
+
+    def state(self):
+        s = np.zeros(31)
+        self._ck(lib().vilf_state_export(self._h, _p(s, C.c_double)))
+        return s
+
+    def set_state(self, s, map_edge, map_surf):
+        s, me, ms = _f64(s), _f32(map_edge), _f32(map_surf)
+        self._ck(lib().vilf_state_import(self._h, _p(s, C.c_double), _p(me, C.c_float), me.shape[0], _p(ms, C.c_float), ms.shape[0]))
+
+    # ---- measurement ----
+    def profile(self, on: bool):
+        self._ck(lib().vilf_profile_enable(self._h, int(on)))
+
+    def profile_read(self, reset: bool = True):
+        ms = np.zeros(7); fr = C.c_int64()
+        self._ck(lib().vilf_profile_read(self._h, _p(ms, C.c_double), C.byref(fr), int(reset)))
+        names = ["extract", "scan_ds", "grid_build", "knn_fit", "solve", "map_update", "frame"]
+        return dict(zip(names, ms.tolist())), fr.value
+
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        self._ck(lib().vilf_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def stream(self) -> int:
+        p = C.c_void_p()
+        self._ck(lib().vilf_get_stream(self._h, C.byref(p)))
+        return p.value or 0
+
+    def counts(self):
+        c = np.zeros(8, np.int32)
+        self._ck(lib().vilf_get_counts(self._h, _p(c, C.c_int32)))
+        return dict(n_edge=int(c[0]), n_surf=int(c[1]), n_ds_edge=int(c[2]), n_ds_surf=int(c[3]), n_map_edge=int(c[4]), n_map_surf=int(c[5]),
+                    status=int(c[6]), frames=int(c[7]))
+
+
+class Batch:
+    """`count` independent sequences stepped in lock-step on one GPU (one launch sequence for all)."""
+
+    def __init__(self, cfg: Config | None = None, count: int = 1, device: int = 0):
+        self.cfg = cfg if cfg is not None else default_config()
+        self.count = count
+        self._hs = (C.c_void_p * count)()
+        rc = lib().vilf_create_batch(C.byref(self.cfg), device, count, self._hs)
+        if rc:
+            raise VilfError(rc, "vilf_create_batch failed (is a CUDA device visible?)")
+        self.seqs = [Odometry(self.cfg, device, _handle=C.c_void_p(self._hs[i]), _owner=False) for i in range(count)]
+
+    def _ck(self, rc):
+        if rc:
+            raise VilfError(rc, lib().vilf_last_error(C.c_void_p(self._hs[0])).decode())
+
+    def close(self):
+        if self._hs is not None:
+            lib().vilf_destroy(C.c_void_p(self._hs[0]))
+            self._hs = None
+            for s in self.seqs:
+                s._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _submit(self, fn, ptrs, ns, ring_ptrs):
+        n = len(ptrs)
+        arr = (C.c_void_p * n)(*ptrs)
+        cnt = (C.c_int * n)(*ns)
+        rarr = None if ring_ptrs is None else (C.c_void_p * n)(*ring_ptrs)
+        t = C.c_int64()
+        self._ck(fn(self._hs, n, arr, cnt, rarr, C.byref(t)))
+        return t.value
+
+    def submit(self, scans, rings=None) -> int:
+        """scans: list of float32 [n_i,4] host arrays (kept alive by the caller until wait)."""
+        ptrs = [s.ctypes.data for s in scans]
+        rp = None if rings is None else [r.ctypes.data for r in rings]
+        return self._submit(lib().vilf_submit_scan_batch, ptrs, [s.shape[0] for s in scans], rp)
+
+    def submit_dev(self, dev_ptrs, ns, ring_dev_ptrs=None) -> int:
+        """dev_ptrs: device addresses (ints) of float32 [n_i,4] arrays already resident in HBM."""
+        return self._submit(lib().vilf_submit_scan_batch_dev, list(dev_ptrs), list(ns), None if ring_dev_ptrs is None else list(ring_dev_ptrs))
+
+    def wait(self, ticket: int):
+        poses = np.zeros((self.count, 7))
+        self._ck(lib().vilf_wait_batch(self._hs, self.count, C.c_int64(ticket), _p(poses, C.c_double)))
+        return poses
+
+
+def host_alloc(nbytes: int) -> np.ndarray:
+    """Pinned host buffer as a uint8 numpy array (freed with host_free)."""
+    p = C.c_void_p()
+    rc = lib().vilf_host_alloc(C.byref(p), C.c_uint64(nbytes))
+    if rc:
+        raise VilfError(rc, "vilf_host_alloc failed")
+    buf = (C.c_uint8 * nbytes).from_address(p.value)
+    a = np.frombuffer(buf, dtype=np.uint8)
+    a.flags.writeable = True
+    return a
+
+
+def host_free(a: np.ndarray) -> None:
+    lib().vilf_host_free(C.c_void_p(a.ctypes.data))

@@ -1,0 +1,450 @@
+// Stage 2/3 — data association: pcl::KdTreeFLANN::setInputCloud / nearestKSearch(k=5) (EM:256-257, :128,
+// :185) replaced by an exact-within-the-gate spatial-hash grid, fused with the per-point line / plane fit of
+// EdgeCostFactor / SurfCostFactor (EM:117-232).
+//
+// Grid: cell edge c = a power of two >= sqrt(knn_gate) (1.0 m for the reference's gate of 1.0 m^2), integer
+// cell coordinates floor(x / c) are exact in fp32, bucket = hash(cell) & (H - 1), H = pow2 >= 2 * points.
+// Build = counting sort (zero, count with atomics, exclusive scan, scatter): 16 B read + 16 B written per
+// map point + 8 B per bucket.  The reordered copy carries the original map index in .w, so neighbour indices
+// are reported in the reference's map order.
+//
+// Query: one warp per feature point.  Lanes 0..26 look up the 27 buckets around the query cell, the candidate
+// lists are flattened with a warp scan and read 32 at a time (one coalesced float4 each); a candidate counts
+// only for the lane whose cell it really lies in (hash collisions are filtered by recomputing the cell).
+// Every point closer than c is inside those 27 cells, hence every neighbour with d^2 < knn_gate is found:
+// the result is exact wherever the reference uses it (EM:129/:189 reject the feature when d^2[4] >= 1).
+// Distances: ((dx*dx)+dy*dy)+dz*dz in fp32 without contraction = FLANN L2_Simple<float>.  Top-5 kept
+// replicated in registers, ordered by (d^2, index): deterministic tie break (tie class T2).
+#include "vilf_internal.cuh"
+
+namespace vilf {
+
+__device__ __forceinline__ uint32_t cell_hash(int x, int y, int z) {
+  return ((uint32_t)x * 73856093u) ^ ((uint32_t)y * 19349663u) ^ ((uint32_t)z * 83492791u);
+}
+__device__ __forceinline__ int grid_buckets(int n, int hcap) {
+  int h = 1024;
+  while (h < 2 * n && h < hcap) h <<= 1;
+  return h;
+}
+__device__ __forceinline__ void cell_of(float4 p, float inv_cell, int& cx, int& cy, int& cz) {
+  cx = (int)floorf(fmul(p.x, inv_cell));
+  cy = (int)floorf(fmul(p.y, inv_cell));
+  cz = (int)floorf(fmul(p.z, inv_cell));
+}
+
+__global__ void __launch_bounds__(256) k_grid_zero(const GridJob* __restrict__ jobs) {
+  const GridJob& J = jobs[blockIdx.y];
+  const int H = grid_buckets(*J.n, J.hcap);
+  for (int i = blockIdx.x * 256 + threadIdx.x; i <= H; i += gridDim.x * 256) J.start[i] = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *J.hvar = H;
+}
+
+__global__ void __launch_bounds__(256) k_grid_count(const GridJob* __restrict__ jobs, float inv_cell) {
+  const GridJob& J = jobs[blockIdx.y];
+  const int n = *J.n;
+  const uint32_t hm = (uint32_t)grid_buckets(n, J.hcap) - 1u;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    int cx, cy, cz;
+    cell_of(J.pts[i], inv_cell, cx, cy, cz);
+    J.rank[i] = atomicAdd(&J.start[cell_hash(cx, cy, cz) & hm], 1u);
+  }
+}
+
+__device__ __forceinline__ void grid_chunk(int total, int b, int& beg, int& end) {
+  int chunk = (total + GRID_G - 1) / GRID_G;
+  chunk = (chunk + 255) / 256 * 256;
+  beg = min(total, b * chunk);
+  end = min(total, beg + chunk);
+}
+
+__global__ void __launch_bounds__(256) k_grid_scan_partial(const GridJob* __restrict__ jobs) {
+  const GridJob& J = jobs[blockIdx.y];
+  const int total = grid_buckets(*J.n, J.hcap) + 1;
+  int beg, end;
+  grid_chunk(total, blockIdx.x, beg, end);
+  uint32_t s = 0;
+  for (int i = beg + threadIdx.x; i < end; i += 256) s += J.start[i];
+  __shared__ uint32_t red[8];
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    J.partial[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_grid_scan_final(const GridJob* __restrict__ jobs) {
+  const GridJob& J = jobs[blockIdx.y];
+  const int total = grid_buckets(*J.n, J.hcap) + 1;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ uint32_t red[256];
+  __shared__ uint32_t wsum[8];
+  uint32_t pre = 0;
+  for (int b = tid; b < (int)blockIdx.x; b += 256) pre += J.partial[b];
+  red[tid] = pre;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) { if (tid < off) red[tid] += red[tid + off]; __syncthreads(); }
+  uint32_t run = red[0];
+  int beg, end;
+  grid_chunk(total, blockIdx.x, beg, end);
+  for (int base = beg; base < end; base += 256) {
+    const int i = base + tid;
+    const uint32_t v = i < end ? J.start[i] : 0u;
+    uint32_t inc = v;  // inclusive warp scan
+    for (int off = 1; off < 32; off <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, off); if (lane >= off) inc += t; }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    uint32_t woff = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { const uint32_t c = wsum[w]; if (w < warp) woff += c; tot += c; }
+    if (i < end) J.start[i] = run + woff + inc - v;
+    run += tot;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) k_grid_scatter(const GridJob* __restrict__ jobs, float inv_cell) {
+  const GridJob& J = jobs[blockIdx.y];
+  const int n = *J.n;
+  const uint32_t hm = (uint32_t)grid_buckets(n, J.hcap) - 1u;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    const float4 p = J.pts[i];
+    int cx, cy, cz;
+    cell_of(p, inv_cell, cx, cy, cz);
+    const uint32_t pos = J.start[cell_hash(cx, cy, cz) & hm] + J.rank[i];
+    J.sorted[pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+  }
+}
+
+void launch_grid_build(const Launch& L, const GridJob* jobs_dev, int njobs, const ConfigDev& cfg) {
+  dim3 g(GRID_G, njobs);
+  k_grid_zero<<<g, 256, 0, L.st>>>(jobs_dev);
+  k_grid_count<<<g, 256, 0, L.st>>>(jobs_dev, cfg.inv_cell);
+  k_grid_scan_partial<<<g, 256, 0, L.st>>>(jobs_dev);
+  k_grid_scan_final<<<g, 256, 0, L.st>>>(jobs_dev);
+  k_grid_scatter<<<g, 256, 0, L.st>>>(jobs_dev, cfg.inv_cell);
+  *L.counter += 5;
+}
+
+// ------------------------------------------------------------------------------------------------
+// warp-cooperative 5-NN
+// ------------------------------------------------------------------------------------------------
+struct Top5 {
+  float d[5];
+  int id[5];
+};
+__device__ __forceinline__ bool closer(float d, int id, float bd, int bid) { return d < bd || (d == bd && id < bid); }
+
+__device__ __forceinline__ void top5_insert(Top5& t, float cd, int ci) {
+  bool placed = false;
+#pragma unroll
+  for (int k = 4; k > 0; --k) {
+    if (!placed) {
+      if (closer(cd, ci, t.d[k - 1], t.id[k - 1])) { t.d[k] = t.d[k - 1]; t.id[k] = t.id[k - 1]; }
+      else { t.d[k] = cd; t.id[k] = ci; placed = true; }
+    }
+  }
+  if (!placed) { t.d[0] = cd; t.id[0] = ci; }
+}
+
+// All 32 lanes of a warp call this with the same query; the result is replicated in every lane.
+__device__ __forceinline__ void warp_knn5(const GridJob& G, float inv_cell, float qx, float qy, float qz, Top5& best) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) { best.d[k] = FLT_MAX; best.id[k] = INT_MAX; }
+  const uint32_t hm = (uint32_t)(*G.hvar) - 1u;
+  int qcx, qcy, qcz;
+  cell_of(make_float4(qx, qy, qz, 0.f), inv_cell, qcx, qcy, qcz);
+  // lane < 27 owns neighbour cell (lane%3-1, (lane/3)%3-1, lane/9-1)
+  int cx = 0, cy = 0, cz = 0;
+  uint32_t s = 0, cnt = 0;
+  if (lane < 27) {
+    cx = qcx + (lane % 3) - 1; cy = qcy + ((lane / 3) % 3) - 1; cz = qcz + (lane / 9) - 1;
+    const uint32_t h = cell_hash(cx, cy, cz) & hm;
+    s = G.start[h];
+    cnt = G.start[h + 1] - s;
+  }
+  uint32_t inc = cnt;
+  for (int off = 1; off < 32; off <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, off); if (lane >= off) inc += t; }
+  const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+  for (uint32_t base = 0; base < total; base += 32) {
+    const uint32_t t = base + lane;
+    // owner = first lane whose inclusive prefix exceeds t (binary search over the replicated prefix)
+    int lo = 0, hi = 31;
+#pragma unroll
+    for (int step = 0; step < 5; ++step) {
+      const int mid = (lo + hi) >> 1;
+      const uint32_t v = __shfl_sync(0xffffffffu, inc, mid);
+      if (v > t) hi = mid; else lo = mid + 1;
+    }
+    const int owner = lo;
+    const uint32_t o_inc = __shfl_sync(0xffffffffu, inc, owner);
+    const uint32_t o_cnt = __shfl_sync(0xffffffffu, cnt, owner);
+    const uint32_t o_s = __shfl_sync(0xffffffffu, s, owner);
+    const int ocx = __shfl_sync(0xffffffffu, cx, owner), ocy = __shfl_sync(0xffffffffu, cy, owner), ocz = __shfl_sync(0xffffffffu, cz, owner);
+    float cd = FLT_MAX;
+    int ci = INT_MAX;
+    bool have = false;
+    if (t < total) {
+      const float4 p = G.sorted[o_s + (t - (o_inc - o_cnt))];
+      int pcx, pcy, pcz;
+      cell_of(p, inv_cell, pcx, pcy, pcz);
+      if (pcx == ocx && pcy == ocy && pcz == ocz) {
+        const float dx = fsub(qx, p.x), dy = fsub(qy, p.y), dz = fsub(qz, p.z);
+        cd = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
+        ci = __float_as_int(p.w);
+        have = closer(cd, ci, best.d[4], best.id[4]);
+      }
+    }
+    unsigned m = __ballot_sync(0xffffffffu, have);
+    while (m) {
+      const int l = __ffs(m) - 1;
+      m &= m - 1;
+      const float d = __shfl_sync(0xffffffffu, cd, l);
+      const int id = __shfl_sync(0xffffffffu, ci, l);
+      if (closer(d, id, best.d[4], best.id[4])) top5_insert(best, d, id);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// line / plane fits (fp64, same operation order as the oracle's restatement of Eigen)
+// ------------------------------------------------------------------------------------------------
+// Symmetric 3x3 eigen-decomposition by cyclic Jacobi (stands in for Eigen::SelfAdjointEigenSolver, EM:150).
+// Returns the two largest eigenvalues and the eigenvector of the largest.
+__device__ void eig3_largest(const double C[3][3], double& w_mid, double& w_max, D3& dir) {
+  double a[3][3], V[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { a[i][j] = C[i][j]; V[i][j] = i == j ? 1.0 : 0.0; }
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    const double off = dadd(dadd(dmul(a[0][1], a[0][1]), dmul(a[0][2], a[0][2])), dmul(a[1][2], a[1][2]));
+    const double diag = dadd(dadd(dmul(a[0][0], a[0][0]), dmul(a[1][1], a[1][1])), dmul(a[2][2], a[2][2]));
+    if (off <= dmul(1e-34, diag) || off == 0.0) break;
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+      for (int q = p + 1; q < 3; ++q) {
+        if (a[p][q] == 0.0) continue;
+        const double theta = dsub(a[q][q], a[p][p]) / dmul(2.0, a[p][q]);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / dadd(fabs(theta), sqrt(dadd(dmul(theta, theta), 1.0)));
+        const double c = 1.0 / sqrt(dadd(dmul(t, t), 1.0)), s = dmul(t, c);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const double akp = a[k][p], akq = a[k][q];
+          a[k][p] = dsub(dmul(c, akp), dmul(s, akq));
+          a[k][q] = dadd(dmul(s, akp), dmul(c, akq));
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const double apk = a[p][k], aqk = a[q][k];
+          a[p][k] = dsub(dmul(c, apk), dmul(s, aqk));
+          a[q][k] = dadd(dmul(s, apk), dmul(c, aqk));
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const double vkp = V[k][p], vkq = V[k][q];
+          V[k][p] = dsub(dmul(c, vkp), dmul(s, vkq));
+          V[k][q] = dadd(dmul(s, vkp), dmul(c, vkq));
+        }
+      }
+  }
+  const double w0 = a[0][0], w1 = a[1][1], w2 = a[2][2];
+  // ascending order with the insertion-sort tie behaviour of the oracle (first of equals stays first)
+  int i0 = 0, i1 = 1, i2 = 2;
+  double s0 = w0, s1 = w1, s2 = w2;
+  if (s1 < s0) { double t = s0; s0 = s1; s1 = t; int ti = i0; i0 = i1; i1 = ti; }
+  if (s2 < s1) {
+    double t = s1; s1 = s2; s2 = t; int ti = i1; i1 = i2; i2 = ti;
+    if (s1 < s0) { t = s0; s0 = s1; s1 = t; ti = i0; i0 = i1; i1 = ti; }
+  }
+  w_mid = s1; w_max = s2;
+  dir = i2 == 0 ? d3(V[0][0], V[1][0], V[2][0]) : (i2 == 1 ? d3(V[0][1], V[1][1], V[2][1]) : d3(V[0][2], V[1][2], V[2][2]));
+}
+
+// 5x3 least squares by Householder QR with column pivoting (stands in for colPivHouseholderQr().solve, EM:198).
+__device__ D3 lstsq5x3(const double Ain[5][3]) {
+  double A[5][3], b[5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) { b[i] = -1.0; for (int j = 0; j < 3; ++j) A[i][j] = Ain[i][j]; }
+  int perm[3] = {0, 1, 2};
+  double maxcol = 0;
+  for (int j = 0; j < 3; ++j) {
+    double s = 0;
+    for (int i = 0; i < 5; ++i) s = dadd(s, dmul(A[i][j], A[i][j]));
+    maxcol = fmax(maxcol, sqrt(s));
+  }
+  const double me = dmul(maxcol, 2.220446049250313e-16);
+  const double thr = dmul(me, me) / 5.0;
+  int npiv = 3;
+  for (int k = 0; k < 3; ++k) {
+    int bestj = k;
+    double bn = -1;
+    for (int j = k; j < 3; ++j) {
+      double s = 0;
+      for (int i = k; i < 5; ++i) s = dadd(s, dmul(A[i][j], A[i][j]));
+      if (s > bn) { bn = s; bestj = j; }
+    }
+    if (npiv == 3 && bn < dmul(thr, (double)(5 - k))) { npiv = k; break; }
+    if (bestj != k) {
+      for (int i = 0; i < 5; ++i) { const double t = A[i][k]; A[i][k] = A[i][bestj]; A[i][bestj] = t; }
+      const int tp = perm[k]; perm[k] = perm[bestj]; perm[bestj] = tp;
+    }
+    double tail = 0;
+    for (int i = k + 1; i < 5; ++i) tail = dadd(tail, dmul(A[i][k], A[i][k]));
+    const double c0 = A[k][k];
+    double beta, tau, v[5];
+    if (tail <= 2.2250738585072014e-308) {
+      tau = 0; beta = c0;
+      for (int i = k + 1; i < 5; ++i) v[i] = 0;
+    } else {
+      beta = sqrt(dadd(dmul(c0, c0), tail));
+      if (c0 >= 0) beta = -beta;
+      for (int i = k + 1; i < 5; ++i) v[i] = A[i][k] / dsub(c0, beta);
+      tau = dsub(beta, c0) / beta;
+    }
+    A[k][k] = beta;
+    for (int i = k + 1; i < 5; ++i) A[i][k] = 0;
+    for (int j = k + 1; j < 3; ++j) {
+      double tmp = A[k][j];
+      for (int i = k + 1; i < 5; ++i) tmp = dadd(tmp, dmul(v[i], A[i][j]));
+      A[k][j] = dsub(A[k][j], dmul(tau, tmp));
+      for (int i = k + 1; i < 5; ++i) A[i][j] = dsub(A[i][j], dmul(dmul(tau, v[i]), tmp));
+    }
+    double tmp = b[k];
+    for (int i = k + 1; i < 5; ++i) tmp = dadd(tmp, dmul(v[i], b[i]));
+    b[k] = dsub(b[k], dmul(tau, tmp));
+    for (int i = k + 1; i < 5; ++i) b[i] = dsub(b[i], dmul(dmul(tau, v[i]), tmp));
+  }
+  double y[3] = {0, 0, 0};
+  for (int k = npiv - 1; k >= 0; --k) {
+    double s = b[k];
+    for (int j = k + 1; j < npiv; ++j) s = dsub(s, dmul(A[k][j], y[j]));
+    y[k] = s / A[k][k];
+  }
+  double n[3];
+  for (int k = 0; k < 3; ++k) n[perm[k]] = y[k];
+  return d3(n[0], n[1], n[2]);
+}
+
+// One warp per voxel-filtered feature point: transform (EM:355-363), 5-NN, fit, factor record.
+__global__ void __launch_bounds__(256) k_knn_fit(LaneDev* lanes, const GridJob* __restrict__ grid_jobs, int lane0, int cur, ConfigDev cfg,
+                                                  const double* pose_override, int want_nn) {
+  const int ln = lane0 + blockIdx.y;
+  const LaneDev& L = lanes[ln];
+  LaneVars& V = *L.v;
+  const int me = V.n_map[0], ms = V.n_map[1];
+  if (!(me > 10 && ms > 50)) return;  // EM:254
+  const int ne = V.n_ds[0], ns = V.n_ds[1];
+  const int lane = threadIdx.x & 31;
+  const int wid = (blockIdx.x * 256 + threadIdx.x) >> 5;
+  const int nw = (gridDim.x * 256) >> 5;
+  double x[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) x[i] = pose_override ? pose_override[i] : V.x[i];
+  if (blockIdx.x == 0 && threadIdx.x == 0) V.opt_ran = 1;
+  for (int q = wid; q < ne + ns; q += nw) {
+    const int w = q < ne ? 0 : 1;
+    const int k = q < ne ? q : q - ne;
+    const float4 p = L.ds[w][k];
+    const float4 pw = associate(x, p);
+    const GridJob& G = grid_jobs[ln * 2 + w];
+    Top5 best;
+    warp_knn5(G, cfg.inv_cell, pw.x, pw.y, pw.z, best);
+    if (lane == 0) {
+      const float4* map = L.map[w][cur];
+      if (want_nn) {
+        for (int j = 0; j < 5; ++j) {
+          L.nn_idx[w][k * 5 + j] = best.id[j] == INT_MAX ? -1 : best.id[j];
+          L.nn_d2[w][k * 5 + j] = best.d[j];
+        }
+      }
+      uint8_t valid = 0;
+      if ((double)best.d[4] < cfg.knn_gate) {  // EM:129 / :189
+        D3 nb[5];
+        for (int j = 0; j < 5; ++j) { const float4 m = map[best.id[j]]; nb[j] = d3((double)m.x, (double)m.y, (double)m.z); }
+        if (w == 0) {  // EM:131-163
+          D3 center = d3(0, 0, 0);
+          for (int j = 0; j < 5; ++j) center = center + nb[j];
+          center = d3(center.x / 5.0, center.y / 5.0, center.z / 5.0);
+          double cov[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+          for (int j = 0; j < 5; ++j) {
+            const D3 z = nb[j] - center;
+            const double v[3] = {z.x, z.y, z.z};
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+              for (int c = 0; c < 3; ++c) cov[r][c] = dadd(cov[r][c], dmul(v[r], v[c]));
+          }
+          double w_mid, w_max;
+          D3 dir;
+          eig3_largest(cov, w_mid, w_max, dir);
+          if (w_max > dmul(3.0, w_mid)) {  // EM:153
+            const D3 a = 0.1 * dir + center, b = -0.1 * dir + center;  // EM:156-157
+            double* o = L.edge_pab + (size_t)k * 9;
+            o[0] = p.x; o[1] = p.y; o[2] = p.z;
+            o[3] = a.x; o[4] = a.y; o[5] = a.z;
+            o[6] = b.x; o[7] = b.y; o[8] = b.z;
+            valid = 1;
+          }
+        } else {  // EM:187-222
+          double A[5][3];
+          for (int j = 0; j < 5; ++j) { A[j][0] = nb[j].x; A[j][1] = nb[j].y; A[j][2] = nb[j].z; }
+          D3 n = lstsq5x3(A);
+          const double nn = norm3(n);
+          const double d = 1.0 / nn;            // EM:199
+          n = d3(n.x / nn, n.y / nn, n.z / nn);  // EM:200
+          bool okp = true;
+          for (int j = 0; j < 5; ++j)
+            if (fabs(dadd(dadd(dadd(dmul(n.x, nb[j].x), dmul(n.y, nb[j].y)), dmul(n.z, nb[j].z)), d)) > 0.2) { okp = false; break; }
+          if (okp) {
+            double* o = L.surf_pnd + (size_t)k * 7;
+            o[0] = p.x; o[1] = p.y; o[2] = p.z;
+            o[3] = n.x; o[4] = n.y; o[5] = n.z; o[6] = d;
+            valid = 1;
+          }
+        }
+      }
+      L.fvalid[w][k] = valid;
+    }
+  }
+}
+
+void launch_knn_fit(const Launch& L, LaneDev* lanes, const GridJob* grid_jobs, int lane0, int nlanes, int cur, const ConfigDev& cfg,
+                    const double* pose_override, int want_nn) {
+  dim3 g(KNN_G, nlanes);
+  k_knn_fit<<<g, 256, 0, L.st>>>(lanes, grid_jobs, lane0, cur, cfg, pose_override, want_nn);
+  ++*L.counter;
+}
+
+// nearestKSearch alone against an explicit map (test entry point vilf_knn5).
+__global__ void __launch_bounds__(256) k_knn_only(const GridJob* __restrict__ job, const float4* __restrict__ q, const int* nq_dev, int* idx,
+                                                   float* d2, float inv_cell) {
+  const int nq = *nq_dev;
+  const int lane = threadIdx.x & 31;
+  const int wid = (blockIdx.x * 256 + threadIdx.x) >> 5;
+  const int nw = (gridDim.x * 256) >> 5;
+  for (int i = wid; i < nq; i += nw) {
+    const float4 p = q[i];
+    Top5 best;
+    warp_knn5(*job, inv_cell, p.x, p.y, p.z, best);
+    if (lane < 5) {
+      float d = best.d[0]; int id = best.id[0];
+#pragma unroll
+      for (int j = 1; j < 5; ++j) if (lane == j) { d = best.d[j]; id = best.id[j]; }
+      idx[i * 5 + lane] = id == INT_MAX ? -1 : id;
+      d2[i * 5 + lane] = d;
+    }
+  }
+}
+
+void launch_knn_only(const Launch& L, const GridJob* job_dev, const float4* q, const int* nq_dev, int* idx, float* d2, const ConfigDev& cfg) {
+  k_knn_only<<<KNN_G, 256, 0, L.st>>>(job_dev, q, nq_dev, idx, d2, cfg.inv_cell);
+  ++*L.counter;
+}
+
+}  // namespace vilf

@@ -1,0 +1,375 @@
+// Stage 3/4 — the 6-DoF pose solve: ceres::Solve(TRUST_REGION, LEVENBERG_MARQUARDT, DENSE_QR,
+// max_num_iterations = 4, HuberLoss(0.1), LocalSE3Parameterization) of EM:263-283 as ONE kernel per outer
+// iteration and sequence: a single CTA evaluates every factor (LF:21-52 edge, LF:79-102 surf), reduces the
+// robustified normal equations (21-entry J^T J, 6-entry J^T r, cost) with warp shuffles + a fixed-order
+// shared-memory tree, and thread 0 runs Ceres' trust-region bookkeeping (Jacobi scaling fixed at iteration
+// 0, LM diagonal clamp, radius update, parameter / function / gradient tolerance exits, step rejection) on
+// the 6x6 system; the pose never leaves the device between iterations.
+//
+// Ceres solves [J S; D] y = [r; 0] by QR; here the same minimiser is obtained from the normal equations
+// (S J^T J S + D^2) y = S J^T r by Cholesky.  The two differ by rounding only (relative 1e-10 on a step of
+// 1e-2), far inside the pose tolerance (1e-4 rad / 1e-3 m); SURVEY §8a row 9 lists the schedule reproduced.
+#include "vilf_internal.cuh"
+
+namespace vilf {
+
+namespace {
+
+constexpr int NACC = 30;  // 21 H + 6 g + cost + n_edge + n_surf
+
+struct LmShared {
+  double x[7], cand[7], params[7];
+  double H[21], g[6], cost;
+  double acc[NACC];
+  double scale[6], diag[6];
+  double radius, decrease_factor, minimum_cost, x_norm, grad_max, model_cost_change, candidate_cost;
+  int iteration, step_successful, reuse_diagonal, num_invalid, done, need_eval, termination, n_edge, n_surf;
+};
+
+__device__ __forceinline__ int hidx(int i, int j) {  // upper triangle, row-major: (i <= j)
+  return i * 6 - i * (i - 1) / 2 + (j - i);
+}
+
+// common.h:137-176 se(3) exponential + LocalSE3Parameterization::Plus (EM:34-49)
+__device__ void se3_plus(const double* x, const double* delta, double* out) {
+  const D3 omega = d3(delta[0], delta[1], delta[2]), ups = d3(delta[3], delta[4], delta[5]);
+  const double theta = norm3(omega);
+  const double half = dmul(0.5, theta);
+  double imag;
+  const double real = cos(half);
+  if (theta < 1e-10) {
+    const double t2 = dmul(theta, theta), t4 = dmul(t2, t2);
+    imag = dadd(dsub(0.5, dmul(0.0208333, t2)), dmul(0.000260417, t4));
+  } else {
+    imag = sin(half) / theta;
+  }
+  Q4 dq; dq.x = dmul(imag, omega.x); dq.y = dmul(imag, omega.y); dq.z = dmul(imag, omega.z); dq.w = real;
+  double J[3][3];
+  if (theta < 1e-10) {  // J = q.matrix()
+    const double tx = dmul(2, dq.x), ty = dmul(2, dq.y), tz = dmul(2, dq.z);
+    const double twx = dmul(tx, dq.w), twy = dmul(ty, dq.w), twz = dmul(tz, dq.w);
+    const double txx = dmul(tx, dq.x), txy = dmul(ty, dq.x), txz = dmul(tz, dq.x);
+    const double tyy = dmul(ty, dq.y), tyz = dmul(tz, dq.y), tzz = dmul(tz, dq.z);
+    J[0][0] = dsub(1, dadd(tyy, tzz)); J[0][1] = dsub(txy, twz); J[0][2] = dadd(txz, twy);
+    J[1][0] = dadd(txy, twz); J[1][1] = dsub(1, dadd(txx, tzz)); J[1][2] = dsub(tyz, twx);
+    J[2][0] = dsub(txz, twy); J[2][1] = dadd(tyz, twx); J[2][2] = dsub(1, dadd(txx, tyy));
+  } else {
+    const double Om[3][3] = {{0, -omega.z, omega.y}, {omega.z, 0, -omega.x}, {-omega.y, omega.x, 0}};
+    double Om2[3][3];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) Om2[i][j] = dadd(dadd(dmul(Om[i][0], Om[0][j]), dmul(Om[i][1], Om[1][j])), dmul(Om[i][2], Om[2][j]));
+    const double a = dsub(1, cos(theta)) / dmul(theta, theta);
+    const double b = dsub(theta, sin(theta)) / pow(theta, 3.0);
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) J[i][j] = dadd(dadd(i == j ? 1.0 : 0.0, dmul(a, Om[i][j])), dmul(b, Om2[i][j]));
+  }
+  const D3 dt = d3(dadd(dadd(dmul(J[0][0], ups.x), dmul(J[0][1], ups.y)), dmul(J[0][2], ups.z)),
+                   dadd(dadd(dmul(J[1][0], ups.x), dmul(J[1][1], ups.y)), dmul(J[1][2], ups.z)),
+                   dadd(dadd(dmul(J[2][0], ups.x), dmul(J[2][1], ups.y)), dmul(J[2][2], ups.z)));
+  Q4 q; q.x = x[0]; q.y = x[1]; q.z = x[2]; q.w = x[3];
+  // Eigen quaternion product dq * q
+  const double px = dsub(dadd(dadd(dmul(dq.w, q.x), dmul(dq.x, q.w)), dmul(dq.y, q.z)), dmul(dq.z, q.y));
+  const double py = dsub(dadd(dadd(dmul(dq.w, q.y), dmul(dq.y, q.w)), dmul(dq.z, q.x)), dmul(dq.x, q.z));
+  const double pz = dsub(dadd(dadd(dmul(dq.w, q.z), dmul(dq.z, q.w)), dmul(dq.x, q.y)), dmul(dq.y, q.x));
+  const double pw = dsub(dsub(dsub(dmul(dq.w, q.w), dmul(dq.x, q.x)), dmul(dq.y, q.y)), dmul(dq.z, q.z));
+  const D3 tp = qrot(dq, d3(x[4], x[5], x[6])) + dt;
+  out[0] = px; out[1] = py; out[2] = pz; out[3] = pw;
+  out[4] = tp.x; out[5] = tp.y; out[6] = tp.z;
+}
+
+__device__ __forceinline__ void huber(double s, double a, double& rho0, double& sq) {
+  const double b = dmul(a, a);
+  if (s > b) {
+    const double r = sqrt(s);
+    rho0 = dsub(dmul(dmul(2, a), r), b);
+    sq = sqrt(fmax(DBL_MIN, a / r));  // Corrector with rho'' <= 0: residual and Jacobian scaled by sqrt(rho')
+  } else {
+    rho0 = s;
+    sq = 1.0;
+  }
+}
+
+__device__ __forceinline__ void accumulate_row(double* acc, const double* J, double r) {
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+#pragma unroll
+    for (int j = i; j < 6; ++j) acc[hidx(i, j)] += J[i] * J[j];
+    acc[21 + i] += J[i] * r;
+  }
+}
+
+// Robustified cost / gradient / normal matrix of every valid factor at pose x; result in S.acc (all threads sync).
+__device__ void evaluate(const LaneDev& L, int ne, int ns, const double* x, double hub, LmShared& S, double (*wred)[NACC]) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double acc[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) acc[i] = 0;
+  Q4 q; q.x = x[0]; q.y = x[1]; q.z = x[2]; q.w = x[3];
+  const D3 t = d3(x[4], x[5], x[6]);
+  for (int i = tid; i < ne + ns; i += LM_THREADS) {
+    if (i < ne) {
+      if (!L.fvalid[0][i]) continue;
+      const double* f = L.edge_pab + (size_t)i * 9;
+      const D3 p = d3(f[0], f[1], f[2]), a = d3(f[3], f[4], f[5]), b = d3(f[6], f[7], f[8]);
+      const D3 lp = qrot(q, p) + t;                    // LF:26
+      const D3 nu = cross3(lp - a, lp - b);            // LF:28
+      const D3 ab = a - b;
+      const double abn = norm3(ab);
+      double r[3] = {nu.x / abn, nu.y / abn, nu.z / abn};  // LF:31-33
+      const double nsab[3][3] = {{0, ab.z, -ab.y}, {-ab.z, 0, ab.x}, {ab.y, -ab.x, 0}};  // -skew(ab)
+      const double jse3[3][6] = {{0, lp.z, -lp.y, 1, 0, 0}, {-lp.z, 0, lp.x, 0, 1, 0}, {lp.y, -lp.x, 0, 0, 0, 1}};  // [-skew(lp) | I], LF:40-42
+      double J[3][6];
+#pragma unroll
+      for (int ii = 0; ii < 3; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < 6; ++jj)
+          J[ii][jj] = dadd(dadd(dmul(nsab[ii][0], jse3[0][jj]), dmul(nsab[ii][1], jse3[1][jj])), dmul(nsab[ii][2], jse3[2][jj])) / abn;  // LF:47
+      double rho0, sq;
+      huber(dadd(dadd(dmul(r[0], r[0]), dmul(r[1], r[1])), dmul(r[2], r[2])), hub, rho0, sq);
+      acc[27] += 0.5 * rho0;
+      acc[28] += 1.0;
+#pragma unroll
+      for (int ii = 0; ii < 3; ++ii) {
+#pragma unroll
+        for (int jj = 0; jj < 6; ++jj) J[ii][jj] = dmul(J[ii][jj], sq);
+        r[ii] = dmul(r[ii], sq);
+        accumulate_row(acc, J[ii], r[ii]);
+      }
+    } else {
+      const int k = i - ne;
+      if (!L.fvalid[1][k]) continue;
+      const double* f = L.surf_pnd + (size_t)k * 7;
+      const D3 p = d3(f[0], f[1], f[2]), n = d3(f[3], f[4], f[5]);
+      const D3 pw = qrot(q, p) + t;                 // LF:83
+      double r = dadd(dot3(n, pw), f[6]);           // LF:84
+      const double jse3[3][6] = {{0, pw.z, -pw.y, 1, 0, 0}, {-pw.z, 0, pw.x, 0, 1, 0}, {pw.y, -pw.x, 0, 0, 0, 1}};
+      double J[6];
+#pragma unroll
+      for (int jj = 0; jj < 6; ++jj) J[jj] = dadd(dadd(dmul(n.x, jse3[0][jj]), dmul(n.y, jse3[1][jj])), dmul(n.z, jse3[2][jj]));  // LF:97
+      double rho0, sq;
+      huber(dmul(r, r), hub, rho0, sq);
+      acc[27] += 0.5 * rho0;
+      acc[29] += 1.0;
+#pragma unroll
+      for (int jj = 0; jj < 6; ++jj) J[jj] = dmul(J[jj], sq);
+      r = dmul(r, sq);
+      accumulate_row(acc, J, r);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) {
+    double v = acc[i];
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (lane == 0) wred[warp][i] = v;
+  }
+  __syncthreads();
+  if (tid < NACC) {
+    double v = 0;
+    for (int w = 0; w < LM_THREADS / 32; ++w) v += wred[w][tid];
+    S.acc[tid] = v;
+  }
+  __syncthreads();
+}
+
+__device__ double norm7(const double* v) {
+  double s = 0;
+  for (int i = 0; i < 7; ++i) s = dadd(s, dmul(v[i], v[i]));
+  return sqrt(s);
+}
+
+__device__ void record(SolveTraceDev& T, const LmShared& S, int valid, int succ, double rel, double stepn) {
+  if (T.n_rows >= MAX_TRACE_ROWS) return;
+  LmRow& r = T.rows[T.n_rows++];
+  r.iteration = S.iteration; r.step_valid = valid; r.step_successful = succ; r.cost = S.cost; r.candidate_cost = S.candidate_cost;
+  r.model_cost_change = S.model_cost_change; r.relative_decrease = rel; r.radius = S.radius; r.step_norm = stepn;
+  for (int i = 0; i < 7; ++i) r.x[i] = S.x[i];
+}
+
+// Take the freshly evaluated normal equations as the linearisation at S.x (EvaluateGradientAndJacobian).
+__device__ void adopt_linearisation(LmShared& S, bool first) {
+  for (int i = 0; i < 21; ++i) S.H[i] = S.acc[i];
+  for (int i = 0; i < 6; ++i) S.g[i] = S.acc[21 + i];
+  S.cost = S.acc[27];
+  if (first)
+    for (int j = 0; j < 6; ++j) S.scale[j] = 1.0 / (1.0 + sqrt(S.H[hidx(j, j)]));  // Jacobi scaling, fixed at iteration 0
+  double ng[6], proj[7];
+  for (int j = 0; j < 6; ++j) ng[j] = -S.g[j];
+  se3_plus(S.x, ng, proj);
+  double gm = 0;
+  for (int i = 0; i < 7; ++i) gm = fmax(gm, fabs(S.x[i] - proj[i]));
+  S.grad_max = gm;
+}
+
+// (S J^T J S + D^2) y = S g by Cholesky; step = -y.  Returns false when the system is not positive definite.
+__device__ bool lm_step(const LmShared& S, double* step) {
+  double A[6][6], rhs[6];
+  for (int i = 0; i < 6; ++i) {
+    for (int j = i; j < 6; ++j) { A[i][j] = S.H[hidx(i, j)] * S.scale[i] * S.scale[j]; A[j][i] = A[i][j]; }
+    const double lm = sqrt(S.diag[i] / S.radius);  // LevenbergMarquardtStrategy: lm_diagonal = sqrt(diagonal / radius)
+    A[i][i] += lm * lm;
+    rhs[i] = S.g[i] * S.scale[i];
+  }
+  double Lc[6][6];
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j <= i; ++j) {
+      double s = A[i][j];
+      for (int k = 0; k < j; ++k) s -= Lc[i][k] * Lc[j][k];
+      if (i == j) {
+        if (!(s > 0)) return false;
+        Lc[i][i] = sqrt(s);
+      } else {
+        Lc[i][j] = s / Lc[j][j];
+      }
+    }
+  double z[6], y[6];
+  for (int i = 0; i < 6; ++i) {
+    double s = rhs[i];
+    for (int k = 0; k < i; ++k) s -= Lc[i][k] * z[k];
+    z[i] = s / Lc[i][i];
+  }
+  for (int i = 5; i >= 0; --i) {
+    double s = z[i];
+    for (int k = i + 1; k < 6; ++k) s -= Lc[k][i] * y[k];
+    y[i] = s / Lc[i][i];
+  }
+  bool finite = true;
+  for (int i = 0; i < 6; ++i) { step[i] = -y[i]; if (!isfinite(step[i])) finite = false; }
+  return finite;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(LM_THREADS, 1) k_solve(LaneDev* lanes, int lane0, int outer, int finalize, ConfigDev cfg, int max_iters) {
+  const LaneDev& L = lanes[lane0 + blockIdx.x];
+  LaneVars& V = *L.v;
+  __shared__ LmShared S;
+  __shared__ double wred[LM_THREADS / 32][NACC];
+  const int tid = threadIdx.x;
+  const bool run = V.opt_ran != 0;  // EM:254 decided by the association kernel
+  const int ne = V.n_ds[0], ns = V.n_ds[1];
+  SolveTraceDev& T = L.trace[outer];
+  if (run) {
+    if (tid == 0) {
+      for (int i = 0; i < 7; ++i) { S.x[i] = V.x[i]; S.params[i] = V.x[i]; }
+      S.radius = 1e4; S.decrease_factor = 2.0; S.minimum_cost = DBL_MAX; S.reuse_diagonal = 0; S.num_invalid = 0;
+      S.model_cost_change = 0; S.candidate_cost = 0; S.iteration = 0; S.step_successful = 1; S.done = 0; S.termination = 0;
+      T.n_rows = 0;
+    }
+    __syncthreads();
+    evaluate(L, ne, ns, S.x, cfg.huber, S, wred);
+    if (tid == 0) {
+      S.n_edge = (int)S.acc[28]; S.n_surf = (int)S.acc[29];
+      T.n_edge = S.n_edge; T.n_surf = S.n_surf;
+      if (S.n_edge + S.n_surf == 0) {
+        S.done = 1; S.termination = 4;
+      } else {
+        S.x_norm = norm7(S.x);
+        adopt_linearisation(S, true);
+        for (int i = 0; i < 21; ++i) T.H0[i] = S.H[i];
+        for (int i = 0; i < 6; ++i) T.g0[i] = S.g[i];
+        T.cost0 = S.cost;
+        record(T, S, 1, 1, 0, 0);
+      }
+    }
+    __syncthreads();
+    for (;;) {  // S.done / S.need_eval are written by thread 0 only between barriers and read by all right after one
+      if (tid == 0 && !S.done) {
+        S.need_eval = 0;
+        // FinalizeIterationAndCheckIfMinimizerCanContinue
+        if (S.step_successful && S.cost < S.minimum_cost) { S.minimum_cost = S.cost; for (int i = 0; i < 7; ++i) S.params[i] = S.x[i]; }
+        if (S.iteration >= max_iters) { S.termination = 0; S.done = 1; }
+        else if (S.step_successful && S.grad_max <= 1e-10) { S.termination = 3; S.done = 1; }
+        else if (S.radius <= 1e-32) { S.termination = 5; S.done = 1; }
+        else {
+          ++S.iteration;
+          if (!S.reuse_diagonal)
+            for (int j = 0; j < 6; ++j) S.diag[j] = fmin(fmax(S.H[hidx(j, j)] * S.scale[j] * S.scale[j], 1e-6), 1e32);
+          double step[6];
+          bool valid = lm_step(S, step);
+          S.reuse_diagonal = 1;
+          if (valid) {  // model_cost_change = -step^T (gs + Hs step / 2)
+            double mc = 0;
+            for (int i = 0; i < 6; ++i) {
+              double hs = 0;
+              for (int j = 0; j < 6; ++j) hs += S.H[i <= j ? hidx(i, j) : hidx(j, i)] * S.scale[i] * S.scale[j] * step[j];
+              mc += step[i] * (S.g[i] * S.scale[i] + 0.5 * hs);
+            }
+            S.model_cost_change = -mc;
+            valid = S.model_cost_change > 0.0;
+          }
+          if (!valid) {  // HandleInvalidStep
+            if (++S.num_invalid >= 5) { S.termination = 5; S.done = 1; record(T, S, 0, 0, 0, 0); }
+            else {
+              S.radius = S.radius / S.decrease_factor; S.decrease_factor *= 2.0; S.reuse_diagonal = 1; S.step_successful = 0;
+              record(T, S, 0, 0, 0, 0);
+            }
+          } else {
+            S.num_invalid = 0;
+            double delta[6];
+            for (int j = 0; j < 6; ++j) delta[j] = step[j] * S.scale[j];
+            se3_plus(S.x, delta, S.cand);
+            S.need_eval = 1;
+          }
+        }
+      }
+      __syncthreads();
+      if (S.done) break;
+      if (S.need_eval) {
+        evaluate(L, ne, ns, S.cand, cfg.huber, S, wred);
+        if (tid == 0) {
+          S.candidate_cost = S.acc[27];
+          double sn = 0;
+          for (int i = 0; i < 7; ++i) sn += (S.x[i] - S.cand[i]) * (S.x[i] - S.cand[i]);
+          sn = sqrt(sn);
+          const double cost_change = S.cost - S.candidate_cost;
+          if (sn <= 1e-8 * (S.x_norm + 1e-8)) { S.termination = 1; S.done = 1; record(T, S, 1, 0, 0, sn); }            // parameter tolerance
+          else if (fabs(cost_change) <= 1e-6 * S.cost) { S.termination = 2; S.done = 1; record(T, S, 1, 0, 0, sn); }    // function tolerance
+          else {
+            const double rel = cost_change / S.model_cost_change;
+            if (rel > 1e-3) {  // HandleSuccessfulStep
+              for (int i = 0; i < 7; ++i) S.x[i] = S.cand[i];
+              S.x_norm = norm7(S.x);
+              adopt_linearisation(S, false);
+              S.step_successful = 1;
+              S.radius = S.radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * rel - 1.0, 3.0));
+              S.radius = fmin(1e16, S.radius);
+              S.decrease_factor = 2.0;
+              S.reuse_diagonal = 0;
+              record(T, S, 1, 1, rel, sn);
+            } else {  // HandleUnsuccessfulStep
+              S.step_successful = 0;
+              S.radius = S.radius / S.decrease_factor; S.decrease_factor *= 2.0; S.reuse_diagonal = 1;
+              record(T, S, 1, 0, rel, sn);
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      for (int i = 0; i < 7; ++i) V.x[i] = S.params[i];
+      T.termination = S.termination;
+      T.final_cost = S.cost;
+    }
+  }
+  if (finalize && tid == 0) {  // EM:291-293: globalOdom from q_w_c / t_w_c (also when the optimisation was skipped)
+    const double* x = V.x;
+    const double tx = dmul(2, x[0]), ty = dmul(2, x[1]), tz = dmul(2, x[2]);
+    const double twx = dmul(tx, x[3]), twy = dmul(ty, x[3]), twz = dmul(tz, x[3]);
+    const double txx = dmul(tx, x[0]), txy = dmul(ty, x[0]), txz = dmul(tz, x[0]);
+    const double tyy = dmul(ty, x[1]), tyz = dmul(tz, x[1]), tzz = dmul(tz, x[2]);
+    double* o = V.odom;
+    o[0] = dsub(1, dadd(tyy, tzz)); o[1] = dsub(txy, twz); o[2] = dadd(txz, twy);
+    o[3] = dadd(txy, twz); o[4] = dsub(1, dadd(txx, tzz)); o[5] = dsub(tyz, twx);
+    o[6] = dsub(txz, twy); o[7] = dadd(tyz, twx); o[8] = dsub(1, dadd(txx, tyy));
+    o[9] = x[4]; o[10] = x[5]; o[11] = x[6];
+    V.frames += 1;
+  }
+}
+
+void launch_solve(const Launch& L, LaneDev* lanes, int lane0, int nlanes, int outer, int finalize, const ConfigDev& cfg, int max_iters) {
+  k_solve<<<nlanes, LM_THREADS, 0, L.st>>>(lanes, lane0, outer, finalize, cfg, max_iters);
+  ++*L.counter;
+}
+
+}  // namespace vilf

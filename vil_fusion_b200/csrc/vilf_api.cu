@@ -1,0 +1,961 @@
+// C ABI of libvilf_cuda.so (include/vilf.h): device context, per-sequence state, the per-frame launch
+// sequence and the stage-level entry points.  No CPU fallback: every entry point needs a CUDA device.
+#include "vilf_internal.cuh"
+#include "../../include/vilf.h"
+
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <new>
+#include <vector>
+
+using namespace vilf;
+
+namespace {
+
+constexpr int RING_SLOTS = 8;
+constexpr int VV_PER_LANE = 4;  // scan edge, scan surf, map edge, map surf
+constexpr int N_STAGE = 7;
+constexpr int MAX_MARKS = 16;
+
+struct Slot {
+  cudaEvent_t done = nullptr;
+  cudaEvent_t stage[MAX_MARKS] = {};  // profiling: event k closes an interval attributed to stage_tag[k]
+  int stage_tag[MAX_MARKS] = {};
+  int n_marks = 0;
+  LaneVars* vars_pin = nullptr;  // [nlanes]
+  int64_t ticket = -1;
+  int lane0 = 0, nl = 0;
+  bool profiled = false, first = false;
+};
+
+struct Ctx {
+  int device = 0;
+  vilf_config ucfg;
+  ConfigDev cfg;
+  int nlanes = 0;
+  cudaStream_t st = nullptr, copy_st = nullptr;
+  int64_t launches = 0;
+  std::vector<void*> allocs;
+  std::vector<void*> pinned;
+  std::vector<LaneDev> lanes_host;
+  LaneDev* lanes_dev = nullptr;
+  LaneVars* vars_dev = nullptr;
+  SolveTraceDev* trace_dev = nullptr;
+  VoxVars* vv_dev = nullptr;  // [nlanes * 4 + 1] (last = aux)
+  SortJob* ring_jobs_dev[2] = {nullptr, nullptr};  // per scan buffer (n = &n_scan[sel])
+  VoxJob* vox_scan_dev = nullptr; SortJob* vox_scan_sort_dev = nullptr;      // [nlanes*2]
+  VoxJob* vox_map_dev[2] = {nullptr, nullptr}; SortJob* vox_map_sort_dev[2] = {nullptr, nullptr};  // [cur][nlanes*2]
+  GridJob* grid_dev[2] = {nullptr, nullptr};                                  // [buf][nlanes*2]
+  // aux (stage-level entry points)
+  int cap_aux = 0;
+  float4* aux_in = nullptr; float4* aux_out = nullptr;
+  int* aux_n = nullptr;      // [4] n_in, n_out, nq, spare
+  double* aux_pose = nullptr;  // [8]
+  int* aux_idx = nullptr; float* aux_d2 = nullptr;
+  VoxJob* aux_vox_dev = nullptr; SortJob* aux_sort_dev = nullptr; GridJob* aux_grid_dev = nullptr;
+  VoxJob aux_vox_host;
+  int* aux_head_cnt = nullptr;
+  // per-lane host state
+  std::vector<int> cur;        // map buffer holding the current local maps
+  std::vector<int> have_map;   // localMapInited / import done
+  std::vector<int> have_feat;  // features of a scan are resident
+  std::vector<int> last_init;  // last map operation was the initialisation (getMapCloud semantics)
+  std::vector<int64_t> frame_no;
+  std::vector<vilf_handle*> handles;
+  // async ring
+  Slot slots[RING_SLOTS];
+  int64_t next_ticket = 0;
+  cudaEvent_t extract_done[2] = {nullptr, nullptr}, h2d_done[2] = {nullptr, nullptr};
+  int64_t scan_sel = 0;
+  // profiling
+  bool profile = false;
+  double stage_ms[N_STAGE] = {0, 0, 0, 0, 0, 0, 0};
+  int64_t prof_frames = 0;
+  char err[512] = {0};
+};
+
+}  // namespace
+
+struct vilf_handle {
+  Ctx* ctx;
+  int lane;
+};
+
+namespace {
+
+#define CK(call)                                                                                          \
+  do {                                                                                                    \
+    cudaError_t e_ = (call);                                                                              \
+    if (e_ != cudaSuccess) {                                                                              \
+      snprintf(C->err, sizeof(C->err), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return VILF_ERR_CUDA;                                                                               \
+    }                                                                                                     \
+  } while (0)
+
+template <class T>
+cudaError_t dalloc(Ctx* C, T** p, size_t count) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 256);
+  if (e != cudaSuccess) return e;
+  C->allocs.push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return cudaMemset(q, 0, count * sizeof(T) + 256);
+}
+
+int fail(Ctx* C, int code, const char* msg) {
+  snprintf(C->err, sizeof(C->err), "%s", msg);
+  return code;
+}
+
+Launch mk(Ctx* C) { Launch L; L.st = C->st; L.counter = &C->launches; return L; }
+
+int pow2_ge(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+int alloc_sort(Ctx* C, SortJob& S, const int* n, const int* bits, int fixed_bits, int npass, int cap, bool digit_start) {
+  S.n = n; S.bits = bits; S.fixed_bits = fixed_bits; S.npass = npass;
+  for (int b = 0; b < 2; ++b) {
+    CK(dalloc(C, &S.key[b], (size_t)cap));
+    CK(dalloc(C, &S.val[b], (size_t)cap));
+  }
+  CK(dalloc(C, &S.hist, (size_t)SORT_G * 256));
+  S.digit_start = nullptr;
+  if (digit_start) CK(dalloc(C, &S.digit_start, 260));
+  return VILF_OK;
+}
+
+int alloc_grid(Ctx* C, GridJob& G, const float4* pts, const int* n, int cap) {
+  G.pts = pts; G.n = n;
+  G.hcap = pow2_ge(2 * cap);
+  if (G.hcap < 1024) G.hcap = 1024;
+  CK(dalloc(C, &G.start, (size_t)G.hcap + 8));
+  CK(dalloc(C, &G.rank, (size_t)cap));
+  CK(dalloc(C, &G.sorted, (size_t)cap));
+  CK(dalloc(C, &G.hvar, 4));
+  CK(dalloc(C, &G.partial, (size_t)GRID_G));
+  return VILF_OK;
+}
+
+int build_ctx(Ctx* C) {
+  const vilf_config& u = C->ucfg;
+  ConfigDev& c = C->cfg;
+  c.n_scan = u.n_scan; c.n_rings = u.n_rings;
+  if (u.n_scan == 0) c.rings_total = u.n_rings;
+  else if (u.n_scan == 16 || u.n_scan == 32 || u.n_scan == 64) c.rings_total = u.n_scan;
+  else c.rings_total = 1;
+  c.lidar_min = u.lidar_min; c.lidar_max = u.lidar_max; c.edge_threshold = u.edge_threshold;
+  c.knn_gate = u.knn_gate; c.huber = u.huber; c.crop_half = u.crop_half;
+  c.edge_leaf = (float)u.edge_leaf; c.surf_leaf = (float)u.surf_leaf;  // setLeafSize takes floats (EM:85-86)
+  float cell = 1.0f / 1024.0f;
+  while ((double)cell * (double)cell < u.knn_gate) cell *= 2.0f;  // power of two >= sqrt(gate)
+  c.inv_cell = 1.0f / cell;
+  c.outer_iters = u.outer_iters; c.lm_max_iters = u.lm_max_iters;
+  c.cap_scan = u.max_scan_points; c.cap_map = u.max_map_points;
+  const int NL = C->nlanes;
+  const int capS = c.cap_scan, capM = c.cap_map + c.cap_scan;
+
+  CK(cudaSetDevice(C->device));
+  CK(cudaStreamCreateWithFlags(&C->st, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&C->copy_st, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    CK(cudaEventCreateWithFlags(&C->extract_done[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&C->h2d_done[i], cudaEventDisableTiming));
+  }
+  for (int s = 0; s < RING_SLOTS; ++s) {
+    CK(cudaEventCreateWithFlags(&C->slots[s].done, cudaEventDisableTiming));
+    for (int k = 0; k < MAX_MARKS; ++k) CK(cudaEventCreate(&C->slots[s].stage[k]));
+    void* p = nullptr;
+    CK(cudaMallocHost(&p, sizeof(LaneVars) * NL));
+    C->pinned.push_back(p);
+    C->slots[s].vars_pin = reinterpret_cast<LaneVars*>(p);
+  }
+  CK(dalloc(C, &C->vars_dev, (size_t)NL));
+  CK(dalloc(C, &C->trace_dev, (size_t)NL * MAX_OUTER));
+  CK(dalloc(C, &C->vv_dev, (size_t)NL * VV_PER_LANE + 1));
+  CK(dalloc(C, &C->lanes_dev, (size_t)NL));
+  C->lanes_host.resize(NL);
+  std::vector<SortJob> ring_jobs[2] = {std::vector<SortJob>(NL), std::vector<SortJob>(NL)};
+  std::vector<VoxJob> vox_scan(NL * 2), vox_map[2] = {std::vector<VoxJob>(NL * 2), std::vector<VoxJob>(NL * 2)};
+  std::vector<SortJob> vox_scan_sort(NL * 2), vox_map_sort(NL * 2);
+  std::vector<GridJob> grid[2] = {std::vector<GridJob>(NL * 2), std::vector<GridJob>(NL * 2)};
+  std::vector<LaneVars> vars0(NL);
+  for (int l = 0; l < NL; ++l) {
+    LaneDev& L = C->lanes_host[l];
+    memset(&L, 0, sizeof(L));
+    L.v = C->vars_dev + l;
+    L.trace = C->trace_dev + (size_t)l * MAX_OUTER;
+    for (int b = 0; b < 2; ++b) {
+      CK(dalloc(C, &L.scan[b], (size_t)capS));
+      CK(dalloc(C, &L.ring_in[b], (size_t)capS));
+    }
+    int rc = alloc_sort(C, L.ring_sort, &L.v->n_scan[0], nullptr, 8, 1, capS, true);
+    if (rc) return rc;
+    for (int b = 0; b < 2; ++b) { ring_jobs[b][l] = L.ring_sort; ring_jobs[b][l].n = &L.v->n_scan[b]; }
+    CK(dalloc(C, &L.sec_cnt, (size_t)MAX_RINGS * SECTORS));
+    CK(dalloc(C, &L.sec_edge, (size_t)MAX_RINGS * SECTORS * EDGES_PER_SECTOR));
+    CK(dalloc(C, &L.sec_edge_src, (size_t)MAX_RINGS * SECTORS * EDGES_PER_SECTOR));
+    CK(dalloc(C, &L.sec_surf, (size_t)capS));
+    CK(dalloc(C, &L.sec_surf_src, (size_t)capS));
+    for (int w = 0; w < 2; ++w) {
+      CK(dalloc(C, &L.feat[w], (size_t)capS));
+      CK(dalloc(C, &L.feat_src[w], (size_t)capS));
+      CK(dalloc(C, &L.ds[w], (size_t)capS));
+      for (int b = 0; b < 2; ++b) CK(dalloc(C, &L.map[w][b], (size_t)capM));
+      CK(dalloc(C, &L.fvalid[w], (size_t)capS));
+      CK(dalloc(C, &L.nn_idx[w], (size_t)capS * 5));
+      CK(dalloc(C, &L.nn_d2[w], (size_t)capS * 5));
+    }
+    CK(dalloc(C, &L.edge_pab, (size_t)capS * 9));
+    CK(dalloc(C, &L.surf_pnd, (size_t)capS * 7));
+    // voxel jobs: scan features (EM:248-251)
+    for (int w = 0; w < 2; ++w) {
+      VoxJob& J = vox_scan[l * 2 + w];
+      memset(&J, 0, sizeof(J));
+      J.in = L.feat[w]; J.n_in = w ? &L.v->n_surf : &L.v->n_edge;
+      J.leaf = w ? c.surf_leaf : c.edge_leaf;
+      J.crop = 0; J.passthrough = 0; J.crop_center = nullptr; J.crop_half = 0;
+      J.out = L.ds[w]; J.n_out = &L.v->n_ds[w]; J.cap_out = capS; J.status = &L.v->status;
+      J.vv = C->vv_dev + l * VV_PER_LANE + w;
+      CK(dalloc(C, &J.head_cnt, (size_t)VOX_G));
+      rc = alloc_sort(C, J.sort, J.n_in, &J.vv->bits, 0, 4, capS, false);
+      if (rc) return rc;
+      vox_scan_sort[l * 2 + w] = J.sort;
+    }
+    // voxel jobs: map maintenance (EM:327-350), one table per source buffer; sort scratch shared by both
+    for (int w = 0; w < 2; ++w) {
+      SortJob srt;
+      VoxVars* vv = C->vv_dev + l * VV_PER_LANE + 2 + w;
+      rc = alloc_sort(C, srt, &L.v->n_cat[w], &vv->bits, 0, 4, capM, false);
+      if (rc) return rc;
+      int* head_cnt = nullptr;
+      CK(dalloc(C, &head_cnt, (size_t)VOX_G));
+      for (int b = 0; b < 2; ++b) {
+        VoxJob& J = vox_map[b][l * 2 + w];
+        memset(&J, 0, sizeof(J));
+        J.in = L.map[w][b]; J.n_in = &L.v->n_cat[w];
+        J.leaf = w ? c.surf_leaf : c.edge_leaf;
+        J.crop = 1; J.passthrough = 0; J.crop_center = &L.v->x[4]; J.crop_half = c.crop_half;
+        J.out = L.map[w][b ^ 1]; J.n_out = &L.v->n_map[w]; J.cap_out = c.cap_map; J.status = &L.v->status;
+        J.vv = vv; J.head_cnt = head_cnt; J.sort = srt;
+      }
+      vox_map_sort[l * 2 + w] = srt;
+    }
+    for (int w = 0; w < 2; ++w) {
+      GridJob G0;
+      rc = alloc_grid(C, G0, L.map[w][0], &L.v->n_map[w], capM);
+      if (rc) return rc;
+      grid[0][l * 2 + w] = G0;
+      GridJob G1 = G0;  // the two buffers are never indexed at the same time: share the grid storage
+      G1.pts = L.map[w][1];
+      grid[1][l * 2 + w] = G1;
+    }
+    LaneVars& V = vars0[l];
+    memset(&V, 0, sizeof(V));
+    V.x[3] = 1.0;                                   // EM:383
+    V.odom[0] = V.odom[4] = V.odom[8] = 1.0;        // EM:88-89
+    V.odom_last[0] = V.odom_last[4] = V.odom_last[8] = 1.0;
+  }
+  CK(cudaMemcpy(C->vars_dev, vars0.data(), sizeof(LaneVars) * NL, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(C->lanes_dev, C->lanes_host.data(), sizeof(LaneDev) * NL, cudaMemcpyHostToDevice));
+  for (int b = 0; b < 2; ++b) {
+    CK(dalloc(C, &C->ring_jobs_dev[b], (size_t)NL));
+    CK(cudaMemcpy(C->ring_jobs_dev[b], ring_jobs[b].data(), sizeof(SortJob) * NL, cudaMemcpyHostToDevice));
+  }
+  CK(dalloc(C, &C->vox_scan_dev, (size_t)NL * 2));
+  CK(cudaMemcpy(C->vox_scan_dev, vox_scan.data(), sizeof(VoxJob) * NL * 2, cudaMemcpyHostToDevice));
+  CK(dalloc(C, &C->vox_scan_sort_dev, (size_t)NL * 2));
+  CK(cudaMemcpy(C->vox_scan_sort_dev, vox_scan_sort.data(), sizeof(SortJob) * NL * 2, cudaMemcpyHostToDevice));
+  for (int b = 0; b < 2; ++b) {
+    CK(dalloc(C, &C->vox_map_dev[b], (size_t)NL * 2));
+    CK(cudaMemcpy(C->vox_map_dev[b], vox_map[b].data(), sizeof(VoxJob) * NL * 2, cudaMemcpyHostToDevice));
+    CK(dalloc(C, &C->vox_map_sort_dev[b], (size_t)NL * 2));
+    CK(cudaMemcpy(C->vox_map_sort_dev[b], vox_map_sort.data(), sizeof(SortJob) * NL * 2, cudaMemcpyHostToDevice));
+    CK(dalloc(C, &C->grid_dev[b], (size_t)NL * 2));
+    CK(cudaMemcpy(C->grid_dev[b], grid[b].data(), sizeof(GridJob) * NL * 2, cudaMemcpyHostToDevice));
+  }
+  // aux
+  C->cap_aux = capM;
+  CK(dalloc(C, &C->aux_in, (size_t)capM));
+  CK(dalloc(C, &C->aux_out, (size_t)capM));
+  CK(dalloc(C, &C->aux_n, 8));
+  CK(dalloc(C, &C->aux_pose, 8));
+  CK(dalloc(C, &C->aux_idx, (size_t)capM * 5));
+  CK(dalloc(C, &C->aux_d2, (size_t)capM * 5));
+  CK(dalloc(C, &C->aux_vox_dev, 1));
+  CK(dalloc(C, &C->aux_sort_dev, 1));
+  CK(dalloc(C, &C->aux_grid_dev, 1));
+  {
+    VoxJob& J = C->aux_vox_host;
+    memset(&J, 0, sizeof(J));
+    J.in = C->aux_in; J.n_in = C->aux_n; J.out = C->aux_out; J.n_out = C->aux_n + 1; J.cap_out = capM;
+    J.status = C->aux_n + 3; J.vv = C->vv_dev + NL * VV_PER_LANE; J.crop_center = C->aux_pose;
+    CK(dalloc(C, &J.head_cnt, (size_t)VOX_G));
+    int rc = alloc_sort(C, J.sort, J.n_in, &J.vv->bits, 0, 4, capM, false);
+    if (rc) return rc;
+    CK(cudaMemcpy(C->aux_sort_dev, &J.sort, sizeof(SortJob), cudaMemcpyHostToDevice));
+    GridJob G;
+    rc = alloc_grid(C, G, C->aux_in, C->aux_n, capM);
+    if (rc) return rc;
+    CK(cudaMemcpy(C->aux_grid_dev, &G, sizeof(GridJob), cudaMemcpyHostToDevice));
+  }
+  C->cur.assign(NL, 0); C->have_map.assign(NL, 0); C->have_feat.assign(NL, 0); C->last_init.assign(NL, 0); C->frame_no.assign(NL, 0);
+  CK(cudaDeviceSynchronize());
+  return VILF_OK;
+}
+
+void destroy_ctx(Ctx* C) {
+  cudaSetDevice(C->device);
+  if (C->st) cudaStreamSynchronize(C->st);
+  if (C->copy_st) cudaStreamSynchronize(C->copy_st);
+  for (void* p : C->allocs) cudaFree(p);
+  for (void* p : C->pinned) cudaFreeHost(p);
+  for (int i = 0; i < 2; ++i) { if (C->extract_done[i]) cudaEventDestroy(C->extract_done[i]); if (C->h2d_done[i]) cudaEventDestroy(C->h2d_done[i]); }
+  for (int s = 0; s < RING_SLOTS; ++s) {
+    if (C->slots[s].done) cudaEventDestroy(C->slots[s].done);
+    for (int k = 0; k < MAX_MARKS; ++k) if (C->slots[s].stage[k]) cudaEventDestroy(C->slots[s].stage[k]);
+  }
+  if (C->st) cudaStreamDestroy(C->st);
+  if (C->copy_st) cudaStreamDestroy(C->copy_st);
+  for (vilf_handle* h : C->handles) delete h;
+  delete C;
+}
+
+int status_to_rc(Ctx* C, int status) {
+  if (status & ST_SECTOR_TOO_LONG) return fail(C, VILF_ERR_UNSUPPORTED, "a ring has more returns than the sector kernel supports (6*2048+10)");
+  if (status & ST_MAP_CAPACITY) return fail(C, VILF_ERR_CAPACITY, "local map exceeds max_map_points");
+  if (status & ST_SCAN_CAPACITY) return fail(C, VILF_ERR_CAPACITY, "scan exceeds max_scan_points");
+  return VILF_OK;
+}
+
+// stage tags: 0 extract, 1 scan downsample, 2 grid build, 3 kNN + fit, 4 solve, 5 map update (-1 = frame start)
+void stage_mark(Ctx* C, Slot* S, int tag) {
+  if (!S || !S->profiled || S->n_marks >= MAX_MARKS) return;
+  cudaEventRecord(S->stage[S->n_marks], C->st);
+  S->stage_tag[S->n_marks++] = tag;
+}
+
+// The per-frame launch sequence for lanes [lane0, lane0+nl), which all share `cur`, `first` and the scan slot.
+// with_extract = 0: features were uploaded by the caller (vilf_update_points / vilf_map_init_points).
+int enqueue_frame(Ctx* C, int lane0, int nl, bool first, bool with_extract, int sel, Slot* S) {
+  const Launch L = mk(C);
+  const ConfigDev& cfg = C->cfg;
+  const int cur = C->cur[lane0];
+  if (S) S->n_marks = 0;
+  stage_mark(C, S, -1);
+  launch_frame_reset(L, C->lanes_dev, lane0, nl, C->vv_dev, VV_PER_LANE, first ? 0 : 1);
+  if (with_extract) launch_extract(L, C->lanes_dev, C->ring_jobs_dev[sel], lane0, nl, sel, cfg);
+  stage_mark(C, S, 0);
+  if (first) {
+    launch_map_init(L, C->lanes_dev, lane0, nl, cur, cfg);
+    stage_mark(C, S, 5);
+    launch_grid_build(L, C->grid_dev[cur] + lane0 * 2, nl * 2, cfg);
+    stage_mark(C, S, 2);
+  } else {
+    launch_voxel(L, C->vox_scan_dev + lane0 * 2, nl * 2, C->vox_scan_sort_dev + lane0 * 2);
+    stage_mark(C, S, 1);
+    for (int it = 0; it < cfg.outer_iters; ++it) {
+      launch_knn_fit(L, C->lanes_dev, C->grid_dev[cur], lane0, nl, cur, cfg, nullptr, 0);
+      stage_mark(C, S, 3);
+      launch_solve(L, C->lanes_dev, lane0, nl, it, it == cfg.outer_iters - 1 ? 1 : 0, cfg, cfg.lm_max_iters);
+      stage_mark(C, S, 4);
+    }
+    launch_map_append(L, C->lanes_dev, lane0, nl, cur, cfg);
+    launch_voxel(L, C->vox_map_dev[cur] + lane0 * 2, nl * 2, C->vox_map_sort_dev[cur] + lane0 * 2);
+    stage_mark(C, S, 5);
+    launch_grid_build(L, C->grid_dev[cur ^ 1] + lane0 * 2, nl * 2, cfg);
+    stage_mark(C, S, 2);
+    for (int l = lane0; l < lane0 + nl; ++l) C->cur[l] = cur ^ 1;
+  }
+  for (int l = lane0; l < lane0 + nl; ++l) {
+    C->have_map[l] = 1; C->have_feat[l] = 1; C->last_init[l] = first ? 1 : 0; C->frame_no[l] += 1;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(C->err, sizeof(C->err), "kernel launch failed: %s", cudaGetErrorString(e));
+    return VILF_ERR_CUDA;
+  }
+  return VILF_OK;
+}
+
+bool lanes_uniform(Ctx* C, int lane0, int nl) {
+  for (int l = lane0 + 1; l < lane0 + nl; ++l)
+    if (C->cur[l] != C->cur[lane0] || C->have_map[l] != C->have_map[lane0]) return false;
+  return true;
+}
+
+int read_vars(Ctx* C, int lane, LaneVars* out) {
+  CK(cudaMemcpyAsync(out, C->vars_dev + lane, sizeof(LaneVars), cudaMemcpyDeviceToHost, C->st));
+  CK(cudaStreamSynchronize(C->st));
+  return VILF_OK;
+}
+
+int submit_common(Ctx* C, int lane0, int nl, const float* const* xyzi, const int* n, const uint16_t* const* ring, bool dev_src, int64_t* ticket) {
+  CK(cudaSetDevice(C->device));
+  for (int i = 0; i < nl; ++i) {
+    if (n[i] < 0 || !xyzi[i]) return fail(C, VILF_ERR_INVALID, "null scan or negative point count");
+    if (n[i] > C->cfg.cap_scan) return fail(C, VILF_ERR_CAPACITY, "scan exceeds max_scan_points");
+    if (C->cfg.n_scan == 0 && (!ring || !ring[i])) return fail(C, VILF_ERR_INVALID, "n_scan == 0 needs explicit ring ids");
+  }
+  if (!lanes_uniform(C, lane0, nl)) return fail(C, VILF_ERR_STATE, "sequences of a batch are not in lock-step");
+  const int64_t t = C->next_ticket;
+  Slot& S = C->slots[t % RING_SLOTS];
+  if (S.ticket >= 0) return fail(C, VILF_ERR_STATE, "too many frames in flight: wait for earlier tickets first");
+  const int sel = (int)(C->scan_sel & 1);
+  C->scan_sel++;
+  // H2D (or D2D) on the copy stream into scan buffer `sel`, which the extract kernels of two frames ago released
+  CK(cudaStreamWaitEvent(C->copy_st, C->extract_done[sel], 0));
+  for (int i = 0; i < nl; ++i) {
+    LaneDev& L = C->lanes_host[lane0 + i];
+    const cudaMemcpyKind kind = dev_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (n[i] > 0) CK(cudaMemcpyAsync(L.scan[sel], xyzi[i], (size_t)n[i] * 16, kind, C->copy_st));
+    if (ring && ring[i] && n[i] > 0) CK(cudaMemcpyAsync(L.ring_in[sel], ring[i], (size_t)n[i] * 2, kind, C->copy_st));
+    S.vars_pin[i].n_scan[sel] = n[i];
+    CK(cudaMemcpyAsync(&L.v->n_scan[sel], &S.vars_pin[i].n_scan[sel], sizeof(int), cudaMemcpyHostToDevice, C->copy_st));
+  }
+  CK(cudaEventRecord(C->h2d_done[sel], C->copy_st));
+  CK(cudaStreamWaitEvent(C->st, C->h2d_done[sel], 0));
+  S.profiled = C->profile;
+  S.first = !C->have_map[lane0];
+  int rc = enqueue_frame(C, lane0, nl, S.first, true, sel, &S);
+  if (rc) return rc;
+  CK(cudaEventRecord(C->extract_done[sel], C->st));  // conservative: the whole frame (the scan is only read by stage 1)
+  CK(cudaMemcpyAsync(S.vars_pin, C->vars_dev + lane0, sizeof(LaneVars) * nl, cudaMemcpyDeviceToHost, C->st));
+  CK(cudaEventRecord(S.done, C->st));
+  S.ticket = t; S.lane0 = lane0; S.nl = nl;
+  C->next_ticket++;
+  *ticket = t;
+  return VILF_OK;
+}
+
+int wait_common(Ctx* C, int lane0, int nl, int64_t ticket, double* poses) {
+  CK(cudaSetDevice(C->device));
+  if (ticket < 0) return fail(C, VILF_ERR_INVALID, "bad ticket");
+  Slot& S = C->slots[ticket % RING_SLOTS];
+  if (S.ticket != ticket || S.lane0 != lane0 || S.nl != nl) return fail(C, VILF_ERR_INVALID, "unknown ticket");
+  CK(cudaEventSynchronize(S.done));
+  S.ticket = -1;
+  if (S.profiled && S.n_marks > 1) {
+    for (int k = 1; k < S.n_marks; ++k) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, S.stage[k - 1], S.stage[k]) == cudaSuccess && S.stage_tag[k] >= 0) C->stage_ms[S.stage_tag[k]] += ms;
+    }
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, S.stage[0], S.stage[S.n_marks - 1]) == cudaSuccess) C->stage_ms[N_STAGE - 1] += ms;
+    C->prof_frames += S.nl;
+  }
+  int status = 0;
+  for (int i = 0; i < nl; ++i) {
+    if (poses) memcpy(poses + 7 * i, S.vars_pin[i].x, 7 * sizeof(double));
+    status |= S.vars_pin[i].status;
+  }
+  return status_to_rc(C, status);
+}
+
+int upload_features(Ctx* C, int lane, const float* edge, int ne, const float* surf, int ns) {
+  if (ne < 0 || ns < 0 || (ne > 0 && !edge) || (ns > 0 && !surf)) return fail(C, VILF_ERR_INVALID, "bad feature clouds");
+  if (ne > C->cfg.cap_scan || ns > C->cfg.cap_scan) return fail(C, VILF_ERR_CAPACITY, "feature cloud exceeds max_scan_points");
+  LaneDev& L = C->lanes_host[lane];
+  if (ne) CK(cudaMemcpyAsync(L.feat[0], edge, (size_t)ne * 16, cudaMemcpyHostToDevice, C->st));
+  if (ns) CK(cudaMemcpyAsync(L.feat[1], surf, (size_t)ns * 16, cudaMemcpyHostToDevice, C->st));
+  int cnt[2] = {ne, ns};
+  CK(cudaMemcpyAsync(&L.v->n_edge, cnt, sizeof(cnt), cudaMemcpyHostToDevice, C->st));  // n_edge, n_surf are adjacent
+  CK(cudaStreamSynchronize(C->st));
+  return VILF_OK;
+}
+
+int finish_sync(Ctx* C, int lane, double* pose_out) {
+  LaneVars V;
+  int rc = read_vars(C, lane, &V);
+  if (rc) return rc;
+  if (pose_out) memcpy(pose_out, V.x, 7 * sizeof(double));
+  return status_to_rc(C, V.status);
+}
+
+int run_aux_voxel(Ctx* C, const float* pts, int n, float leaf, int crop, const double* center, double half, const double* mn, const double* mx,
+                  int passthrough, float* out, int cap, int* n_out, int* guard) {
+  CK(cudaSetDevice(C->device));
+  if (n < 0 || (n > 0 && !pts) || !n_out) return fail(C, VILF_ERR_INVALID, "bad cloud");
+  if (n > C->cap_aux) return fail(C, VILF_ERR_CAPACITY, "cloud exceeds max_map_points + max_scan_points");
+  VoxJob J = C->aux_vox_host;
+  J.leaf = leaf; J.crop = crop; J.passthrough = passthrough; J.crop_half = half;
+  if (crop == 2) for (int a = 0; a < 3; ++a) { J.crop_lo[a] = (float)mn[a]; J.crop_hi[a] = (float)mx[a]; }
+  CK(cudaMemcpyAsync(C->aux_vox_dev, &J, sizeof(J), cudaMemcpyHostToDevice, C->st));
+  if (n) CK(cudaMemcpyAsync(C->aux_in, pts, (size_t)n * 16, cudaMemcpyHostToDevice, C->st));
+  int hdr[4] = {n, 0, 0, 0};
+  CK(cudaMemcpyAsync(C->aux_n, hdr, sizeof(hdr), cudaMemcpyHostToDevice, C->st));
+  if (crop == 1) CK(cudaMemcpyAsync(C->aux_pose, center, 3 * sizeof(double), cudaMemcpyHostToDevice, C->st));
+  VoxVars vv;
+  memset(&vv, 0, sizeof(vv));
+  vv.bbox[0] = vv.bbox[1] = vv.bbox[2] = INT_MAX;
+  vv.bbox[3] = vv.bbox[4] = vv.bbox[5] = INT_MIN;
+  CK(cudaMemcpyAsync(J.vv, &vv, sizeof(vv), cudaMemcpyHostToDevice, C->st));
+  CK(cudaStreamSynchronize(C->st));  // the staged host structs above live on this stack frame
+  launch_voxel(mk(C), C->aux_vox_dev, 1, C->aux_sort_dev);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(hdr, C->aux_n, sizeof(hdr), cudaMemcpyDeviceToHost, C->st));
+  CK(cudaMemcpyAsync(&vv, J.vv, sizeof(vv), cudaMemcpyDeviceToHost, C->st));
+  CK(cudaStreamSynchronize(C->st));
+  *n_out = hdr[1];
+  if (guard) *guard = vv.guard;
+  if (hdr[1] > cap) return fail(C, VILF_ERR_CAPACITY, "output buffer too small");
+  if (out && hdr[1] > 0) CK(cudaMemcpy(out, C->aux_out, (size_t)hdr[1] * 16, cudaMemcpyDeviceToHost));
+  return VILF_OK;
+}
+
+// Upload explicit factors into the lane's factor slots and run the solve kernel (vilf_solve / vilf_normal_equations).
+int run_explicit_solve(Ctx* C, int lane, const double* pose, const double* edge_pab, int ne, const double* surf_pnd, int ns, int max_iters,
+                       double* pose_out, SolveTraceDev* trace_out) {
+  CK(cudaSetDevice(C->device));
+  if (ne < 0 || ns < 0 || ne > C->cfg.cap_scan || ns > C->cfg.cap_scan) return fail(C, VILF_ERR_CAPACITY, "too many factors");
+  LaneDev& L = C->lanes_host[lane];
+  LaneVars V;
+  int rc = read_vars(C, lane, &V);
+  if (rc) return rc;
+  LaneVars W = V;
+  memcpy(W.x, pose, 7 * sizeof(double));
+  W.n_ds[0] = ne; W.n_ds[1] = ns; W.opt_ran = 1;
+  CK(cudaMemcpyAsync(C->vars_dev + lane, &W, sizeof(W), cudaMemcpyHostToDevice, C->st));
+  if (ne) {
+    CK(cudaMemcpyAsync(L.edge_pab, edge_pab, (size_t)ne * 9 * sizeof(double), cudaMemcpyHostToDevice, C->st));
+    CK(cudaMemsetAsync(L.fvalid[0], 1, (size_t)ne, C->st));
+  }
+  if (ns) {
+    CK(cudaMemcpyAsync(L.surf_pnd, surf_pnd, (size_t)ns * 7 * sizeof(double), cudaMemcpyHostToDevice, C->st));
+    CK(cudaMemsetAsync(L.fvalid[1], 1, (size_t)ns, C->st));
+  }
+  launch_solve(mk(C), C->lanes_dev, lane, 1, 0, 0, C->cfg, max_iters);
+  CK(cudaGetLastError());
+  LaneVars R;
+  CK(cudaMemcpyAsync(&R, C->vars_dev + lane, sizeof(R), cudaMemcpyDeviceToHost, C->st));
+  CK(cudaMemcpyAsync(trace_out, L.trace, sizeof(SolveTraceDev), cudaMemcpyDeviceToHost, C->st));
+  CK(cudaMemcpyAsync(C->vars_dev + lane, &V, sizeof(V), cudaMemcpyHostToDevice, C->st));  // restore pose / counts
+  CK(cudaStreamSynchronize(C->st));
+  if (pose_out) memcpy(pose_out, R.x, 7 * sizeof(double));
+  return VILF_OK;
+}
+
+}  // namespace
+
+#define HCHECK(h)                              \
+  if (!(h) || !(h)->ctx) return VILF_ERR_INVALID; \
+  Ctx* C = (h)->ctx;                           \
+  (void)C
+
+extern "C" {
+
+int vilf_default_config(vilf_config* c) {
+  if (!c) return VILF_ERR_INVALID;
+  c->n_scan = 64; c->n_rings = 64;
+  c->lidar_min = 3.0; c->lidar_max = 90.0; c->edge_threshold = 0.1;
+  c->edge_leaf = 0.4; c->surf_leaf = 0.8; c->crop_half = 100.0; c->knn_gate = 1.0; c->huber = 0.1;
+  c->outer_iters = 2; c->lm_max_iters = 4;
+  c->max_scan_points = 300000; c->max_map_points = 1 << 20;
+  return VILF_OK;
+}
+
+int vilf_create_batch(const vilf_config* cfg, int device, int count, vilf_handle** out) {
+  if (!cfg || !out || count < 1 || count > 64) return VILF_ERR_INVALID;
+  if (cfg->n_scan < 0 || (cfg->n_scan == 0 && (cfg->n_rings < 1 || cfg->n_rings > MAX_RINGS))) return VILF_ERR_INVALID;
+  if (cfg->outer_iters < 1 || cfg->outer_iters > MAX_OUTER || cfg->lm_max_iters < 0) return VILF_ERR_INVALID;
+  if (cfg->max_scan_points < 1024 || cfg->max_map_points < 1024 || !(cfg->edge_leaf > 0) || !(cfg->surf_leaf > 0) || !(cfg->knn_gate > 0)) return VILF_ERR_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return VILF_ERR_CUDA;
+  Ctx* C = new (std::nothrow) Ctx();
+  if (!C) return VILF_ERR_CUDA;
+  C->device = device; C->ucfg = *cfg; C->nlanes = count;
+  int rc = build_ctx(C);
+  if (rc != VILF_OK) {
+    fprintf(stderr, "vilf_create: %s\n", C->err);
+    destroy_ctx(C);
+    return rc;
+  }
+  for (int i = 0; i < count; ++i) {
+    vilf_handle* h = new vilf_handle{C, i};
+    C->handles.push_back(h);
+    out[i] = h;
+  }
+  return VILF_OK;
+}
+
+int vilf_create(const vilf_config* cfg, int device, vilf_handle** out) { return vilf_create_batch(cfg, device, 1, out); }
+
+int vilf_destroy(vilf_handle* h) {
+  if (!h || !h->ctx) return VILF_ERR_INVALID;
+  destroy_ctx(h->ctx);
+  return VILF_OK;
+}
+
+const char* vilf_last_error(const vilf_handle* h) { return (h && h->ctx) ? h->ctx->err : "invalid handle"; }
+
+int vilf_host_alloc(void** p, uint64_t bytes) { return cudaMallocHost(p, bytes) == cudaSuccess ? VILF_OK : VILF_ERR_CUDA; }
+int vilf_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? VILF_OK : VILF_ERR_CUDA; }
+
+int vilf_submit_scan(vilf_handle* h, const float* xyzi, int n, const uint16_t* ring, int64_t* ticket) {
+  HCHECK(h);
+  if (!ticket) return VILF_ERR_INVALID;
+  return submit_common(C, h->lane, 1, &xyzi, &n, ring ? &ring : nullptr, false, ticket);
+}
+int vilf_wait(vilf_handle* h, int64_t ticket, double pose_out[7]) {
+  HCHECK(h);
+  return wait_common(C, h->lane, 1, ticket, pose_out);
+}
+int vilf_process_scan(vilf_handle* h, const float* xyzi, int n, const uint16_t* ring, double pose_out[7]) {
+  int64_t t = 0;
+  int rc = vilf_submit_scan(h, xyzi, n, ring, &t);
+  if (rc) return rc;
+  return vilf_wait(h, t, pose_out);
+}
+
+static int batch_check(vilf_handle* const* hs, int count) {
+  if (!hs || count < 1 || !hs[0] || !hs[0]->ctx) return VILF_ERR_INVALID;
+  for (int i = 0; i < count; ++i)
+    if (!hs[i] || hs[i]->ctx != hs[0]->ctx || hs[i]->lane != hs[0]->lane + i) return VILF_ERR_INVALID;
+  return VILF_OK;
+}
+int vilf_submit_scan_batch(vilf_handle* const* hs, int count, const float* const* xyzi, const int* n, const uint16_t* const* ring, int64_t* ticket) {
+  if (batch_check(hs, count) || !xyzi || !n || !ticket) return VILF_ERR_INVALID;
+  return submit_common(hs[0]->ctx, hs[0]->lane, count, xyzi, n, ring, false, ticket);
+}
+int vilf_submit_scan_batch_dev(vilf_handle* const* hs, int count, const float* const* xyzi_dev, const int* n, const uint16_t* const* ring_dev,
+                               int64_t* ticket) {
+  if (batch_check(hs, count) || !xyzi_dev || !n || !ticket) return VILF_ERR_INVALID;
+  return submit_common(hs[0]->ctx, hs[0]->lane, count, xyzi_dev, n, ring_dev, true, ticket);
+}
+int vilf_wait_batch(vilf_handle* const* hs, int count, int64_t ticket, double* poses_out) {
+  if (batch_check(hs, count)) return VILF_ERR_INVALID;
+  return wait_common(hs[0]->ctx, hs[0]->lane, count, ticket, poses_out);
+}
+
+int vilf_feature_extract(vilf_handle* h, const float* xyzi, int n, const uint16_t* ring, int* n_edge, int* n_surf) {
+  HCHECK(h);
+  CK(cudaSetDevice(C->device));
+  if (n < 0 || (n > 0 && !xyzi)) return fail(C, VILF_ERR_INVALID, "bad scan");
+  if (n > C->cfg.cap_scan) return fail(C, VILF_ERR_CAPACITY, "scan exceeds max_scan_points");
+  if (C->cfg.n_scan == 0 && !ring) return fail(C, VILF_ERR_INVALID, "n_scan == 0 needs explicit ring ids");
+  LaneDev& L = C->lanes_host[h->lane];
+  CK(cudaStreamSynchronize(C->st));
+  CK(cudaStreamSynchronize(C->copy_st));
+  if (n) CK(cudaMemcpyAsync(L.scan[0], xyzi, (size_t)n * 16, cudaMemcpyHostToDevice, C->st));
+  if (ring && n) CK(cudaMemcpyAsync(L.ring_in[0], ring, (size_t)n * 2, cudaMemcpyHostToDevice, C->st));
+  CK(cudaMemcpyAsync(&L.v->n_scan[0], &n, sizeof(int), cudaMemcpyHostToDevice, C->st));
+  CK(cudaStreamSynchronize(C->st));
+  launch_extract(mk(C), C->lanes_dev, C->ring_jobs_dev[0], h->lane, 1, 0, C->cfg);
+  CK(cudaGetLastError());
+  LaneVars V;
+  int rc = read_vars(C, h->lane, &V);
+  if (rc) return rc;
+  C->have_feat[h->lane] = 1;
+  if (n_edge) *n_edge = V.n_edge;
+  if (n_surf) *n_surf = V.n_surf;
+  return status_to_rc(C, V.status);
+}
+
+int vilf_get_features(vilf_handle* h, int which, float* pts, int32_t* src, int cap, int* n) {
+  HCHECK(h);
+  CK(cudaSetDevice(C->device));
+  if (which < 0 || which > 1 || !n) return VILF_ERR_INVALID;
+  LaneVars V;
+  int rc = read_vars(C, h->lane, &V);
+  if (rc) return rc;
+  const int cnt = which ? V.n_surf : V.n_edge;
+  *n = cnt;
+  if (cnt > cap && (pts || src)) return fail(C, VILF_ERR_CAPACITY, "output buffer too small");
+  LaneDev& L = C->lanes_host[h->lane];
+  if (pts && cnt) CK(cudaMemcpy(pts, L.feat[which], (size_t)cnt * 16, cudaMemcpyDeviceToHost));
+  if (src && cnt) CK(cudaMemcpy(src, L.feat_src[which], (size_t)cnt * 4, cudaMemcpyDeviceToHost));
+  return VILF_OK;
+}
+
+static int map_init_impl(Ctx* C, int lane) {
+  const Launch L = mk(C);
+  launch_map_init(L, C->lanes_dev, lane, 1, C->cur[lane], C->cfg);
+  launch_grid_build(L, C->grid_dev[C->cur[lane]] + lane * 2, 2, C->cfg);
+  CK(cudaGetLastError());
+  C->have_map[lane] = 1; C->last_init[lane] = 1;
+  return finish_sync(C, lane, nullptr);
+}
+int vilf_map_init(vilf_handle* h) {
+  HCHECK(h);
+  CK(cudaSetDevice(C->device));
+  if (!C->have_feat[h->lane]) return fail(C, VILF_ERR_STATE, "no extracted features resident");
+  return map_init_impl(C, h->lane);
+}
+int vilf_map_init_points(vilf_handle* h, const float* edge, int n_edge, const float* surf, int n_surf) {
+  HCHECK(h);
+  CK(cudaSetDevice(C->device));
+  int rc = upload_features(C, h->lane, edge, n_edge, surf, n_surf);
+  if (rc) return rc;
+  C->have_feat[h->lane] = 1;
+  return map_init_impl(C, h->lane);
+}
+
+static int update_impl(Ctx* C, int lane, double* pose_out) {
+  if (!C->have_map[lane]) return fail(C, VILF_ERR_STATE, "local map not initialised");
+  int rc = enqueue_frame(C, lane, 1, false, false, 0, nullptr);
+  if (rc) return rc;
+  return finish_sync(C, lane, pose_out);
+}
+int vilf_update(vilf_handle* h, double pose_out[7]) {
+  HCHECK(h);
+  CK(cudaSetDevice(C->device));
+  if (!C->have_feat[h->lane]) return fail(C, VILF_ERR_STATE, "no extracted features resident");
+  return update_impl(C, h->lane, pose_out);
+}
+int vilf_update_points(vilf_handle* h, const float* edge, int n_edge, const float* surf, int n_surf, double pose_out[7]) {
+  HCHECK(h);
+  CK(cudaSetDevice(C->device));
+  int rc = upload_features(C, h->lane, edge, n_edge, surf, n_surf);
+  if (rc) return rc;
+  C->have_feat[h->lane] = 1;
+  return update_impl(C, h->lane, pose_out);
+}
+
+int vilf_get_pose(vilf_handle* h, double pose_out[7], double* rt12) {
+  HCHECK(h);
+  CK(cudaSetDevice(C->device));
+  LaneVars V;
+  int rc = read_vars(C, h->lane, &V);
+  if (rc) return rc;
+  if (pose_out) memcpy(pose_out, V.x, 7 * sizeof(double));
+  if (rt12) memcpy(rt12, V.odom, 12 * sizeof(double));
+  return VILF_OK;
+}
+
+int vilf_get_cloud(vilf_handle* h, int which, float* out, int cap, int* n) {
+  HCHECK(h);
+  CK(cudaSetDevice(C->device));
+  if (which < 0 || which > 5 || !n) return VILF_ERR_INVALID;
+  LaneVars V;
+  int rc = read_vars(C, h->lane, &V);
+  if (rc) return rc;
+  LaneDev& L = C->lanes_host[h->lane];
+  const int cur = C->cur[h->lane];
+  const float4* part[2] = {nullptr, nullptr};
+  int cnt[2] = {0, 0};
+  if (which <= 1) { part[0] = L.map[which][cur]; cnt[0] = V.n_map[which]; }
+  else if (which <= 3) { part[0] = L.ds[which - 2]; cnt[0] = V.n_ds[which - 2]; }
+  else if (C->last_init[h->lane]) {  // EM:110-114
+    part[0] = L.feat[0]; cnt[0] = V.n_edge; part[1] = L.feat[1]; cnt[1] = V.n_surf;
+  } else if (which == 4) {  // EM:315, :323: the world-frame features appended to the previous buffer
+    for (int w = 0; w < 2; ++w) { part[w] = L.map[w][cur ^ 1] + (V.n_cat[w] - V.n_ds[w]); cnt[w] = V.n_ds[w]; }
+  } else {                  // EM:304-305
+    for (int w = 0; w < 2; ++w) { part[w] = L.ds[w]; cnt[w] = V.n_ds[w]; }
+  }
+  *n = cnt[0] + cnt[1];
+  if (!out) return VILF_OK;
+  if (*n > cap) return fail(C, VILF_ERR_CAPACITY, "output buffer too small");
+  if (cnt[0]) CK(cudaMemcpy(out, part[0], (size_t)cnt[0] * 16, cudaMemcpyDeviceToHost));
+  if (cnt[1]) CK(cudaMemcpy(out + (size_t)cnt[0] * 4, part[1], (size_t)cnt[1] * 16, cudaMemcpyDeviceToHost));
+  return VILF_OK;
+}
+
+int vilf_voxel_downsample(vilf_handle* h, const float* pts, int n, float leaf, float* out, int cap, int* n_out, int* guard) {
+  HCHECK(h);
+  if (!(leaf > 0)) return VILF_ERR_INVALID;
+  return run_aux_voxel(C, pts, n, leaf, 0, nullptr, 0, nullptr, nullptr, 0, out, cap, n_out, guard);
+}
+int vilf_crop_voxel_downsample(vilf_handle* h, const float* pts, int n, const double center[3], double half, float leaf, float* out, int cap, int* n_out) {
+  HCHECK(h);
+  if (!(leaf > 0) || !center) return VILF_ERR_INVALID;
+  return run_aux_voxel(C, pts, n, leaf, 1, center, half, nullptr, nullptr, 0, out, cap, n_out, nullptr);
+}
+int vilf_crop_box(vilf_handle* h, const float* pts, int n, const double mn[3], const double mx[3], float* out, int cap, int* n_out) {
+  HCHECK(h);
+  if (!mn || !mx) return VILF_ERR_INVALID;
+  return run_aux_voxel(C, pts, n, 1.0f, 2, nullptr, 0, mn, mx, 1, out, cap, n_out, nullptr);
+}
+
+int vilf_knn5(vilf_handle* h, const float* map, int m, const float* q, int nq, int32_t* idx, float* d2) {
+  HCHECK(h);
+  CK(cudaSetDevice(C->device));
+  if (m < 0 || nq < 0 || (m > 0 && !map) || (nq > 0 && (!q || !idx || !d2))) return fail(C, VILF_ERR_INVALID, "bad arguments");
+  if (m > C->cap_aux || nq > C->cap_aux) return fail(C, VILF_ERR_CAPACITY, "map or query set exceeds capacity");
+  if (m) CK(cudaMemcpyAsync(C->aux_in, map, (size_t)m * 16, cudaMemcpyHostToDevice, C->st));
+  if (nq) CK(cudaMemcpyAsync(C->aux_out, q, (size_t)nq * 16, cudaMemcpyHostToDevice, C->st));
+  int hdr[4] = {m, 0, nq, 0};
+  CK(cudaMemcpyAsync(C->aux_n, hdr, sizeof(hdr), cudaMemcpyHostToDevice, C->st));
+  CK(cudaStreamSynchronize(C->st));
+  const Launch L = mk(C);
+  launch_grid_build(L, C->aux_grid_dev, 1, C->cfg);
+  launch_knn_only(L, C->aux_grid_dev, C->aux_out, C->aux_n + 2, C->aux_idx, C->aux_d2, C->cfg);
+  CK(cudaGetLastError());
+  if (nq) {
+    CK(cudaMemcpyAsync(idx, C->aux_idx, (size_t)nq * 5 * 4, cudaMemcpyDeviceToHost, C->st));
+    CK(cudaMemcpyAsync(d2, C->aux_d2, (size_t)nq * 5 * 4, cudaMemcpyDeviceToHost, C->st));
+  }
+  CK(cudaStreamSynchronize(C->st));
+  return VILF_OK;
+}
+
+int vilf_factors(vilf_handle* h, const double pose[7], const float* edge, int n_edge, const float* surf, int n_surf, uint8_t* edge_valid,
+                 double* edge_ab, int32_t* edge_nn, float* edge_d2, uint8_t* surf_valid, double* surf_nd, int32_t* surf_nn, float* surf_d2) {
+  HCHECK(h);
+  CK(cudaSetDevice(C->device));
+  const int lane = h->lane;
+  if (!pose || n_edge < 0 || n_surf < 0) return VILF_ERR_INVALID;
+  if (n_edge > C->cfg.cap_scan || n_surf > C->cfg.cap_scan) return fail(C, VILF_ERR_CAPACITY, "feature cloud exceeds max_scan_points");
+  if (!C->have_map[lane]) return fail(C, VILF_ERR_STATE, "local map not initialised");
+  LaneDev& L = C->lanes_host[lane];
+  LaneVars V;
+  int rc = read_vars(C, lane, &V);
+  if (rc) return rc;
+  LaneVars W = V;
+  W.n_ds[0] = n_edge; W.n_ds[1] = n_surf;
+  CK(cudaMemcpyAsync(C->vars_dev + lane, &W, sizeof(W), cudaMemcpyHostToDevice, C->st));
+  if (n_edge) CK(cudaMemcpyAsync(L.ds[0], edge, (size_t)n_edge * 16, cudaMemcpyHostToDevice, C->st));
+  if (n_surf) CK(cudaMemcpyAsync(L.ds[1], surf, (size_t)n_surf * 16, cudaMemcpyHostToDevice, C->st));
+  CK(cudaMemcpyAsync(C->aux_pose, pose, 7 * sizeof(double), cudaMemcpyHostToDevice, C->st));
+  for (int w = 0; w < 2; ++w) {
+    const int n = w ? n_surf : n_edge;
+    if (!n) continue;
+    CK(cudaMemsetAsync(L.fvalid[w], 0, (size_t)n, C->st));
+    CK(cudaMemsetAsync(L.nn_idx[w], 0xff, (size_t)n * 20, C->st));
+    CK(cudaMemsetAsync(L.nn_d2[w], 0, (size_t)n * 20, C->st));
+  }
+  CK(cudaMemsetAsync(L.edge_pab, 0, (size_t)(n_edge > 0 ? n_edge : 1) * 72, C->st));
+  CK(cudaMemsetAsync(L.surf_pnd, 0, (size_t)(n_surf > 0 ? n_surf : 1) * 56, C->st));
+  launch_knn_fit(mk(C), C->lanes_dev, C->grid_dev[C->cur[lane]], lane, 1, C->cur[lane], C->cfg, C->aux_pose, 1);
+  CK(cudaGetLastError());
+  std::vector<double> pab((size_t)(n_edge > 0 ? n_edge : 1) * 9), pnd((size_t)(n_surf > 0 ? n_surf : 1) * 7);
+  if (n_edge) {
+    CK(cudaMemcpyAsync(pab.data(), L.edge_pab, (size_t)n_edge * 72, cudaMemcpyDeviceToHost, C->st));
+    if (edge_valid) CK(cudaMemcpyAsync(edge_valid, L.fvalid[0], (size_t)n_edge, cudaMemcpyDeviceToHost, C->st));
+    if (edge_nn) CK(cudaMemcpyAsync(edge_nn, L.nn_idx[0], (size_t)n_edge * 20, cudaMemcpyDeviceToHost, C->st));
+    if (edge_d2) CK(cudaMemcpyAsync(edge_d2, L.nn_d2[0], (size_t)n_edge * 20, cudaMemcpyDeviceToHost, C->st));
+  }
+  if (n_surf) {
+    CK(cudaMemcpyAsync(pnd.data(), L.surf_pnd, (size_t)n_surf * 56, cudaMemcpyDeviceToHost, C->st));
+    if (surf_valid) CK(cudaMemcpyAsync(surf_valid, L.fvalid[1], (size_t)n_surf, cudaMemcpyDeviceToHost, C->st));
+    if (surf_nn) CK(cudaMemcpyAsync(surf_nn, L.nn_idx[1], (size_t)n_surf * 20, cudaMemcpyDeviceToHost, C->st));
+    if (surf_d2) CK(cudaMemcpyAsync(surf_d2, L.nn_d2[1], (size_t)n_surf * 20, cudaMemcpyDeviceToHost, C->st));
+  }
+  CK(cudaMemcpyAsync(C->vars_dev + lane, &V, sizeof(V), cudaMemcpyHostToDevice, C->st));  // restore counts
+  CK(cudaStreamSynchronize(C->st));
+  if (edge_ab) for (int i = 0; i < n_edge; ++i) memcpy(edge_ab + (size_t)i * 6, pab.data() + (size_t)i * 9 + 3, 6 * sizeof(double));
+  if (surf_nd) for (int i = 0; i < n_surf; ++i) memcpy(surf_nd + (size_t)i * 4, pnd.data() + (size_t)i * 7 + 3, 4 * sizeof(double));
+  return VILF_OK;
+}
+
+int vilf_normal_equations(vilf_handle* h, const double pose[7], const double* edge_pab, int n_edge, const double* surf_pnd, int n_surf,
+                          double H21[21], double g6[6], double* cost) {
+  HCHECK(h);
+  if (!pose) return VILF_ERR_INVALID;
+  SolveTraceDev T;
+  int rc = run_explicit_solve(C, h->lane, pose, edge_pab, n_edge, surf_pnd, n_surf, 0, nullptr, &T);
+  if (rc) return rc;
+  if (H21) memcpy(H21, T.H0, sizeof(T.H0));
+  if (g6) memcpy(g6, T.g0, sizeof(T.g0));
+  if (cost) *cost = T.cost0;
+  return VILF_OK;
+}
+
+int vilf_solve(vilf_handle* h, double pose_inout[7], const double* edge_pab, int n_edge, const double* surf_pnd, int n_surf, int max_iters,
+               double* trace, int max_rows, int* n_rows, int* termination) {
+  HCHECK(h);
+  if (!pose_inout || max_iters < 0) return VILF_ERR_INVALID;
+  SolveTraceDev T;
+  double pose_in[7];
+  memcpy(pose_in, pose_inout, sizeof(pose_in));
+  int rc = run_explicit_solve(C, h->lane, pose_in, edge_pab, n_edge, surf_pnd, n_surf, max_iters, pose_inout, &T);
+  if (rc) return rc;
+  int n = 0;
+  for (int r = 0; r < T.n_rows && r < MAX_TRACE_ROWS && trace && n < max_rows; ++r, ++n) memcpy(trace + (size_t)16 * n, &T.rows[r], 16 * sizeof(double));
+  if (n_rows) *n_rows = n;
+  if (termination) *termination = T.termination;
+  return VILF_OK;
+}
+
+int vilf_get_solves(vilf_handle* h, double* out, int max_rows, int* n_rows) {
+  HCHECK(h);
+  CK(cudaSetDevice(C->device));
+  if (!out || !n_rows) return VILF_ERR_INVALID;
+  SolveTraceDev T[MAX_OUTER];
+  CK(cudaStreamSynchronize(C->st));
+  CK(cudaMemcpy(T, C->lanes_host[h->lane].trace, sizeof(T), cudaMemcpyDeviceToHost));
+  int n = 0;
+  for (int o = 0; o < C->cfg.outer_iters && n < max_rows; ++o) {
+    if (T[o].termination < 0 && T[o].n_rows == 0) continue;
+    double* r = out + (size_t)8 * n++;
+    r[0] = T[o].n_edge; r[1] = T[o].n_surf; r[2] = T[o].termination; r[3] = T[o].n_rows;
+    r[4] = T[o].cost0; r[5] = T[o].final_cost; r[6] = r[7] = 0;
+  }
+  *n_rows = n;
+  return VILF_OK;
+}
+
+int vilf_state_export(vilf_handle* h, double s[31]) {
+  HCHECK(h);
+  CK(cudaSetDevice(C->device));
+  if (!s) return VILF_ERR_INVALID;
+  LaneVars V;
+  int rc = read_vars(C, h->lane, &V);
+  if (rc) return rc;
+  memcpy(s, V.x, 7 * sizeof(double));
+  memcpy(s + 7, V.odom, 12 * sizeof(double));
+  memcpy(s + 19, V.odom_last, 12 * sizeof(double));
+  return VILF_OK;
+}
+
+int vilf_state_import(vilf_handle* h, const double s[31], const float* map_edge, int n_edge, const float* map_surf, int n_surf) {
+  HCHECK(h);
+  CK(cudaSetDevice(C->device));
+  const int lane = h->lane;
+  if (!s || n_edge < 0 || n_surf < 0 || (n_edge && !map_edge) || (n_surf && !map_surf)) return VILF_ERR_INVALID;
+  const int capM = C->cfg.cap_map + C->cfg.cap_scan;
+  if (n_edge > capM || n_surf > capM) return fail(C, VILF_ERR_CAPACITY, "map exceeds capacity");
+  LaneDev& L = C->lanes_host[lane];
+  LaneVars V;
+  int rc = read_vars(C, lane, &V);
+  if (rc) return rc;
+  memcpy(V.x, s, 7 * sizeof(double));
+  memcpy(V.odom, s + 7, 12 * sizeof(double));
+  memcpy(V.odom_last, s + 19, 12 * sizeof(double));
+  V.n_map[0] = n_edge; V.n_map[1] = n_surf; V.status = 0;
+  const int cur = C->cur[lane];
+  CK(cudaMemcpyAsync(C->vars_dev + lane, &V, sizeof(V), cudaMemcpyHostToDevice, C->st));
+  if (n_edge) CK(cudaMemcpyAsync(L.map[0][cur], map_edge, (size_t)n_edge * 16, cudaMemcpyHostToDevice, C->st));
+  if (n_surf) CK(cudaMemcpyAsync(L.map[1][cur], map_surf, (size_t)n_surf * 16, cudaMemcpyHostToDevice, C->st));
+  launch_grid_build(mk(C), C->grid_dev[cur] + lane * 2, 2, C->cfg);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(C->st));
+  C->have_map[lane] = 1;
+  return VILF_OK;
+}
+
+int vilf_profile_enable(vilf_handle* h, int on) {
+  HCHECK(h);
+  C->profile = on != 0;
+  return VILF_OK;
+}
+int vilf_profile_read(vilf_handle* h, double ms_out[7], int64_t* frames, int reset) {
+  HCHECK(h);
+  if (ms_out) memcpy(ms_out, C->stage_ms, sizeof(C->stage_ms));
+  if (frames) *frames = C->prof_frames;
+  if (reset) { memset(C->stage_ms, 0, sizeof(C->stage_ms)); C->prof_frames = 0; }
+  return VILF_OK;
+}
+int vilf_launch_count(vilf_handle* h, int64_t* launches) {
+  HCHECK(h);
+  if (!launches) return VILF_ERR_INVALID;
+  *launches = C->launches;
+  return VILF_OK;
+}
+int vilf_get_stream(vilf_handle* h, void** cuda_stream) {
+  HCHECK(h);
+  if (!cuda_stream) return VILF_ERR_INVALID;
+  *cuda_stream = (void*)C->st;
+  return VILF_OK;
+}
+int vilf_get_counts(vilf_handle* h, int32_t out8[8]) {
+  HCHECK(h);
+  CK(cudaSetDevice(C->device));
+  if (!out8) return VILF_ERR_INVALID;
+  LaneVars V;
+  int rc = read_vars(C, h->lane, &V);
+  if (rc) return rc;
+  out8[0] = V.n_edge; out8[1] = V.n_surf; out8[2] = V.n_ds[0]; out8[3] = V.n_ds[1];
+  out8[4] = V.n_map[0]; out8[5] = V.n_map[1]; out8[6] = V.status; out8[7] = V.frames;
+  return VILF_OK;
+}
+
+}  // extern "C"

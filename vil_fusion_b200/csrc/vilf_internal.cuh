@@ -1,0 +1,203 @@
+// Internal declarations shared by the kernels of libvilf_cuda.so (sm_100a only).
+// Data layout in HBM, per sequence ("lane"): see DESIGN.md §3.  Every kernel is launched with a fixed
+// grid (x = work, y = lane or job) and reads its element counts from device memory, so that a frame is
+// a static launch sequence (CUDA-graph friendly) with no host round trip between the stages.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <float.h>
+#include <limits.h>
+#include <math.h>
+
+namespace vilf {
+
+constexpr int MAX_RINGS = 128;       // ring ids are 8-bit sort keys; 255 = dropped point
+constexpr int SECTORS = 6;           // FE:206
+constexpr int EDGES_PER_SECTOR = 20; // FE:131
+constexpr int MAX_SECTOR = 2048;     // elements per (ring, sector) the selection kernel stages in shared memory
+constexpr int SORT_G = 128;          // max CTAs per radix-sort job
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_TILE = 1024;      // 256 threads x 4 keys
+constexpr int SORT_MIN_CHUNK = 2048;
+constexpr int VOX_G = 148;           // CTAs per voxel job for the bbox / head / centroid kernels
+constexpr int GRID_G = 148;          // CTAs per hash-grid job
+constexpr int KNN_G = 148 * 4;       // CTAs (8 warps each) of the kNN + fit kernel per lane
+constexpr int LM_THREADS = 512;
+constexpr int MAX_TRACE_ROWS = 8;
+constexpr int MAX_OUTER = 4;
+
+// status bits (LaneVars::status)
+constexpr int ST_SECTOR_TOO_LONG = 1;
+constexpr int ST_MAP_CAPACITY = 2;
+constexpr int ST_SCAN_CAPACITY = 4;
+
+struct ConfigDev {
+  int n_scan, n_rings, rings_total;
+  double lidar_min, lidar_max, edge_threshold, knn_gate, huber, crop_half;
+  float edge_leaf, surf_leaf;
+  float inv_cell;  // 1 / hash-grid cell edge (a power of two >= sqrt(knn_gate))
+  int outer_iters, lm_max_iters;
+  int cap_scan, cap_map;
+};
+
+// One iteration row of the trust-region trace (same columns as the oracle's LmIter).
+struct LmRow {
+  double iteration, step_valid, step_successful, cost, candidate_cost, model_cost_change, relative_decrease, radius, step_norm;
+  double x[7];
+};
+struct SolveTraceDev {
+  int n_edge, n_surf, termination, n_rows;
+  double H0[21], g0[6], cost0, final_cost;
+  LmRow rows[MAX_TRACE_ROWS];
+};
+
+// Per-lane scalars living in device memory.
+struct LaneVars {
+  int n_scan[2];    // points in scan buffer 0 / 1 (written by the host copy of that buffer)
+  int n_edge, n_surf;
+  int n_ds[2];      // voxel-filtered scan features (edge, surf)
+  int n_map[2];     // local map sizes
+  int n_cat[2];     // map + appended scan features = input size of the map maintenance voxel job
+  int status;
+  int opt_ran;
+  int frames;
+  int pad_;
+  double x[7];      // parameter_opti (EM:383)
+  double odom[12];  // globalOdom: R row-major, t (EM:387)
+  double odom_last[12];
+};
+
+struct SortJob {
+  const int* n;           // element count
+  const int* bits;        // significant key bits (device) or null -> fixed_bits
+  int fixed_bits;
+  int npass;              // 1 or 4; digit width = ceil(bits / npass) <= 8
+  uint32_t* key[2];
+  uint32_t* val[2];
+  uint32_t* hist;         // [SORT_G][256]
+  uint32_t* digit_start;  // optional [257]: exclusive digit offsets of pass 0 (+ total)
+};
+
+struct VoxVars {
+  int bbox[6];    // ordered-int min x,y,z / max x,y,z
+  int n_valid;    // points inside the crop box (== n_in without crop)
+  int min_b[3], div_b[3];
+  int bits;       // significant bits of (voxel index | sentinel)
+  int guard;      // PCL "leaf size too small" guard fired: output = input
+  int total;      // dx*dy*dz (sentinel key of cropped-out points)
+};
+
+struct VoxJob {
+  const float4* in;
+  const int* n_in;
+  float leaf;
+  int crop;                 // 0 none; 1 box = crop_center +- crop_half (EM:327-336); 2 explicit fp32 bounds
+  float crop_lo[3], crop_hi[3];
+  int passthrough;          // 1: no voxel filter, output = (cropped) input in order
+  const double* crop_center;  // 3 doubles on the device (pose translation)
+  double crop_half;
+  float4* out;
+  int* n_out;
+  int cap_out;
+  int* status;              // lane status word (capacity overflow)
+  VoxVars* vv;
+  int* head_cnt;            // [VOX_G]
+  SortJob sort;
+};
+
+struct GridJob {
+  const float4* pts;
+  const int* n;
+  uint32_t* start;    // [hcap + 1] bucket counts, then exclusive offsets (start[H] = n)
+  uint32_t* rank;     // [cap] slot of each point inside its bucket
+  float4* sorted;     // [cap] x, y, z, original index (bits)
+  int* hvar;          // buckets in use (power of two)
+  uint32_t* partial;  // [GRID_G]
+  int hcap;
+};
+
+// Per-lane device pointers.
+struct LaneDev {
+  LaneVars* v;
+  SolveTraceDev* trace;              // [MAX_OUTER]
+  float4* scan[2]; uint16_t* ring_in[2];  // double buffered: H2D of frame t+1 overlaps the kernels of frame t
+  // stage 1
+  SortJob ring_sort;   // keys = ring id, values = scan index
+  int2* sec_cnt;       // [MAX_RINGS*6] (edges, surfs) chosen per sector
+  float4* sec_edge; int* sec_edge_src;   // [MAX_RINGS*6*20]
+  float4* sec_surf; int* sec_surf_src;   // [cap_scan] indexed from the sector's first element
+  float4* feat[2]; int* feat_src[2];     // edge / surf features [cap_scan]
+  // stage 2: voxel-filtered scan features
+  float4* ds[2];
+  // maps: [which][buffer] double buffered, capacity cap_map + cap_scan
+  float4* map[2][2];
+  // factors (one slot per voxel-filtered feature)
+  uint8_t* fvalid[2];
+  double* edge_pab;    // [cap][9]
+  double* surf_pnd;    // [cap][7]
+  int* nn_idx[2]; float* nn_d2[2];  // [cap][5] (test hooks)
+};
+
+// ---- ordered-int float mapping for atomicMin/atomicMax ----
+__device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7FFFFFFF; }
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
+
+// fp32 arithmetic that must round exactly like the reference's scalar SSE code (no contraction).
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+
+// ---- double-precision rigid-body helpers (Eigen 3.3.7 operation order) ----
+struct D3 { double x, y, z; };
+__device__ __forceinline__ D3 d3(double x, double y, double z) { D3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ D3 operator+(D3 a, D3 b) { return d3(dadd(a.x, b.x), dadd(a.y, b.y), dadd(a.z, b.z)); }
+__device__ __forceinline__ D3 operator-(D3 a, D3 b) { return d3(dsub(a.x, b.x), dsub(a.y, b.y), dsub(a.z, b.z)); }
+__device__ __forceinline__ D3 operator*(double s, D3 a) { return d3(dmul(s, a.x), dmul(s, a.y), dmul(s, a.z)); }
+__device__ __forceinline__ double dot3(D3 a, D3 b) { return dadd(dadd(dmul(a.x, b.x), dmul(a.y, b.y)), dmul(a.z, b.z)); }
+__device__ __forceinline__ D3 cross3(D3 a, D3 b) {
+  return d3(dsub(dmul(a.y, b.z), dmul(a.z, b.y)), dsub(dmul(a.z, b.x), dmul(a.x, b.z)), dsub(dmul(a.x, b.y), dmul(a.y, b.x)));
+}
+__device__ __forceinline__ double norm3(D3 a) { return sqrt(dot3(a, a)); }
+struct Q4 { double x, y, z, w; };
+// Eigen QuaternionBase::_transformVector: v + w*uv + qv x uv, uv = 2 (qv x v)   (EM:358, LF:26, LF:83)
+__device__ __forceinline__ D3 qrot(Q4 q, D3 v) {
+  D3 qv = d3(q.x, q.y, q.z);
+  D3 uv = cross3(qv, v);
+  uv = uv + uv;
+  return (v + q.w * uv) + cross3(qv, uv);
+}
+// pointAssociaToMap (EM:355-363): fp64 transform, fp32 store.
+__device__ __forceinline__ float4 associate(const double* x, float4 p) {
+  Q4 q; q.x = x[0]; q.y = x[1]; q.z = x[2]; q.w = x[3];
+  D3 w = qrot(q, d3((double)p.x, (double)p.y, (double)p.z)) + d3(x[4], x[5], x[6]);
+  return make_float4((float)w.x, (float)w.y, (float)w.z, p.w);
+}
+
+// ---- launch helpers implemented in the .cu files (all asynchronous on `st`) ----
+struct Launch {
+  cudaStream_t st;
+  int64_t* counter;  // kernels launched
+};
+
+// k_sort.cu
+void launch_sort_pass(const Launch& L, const SortJob* jobs_dev, int njobs, int pass);  // hist + scatter on stored keys
+void launch_sort_scatter(const Launch& L, const SortJob* jobs_dev, int njobs, int pass);
+// k_extract.cu
+void launch_frame_reset(const Launch& L, LaneDev* lanes, int lane0, int nlanes, VoxVars* vv, int vv_per_lane, int predict);
+void launch_extract(const Launch& L, LaneDev* lanes, const SortJob* ring_jobs, int lane0, int nlanes, int sel, const ConfigDev& cfg);
+// k_voxel.cu
+void launch_voxel(const Launch& L, const VoxJob* jobs_dev, int njobs, const SortJob* sort_jobs_dev);
+void launch_map_append(const Launch& L, LaneDev* lanes, int lane0, int nlanes, int cur, const ConfigDev& cfg);
+void launch_map_init(const Launch& L, LaneDev* lanes, int lane0, int nlanes, int cur, const ConfigDev& cfg);
+// k_knn.cu
+void launch_grid_build(const Launch& L, const GridJob* jobs_dev, int njobs, const ConfigDev& cfg);
+void launch_knn_fit(const Launch& L, LaneDev* lanes, const GridJob* grid_jobs, int lane0, int nlanes, int cur, const ConfigDev& cfg,
+                    const double* pose_override, int want_nn);
+void launch_knn_only(const Launch& L, const GridJob* job_dev, const float4* q, const int* nq_dev, int* idx, float* d2, const ConfigDev& cfg);
+// k_solve.cu
+void launch_solve(const Launch& L, LaneDev* lanes, int lane0, int nlanes, int outer, int finalize, const ConfigDev& cfg, int max_iters);
+
+}  // namespace vilf
