@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py — scans/s of the scan-to-map lidar odometry hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--seqs S] [--workload hdl64|vlp32|beams128]
+
+A "step" is one lock-step frame of every sequence in the job: S independent synthetic sequences per GPU
+(independent worlds, trajectories and noise), N GPUs, so one step = S*N scans.  Frame 0 of every sequence
+(localMapInited) and W-1 further frames are warm-up; exactly K steps are timed.
+
+  value   whole-job scans/s with the scans already resident in HBM (device-to-device copy into the scan slot)
+  e2e     the same through the public C ABI with HOST (pinned) scan buffers: per step H2D of S scans, D2H of S poses
+  roofline  the kernel with the largest share of the step, timed with CUDA events inside the library in a
+            second pass over the same frames; algorithmic bytes per SURVEY.md §8(d) / DESIGN.md §6
+  cpu_baseline  the CPU oracle (restated reference path) on all host cores, one sequence per core, bounded sample
+
+Multi-GPU: replicas only — every rank runs its own sequences, no collective on the data path;
+torch.distributed (NCCL) is used for the start/stop barrier and the max-over-ranks of the device time.
+--impl reference times the reference's CPU path (the oracle restatement; the ROS node cannot be built
+offline) on the host cores and prints the same JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from vil_fusion_b200 import replicas, synth  # noqa: E402
+
+WORKLOADS = {
+    "hdl64": dict(sensor="hdl64", n_scan=64, n_rings=64, desc="synthetic HDL-64E 64x1800 sequence(s), leaf 0.4/0.8 (configs[3] per-GPU unit)"),
+    "vlp32": dict(sensor="vlp32", n_scan=32, n_rings=32, desc="synthetic 32x1800 sequence(s), leaf 0.4/0.8 (configs[1])"),
+    "beams128": dict(sensor="beams128", n_scan=0, n_rings=128, desc="synthetic 128x2048 sequence(s), explicit ring ids (configs[4] shape)"),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="hdl64", choices=sorted(WORKLOADS))
+    ap.add_argument("--seqs", type=int, default=8, help="independent sequences per GPU, stepped in lock-step")
+    ap.add_argument("--depth", type=int, default=3, help="frames in flight (submit ahead of wait)")
+    ap.add_argument("--cpu-frames", type=int, default=60, help="frames per core of the bounded CPU sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-roofline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle, one sequence per core
+# ---------------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    idx, scans, rings, n_scan, n_rings, barrier = args
+    from oracle import orc
+    cfg = orc.config(n_scan=n_scan, n_rings=n_rings)
+    od = orc.Odometry(cfg)
+    barrier.wait()
+    t0 = time.perf_counter()
+    for x, r in zip(scans, rings):
+        od.process_scan(x, r if n_scan == 0 else None)
+    dt = time.perf_counter() - t0
+    tm = od.timing()
+    return dt, tm
+
+
+def cpu_baseline(workload: str, frames: int, cores: int | None = None):
+    """scans/s of the CPU oracle with `cores` independent sequences on `cores` processes."""
+    from oracle import orc
+    orc.build()
+    w = WORKLOADS[workload]
+    cores = cores or (os.cpu_count() or 1)
+    data = []
+    for c in range(cores):
+        seq = synth.Sequence(w["sensor"], frames, seed=100 + c)
+        sc = [seq[i] for i in range(frames)]
+        data.append(([s[0] for s in sc], [s[1] for s in sc]))
+    ctx = mp.get_context("fork")
+    mgr_barrier = ctx.Barrier(cores)
+    res_q = ctx.Queue()
+
+    def run(idx):
+        res_q.put(_cpu_worker((idx, data[idx][0], data[idx][1], w["n_scan"], w["n_rings"], mgr_barrier)))
+
+    procs = [ctx.Process(target=run, args=(i,)) for i in range(cores)]
+    for p in procs:
+        p.start()
+    res = [res_q.get() for _ in procs]
+    for p in procs:
+        p.join()
+    wall = max(r[0] for r in res)
+    per_stage = {k: float(np.mean([r[1][k] for r in res])) for k in ("extract", "scan_ds", "kd_build", "assoc", "solve", "map_update")}
+    return dict(value=cores * frames / wall, unit="scans/s", cores=cores, kind="port",
+                sample=f"{cores} independent {workload} sequences x {frames} frames (frame 0 = map init), one per core, oracle -O3 single-thread each",
+                seconds=wall, per_stage_s_per_seq=per_stage)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# clocks sampler
+# ---------------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device: int):
+        self.device = device
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=float(max(mx)) if mx else None, reasons=sorted(reasons), samples=len(sm))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------
+def algorithmic_bytes(phase: str, kernel: str, c: dict) -> float | None:
+    """Algorithmic bytes of ONE launch (all S sequences of the rank), SURVEY.md §8(d) figures; c = mean counts per sequence."""
+    N, F, Q, M, S = c["n_scan"], c["n_edge"] + c["n_surf"], c["n_ds"], c["n_map"], c["seqs"]
+    per = {
+        ("extract", "k_sort_hist<KeyGenRing>"): 16 * N,
+        ("extract", "k_sort_scatter"): 16 * N,
+        ("extract", "k_sector_select"): 16 * N + 16 * F,
+        ("extract", "k_compact_features"): 32 * F,
+        ("assoc_solve", "k_knn_fit"): 56 * Q + 16 * M + 96 * Q,
+        ("assoc_solve", "k_solve"): 96 * Q,
+        ("grid_build", None): 32 * M,
+        ("scan_ds", None): 16 * F + 16 * Q,
+        ("map_update", None): 16 * (M + Q) + 16 * M,
+    }
+    v = per.get((phase, kernel), per.get((phase, None)))
+    return None if v is None else float(v) * S
+
+
+def run_gpu(args, rank: int, world: int, local_rank: int):
+    import torch
+    from vil_fusion_b200 import cabi
+
+    torch.cuda.set_device(local_rank)
+    w = WORKLOADS[args.workload]
+    S, K, W, D = args.seqs, args.steps, max(args.warmup, 3), max(1, min(args.depth, 6))
+    F = K + W
+    # ---- synthetic input: S independent sequences for this rank, staged in pinned host memory ----
+    t_gen = time.time()
+    seqs = [synth.Sequence(w["sensor"], F, seed=sd) for sd in replicas.sequence_seeds(rank, world, S)]
+    cap = seqs[0].sensor.rings * seqs[0].sensor.n_az
+    host = cabi.host_alloc(S * F * cap * 16).view(np.float32).reshape(S, F, cap, 4)
+    host_ring = cabi.host_alloc(S * F * cap * 2).view(np.uint16).reshape(S, F, cap)
+    counts = np.zeros((S, F), np.int32)
+    for s in range(S):
+        for f in range(F):
+            x, r = seqs[s][f]
+            counts[s, f] = x.shape[0]
+            host[s, f, : x.shape[0]] = x
+            host_ring[s, f, : x.shape[0]] = r
+    t_gen = time.time() - t_gen
+    use_ring = w["n_scan"] == 0
+    dev = torch.empty((S, F, cap, 4), dtype=torch.float32, device="cuda")
+    dev.copy_(torch.from_numpy(host), non_blocking=False)
+    dev_ring = torch.empty((S, F, cap), dtype=torch.int16, device="cuda")
+    dev_ring.copy_(torch.from_numpy(host_ring.view(np.int16)), non_blocking=False)
+    torch.cuda.synchronize()
+
+    cfg = cabi.default_config(n_scan=w["n_scan"], n_rings=w["n_rings"], max_scan_points=max(cap, 1024))
+
+    barrier = replicas.barrier
+
+    def run_pass(mode: str, profile: bool = False):
+        """One full pass (W warm-up + K timed steps) on fresh sequences. mode: 'dev' | 'host'. Returns (ms, launches, batch)."""
+        b = cabi.Batch(cfg, S, device=local_rank)
+        stream = torch.cuda.ExternalStream(b.seqs[0].stream())
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tickets = []
+
+        def submit(f):
+            if mode == "dev":
+                ptrs = [dev[s, f].data_ptr() for s in range(S)]
+                rp = [dev_ring[s, f].data_ptr() for s in range(S)] if use_ring else None
+                return b.submit_dev(ptrs, [int(counts[s, f]) for s in range(S)], rp)
+            return b.submit([host[s, f, : counts[s, f]] for s in range(S)], [host_ring[s, f, : counts[s, f]] for s in range(S)] if use_ring else None)
+
+        poses = None
+        for f in range(W):
+            poses = b.wait(submit(f))
+        if profile:
+            b.seqs[0].profile(True)
+        barrier()
+        l0 = b.seqs[0].launch_count()
+        ev0.record(stream)
+        t0 = time.perf_counter()
+        for f in range(W, F):
+            tickets.append(submit(f))
+            if len(tickets) >= D:
+                poses = b.wait(tickets.pop(0))
+        while tickets:
+            poses = b.wait(tickets.pop(0))
+        ev1.record(stream)
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        ms = ev0.elapsed_time(ev1)
+        launches = b.seqs[0].launch_count() - l0
+        return ms, wall_ms, launches, b, poses
+
+    clocks = Clocks(local_rank)
+    clocks.start()
+    ms_dev, wall_dev, launches, b_dev, poses_dev = run_pass("dev")
+    clk = clocks.stop()
+    cnt = [b_dev.seqs[s].counts() for s in range(S)]
+    b_dev.close()
+    ms_host, wall_host, _, b_host, poses_host = run_pass("host")
+    b_host.close()
+    same = bool(np.array_equal(poses_dev, poses_host))
+
+    roof = None
+    kern_table = None
+    if not args.no_roofline:
+        ms_p, _, _, b_p, _ = run_pass("dev", profile=True)
+        kt = b_p.seqs[0].profile_kernels()
+        stage, frames = b_p.seqs[0].profile_read(reset=False)
+        b_p.close()
+        mean_counts = dict(
+            n_scan=float(counts[:, W:].mean()), n_edge=float(np.mean([c["n_edge"] for c in cnt])), n_surf=float(np.mean([c["n_surf"] for c in cnt])),
+            n_ds=float(np.mean([c["n_ds_edge"] + c["n_ds_surf"] for c in cnt])), n_map=float(np.mean([c["n_map_edge"] + c["n_map_surf"] for c in cnt])), seqs=S)
+        tot = sum(v[0] for v in kt.values()) or 1.0
+        kern_table = sorted(([f"{p}/{k}", v[0], v[1]] for (p, k), v in kt.items()), key=lambda r: -r[1])
+        (dp, dk), (dms, dn) = max(kt.items(), key=lambda kv: kv[1][0])
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        ab = algorithmic_bytes(dp, dk, mean_counts)
+        dur_s = dms / max(dn, 1) * 1e-3
+        ach = (ab / dur_s / 1e9) if ab else None
+        roof = dict(bound="hbm", kernel=f"{dp}/{dk}", achieved=ach, peak=peak, unit="GB/s", frac=(ach / peak) if ach else None, traffic=None,
+                    peak_source="MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                    share_of_step=dms / tot, launches_timed=dn, avg_launch_us=dur_s * 1e6, algorithmic_bytes_per_launch=ab,
+                    note="event-to-event interval (includes the launch gap); per-frame working set is L2-resident, so this path is latency-, not HBM-bound (DESIGN.md §6)")
+
+    # ---- max over ranks ----
+    ms_dev_max, ms_host_max = replicas.max_over_ranks([ms_dev, ms_host], device="cuda")
+    scans = replicas.job_scans(world, S, K)
+    out = dict(
+        metric="scans/s scan-to-map (HDL-64 synthetic)" if args.workload == "hdl64" else f"scans/s scan-to-map ({args.workload} synthetic)",
+        value=scans / (ms_dev_max * 1e-3), unit="scans/s", n_gpus=world, steps=K, warmup=W, ms_per_step=ms_dev_max / K,
+        higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32 geometry / f64 solve", data="synthetic",
+        config=dict(workload=w["desc"], sequences_per_gpu=S, scans_per_step=S * world, points_per_scan=int(counts[:, W:].mean()),
+                    frames_in_flight=D, l2="inputs of one step are distinct frames (S x 1.8 MB) and all K steps use fresh scans; no cache flush needed",
+                    parallelism=f"{world} replica(s) x {S} lock-step sequences, no collective"),
+        e2e=dict(value=scans / (ms_host_max * 1e-3), unit="scans/s", h2d_bytes_per_step=int(counts[:, W:].mean() * 16 * S), d2h_bytes_per_step=int(S * 7 * 8),
+                 ms_per_step=ms_host_max / K, poses_equal_to_device_resident_run=same),
+        gpu_launches=int(launches), clocks=clk,
+        wall_ms=dict(dev=wall_dev, host=wall_host), gen_s=t_gen,
+    )
+    if roof:
+        out["roofline"] = roof
+        out["kernels_ms"] = kern_table[:12]
+        out["stage_ms"] = stage
+    return out
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb = cpu_baseline(args.workload, max(10, min(args.cpu_frames, args.steps + args.warmup)))
+        w = WORKLOADS[args.workload]
+        print(json.dumps(dict(
+            impl="reference", metric="scans/s scan-to-map (HDL-64 synthetic)" if args.workload == "hdl64" else f"scans/s scan-to-map ({args.workload} synthetic)",
+            value=cb["value"], unit="scans/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * cb["cores"] / cb["value"],
+            higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32 geometry / f64 solve", data="synthetic",
+            config=dict(workload=w["desc"], parallelism=f"{cb['cores']} host processes, one sequence each"),
+            cpu_baseline=cb, e2e=dict(value=cb["value"], unit="scans/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0,
+            note="reference ROS node cannot be built offline (no ROS/PCL/Ceres); this is the CPU restatement under oracle/ (DESIGN.md §2)")))
+        return
+
+    cb = None
+    if rank == 0 and world == 1 and not args.no_cpu:  # before CUDA is initialised in this process (the workers are forked)
+        try:
+            cb = cpu_baseline(args.workload, args.cpu_frames)
+        except Exception as e:  # the GPU numbers stand on their own
+            cb = dict(error=repr(e))
+    import torch
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    out = run_gpu(args, rank, world, local_rank)
+    if rank == 0:
+        if cb is not None:
+            out["cpu_baseline"] = cb
+        print(json.dumps(out))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -149,6 +149,11 @@ int vilf_state_import(vilf_handle* h, const double state31[31], const float* map
  * Profiling adds event records between stages; enable only for roofline runs. */
 int vilf_profile_enable(vilf_handle* h, int on);
 int vilf_profile_read(vilf_handle* h, double ms_out[7], int64_t* frames, int reset);
+/* Per-kernel view of the same events: tag = phase * 32 + kernel, phase 0 extract, 1 scan downsample,
+ * 2 association + solve, 3 map update, 4 grid build; n_tags must be 160.  An interval runs from the end of the
+ * previous kernel to the end of this one, i.e. it includes the launch gap. */
+int vilf_profile_read_kernels(vilf_handle* h, double* ms_out, int64_t* launches_out, int n_tags, int reset);
+const char* vilf_profile_kernel_name(int kernel);
 /* Number of kernels this library has launched on the handle's context since creation. */
 int vilf_launch_count(vilf_handle* h, int64_t* launches);
 /* The CUDA stream all work of this handle is issued on (for external cudaEvent timing). */

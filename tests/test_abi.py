@@ -1,0 +1,69 @@
+"""The C-ABI shared library: loads, exports every symbol include/vilf.h declares, and fails loudly without a GPU."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "vilf.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(vilf_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_and_binding_agree(cabi):
+    assert header_symbols() == sorted(cabi.SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol(cabi):
+    lib = cabi.lib()
+    for s in header_symbols():
+        assert hasattr(lib, s), f"libvilf_cuda.so does not export {s}"
+
+
+def test_default_config_is_the_reference_yaml(cabi):
+    c = cabi.default_config()
+    # config/kitti/velodyne_param_64.yaml:9-23 + hard-coded constants
+    assert (c.n_scan, c.lidar_min, c.lidar_max, c.edge_threshold) == (64, 3.0, 90.0, 0.1)
+    assert (c.edge_leaf, c.surf_leaf, c.crop_half, c.knn_gate, c.huber) == (0.4, 0.8, 100.0, 1.0, 0.1)
+    assert (c.outer_iters, c.lm_max_iters) == (2, 4)
+
+
+def test_config_struct_layout_matches_header(cabi):
+    # 2 x int32, 8 x double, 4 x int32 -> 8 + 64 + 16
+    assert C.sizeof(cabi.Config) == 88
+
+
+def test_invalid_arguments_are_rejected_without_touching_cuda(cabi):
+    lib = cabi.lib()
+    h = C.c_void_p()
+    cfg = cabi.default_config()
+    assert lib.vilf_create(None, 0, C.byref(h)) == 1
+    cfg.outer_iters = 0
+    assert lib.vilf_create(C.byref(cfg), 0, C.byref(h)) == 1
+    assert lib.vilf_process_scan(None, None, 0, None, None) == 1
+    assert lib.vilf_destroy(None) == 1
+
+
+def test_no_cpu_fallback(cabi):
+    """Without a CUDA device the product path must refuse to run (no oracle / CPU route behind the ABI)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(cabi.VilfError) as e:
+        cabi.Odometry(cabi.default_config())
+    assert e.value.code == 2
+
+
+def test_product_package_does_not_import_the_oracle():
+    """Nothing under vil_fusion_b200/ (the product) may import, link or load anything under oracle/."""
+    pkg = os.path.join(ROOT, "vil_fusion_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".c", ".cpp")) or f == "Makefile":
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), f
+                assert "liborc" not in txt and "orc_capi" not in txt and "oracle/" not in txt, f

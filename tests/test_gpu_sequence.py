@@ -1,0 +1,200 @@
+"""End-to-end parity of the per-frame path (C ABI) against the CPU oracle: free-running and teacher-forced
+sequences, every sensor layout, the lock-step batch, the asynchronous API, state export/import."""
+import numpy as np
+import pytest
+
+from conftest import pose_err
+
+pytestmark = pytest.mark.gpu
+
+TOL_ROT, TOL_TRANS, TOL_MAP = 1e-4, 1e-3, 1e-5  # BASELINE.json north_star tolerances
+
+
+def run_pair(cabi, orc, synth, sensor, n_scan, n_rings, frames, seed, cap_scan, use_ring=False):
+    seq = synth.Sequence(sensor, frames, seed=seed)
+    o = orc.Odometry(orc.config(n_scan=n_scan, n_rings=n_rings))
+    g = cabi.Odometry(cabi.default_config(n_scan=n_scan, n_rings=n_rings, max_scan_points=cap_scan, max_map_points=1 << 19))
+    worst = (0.0, 0.0)
+    for i in range(frames):
+        x, r = seq[i]
+        po, _, _ = o.process_scan(x, r if use_ring else None)
+        pg = g.process_scan(x, r if use_ring else None)
+        e = pose_err(po, pg)
+        worst = (max(worst[0], e[0]), max(worst[1], e[1]))
+        assert e[0] <= TOL_ROT and e[1] <= TOL_TRANS, (i, e)
+    return o, g, worst
+
+
+def maps_close(orc, cabi, o, g):
+    for which in (0, 1):
+        mo, mg = o.cloud(which), g.cloud(which)
+        assert mo.shape == mg.shape
+        assert np.abs(mo - mg).max() <= TOL_MAP
+
+
+def test_hdl64_100_frames_free_running(cabi, orc, synth):
+    """configs[0]: 100-frame HDL-64E sequence, GPU free-running against the CPU oracle."""
+    o, g, worst = run_pair(cabi, orc, synth, "hdl64", 64, 64, 100, 0, 116000)
+    maps_close(orc, cabi, o, g)
+    so, sg = o.solves(), g.solves()
+    assert np.array_equal(so[:, :4], sg[:, :4])  # same factor counts, termination and iteration counts
+    c = g.counts()
+    assert c["frames"] == 99 and c["status"] == 0
+    assert np.array_equal(o.cloud(orc.NO_REGISTERED), g.cloud(cabi.NO_REGISTERED))
+    assert np.abs(o.cloud(orc.REGISTERED) - g.cloud(cabi.REGISTERED)).max() <= TOL_MAP
+    g.close()
+
+
+def test_vlp32_and_16_and_128(cabi, orc, synth):
+    for sensor, n_scan, n_rings, cap, ring in (("vlp32", 32, 32, 58000, False), ("vlp16", 16, 16, 10000, False), ("beams128", 0, 128, 263000, True)):
+        o, g, _ = run_pair(cabi, orc, synth, sensor, n_scan, n_rings, 8, 5, cap, use_ring=ring)
+        maps_close(orc, cabi, o, g)
+        g.close()
+
+
+def test_golden_sequence(cabi, golden):
+    g = cabi.Odometry(cabi.default_config(n_scan=16, n_rings=16, max_scan_points=10000, max_map_points=1 << 16))
+    for i in range(golden["poses"].shape[0]):
+        p = g.process_scan(golden[f"scan{i}"])
+        e = pose_err(p, golden["poses"][i])
+        assert e[0] <= TOL_ROT and e[1] <= TOL_TRANS, (i, e)
+    assert np.abs(g.cloud(0) - golden["final_map_edge"]).max() <= TOL_MAP
+    assert np.abs(g.cloud(1) - golden["final_map_surf"]).max() <= TOL_MAP
+    g.close()
+
+
+def test_teacher_forced(cabi, orc, synth):
+    """Every frame starts from the oracle's state (pose, previous pose, both maps): per-frame parity without feedback."""
+    frames = 25
+    seq = synth.Sequence("hdl64", frames, seed=3)
+    o = orc.Odometry(orc.config())
+    g = cabi.Odometry(cabi.default_config(max_scan_points=116000, max_map_points=1 << 19))
+    x, _ = seq[0]
+    o.process_scan(x)
+    for i in range(1, frames):
+        g.set_state(o.state(), o.cloud(orc.MAP_EDGE), o.cloud(orc.MAP_SURF))
+        x, _ = seq[i]
+        po, _, _ = o.process_scan(x)
+        g.feature_extract(x)
+        pg = g.update()
+        e = pose_err(po, pg)
+        assert e[0] <= TOL_ROT and e[1] <= TOL_TRANS, (i, e)
+        assert np.abs(o.cloud(orc.MAP_SURF) - g.cloud(1)).max() <= TOL_MAP
+        assert np.abs(g.state() - o.state()).max() < 1e-6
+    g.close()
+
+
+def test_method_surface_equals_fused_path(cabi, synth):
+    """extractFeature -> localMapInited / optimation_processing call by call == vilf_process_scan."""
+    seq = synth.Sequence("vlp32", 6, seed=8)
+    cfg = cabi.default_config(n_scan=32, n_rings=32, max_scan_points=58000, max_map_points=1 << 18)
+    a, b, c = cabi.Odometry(cfg), cabi.Odometry(cfg), cabi.Odometry(cfg)
+    for i in range(6):
+        x, _ = seq[i]
+        pa = a.process_scan(x)
+        b.feature_extract(x)
+        if i == 0:
+            b.map_init()
+            pb = b.pose()[0]
+        else:
+            pb = b.update()
+        e, _ = b.features(0)
+        s, _ = b.features(1)
+        if i == 0:
+            c.map_init(e, s)
+            pc = c.pose()[0]
+        else:
+            pc = c.update(e, s)  # host clouds, like the reference's optimation_processing(edge, surf)
+        assert np.array_equal(pa, pb) and np.array_equal(pa, pc), i
+    for which in range(4):
+        assert np.array_equal(a.cloud(which), b.cloud(which)) and np.array_equal(a.cloud(which), c.cloud(which))
+    pose, rt = a.pose()
+    R = rt[:9].reshape(3, 3)
+    assert np.allclose(R @ R.T, np.eye(3), atol=1e-12) and np.array_equal(rt[9:], pose[4:])
+    for o in (a, b, c):
+        o.close()
+
+
+def test_batch_lockstep_equals_single(cabi, synth):
+    S, frames = 3, 7
+    seqs = [synth.Sequence("vlp32", frames, seed=20 + s) for s in range(S)]
+    cfg = cabi.default_config(n_scan=32, n_rings=32, max_scan_points=58000, max_map_points=1 << 18)
+    singles = [cabi.Odometry(cfg) for _ in range(S)]
+    batch = cabi.Batch(cfg, S)
+    for f in range(frames):
+        scans = [np.ascontiguousarray(seqs[s][f][0]) for s in range(S)]
+        poses = batch.wait(batch.submit(scans))
+        for s in range(S):
+            assert np.array_equal(poses[s], singles[s].process_scan(scans[s])), (f, s)
+    for s in range(S):
+        for which in (0, 1):
+            assert np.array_equal(batch.seqs[s].cloud(which), singles[s].cloud(which))
+        singles[s].close()
+    batch.close()
+
+
+def test_async_pipeline_equals_blocking(cabi, synth):
+    frames = 12
+    seq = synth.Sequence("vlp32", frames, seed=31)
+    scans = [np.ascontiguousarray(seq[i][0]) for i in range(frames)]
+    cfg = cabi.default_config(n_scan=32, n_rings=32, max_scan_points=58000, max_map_points=1 << 18)
+    a, b = cabi.Odometry(cfg), cabi.Odometry(cfg)
+    ref = [a.process_scan(x) for x in scans]
+    tickets, got = [], []
+    for x in scans:
+        tickets.append(b.submit_scan(x))
+        if len(tickets) == 4:
+            got.append(b.wait(tickets.pop(0)))
+    while tickets:
+        got.append(b.wait(tickets.pop(0)))
+    assert all(np.array_equal(r, p) for r, p in zip(ref, got))
+    # more than 8 frames in flight is refused, not silently dropped
+    c = cabi.Odometry(cfg)
+    ts = [c.submit_scan(x) for x in scans[:8]]
+    with pytest.raises(cabi.VilfError) as e:
+        c.submit_scan(scans[8])
+    assert e.value.code == 5
+    for t in ts:
+        c.wait(t)
+    for o in (a, b, c):
+        o.close()
+
+
+def test_state_roundtrip_and_sequence_errors(cabi, synth):
+    seq = synth.Sequence("vlp32", 5, seed=40)
+    cfg = cabi.default_config(n_scan=32, n_rings=32, max_scan_points=58000, max_map_points=1 << 18)
+    a = cabi.Odometry(cfg)
+    with pytest.raises(cabi.VilfError) as e:
+        a.update()
+    assert e.value.code == 5
+    for i in range(3):
+        a.process_scan(seq[i][0])
+    b = cabi.Odometry(cfg)
+    b.set_state(a.state(), a.cloud(0), a.cloud(1))
+    for i in range(3, 5):
+        assert np.array_equal(a.process_scan(seq[i][0]), b.process_scan(seq[i][0]))
+    a.close(); b.close()
+
+
+def test_map_too_small_skips_optimisation(cabi, orc):
+    """EM:254 guard: the pose stays at the prediction, the map is still maintained."""
+    rng = np.random.default_rng(0)
+    e = np.zeros((5, 4), np.float32); e[:, :3] = rng.normal(0, 5, (5, 3))
+    s = np.zeros((30, 4), np.float32); s[:, :3] = rng.normal(0, 5, (30, 3))
+    g = cabi.Odometry(cabi.default_config(max_scan_points=2048, max_map_points=4096))
+    o = orc.Odometry(orc.config())
+    g.map_init(e, s); o.init_map(e, s)
+    pg, po = g.update(e, s), o.update(e, s)
+    assert np.array_equal(pg, po) and len(g.solves()) == 0
+    assert np.array_equal(g.cloud(0), o.cloud(orc.MAP_EDGE)) and np.array_equal(g.cloud(1), o.cloud(orc.MAP_SURF))
+    g.close()
+
+
+def test_map_capacity_overflow_is_reported(cabi, synth):
+    seq = synth.Sequence("vlp32", 3, seed=41)
+    g = cabi.Odometry(cabi.default_config(n_scan=32, n_rings=32, max_scan_points=58000, max_map_points=1024))
+    g.process_scan(seq[0][0])
+    with pytest.raises(cabi.VilfError) as e:
+        g.process_scan(seq[1][0])
+    assert e.value.code == 3
+    g.close()

@@ -40,7 +40,7 @@ SYMBOLS = [
     "vilf_feature_extract", "vilf_get_features", "vilf_map_init", "vilf_map_init_points", "vilf_update", "vilf_update_points",
     "vilf_get_pose", "vilf_get_cloud", "vilf_voxel_downsample", "vilf_crop_voxel_downsample", "vilf_crop_box", "vilf_knn5",
     "vilf_factors", "vilf_normal_equations", "vilf_solve", "vilf_get_solves", "vilf_state_export", "vilf_state_import",
-    "vilf_profile_enable", "vilf_profile_read", "vilf_launch_count", "vilf_get_stream", "vilf_get_counts",
+    "vilf_profile_enable", "vilf_profile_read", "vilf_profile_read_kernels", "vilf_profile_kernel_name", "vilf_launch_count", "vilf_get_stream", "vilf_get_counts",
 ]
 
 _lib = None
@@ -258,6 +258,17 @@ class Odometry:
         self._ck(lib().vilf_profile_read(self._h, _p(ms, C.c_double), C.byref(fr), int(reset)))
         names = ["extract", "scan_ds", "grid_build", "knn_fit", "solve", "map_update", "frame"]
         return dict(zip(names, ms.tolist())), fr.value
+
+    def profile_kernels(self, reset: bool = True):
+        """{(phase, kernel name): (ms, launches)} accumulated since the last reset."""
+        ms = np.zeros(160); cnt = np.zeros(160, np.int64)
+        self._ck(lib().vilf_profile_read_kernels(self._h, _p(ms, C.c_double), _p(cnt, C.c_int64), 160, int(reset)))
+        lib().vilf_profile_kernel_name.restype = C.c_char_p
+        phases = ["extract", "scan_ds", "assoc_solve", "map_update", "grid_build"]
+        out = {}
+        for tag in np.nonzero(cnt)[0]:
+            out[(phases[tag // 32], lib().vilf_profile_kernel_name(int(tag % 32)).decode())] = (float(ms[tag]), int(cnt[tag]))
+        return out
 
     def launch_count(self) -> int:
         n = C.c_int64()

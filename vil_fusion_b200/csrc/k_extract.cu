@@ -73,6 +73,7 @@ __global__ void k_frame_reset(LaneDev* lanes, int lane0, int nlanes, VoxVars* vv
   if (t < nlanes) {
     LaneVars& L = *lanes[lane0 + t].v;
     L.opt_ran = 0;
+    L.status = 0;  // error bits describe the current frame
     if (predict) {  // EM:238-243
       double inv[12], rel[12], est[12];
       iso_inv(L.odom_last, inv);
@@ -91,7 +92,7 @@ __global__ void k_frame_reset(LaneDev* lanes, int lane0, int nlanes, VoxVars* vv
 
 void launch_frame_reset(const Launch& L, LaneDev* lanes, int lane0, int nlanes, VoxVars* vv, int vv_per_lane, int predict) {
   k_frame_reset<<<1, 1024, 0, L.st>>>(lanes, lane0, nlanes, vv, vv_per_lane, predict);
-  ++*L.counter;
+  L.tick(K_RESET);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -317,13 +318,13 @@ void launch_extract(const Launch& L, LaneDev* lanes, const SortJob* ring_jobs, i
   gen.lanes = lanes; gen.lane0 = lane0; gen.sel = sel; gen.cfg = cfg;
   dim3 gs(SORT_G, nlanes);
   k_sort_hist<KeyGenRing, true><<<gs, SORT_THREADS, 0, L.st>>>(ring_jobs + lane0, 0, gen);
-  ++*L.counter;
+  L.tick(K_RING_KEYHIST);
   launch_sort_scatter(L, ring_jobs + lane0, nlanes, 0);
   dim3 g2(cfg.rings_total * SECTORS, nlanes);
   k_sector_select<<<g2, 256, SEC_SMEM, L.st>>>(lanes, lane0, sel, cfg);
-  ++*L.counter;
+  L.tick(K_SECTOR);
   k_compact_features<<<g2, 256, 0, L.st>>>(lanes, lane0, cfg);
-  ++*L.counter;
+  L.tick(K_COMPACT);
 }
 
 }  // namespace vilf

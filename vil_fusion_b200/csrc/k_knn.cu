@@ -122,11 +122,15 @@ __global__ void __launch_bounds__(256) k_grid_scatter(const GridJob* __restrict_
 void launch_grid_build(const Launch& L, const GridJob* jobs_dev, int njobs, const ConfigDev& cfg) {
   dim3 g(GRID_G, njobs);
   k_grid_zero<<<g, 256, 0, L.st>>>(jobs_dev);
+  L.tick(K_GRID_ZERO);
   k_grid_count<<<g, 256, 0, L.st>>>(jobs_dev, cfg.inv_cell);
+  L.tick(K_GRID_COUNT);
   k_grid_scan_partial<<<g, 256, 0, L.st>>>(jobs_dev);
+  L.tick(K_GRID_SCAN_PARTIAL);
   k_grid_scan_final<<<g, 256, 0, L.st>>>(jobs_dev);
+  L.tick(K_GRID_SCAN_FINAL);
   k_grid_scatter<<<g, 256, 0, L.st>>>(jobs_dev, cfg.inv_cell);
-  *L.counter += 5;
+  L.tick(K_GRID_SCATTER);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -418,7 +422,7 @@ void launch_knn_fit(const Launch& L, LaneDev* lanes, const GridJob* grid_jobs, i
                     const double* pose_override, int want_nn) {
   dim3 g(KNN_G, nlanes);
   k_knn_fit<<<g, 256, 0, L.st>>>(lanes, grid_jobs, lane0, cur, cfg, pose_override, want_nn);
-  ++*L.counter;
+  L.tick(K_KNN_FIT);
 }
 
 // nearestKSearch alone against an explicit map (test entry point vilf_knn5).
@@ -444,7 +448,7 @@ __global__ void __launch_bounds__(256) k_knn_only(const GridJob* __restrict__ jo
 
 void launch_knn_only(const Launch& L, const GridJob* job_dev, const float4* q, const int* nq_dev, int* idx, float* d2, const ConfigDev& cfg) {
   k_knn_only<<<KNN_G, 256, 0, L.st>>>(job_dev, q, nq_dev, idx, d2, cfg.inv_cell);
-  ++*L.counter;
+  L.tick(K_KNN_ONLY);
 }
 
 }  // namespace vilf

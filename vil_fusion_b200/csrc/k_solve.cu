@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(LM_THREADS, 1) k_solve(LaneDev* lanes, int lan
 
 void launch_solve(const Launch& L, LaneDev* lanes, int lane0, int nlanes, int outer, int finalize, const ConfigDev& cfg, int max_iters) {
   k_solve<<<nlanes, LM_THREADS, 0, L.st>>>(lanes, lane0, outer, finalize, cfg, max_iters);
-  ++*L.counter;
+  L.tick(K_SOLVE);
 }
 
 }  // namespace vilf

@@ -103,13 +103,13 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const SortJob* __
 void launch_sort_scatter(const Launch& L, const SortJob* jobs_dev, int njobs, int pass) {
   dim3 grid(SORT_G, njobs);
   k_sort_scatter<<<grid, SORT_THREADS, 0, L.st>>>(jobs_dev, pass);
-  ++*L.counter;
+  L.tick(K_SORT_SCATTER);
 }
 
 void launch_sort_pass(const Launch& L, const SortJob* jobs_dev, int njobs, int pass) {
   dim3 grid(SORT_G, njobs);
   k_sort_hist<KeyGenNone, false><<<grid, SORT_THREADS, 0, L.st>>>(jobs_dev, pass, KeyGenNone());
-  ++*L.counter;
+  L.tick(K_SORT_HIST);
   launch_sort_scatter(L, jobs_dev, njobs, pass);
 }
 

@@ -214,18 +214,18 @@ __global__ void __launch_bounds__(256) k_vox_centroid(const VoxJob* __restrict__
 void launch_voxel(const Launch& L, const VoxJob* jobs_dev, int njobs, const SortJob* sort_jobs_dev) {
   dim3 gv(VOX_G, njobs);
   k_vox_bbox<<<gv, 256, 0, L.st>>>(jobs_dev);
-  ++*L.counter;
+  L.tick(K_VOX_BBOX);
   KeyGenVoxel gen;
   gen.jobs = jobs_dev;
   dim3 gs(SORT_G, njobs);
   k_sort_hist<KeyGenVoxel, true><<<gs, SORT_THREADS, 0, L.st>>>(sort_jobs_dev, 0, gen);
-  ++*L.counter;
+  L.tick(K_VOX_KEYHIST);
   launch_sort_scatter(L, sort_jobs_dev, njobs, 0);
   for (int pass = 1; pass < 4; ++pass) launch_sort_pass(L, sort_jobs_dev, njobs, pass);
   k_vox_heads<<<gv, 256, 0, L.st>>>(jobs_dev);
-  ++*L.counter;
+  L.tick(K_VOX_HEADS);
   k_vox_centroid<<<gv, 256, 0, L.st>>>(jobs_dev);
-  ++*L.counter;
+  L.tick(K_VOX_CENTROID);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -279,14 +279,14 @@ __global__ void k_map_init_commit(LaneDev* lanes, int lane0, ConfigDev cfg) {
 void launch_map_append(const Launch& L, LaneDev* lanes, int lane0, int nlanes, int cur, const ConfigDev& cfg) {
   dim3 g(64, nlanes);
   k_map_append<<<g, 256, 0, L.st>>>(lanes, lane0, cur, cfg);
-  ++*L.counter;
+  L.tick(K_MAP_APPEND);
 }
 void launch_map_init(const Launch& L, LaneDev* lanes, int lane0, int nlanes, int cur, const ConfigDev& cfg) {
   dim3 g(148, nlanes);
   k_map_init<<<g, 256, 0, L.st>>>(lanes, lane0, cur, cfg);
-  ++*L.counter;
+  L.tick(K_MAP_INIT);
   k_map_init_commit<<<1, nlanes, 0, L.st>>>(lanes, lane0, cfg);
-  ++*L.counter;
+  L.tick(K_MAP_INIT);
 }
 
 }  // namespace vilf

@@ -16,13 +16,13 @@ namespace {
 constexpr int RING_SLOTS = 8;
 constexpr int VV_PER_LANE = 4;  // scan edge, scan surf, map edge, map surf
 constexpr int N_STAGE = 7;
-constexpr int MAX_MARKS = 16;
+constexpr int MAX_MARKS = PROF_MAX_EVENTS;
 
 struct Slot {
   cudaEvent_t done = nullptr;
-  cudaEvent_t stage[MAX_MARKS] = {};  // profiling: event k closes an interval attributed to stage_tag[k]
+  cudaEvent_t stage[MAX_MARKS] = {};  // profiling: event k closes an interval attributed to stage_tag[k] (phase*32 + kernel)
   int stage_tag[MAX_MARKS] = {};
-  int n_marks = 0;
+  ProfSink sink;
   LaneVars* vars_pin = nullptr;  // [nlanes]
   int64_t ticket = -1;
   int lane0 = 0, nl = 0;
@@ -70,7 +70,9 @@ struct Ctx {
   int64_t scan_sel = 0;
   // profiling
   bool profile = false;
-  double stage_ms[N_STAGE] = {0, 0, 0, 0, 0, 0, 0};
+  double kernel_ms[PROF_TAGS] = {};
+  int64_t kernel_cnt[PROF_TAGS] = {};
+  double frame_ms = 0;
   int64_t prof_frames = 0;
   char err[512] = {0};
 };
@@ -108,7 +110,7 @@ int fail(Ctx* C, int code, const char* msg) {
   return code;
 }
 
-Launch mk(Ctx* C) { Launch L; L.st = C->st; L.counter = &C->launches; return L; }
+Launch mk(Ctx* C, ProfSink* sink = nullptr) { Launch L; L.st = C->st; L.counter = &C->launches; L.prof = sink; return L; }
 
 int pow2_ge(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
@@ -327,43 +329,41 @@ int status_to_rc(Ctx* C, int status) {
   return VILF_OK;
 }
 
-// stage tags: 0 extract, 1 scan downsample, 2 grid build, 3 kNN + fit, 4 solve, 5 map update (-1 = frame start)
-void stage_mark(Ctx* C, Slot* S, int tag) {
-  if (!S || !S->profiled || S->n_marks >= MAX_MARKS) return;
-  cudaEventRecord(S->stage[S->n_marks], C->st);
-  S->stage_tag[S->n_marks++] = tag;
-}
-
 // The per-frame launch sequence for lanes [lane0, lane0+nl), which all share `cur`, `first` and the scan slot.
 // with_extract = 0: features were uploaded by the caller (vilf_update_points / vilf_map_init_points).
 int enqueue_frame(Ctx* C, int lane0, int nl, bool first, bool with_extract, int sel, Slot* S) {
-  const Launch L = mk(C);
+  ProfSink* sink = nullptr;
+  if (S && S->profiled) {
+    sink = &S->sink;
+    sink->ev = S->stage; sink->tag = S->stage_tag; sink->n = 0; sink->cap = MAX_MARKS; sink->phase = 0;
+    cudaEventRecord(sink->ev[0], C->st);  // frame start
+    sink->tag[sink->n++] = -1;
+  }
+  const Launch L = mk(C, sink);
+  auto phase = [&](int p) { if (sink) sink->phase = p; };
   const ConfigDev& cfg = C->cfg;
   const int cur = C->cur[lane0];
-  if (S) S->n_marks = 0;
-  stage_mark(C, S, -1);
+  phase(0);
   launch_frame_reset(L, C->lanes_dev, lane0, nl, C->vv_dev, VV_PER_LANE, first ? 0 : 1);
   if (with_extract) launch_extract(L, C->lanes_dev, C->ring_jobs_dev[sel], lane0, nl, sel, cfg);
-  stage_mark(C, S, 0);
   if (first) {
+    phase(3);
     launch_map_init(L, C->lanes_dev, lane0, nl, cur, cfg);
-    stage_mark(C, S, 5);
+    phase(4);
     launch_grid_build(L, C->grid_dev[cur] + lane0 * 2, nl * 2, cfg);
-    stage_mark(C, S, 2);
   } else {
+    phase(1);
     launch_voxel(L, C->vox_scan_dev + lane0 * 2, nl * 2, C->vox_scan_sort_dev + lane0 * 2);
-    stage_mark(C, S, 1);
+    phase(2);
     for (int it = 0; it < cfg.outer_iters; ++it) {
       launch_knn_fit(L, C->lanes_dev, C->grid_dev[cur], lane0, nl, cur, cfg, nullptr, 0);
-      stage_mark(C, S, 3);
       launch_solve(L, C->lanes_dev, lane0, nl, it, it == cfg.outer_iters - 1 ? 1 : 0, cfg, cfg.lm_max_iters);
-      stage_mark(C, S, 4);
     }
+    phase(3);
     launch_map_append(L, C->lanes_dev, lane0, nl, cur, cfg);
     launch_voxel(L, C->vox_map_dev[cur] + lane0 * 2, nl * 2, C->vox_map_sort_dev[cur] + lane0 * 2);
-    stage_mark(C, S, 5);
+    phase(4);
     launch_grid_build(L, C->grid_dev[cur ^ 1] + lane0 * 2, nl * 2, cfg);
-    stage_mark(C, S, 2);
     for (int l = lane0; l < lane0 + nl; ++l) C->cur[l] = cur ^ 1;
   }
   for (int l = lane0; l < lane0 + nl; ++l) {
@@ -434,14 +434,18 @@ int wait_common(Ctx* C, int lane0, int nl, int64_t ticket, double* poses) {
   if (S.ticket != ticket || S.lane0 != lane0 || S.nl != nl) return fail(C, VILF_ERR_INVALID, "unknown ticket");
   CK(cudaEventSynchronize(S.done));
   S.ticket = -1;
-  if (S.profiled && S.n_marks > 1) {
-    for (int k = 1; k < S.n_marks; ++k) {
+  if (S.profiled && S.sink.n > 1) {
+    for (int k = 1; k < S.sink.n; ++k) {
       float ms = 0;
-      if (cudaEventElapsedTime(&ms, S.stage[k - 1], S.stage[k]) == cudaSuccess && S.stage_tag[k] >= 0) C->stage_ms[S.stage_tag[k]] += ms;
+      const int tag = S.stage_tag[k];
+      if (cudaEventElapsedTime(&ms, S.stage[k - 1], S.stage[k]) == cudaSuccess && tag >= 0 && tag < PROF_TAGS) {
+        C->kernel_ms[tag] += ms;
+        C->kernel_cnt[tag] += 1;
+      }
     }
     float ms = 0;
-    if (cudaEventElapsedTime(&ms, S.stage[0], S.stage[S.n_marks - 1]) == cudaSuccess) C->stage_ms[N_STAGE - 1] += ms;
-    C->prof_frames += S.nl;
+    if (cudaEventElapsedTime(&ms, S.stage[0], S.stage[S.sink.n - 1]) == cudaSuccess) C->frame_ms += ms;
+    C->prof_frames += 1;
   }
   int status = 0;
   for (int i = 0; i < nl; ++i) {
@@ -638,6 +642,7 @@ int vilf_feature_extract(vilf_handle* h, const float* xyzi, int n, const uint16_
   if (n) CK(cudaMemcpyAsync(L.scan[0], xyzi, (size_t)n * 16, cudaMemcpyHostToDevice, C->st));
   if (ring && n) CK(cudaMemcpyAsync(L.ring_in[0], ring, (size_t)n * 2, cudaMemcpyHostToDevice, C->st));
   CK(cudaMemcpyAsync(&L.v->n_scan[0], &n, sizeof(int), cudaMemcpyHostToDevice, C->st));
+  CK(cudaMemsetAsync(&L.v->status, 0, sizeof(int), C->st));
   CK(cudaStreamSynchronize(C->st));
   launch_extract(mk(C), C->lanes_dev, C->ring_jobs_dev[0], h->lane, 1, 0, C->cfg);
   CK(cudaGetLastError());
@@ -927,12 +932,40 @@ int vilf_profile_enable(vilf_handle* h, int on) {
   C->profile = on != 0;
   return VILF_OK;
 }
+static void prof_reset(Ctx* C) {
+  memset(C->kernel_ms, 0, sizeof(C->kernel_ms));
+  memset(C->kernel_cnt, 0, sizeof(C->kernel_cnt));
+  C->frame_ms = 0; C->prof_frames = 0;
+}
 int vilf_profile_read(vilf_handle* h, double ms_out[7], int64_t* frames, int reset) {
   HCHECK(h);
-  if (ms_out) memcpy(ms_out, C->stage_ms, sizeof(C->stage_ms));
+  if (ms_out) {
+    for (int i = 0; i < N_STAGE; ++i) ms_out[i] = 0;
+    for (int tag = 0; tag < PROF_TAGS; ++tag) {
+      const int ph = tag / 32, k = tag % 32;
+      int stage = ph == 0 ? 0 : ph == 1 ? 1 : ph == 4 ? 2 : ph == 3 ? 5 : (k == K_SOLVE ? 4 : 3);
+      ms_out[stage] += C->kernel_ms[tag];
+    }
+    ms_out[N_STAGE - 1] = C->frame_ms;
+  }
   if (frames) *frames = C->prof_frames;
-  if (reset) { memset(C->stage_ms, 0, sizeof(C->stage_ms)); C->prof_frames = 0; }
+  if (reset) prof_reset(C);
   return VILF_OK;
+}
+int vilf_profile_read_kernels(vilf_handle* h, double* ms_out, int64_t* launches_out, int n_tags, int reset) {
+  HCHECK(h);
+  if (n_tags != PROF_TAGS) return VILF_ERR_INVALID;
+  if (ms_out) memcpy(ms_out, C->kernel_ms, sizeof(C->kernel_ms));
+  if (launches_out) memcpy(launches_out, C->kernel_cnt, sizeof(C->kernel_cnt));
+  if (reset) prof_reset(C);
+  return VILF_OK;
+}
+const char* vilf_profile_kernel_name(int kernel) {
+  static const char* names[K_COUNT] = {"k_frame_reset", "k_sort_hist<KeyGenRing>", "k_sort_hist", "k_sort_scatter", "k_sector_select", "k_compact_features",
+                                       "k_vox_bbox", "k_sort_hist<KeyGenVoxel>", "k_vox_heads", "k_vox_centroid", "k_map_append", "k_map_init",
+                                       "k_grid_zero", "k_grid_count", "k_grid_scan_partial", "k_grid_scan_final", "k_grid_scatter", "k_knn_fit",
+                                       "k_knn_only", "k_solve"};
+  return (kernel >= 0 && kernel < K_COUNT) ? names[kernel] : "";
 }
 int vilf_launch_count(vilf_handle* h, int64_t* launches) {
   HCHECK(h);

@@ -177,9 +177,32 @@ __device__ __forceinline__ float4 associate(const double* x, float4 p) {
 }
 
 // ---- launch helpers implemented in the .cu files (all asynchronous on `st`) ----
+enum KernelId {
+  K_RESET = 0, K_RING_KEYHIST, K_SORT_HIST, K_SORT_SCATTER, K_SECTOR, K_COMPACT, K_VOX_BBOX, K_VOX_KEYHIST, K_VOX_HEADS, K_VOX_CENTROID,
+  K_MAP_APPEND, K_MAP_INIT, K_GRID_ZERO, K_GRID_COUNT, K_GRID_SCAN_PARTIAL, K_GRID_SCAN_FINAL, K_GRID_SCATTER, K_KNN_FIT, K_KNN_ONLY,
+  K_SOLVE, K_COUNT
+};
+constexpr int PROF_PHASES = 5;      // 0 extract, 1 scan downsample, 2 association + solve, 3 map update, 4 grid build
+constexpr int PROF_TAGS = PROF_PHASES * 32;
+constexpr int PROF_MAX_EVENTS = 96;
+
+// Optional per-kernel timing: one CUDA event after every launch, tagged (phase, kernel).
+struct ProfSink {
+  cudaEvent_t* ev;
+  int* tag;
+  int n, cap, phase;
+};
 struct Launch {
   cudaStream_t st;
   int64_t* counter;  // kernels launched
+  ProfSink* prof;    // null unless profiling
+  void tick(int kid) const {
+    ++*counter;
+    if (prof && prof->n < prof->cap) {
+      cudaEventRecord(prof->ev[prof->n], st);
+      prof->tag[prof->n++] = kid + 32 * prof->phase;
+    }
+  }
 };
 
 // k_sort.cu

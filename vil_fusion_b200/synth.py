@@ -13,10 +13,14 @@ arrival order == azimuth order inside a ring, featureExtraction.hpp:108), plus
 the uint16 ring id of every return (needed for beam counts the reference's
 angle formulas do not cover, featureExtraction.hpp:103-106).
 
-numpy only: runs identically in the CPU container and on the GPU box.
+The ray cast itself is a small C/OpenMP helper (synth_native.c, ~2 ms per HDL-64 scan) with a counter-based
+RNG, so a scan depends only on (seed, frame).
 """
 from __future__ import annotations
 
+import ctypes as C
+import os
+import subprocess
 from dataclasses import dataclass
 
 import numpy as np
@@ -61,13 +65,19 @@ def vlp32() -> Sensor:
     return Sensor("vlp32", e, 1800, 32)
 
 
+def vlp16(n_az: int = 600) -> Sensor:
+    """16-beam table for the reference's N_SCANS == 16 branch: scanID = int((angle + 15) / 2 + 0.5), FE:77."""
+    r = np.arange(16, dtype=np.float64)
+    return Sensor("vlp16", -15.0 + 2.0 * r, n_az, 16)
+
+
 def beams128() -> Sensor:
     """128-beam sensor; outside the reference's angle formulas -> explicit ring ids."""
     e = np.linspace(12.0, -25.0, 128)
     return Sensor("beams128", e, 2048, 0)
 
 
-SENSORS = {"hdl64": hdl64, "vlp32": vlp32, "beams128": beams128}
+SENSORS = {"hdl64": hdl64, "vlp32": vlp32, "beams128": beams128, "vlp16": vlp16}
 
 
 @dataclass
@@ -150,100 +160,57 @@ def _ray_dirs(sensor: Sensor) -> np.ndarray:
     return d  # [rings, n_az, 3]
 
 
-def _cast_numpy(d, t, near, ground_z):
-    """Nearest positive hit distance per ray (inf = no hit): ground plane + boxes (slab test)."""
-    with np.errstate(divide="ignore", invalid="ignore"):
-        s = (ground_z - t[2]) / d[:, 2]
-    s = np.where((d[:, 2] < -1e-9) & (s > 0), s, np.inf)
-    with np.errstate(divide="ignore", invalid="ignore"):
-        inv = 1.0 / d
-    for j in range(0, near.shape[0], 16):
-        bb = near[j:j + 16]
-        with np.errstate(invalid="ignore"):
-            lo = (bb[None, :, 0:3] - t[None, None, :]) * inv[:, None, :]
-            hi = (bb[None, :, 3:6] - t[None, None, :]) * inv[:, None, :]
-        tmin = np.fmin(lo, hi).max(axis=2)
-        tmax = np.fmax(lo, hi).min(axis=2)
-        hit = (tmax >= np.maximum(tmin, 0.0))
-        sb = np.where(hit, np.where(tmin > 0, tmin, np.inf), np.inf).min(axis=1)
-        s = np.minimum(s, sb)
-    return s
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_NATIVE_SRC = os.path.join(_HERE, "synth_native.c")
+_NATIVE_LIB = os.path.join(_HERE, "libvilf_synth.so")
+_native = None
 
 
-try:  # same arithmetic, ~100x faster; numpy path kept as the fallback
-    import numba as _nb
-
-    @_nb.njit(parallel=True, cache=False)
-    def _cast_numba(d, t, near, ground_z):
-        n = d.shape[0]
-        nb = near.shape[0]
-        out = np.empty(n, dtype=np.float64)
-        for i in _nb.prange(n):
-            best = np.inf
-            dz = d[i, 2]
-            if dz < -1e-9:
-                sg = (ground_z - t[2]) / dz
-                if sg > 0:
-                    best = sg
-            i0 = 1.0 / d[i, 0]
-            i1 = 1.0 / d[i, 1]
-            i2 = 1.0 / d[i, 2]
-            for j in range(nb):
-                lo = (near[j, 0] - t[0]) * i0
-                hi = (near[j, 3] - t[0]) * i0
-                tmin = min(lo, hi)
-                tmax = max(lo, hi)
-                lo = (near[j, 1] - t[1]) * i1
-                hi = (near[j, 4] - t[1]) * i1
-                tmin = max(tmin, min(lo, hi))
-                tmax = min(tmax, max(lo, hi))
-                lo = (near[j, 2] - t[2]) * i2
-                hi = (near[j, 5] - t[2]) * i2
-                tmin = max(tmin, min(lo, hi))
-                tmax = min(tmax, max(lo, hi))
-                if tmax >= tmin and tmin > 0.0 and tmin < best:
-                    best = tmin
-            out[i] = best
-        return out
-
-    _cast = _cast_numba
-except Exception:  # pragma: no cover
-    _cast = _cast_numpy
+def build_native(force: bool = False) -> None:
+    """gcc -O3 -fopenmp synth_native.c -> libvilf_synth.so (called by __graft_entry__.build())."""
+    if force or not os.path.exists(_NATIVE_LIB) or os.path.getmtime(_NATIVE_SRC) > os.path.getmtime(_NATIVE_LIB):
+        subprocess.run(["gcc", "-O3", "-fopenmp", "-fPIC", "-shared", "-o", _NATIVE_LIB, _NATIVE_SRC, "-lm"], check=True, capture_output=True)
 
 
-def raycast(world: World, sensor: Sensor, R: np.ndarray, t: np.ndarray, rng: np.random.Generator,
-            noise: float = 0.01, max_range: float = 120.0):
-    """One scan: returns (xyzi float32 [n,4], ring uint16 [n])."""
-    dirs_s = _ray_dirs(sensor)  # sensor frame
-    rings, n_az, _ = dirs_s.shape
-    d = dirs_s.reshape(-1, 3) @ R.T  # world-frame directions
-    # cull boxes that cannot be hit inside max_range
-    b = world.boxes
-    cx = np.clip(t[0], b[:, 0], b[:, 3]) - t[0]
-    cy = np.clip(t[1], b[:, 1], b[:, 4]) - t[1]
-    near = b[cx * cx + cy * cy < max_range * max_range]
-    s = _cast(np.ascontiguousarray(d), np.ascontiguousarray(t, dtype=np.float64),
-              np.ascontiguousarray(near), float(world.ground_z))
-    ok = np.isfinite(s) & (s < max_range)
-    s = s + rng.normal(0.0, noise, s.shape)
-    with np.errstate(invalid="ignore"):
-        p = dirs_s.reshape(-1, 3) * s[:, None]
-    inten = rng.uniform(0.0, 1.0, s.shape)
-    ring = np.repeat(np.arange(rings, dtype=np.uint16), n_az)
-    ok &= s > 0.5
-    xyzi = np.concatenate([p, inten[:, None]], axis=1)[ok].astype(np.float32)
-    return np.ascontiguousarray(xyzi), np.ascontiguousarray(ring[ok])
+def _lib():
+    global _native
+    if _native is None:
+        build_native()
+        _native = C.CDLL(_NATIVE_LIB)
+        _native.synth_scan.restype = C.c_int
+    return _native
+
+
+def raycast(world: World, sensor: Sensor, R: np.ndarray, t: np.ndarray, seed: int, frame: int,
+            noise: float = 0.01, max_range: float = 120.0, order: int = 0):
+    """One scan: returns (xyzi float32 [n,4], ring uint16 [n]).  order 0 = ring-major, 1 = firing order."""
+    n = sensor.rings * sensor.n_az
+    xyzi = np.empty((n, 4), np.float32)
+    ring = np.empty(n, np.uint16)
+    boxes = np.ascontiguousarray(world.boxes, dtype=np.float64)
+    Rm = np.ascontiguousarray(R, dtype=np.float64)
+    tv = np.ascontiguousarray(t, dtype=np.float64)
+    elev = np.ascontiguousarray(np.deg2rad(sensor.elev_deg), dtype=np.float64)
+    dp = C.POINTER(C.c_double)
+    m = _lib().synth_scan(boxes.ctypes.data_as(dp), boxes.shape[0], C.c_double(world.ground_z), Rm.ctypes.data_as(dp), tv.ctypes.data_as(dp),
+                          elev.ctypes.data_as(dp), sensor.rings, sensor.n_az, C.c_double(noise), C.c_double(max_range),
+                          C.c_uint64(seed), C.c_uint64(frame), order, xyzi.ctypes.data_as(C.POINTER(C.c_float)),
+                          ring.ctypes.data_as(C.POINTER(C.c_uint16)))
+    if m < 0:
+        raise MemoryError("synth_scan")
+    return np.ascontiguousarray(xyzi[:m]), np.ascontiguousarray(ring[:m])
 
 
 class Sequence:
     """Lazy seeded sequence of scans: seq[i] -> (xyzi, ring); deterministic per (seed, i)."""
 
     def __init__(self, sensor: str = "hdl64", n_frames: int = 100, seed: int = 0,
-                 density: float = 1.0, noise: float = 0.01, speed: float = 1.0):
+                 density: float = 1.0, noise: float = 0.01, speed: float = 1.0, order: int = 0):
         self.sensor = SENSORS[sensor]()
         self.n_frames = n_frames
         self.seed = seed
         self.noise = noise
+        self.order = order
         self.world = make_world(seed, length=max(400.0, n_frames * speed + 300.0), density=density)
         self.R, self.t = trajectory(n_frames, seed, speed)
 
@@ -251,8 +218,7 @@ class Sequence:
         return self.n_frames
 
     def __getitem__(self, i: int):
-        rng = np.random.default_rng([self.seed, 77, i])
-        return raycast(self.world, self.sensor, self.R[i], self.t[i], rng, noise=self.noise)
+        return raycast(self.world, self.sensor, self.R[i], self.t[i], self.seed, i, noise=self.noise, order=self.order)
 
     def gt_pose(self, i: int):
         return self.R[i], self.t[i]
