@@ -223,8 +223,9 @@ def test_knn_edge_cases(g64, orc):
     assert np.array_equal(gd[inside], od[inside])
 
 
-def test_knn_bruteforce_large(g64):
+def test_knn_bruteforce_large(cabi):
     """Full-size property (1e6-point map, config 3/5 scale): inside the gate the result equals brute force on a sample."""
+    g64 = cabi.Odometry(cabi.default_config(max_scan_points=4096, max_map_points=1 << 20))
     rng = np.random.default_rng(11)
     m = 1_000_000
     mp = np.zeros((m, 4), np.float32)
@@ -240,6 +241,7 @@ def test_knn_bruteforce_large(g64):
         assert np.array_equal(gd[r][ins], bf[o][ins])
         assert np.array_equal(gi[r][ins], o[ins]) or len(set(bf[o][ins])) < ins.sum()
     assert np.all(np.diff(gd, axis=1) >= 0)  # ascending
+    g64.close()
 
 
 # ---------------- factors / normal equations / solve ----------------

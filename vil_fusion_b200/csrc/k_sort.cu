@@ -8,6 +8,10 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const SortJob* __
   const int n = *J.n;
   int chunk, geff;
   sort_geometry(n, chunk, geff);
+  if (geff == 0 && blockIdx.x == 0 && pass == 0 && J.digit_start != nullptr) {  // empty input: all digit ranges are empty
+    J.digit_start[threadIdx.x] = 0;
+    if (threadIdx.x == 255) J.digit_start[256] = 0;
+  }
   if ((int)blockIdx.x >= geff) return;
   const int bits = J.bits ? *J.bits : J.fixed_bits;
   const int w = sort_width(bits, J.npass);
