@@ -56,6 +56,8 @@ typedef struct vilf_config {
   int32_t lm_max_iters;    /* EM:277 max_num_iterations (4) */
   int32_t max_scan_points; /* capacity: points per scan */
   int32_t max_map_points;  /* capacity: points per local map (edge and surf each) */
+  int32_t max_ring_points; /* capacity: returns per ring (sizes the selection kernel's shared memory); 0 = 12298, the kernel's limit */
+  int32_t reserved_;
 } vilf_config;
 
 int vilf_default_config(vilf_config* cfg);

@@ -33,8 +33,8 @@ def test_default_config_is_the_reference_yaml(cabi):
 
 
 def test_config_struct_layout_matches_header(cabi):
-    # 2 x int32, 8 x double, 4 x int32 -> 8 + 64 + 16
-    assert C.sizeof(cabi.Config) == 88
+    # 2 x int32, 8 x double, 6 x int32 -> 8 + 64 + 24
+    assert C.sizeof(cabi.Config) == 96
 
 
 def test_invalid_arguments_are_rejected_without_touching_cuda(cabi):

@@ -209,6 +209,7 @@ def test_knn_edge_cases(g64, orc):
     gi, gd = g64.knn5(mp, q)
     oi, od = orc.knn(mp, q)
     assert np.array_equal(gi[0, :3], oi[0, :3]) and (gi[0, 3:] == -1).all() and (gi[1] == -1).all()
+    assert np.all(gd[0, 3:] > 1e30) and np.all(gd[1] > 1e30)  # nothing inside the gate: FLT_MAX
     # exact ties: duplicate map points -> lowest index first, distances equal
     dup = np.repeat(np.array([[1, 1, 1, 0]], np.float32), 8, axis=0)
     gi, gd = g64.knn5(dup, np.array([[1.1, 1, 1, 0]], np.float32))

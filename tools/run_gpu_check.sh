@@ -1,0 +1,8 @@
+python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+for s in 8 16 32; do python bench.py --steps 100 --warmup 5 --seqs $s --no-cpu > gpurun_out/c$s.json 2> gpurun_out/c$s.err; python - <<PY
+import json
+d=json.load(open("gpurun_out/c$s.json"))
+print("S=$s value %.0f e2e %.0f ms/step %.3f launches %d"%(d["value"],d["e2e"]["value"],d["ms_per_step"],d["gpu_launches"]))
+for k in d.get("kernels_ms",[]): print("   %-40s %8.2f ms %5d  %.1f us"%(k[0],k[1],k[2],1e3*k[1]/k[2]))
+PY
+done

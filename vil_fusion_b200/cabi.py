@@ -29,7 +29,7 @@ class Config(C.Structure):
         ("edge_leaf", C.c_double), ("surf_leaf", C.c_double), ("crop_half", C.c_double),
         ("knn_gate", C.c_double), ("huber", C.c_double),
         ("outer_iters", C.c_int32), ("lm_max_iters", C.c_int32),
-        ("max_scan_points", C.c_int32), ("max_map_points", C.c_int32),
+        ("max_scan_points", C.c_int32), ("max_map_points", C.c_int32), ("max_ring_points", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 

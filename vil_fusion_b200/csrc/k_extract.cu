@@ -1,7 +1,7 @@
 // Stage 1 — featureExtraction::extractFeature (FE:223-232) on the device.
 //
 //   k_frame_reset        per-frame scratch reset + constant-velocity pose prediction (EM:238-243)
-//   k_sort_hist<KeyGenRing>  getLaserCloud (FE:54-110): range gate + vertical-angle -> ring id, as the
+//   k_sort_keyhist<KeyGenRing>  getLaserCloud (FE:54-110): range gate + vertical-angle -> ring id, as the
 //                        8-bit key of a single stable radix pass (arrival order kept inside a ring, FE:108)
 //   k_sector_select      featureEdge_Surf + featureExtractionFromSector (FE:112-220): one CTA per
 //                        (ring, sector): 11-tap fp32 curvature, rank-sort in shared memory, warp-serial
@@ -15,26 +15,33 @@ namespace vilf {
 // ------------------------------------------------------------------------------------------------
 // frame reset + prediction
 // ------------------------------------------------------------------------------------------------
-__device__ void mat3_mul(const double* a, const double* b, double* r) {
+__device__ __forceinline__ void mat3_mul(const double* a, const double* b, double* r) {
+#pragma unroll
   for (int i = 0; i < 3; ++i)
+#pragma unroll
     for (int j = 0; j < 3; ++j)
       r[i * 3 + j] = dadd(dadd(dmul(a[i * 3 + 0], b[0 * 3 + j]), dmul(a[i * 3 + 1], b[1 * 3 + j])), dmul(a[i * 3 + 2], b[2 * 3 + j]));
 }
-__device__ void mat3_vec(const double* a, const double* v, double* r) {
+__device__ __forceinline__ void mat3_vec(const double* a, const double* v, double* r) {
+#pragma unroll
   for (int i = 0; i < 3; ++i) r[i] = dadd(dadd(dmul(a[i * 3 + 0], v[0]), dmul(a[i * 3 + 1], v[1])), dmul(a[i * 3 + 2], v[2]));
 }
 // Eigen Transform<double,3,Isometry> product: (A*B).R = A.R*B.R, (A*B).t = A.R*B.t + A.t
-__device__ void iso_mul(const double* a, const double* b, double* r) {
+__device__ __forceinline__ void iso_mul(const double* a, const double* b, double* r) {
   mat3_mul(a, b, r);
   double v[3];
   mat3_vec(a, b + 9, v);
+#pragma unroll
   for (int i = 0; i < 3; ++i) r[9 + i] = dadd(v[i], a[9 + i]);
 }
-__device__ void iso_inv(const double* a, double* r) {
+__device__ __forceinline__ void iso_inv(const double* a, double* r) {
+#pragma unroll
   for (int i = 0; i < 3; ++i)
+#pragma unroll
     for (int j = 0; j < 3; ++j) r[i * 3 + j] = a[j * 3 + i];
   double v[3];
   mat3_vec(r, a + 9, v);
+#pragma unroll
   for (int i = 0; i < 3; ++i) r[9 + i] = -v[i];
 }
 // Eigen Quaternion(Matrix3) assignment (EM:242)
@@ -75,11 +82,14 @@ __global__ void k_frame_reset(LaneDev* lanes, int lane0, int nlanes, VoxVars* vv
     L.opt_ran = 0;
     L.status = 0;  // error bits describe the current frame
     if (predict) {  // EM:238-243
-      double inv[12], rel[12], est[12];
-      iso_inv(L.odom_last, inv);
-      iso_mul(inv, L.odom, rel);
-      iso_mul(L.odom, rel, est);
-      for (int i = 0; i < 12; ++i) { L.odom_last[i] = L.odom[i]; L.odom[i] = est[i]; }
+      double inv[12], rel[12], est[12], od[12], ol[12];
+#pragma unroll
+      for (int i = 0; i < 12; ++i) { od[i] = L.odom[i]; ol[i] = L.odom_last[i]; }
+      iso_inv(ol, inv);
+      iso_mul(inv, od, rel);
+      iso_mul(od, rel, est);
+#pragma unroll
+      for (int i = 0; i < 12; ++i) { L.odom_last[i] = od[i]; L.odom[i] = est[i]; }
       double q[4];
       mat_to_quat(est, q);
       L.x[0] = q[0]; L.x[1] = q[1]; L.x[2] = q[2]; L.x[3] = q[3];
@@ -91,7 +101,7 @@ __global__ void k_frame_reset(LaneDev* lanes, int lane0, int nlanes, VoxVars* vv
 }
 
 void launch_frame_reset(const Launch& L, LaneDev* lanes, int lane0, int nlanes, VoxVars* vv, int vv_per_lane, int predict) {
-  k_frame_reset<<<1, 1024, 0, L.st>>>(lanes, lane0, nlanes, vv, vv_per_lane, predict);
+  k_frame_reset<<<1, 256, 0, L.st>>>(lanes, lane0, nlanes, vv, vv_per_lane, predict);
   L.tick(K_RESET);
 }
 
@@ -135,9 +145,11 @@ struct KeyGenRing {
 // ------------------------------------------------------------------------------------------------
 // per-(ring, sector) selection
 // ------------------------------------------------------------------------------------------------
-constexpr int SEC_PTS = MAX_SECTOR + 10;
-constexpr size_t SEC_SMEM = sizeof(float4) * SEC_PTS + sizeof(double) * MAX_SECTOR + sizeof(uint32_t) * SEC_PTS +
-                            sizeof(uint16_t) * MAX_SECTOR + ((SEC_PTS + 15) / 16) * 16;
+// dynamic shared memory of the selection kernel for sectors of up to ms elements (ms + 10 staged points)
+static inline size_t sector_smem(int ms) {
+  const size_t pts = (size_t)ms + 10;
+  return sizeof(float4) * pts + sizeof(double) * ms + sizeof(uint32_t) * pts + sizeof(uint16_t) * ms + (pts + 15) / 16 * 16 + 16;
+}
 
 __device__ __forceinline__ bool sector_range(int n_r, int s, int& start, int& m) {
   if (n_r < 131) return false;                 // FE:179
@@ -159,7 +171,8 @@ __global__ void __launch_bounds__(256) k_sector_select(LaneDev* lanes, int lane0
   const int n_r = (int)rs[r + 1] - ring_beg;
   int start = 0, m = 0;
   bool ok = sector_range(n_r, s, start, m);
-  if (ok && m > MAX_SECTOR) {
+  const int MS = cfg.max_sector;  // multiple of 8
+  if (ok && m > MS) {
     if (tid == 0) atomicOr(&L.v->status, ST_SECTOR_TOO_LONG);
     ok = false;
   }
@@ -169,10 +182,10 @@ __global__ void __launch_bounds__(256) k_sector_select(LaneDev* lanes, int lane0
   }
   extern __shared__ __align__(16) unsigned char smem[];
   float4* pts = reinterpret_cast<float4*>(smem);                              // ring points start .. start+m+9
-  double* val = reinterpret_cast<double*>(smem + sizeof(float4) * SEC_PTS);   // curvature of element e
-  uint32_t* srcs = reinterpret_cast<uint32_t*>(val + MAX_SECTOR);             // scan index of each staged point
-  uint16_t* sorted = reinterpret_cast<uint16_t*>(srcs + SEC_PTS);             // elements in ascending (curvature, index)
-  uint8_t* picked = reinterpret_cast<uint8_t*>(sorted + MAX_SECTOR);          // cloudNeighborPicked as flags
+  double* val = reinterpret_cast<double*>(smem + sizeof(float4) * (MS + 10)); // curvature of element e
+  uint32_t* srcs = reinterpret_cast<uint32_t*>(val + MS);                     // scan index of each staged point
+  uint16_t* sorted = reinterpret_cast<uint16_t*>(srcs + MS + 10);             // elements in ascending (curvature, index)
+  uint8_t* picked = reinterpret_cast<uint8_t*>(sorted + MS);                  // cloudNeighborPicked as flags
 
   const uint32_t* perm = L.ring_sort.val[1];  // scan indices in (ring, arrival) order after the single pass
   for (int k = tid; k < m + 10; k += 256) {
@@ -297,27 +310,42 @@ __global__ void __launch_bounds__(256) k_compact_features(LaneDev* lanes, int la
   int start = 0, m = 0;
   sector_range((int)rs[r + 1] - ring_beg, s, start, m);
   const int sbase = ring_beg + 5 + start;
+  // copy + getMinMax3D of both feature clouds for the voxel filter that follows (EM:248-251)
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  int cnt = 0;
   for (int k = tid; k < c.x; k += 256) {
-    L.feat[0][oe + k] = L.sec_edge[blockIdx.x * EDGES_PER_SECTOR + k];
+    const float4 p = L.sec_edge[blockIdx.x * EDGES_PER_SECTOR + k];
+    L.feat[0][oe + k] = p;
     L.feat_src[0][oe + k] = L.sec_edge_src[blockIdx.x * EDGES_PER_SECTOR + k];
+    mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x); mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
+    mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z); ++cnt;
   }
+  __shared__ float bb_sm[7 * 8];
+  bbox_commit(L.vv + 0, mn, mx, cnt, bb_sm);
+  for (int a = 0; a < 3; ++a) { mn[a] = FLT_MAX; mx[a] = -FLT_MAX; }
+  cnt = 0;
   for (int k = tid; k < c.y; k += 256) {
-    L.feat[1][os + k] = L.sec_surf[sbase + k];
+    const float4 p = L.sec_surf[sbase + k];
+    L.feat[1][os + k] = p;
     L.feat_src[1][os + k] = L.sec_surf_src[sbase + k];
+    mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x); mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
+    mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z); ++cnt;
   }
+  bbox_commit(L.vv + 1, mn, mx, cnt, bb_sm);
   if (blockIdx.x == gridDim.x - 1 && tid == 0) { L.v->n_edge = oe + c.x; L.v->n_surf = os + c.y; }
 }
 
 void launch_extract(const Launch& L, LaneDev* lanes, const SortJob* ring_jobs, int lane0, int nlanes, int sel, const ConfigDev& cfg) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(k_sector_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEC_SMEM);
+    cudaFuncSetAttribute(k_sector_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_smem(MAX_SECTOR));
     attr_set = true;
   }
+  const size_t SEC_SMEM = sector_smem(cfg.max_sector);
   KeyGenRing gen;
   gen.lanes = lanes; gen.lane0 = lane0; gen.sel = sel; gen.cfg = cfg;
   dim3 gs(SORT_G, nlanes);
-  k_sort_hist<KeyGenRing, true><<<gs, SORT_THREADS, 0, L.st>>>(ring_jobs + lane0, 0, gen);
+  k_sort_keyhist<KeyGenRing><<<gs, SORT_THREADS, 0, L.st>>>(ring_jobs + lane0, gen);
   L.tick(K_RING_KEYHIST);
   launch_sort_scatter(L, ring_jobs + lane0, nlanes, 0);
   dim3 g2(cfg.rings_total * SECTORS, nlanes);

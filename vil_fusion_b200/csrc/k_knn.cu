@@ -12,7 +12,8 @@
 // lists are flattened with a warp scan and read 32 at a time (one coalesced float4 each); a candidate counts
 // only for the lane whose cell it really lies in (hash collisions are filtered by recomputing the cell).
 // Every point closer than c is inside those 27 cells, hence every neighbour with d^2 < knn_gate is found:
-// the result is exact wherever the reference uses it (EM:129/:189 reject the feature when d^2[4] >= 1).
+// the result is exact wherever the reference uses it (EM:129/:189 reject the feature when d^2[4] >= 1); candidates
+// at or beyond the gate are dropped on sight (their slots stay idx -1, d^2 FLT_MAX).
 // Distances: ((dx*dx)+dy*dy)+dz*dz in fp32 without contraction = FLANN L2_Simple<float>.  Top-5 kept
 // replicated in registers, ordered by (d^2, index): deterministic tie break (tie class T2).
 #include "vilf_internal.cuh"
@@ -155,7 +156,7 @@ __device__ __forceinline__ void top5_insert(Top5& t, float cd, int ci) {
 }
 
 // All 32 lanes of a warp call this with the same query; the result is replicated in every lane.
-__device__ __forceinline__ void warp_knn5(const GridJob& G, float inv_cell, float qx, float qy, float qz, Top5& best) {
+__device__ __forceinline__ void warp_knn5(const GridJob& G, float inv_cell, double gate, float qx, float qy, float qz, Top5& best) {
   const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int k = 0; k < 5; ++k) { best.d[k] = FLT_MAX; best.id[k] = INT_MAX; }
@@ -200,7 +201,8 @@ __device__ __forceinline__ void warp_knn5(const GridJob& G, float inv_cell, floa
         const float dx = fsub(qx, p.x), dy = fsub(qy, p.y), dz = fsub(qz, p.z);
         cd = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
         ci = __float_as_int(p.w);
-        have = closer(cd, ci, best.d[4], best.id[4]);
+        // neighbours at or beyond the gate can never be used (EM:129 / :189 reject the feature), so they never enter the list
+        have = (double)cd < gate && closer(cd, ci, best.d[4], best.id[4]);
       }
     }
     unsigned m = __ballot_sync(0xffffffffu, have);
@@ -335,9 +337,9 @@ __device__ D3 lstsq5x3(const double Ain[5][3]) {
   return d3(n[0], n[1], n[2]);
 }
 
-// One warp per voxel-filtered feature point: transform (EM:355-363), 5-NN, fit, factor record.
-__global__ void __launch_bounds__(256) k_knn_fit(LaneDev* lanes, const GridJob* __restrict__ grid_jobs, int lane0, int cur, ConfigDev cfg,
-                                                  const double* pose_override, int want_nn) {
+// Association, kernel 1: one warp per voxel-filtered feature point: transform (EM:355-363) + 5-NN (EM:128 / :185).
+__global__ void __launch_bounds__(256) k_knn_assoc(LaneDev* lanes, const GridJob* __restrict__ grid_jobs, int lane0, ConfigDev cfg,
+                                                    const double* pose_override) {
   const int ln = lane0 + blockIdx.y;
   const LaneDev& L = lanes[ln];
   LaneVars& V = *L.v;
@@ -354,80 +356,100 @@ __global__ void __launch_bounds__(256) k_knn_fit(LaneDev* lanes, const GridJob* 
   for (int q = wid; q < ne + ns; q += nw) {
     const int w = q < ne ? 0 : 1;
     const int k = q < ne ? q : q - ne;
-    const float4 p = L.ds[w][k];
-    const float4 pw = associate(x, p);
-    const GridJob& G = grid_jobs[ln * 2 + w];
+    const float4 pw = associate(x, L.ds[w][k]);
     Top5 best;
-    warp_knn5(G, cfg.inv_cell, pw.x, pw.y, pw.z, best);
-    if (lane == 0) {
-      const float4* map = L.map[w][cur];
-      if (want_nn) {
-        for (int j = 0; j < 5; ++j) {
-          L.nn_idx[w][k * 5 + j] = best.id[j] == INT_MAX ? -1 : best.id[j];
-          L.nn_d2[w][k * 5 + j] = best.d[j];
-        }
-      }
-      uint8_t valid = 0;
-      if ((double)best.d[4] < cfg.knn_gate) {  // EM:129 / :189
-        D3 nb[5];
-        for (int j = 0; j < 5; ++j) { const float4 m = map[best.id[j]]; nb[j] = d3((double)m.x, (double)m.y, (double)m.z); }
-        if (w == 0) {  // EM:131-163
-          D3 center = d3(0, 0, 0);
-          for (int j = 0; j < 5; ++j) center = center + nb[j];
-          center = d3(center.x / 5.0, center.y / 5.0, center.z / 5.0);
-          double cov[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-          for (int j = 0; j < 5; ++j) {
-            const D3 z = nb[j] - center;
-            const double v[3] = {z.x, z.y, z.z};
+    warp_knn5(grid_jobs[ln * 2 + w], cfg.inv_cell, cfg.knn_gate, pw.x, pw.y, pw.z, best);
+    if (lane < 5) {
+      float d = best.d[0]; int id = best.id[0];
 #pragma unroll
-            for (int r = 0; r < 3; ++r)
-#pragma unroll
-              for (int c = 0; c < 3; ++c) cov[r][c] = dadd(cov[r][c], dmul(v[r], v[c]));
-          }
-          double w_mid, w_max;
-          D3 dir;
-          eig3_largest(cov, w_mid, w_max, dir);
-          if (w_max > dmul(3.0, w_mid)) {  // EM:153
-            const D3 a = 0.1 * dir + center, b = -0.1 * dir + center;  // EM:156-157
-            double* o = L.edge_pab + (size_t)k * 9;
-            o[0] = p.x; o[1] = p.y; o[2] = p.z;
-            o[3] = a.x; o[4] = a.y; o[5] = a.z;
-            o[6] = b.x; o[7] = b.y; o[8] = b.z;
-            valid = 1;
-          }
-        } else {  // EM:187-222
-          double A[5][3];
-          for (int j = 0; j < 5; ++j) { A[j][0] = nb[j].x; A[j][1] = nb[j].y; A[j][2] = nb[j].z; }
-          D3 n = lstsq5x3(A);
-          const double nn = norm3(n);
-          const double d = 1.0 / nn;            // EM:199
-          n = d3(n.x / nn, n.y / nn, n.z / nn);  // EM:200
-          bool okp = true;
-          for (int j = 0; j < 5; ++j)
-            if (fabs(dadd(dadd(dadd(dmul(n.x, nb[j].x), dmul(n.y, nb[j].y)), dmul(n.z, nb[j].z)), d)) > 0.2) { okp = false; break; }
-          if (okp) {
-            double* o = L.surf_pnd + (size_t)k * 7;
-            o[0] = p.x; o[1] = p.y; o[2] = p.z;
-            o[3] = n.x; o[4] = n.y; o[5] = n.z; o[6] = d;
-            valid = 1;
-          }
-        }
-      }
-      L.fvalid[w][k] = valid;
+      for (int j = 1; j < 5; ++j) if (lane == j) { d = best.d[j]; id = best.id[j]; }
+      L.nn_idx[w][k * 5 + lane] = id == INT_MAX ? -1 : id;
+      L.nn_d2[w][k * 5 + lane] = d;
     }
+  }
+}
+
+// Association, kernel 2: one THREAD per feature point (so the FP64 pipe runs full warps): the 3x3 eigen line fit
+// (EM:131-163) or the 5x3 least-squares plane fit (EM:187-222) on the five neighbours, and the factor record.
+__global__ void __launch_bounds__(128) k_fit(LaneDev* lanes, int lane0, int cur, ConfigDev cfg) {
+  const LaneDev& L = lanes[lane0 + blockIdx.y];
+  const LaneVars& V = *L.v;
+  if (!(V.n_map[0] > 10 && V.n_map[1] > 50)) return;  // EM:254
+  const int ne = V.n_ds[0], ns = V.n_ds[1];
+  for (int q = blockIdx.x * 128 + threadIdx.x; q < ne + ns; q += gridDim.x * 128) {
+    const int w = q < ne ? 0 : 1;
+    const int k = q < ne ? q : q - ne;
+    uint8_t valid = 0;
+    if ((double)L.nn_d2[w][k * 5 + 4] < cfg.knn_gate) {  // EM:129 / :189
+      const float4* map = L.map[w][cur];
+      const float4 p = L.ds[w][k];
+      D3 nb[5];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) { const float4 m = map[L.nn_idx[w][k * 5 + j]]; nb[j] = d3((double)m.x, (double)m.y, (double)m.z); }
+      if (w == 0) {
+        D3 center = d3(0, 0, 0);
+#pragma unroll
+        for (int j = 0; j < 5; ++j) center = center + nb[j];
+        center = d3(center.x / 5.0, center.y / 5.0, center.z / 5.0);
+        double cov[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          const D3 z = nb[j] - center;
+          const double v[3] = {z.x, z.y, z.z};
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) cov[r][c] = dadd(cov[r][c], dmul(v[r], v[c]));
+        }
+        double w_mid, w_max;
+        D3 dir;
+        eig3_largest(cov, w_mid, w_max, dir);
+        if (w_max > dmul(3.0, w_mid)) {  // EM:153
+          const D3 a = 0.1 * dir + center, b = -0.1 * dir + center;  // EM:156-157
+          double* o = L.edge_pab + (size_t)k * 9;
+          o[0] = p.x; o[1] = p.y; o[2] = p.z;
+          o[3] = a.x; o[4] = a.y; o[5] = a.z;
+          o[6] = b.x; o[7] = b.y; o[8] = b.z;
+          valid = 1;
+        }
+      } else {
+        double A[5][3];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) { A[j][0] = nb[j].x; A[j][1] = nb[j].y; A[j][2] = nb[j].z; }
+        D3 n = lstsq5x3(A);
+        const double nn = norm3(n);
+        const double d = 1.0 / nn;            // EM:199
+        n = d3(n.x / nn, n.y / nn, n.z / nn);  // EM:200
+        bool okp = true;
+#pragma unroll
+        for (int j = 0; j < 5; ++j)
+          if (fabs(dadd(dadd(dadd(dmul(n.x, nb[j].x), dmul(n.y, nb[j].y)), dmul(n.z, nb[j].z)), d)) > 0.2) okp = false;  // EM:203-213
+        if (okp) {
+          double* o = L.surf_pnd + (size_t)k * 7;
+          o[0] = p.x; o[1] = p.y; o[2] = p.z;
+          o[3] = n.x; o[4] = n.y; o[5] = n.z; o[6] = d;
+          valid = 1;
+        }
+      }
+    }
+    L.fvalid[w][k] = valid;
   }
 }
 
 void launch_knn_fit(const Launch& L, LaneDev* lanes, const GridJob* grid_jobs, int lane0, int nlanes, int cur, const ConfigDev& cfg,
                     const double* pose_override, int want_nn) {
+  (void)want_nn;
   dim3 g(KNN_G, nlanes);
-  k_knn_fit<<<g, 256, 0, L.st>>>(lanes, grid_jobs, lane0, cur, cfg, pose_override, want_nn);
+  k_knn_assoc<<<g, 256, 0, L.st>>>(lanes, grid_jobs, lane0, cfg, pose_override);
   L.tick(K_KNN_FIT);
+  dim3 g2(FIT_G, nlanes);
+  k_fit<<<g2, 128, 0, L.st>>>(lanes, lane0, cur, cfg);
+  L.tick(K_FIT);
 }
 
 // nearestKSearch alone against an explicit map (test entry point vilf_knn5).
 __global__ void __launch_bounds__(256) k_knn_only(const GridJob* __restrict__ job, const float4* __restrict__ q, const int* nq_dev, int* idx,
-                                                   float* d2, float inv_cell) {
+                                                   float* d2, float inv_cell, double gate) {
   const int nq = *nq_dev;
   const int lane = threadIdx.x & 31;
   const int wid = (blockIdx.x * 256 + threadIdx.x) >> 5;
@@ -435,7 +457,7 @@ __global__ void __launch_bounds__(256) k_knn_only(const GridJob* __restrict__ jo
   for (int i = wid; i < nq; i += nw) {
     const float4 p = q[i];
     Top5 best;
-    warp_knn5(*job, inv_cell, p.x, p.y, p.z, best);
+    warp_knn5(*job, inv_cell, gate, p.x, p.y, p.z, best);
     if (lane < 5) {
       float d = best.d[0]; int id = best.id[0];
 #pragma unroll
@@ -447,7 +469,7 @@ __global__ void __launch_bounds__(256) k_knn_only(const GridJob* __restrict__ jo
 }
 
 void launch_knn_only(const Launch& L, const GridJob* job_dev, const float4* q, const int* nq_dev, int* idx, float* d2, const ConfigDev& cfg) {
-  k_knn_only<<<KNN_G, 256, 0, L.st>>>(job_dev, q, nq_dev, idx, d2, cfg.inv_cell);
+  k_knn_only<<<KNN_G, 256, 0, L.st>>>(job_dev, q, nq_dev, idx, d2, cfg.inv_cell, cfg.knn_gate);
   L.tick(K_KNN_ONLY);
 }
 

@@ -1,15 +1,19 @@
 // Stage 3/4 — the 6-DoF pose solve: ceres::Solve(TRUST_REGION, LEVENBERG_MARQUARDT, DENSE_QR,
 // max_num_iterations = 4, HuberLoss(0.1), LocalSE3Parameterization) of EM:263-283 as ONE kernel per outer
-// iteration and sequence: a single CTA evaluates every factor (LF:21-52 edge, LF:79-102 surf), reduces the
-// robustified normal equations (21-entry J^T J, 6-entry J^T r, cost) with warp shuffles + a fixed-order
-// shared-memory tree, and thread 0 runs Ceres' trust-region bookkeeping (Jacobi scaling fixed at iteration
-// 0, LM diagonal clamp, radius update, parameter / function / gradient tolerance exits, step rejection) on
-// the 6x6 system; the pose never leaves the device between iterations.
+// iteration: one thread-block CLUSTER of 8 CTAs per sequence.  Every CTA evaluates its share of the factors
+// (LF:21-52 edge, LF:79-102 surf) and reduces its robustified normal equations (21-entry J^T J, 6-entry
+// J^T r, cost) with warp shuffles + a fixed-order shared-memory tree; the leader CTA gathers the 8 partials
+// over distributed shared memory (fixed order -> deterministic) and its thread 0 runs Ceres' trust-region
+// bookkeeping (Jacobi scaling fixed at iteration 0, LM diagonal clamp, radius update, parameter / function /
+// gradient tolerance exits, step rejection) on the 6x6 system; the candidate pose is broadcast back through
+// DSMEM, so the pose never leaves the SMs between iterations.  (The FP64 work of one evaluation, ~6 k factors
+// x ~300 instructions, is what bounds this kernel: one SM took 27 us per evaluation, 8 SMs take ~4.)
 //
 // Ceres solves [J S; D] y = [r; 0] by QR; here the same minimiser is obtained from the normal equations
 // (S J^T J S + D^2) y = S J^T r by Cholesky.  The two differ by rounding only (relative 1e-10 on a step of
 // 1e-2), far inside the pose tolerance (1e-4 rad / 1e-3 m); SURVEY §8a row 9 lists the schedule reproduced.
 #include "vilf_internal.cuh"
+#include <cooperative_groups.h>
 
 namespace vilf {
 
@@ -20,7 +24,8 @@ constexpr int NACC = 30;  // 21 H + 6 g + cost + n_edge + n_surf
 struct LmShared {
   double x[7], cand[7], params[7];
   double H[21], g[6], cost;
-  double acc[NACC];
+  double acc[NACC];   // cluster-wide sums (leader only)
+  double part[NACC];  // this CTA's partial sums (read by the leader over DSMEM)
   double scale[6], diag[6];
   double radius, decrease_factor, minimum_cost, x_norm, grad_max, model_cost_change, candidate_cost;
   int iteration, step_successful, reuse_diagonal, num_invalid, done, need_eval, termination, n_edge, n_surf;
@@ -99,14 +104,15 @@ __device__ __forceinline__ void accumulate_row(double* acc, const double* J, dou
 }
 
 // Robustified cost / gradient / normal matrix of every valid factor at pose x; result in S.acc (all threads sync).
-__device__ void evaluate(const LaneDev& L, int ne, int ns, const double* x, double hub, LmShared& S, double (*wred)[NACC]) {
+// Partial sums of this CTA (factor slots first, first + stride, ...) into S.part; ends with a CTA barrier.
+__device__ void evaluate(const LaneDev& L, int ne, int ns, const double* x, double hub, LmShared& S, double (*wred)[NACC], int first, int stride) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double acc[NACC];
 #pragma unroll
   for (int i = 0; i < NACC; ++i) acc[i] = 0;
   Q4 q; q.x = x[0]; q.y = x[1]; q.z = x[2]; q.w = x[3];
   const D3 t = d3(x[4], x[5], x[6]);
-  for (int i = tid; i < ne + ns; i += LM_THREADS) {
+  for (int i = first; i < ne + ns; i += stride) {
     if (i < ne) {
       if (!L.fvalid[0][i]) continue;
       const double* f = L.edge_pab + (size_t)i * 9;
@@ -166,7 +172,7 @@ __device__ void evaluate(const LaneDev& L, int ne, int ns, const double* x, doub
   if (tid < NACC) {
     double v = 0;
     for (int w = 0; w < LM_THREADS / 32; ++w) v += wred[w][tid];
-    S.acc[tid] = v;
+    S.part[tid] = v;
   }
   __syncthreads();
 }
@@ -239,25 +245,46 @@ __device__ bool lm_step(const LmShared& S, double* step) {
 
 }  // namespace
 
-__global__ void __launch_bounds__(LM_THREADS, 1) k_solve(LaneDev* lanes, int lane0, int outer, int finalize, ConfigDev cfg, int max_iters) {
-  const LaneDev& L = lanes[lane0 + blockIdx.x];
+__global__ void __cluster_dims__(LM_CLUSTER, 1, 1) __launch_bounds__(LM_THREADS, 1)
+k_solve(LaneDev* lanes, int lane0, int outer, int finalize, ConfigDev cfg, int max_iters) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const LaneDev& L = lanes[lane0 + blockIdx.y];
   LaneVars& V = *L.v;
   __shared__ LmShared S;
   __shared__ double wred[LM_THREADS / 32][NACC];
+  LmShared* lead = cluster.map_shared_rank(&S, 0);  // the leader's state, visible to the whole cluster
   const int tid = threadIdx.x;
+  const bool leader = rank == 0;
   const bool run = V.opt_ran != 0;  // EM:254 decided by the association kernel
   const int ne = V.n_ds[0], ns = V.n_ds[1];
+  const int first = rank * LM_THREADS + tid, stride = LM_CLUSTER * LM_THREADS;
   SolveTraceDev& T = L.trace[outer];
+  // leader: gather the 8 partials in rank order
+  auto gather = [&]() {
+    if (leader && tid < NACC) {
+      double v = 0;
+      for (int r = 0; r < LM_CLUSTER; ++r) v += cluster.map_shared_rank(&S, r)->part[tid];
+      S.acc[tid] = v;
+    }
+    if (leader) __syncthreads();
+  };
   if (run) {
-    if (tid == 0) {
+    if (leader && tid == 0) {
       for (int i = 0; i < 7; ++i) { S.x[i] = V.x[i]; S.params[i] = V.x[i]; }
       S.radius = 1e4; S.decrease_factor = 2.0; S.minimum_cost = DBL_MAX; S.reuse_diagonal = 0; S.num_invalid = 0;
       S.model_cost_change = 0; S.candidate_cost = 0; S.iteration = 0; S.step_successful = 1; S.done = 0; S.termination = 0;
+      S.need_eval = 0;
       T.n_rows = 0;
     }
-    __syncthreads();
-    evaluate(L, ne, ns, S.x, cfg.huber, S, wred);
-    if (tid == 0) {
+    double xl[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) xl[i] = V.x[i];
+    evaluate(L, ne, ns, xl, cfg.huber, S, wred, first, stride);
+    cluster.sync();
+    gather();
+    if (leader && tid == 0) {
       S.n_edge = (int)S.acc[28]; S.n_surf = (int)S.acc[29];
       T.n_edge = S.n_edge; T.n_surf = S.n_surf;
       if (S.n_edge + S.n_surf == 0) {
@@ -271,9 +298,9 @@ __global__ void __launch_bounds__(LM_THREADS, 1) k_solve(LaneDev* lanes, int lan
         record(T, S, 1, 1, 0, 0);
       }
     }
-    __syncthreads();
-    for (;;) {  // S.done / S.need_eval are written by thread 0 only between barriers and read by all right after one
-      if (tid == 0 && !S.done) {
+    cluster.sync();
+    for (;;) {  // done / need_eval / cand are written by the leader's thread 0 between cluster barriers and read right after one
+      if (leader && tid == 0 && !S.done) {
         S.need_eval = 0;
         // FinalizeIterationAndCheckIfMinimizerCanContinue
         if (S.step_successful && S.cost < S.minimum_cost) { S.minimum_cost = S.cost; for (int i = 0; i < 7; ++i) S.params[i] = S.x[i]; }
@@ -312,11 +339,16 @@ __global__ void __launch_bounds__(LM_THREADS, 1) k_solve(LaneDev* lanes, int lan
           }
         }
       }
-      __syncthreads();
-      if (S.done) break;
-      if (S.need_eval) {
-        evaluate(L, ne, ns, S.cand, cfg.huber, S, wred);
-        if (tid == 0) {
+      cluster.sync();
+      const int done = lead->done, need = lead->need_eval;
+      if (done) break;
+      if (need) {
+#pragma unroll
+        for (int i = 0; i < 7; ++i) xl[i] = lead->cand[i];
+        evaluate(L, ne, ns, xl, cfg.huber, S, wred, first, stride);
+        cluster.sync();
+        gather();
+        if (leader && tid == 0) {
           S.candidate_cost = S.acc[27];
           double sn = 0;
           for (int i = 0; i < 7; ++i) sn += (S.x[i] - S.cand[i]) * (S.x[i] - S.cand[i]);
@@ -344,16 +376,16 @@ __global__ void __launch_bounds__(LM_THREADS, 1) k_solve(LaneDev* lanes, int lan
           }
         }
       }
-      __syncthreads();
+      cluster.sync();
     }
-    if (tid == 0) {
+    if (leader && tid == 0) {
       for (int i = 0; i < 7; ++i) V.x[i] = S.params[i];
       T.termination = S.termination;
       T.final_cost = S.cost;
     }
   }
-  if (finalize && tid == 0) {  // EM:291-293: globalOdom from q_w_c / t_w_c (also when the optimisation was skipped)
-    const double* x = V.x;
+  if (finalize && leader && tid == 0) {  // EM:291-293: globalOdom from q_w_c / t_w_c (also when the optimisation was skipped)
+    const double* x = run ? S.params : V.x;
     const double tx = dmul(2, x[0]), ty = dmul(2, x[1]), tz = dmul(2, x[2]);
     const double twx = dmul(tx, x[3]), twy = dmul(ty, x[3]), twz = dmul(tz, x[3]);
     const double txx = dmul(tx, x[0]), txy = dmul(ty, x[0]), txz = dmul(tz, x[0]);
@@ -365,10 +397,12 @@ __global__ void __launch_bounds__(LM_THREADS, 1) k_solve(LaneDev* lanes, int lan
     o[9] = x[4]; o[10] = x[5]; o[11] = x[6];
     V.frames += 1;
   }
+  cluster.sync();  // no CTA may exit while the leader can still read its shared memory
 }
 
 void launch_solve(const Launch& L, LaneDev* lanes, int lane0, int nlanes, int outer, int finalize, const ConfigDev& cfg, int max_iters) {
-  k_solve<<<nlanes, LM_THREADS, 0, L.st>>>(lanes, lane0, outer, finalize, cfg, max_iters);
+  dim3 grid(LM_CLUSTER, nlanes);
+  k_solve<<<grid, LM_THREADS, 0, L.st>>>(lanes, lane0, outer, finalize, cfg, max_iters);
   L.tick(K_SOLVE);
 }
 

@@ -1,4 +1,4 @@
-// Radix-sort scatter kernel and the launchers of the generic (stored-key) passes.  See k_sort.cuh.
+// Radix-sort scatter kernel.  See k_sort.cuh.
 #include "k_sort.cuh"
 
 namespace vilf {
@@ -8,44 +8,47 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const SortJob* __
   const int n = *J.n;
   int chunk, geff;
   sort_geometry(n, chunk, geff);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (geff == 0 && blockIdx.x == 0 && pass == 0 && J.digit_start != nullptr) {  // empty input: all digit ranges are empty
-    J.digit_start[threadIdx.x] = 0;
-    if (threadIdx.x == 255) J.digit_start[256] = 0;
+    J.digit_start[tid] = 0;
+    if (tid == 255) J.digit_start[256] = 0;
   }
   if ((int)blockIdx.x >= geff) return;
   const int bits = J.bits ? *J.bits : J.fixed_bits;
-  const int w = sort_width(bits, J.npass);
+  const int P = sort_passes(bits, J.npass);
+  if (pass >= P) return;
+  const int w = sort_width(bits, P);
   const uint32_t mask = (1u << w) - 1u;
   const int shift = pass * w;
-  const int nb = 1 << w;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool count_next = pass + 1 < P;
+  const int shift_next = shift + w;
 
-  __shared__ uint32_t base[256];        // running global offset of this CTA per digit
-  __shared__ uint32_t wcnt[8][256];     // per-warp digit counters of the current tile
-  __shared__ uint32_t scan_buf[256];
+  __shared__ uint32_t base[SORT_RADIX];        // running global offset of this CTA per digit
+  __shared__ uint32_t wcnt[8][SORT_RADIX];     // per-warp digit counters of the current tile
+  __shared__ uint32_t scan_buf[SORT_THREADS];
 
-  // 1. digit offsets of this CTA: exclusive scan of the digit totals + counts of the CTAs before it.
-  uint32_t tot = 0, pre = 0;
-  if (tid < nb) {
-    for (int b = 0; b < geff; ++b) {
-      uint32_t v = J.hist[b * 256 + tid];
-      if (b < (int)blockIdx.x) pre += v;
-      tot += v;
-    }
+  // 1. digit offsets of this CTA: exclusive scan of the digit totals + counts of the CTAs before it (digits 2t, 2t+1).
+  uint32_t tot0 = 0, tot1 = 0, pre0 = 0, pre1 = 0;
+  for (int b = 0; b < geff; ++b) {
+    const uint2 v = *reinterpret_cast<const uint2*>(sort_hist(J, pass, b) + 2 * tid);
+    if (b < (int)blockIdx.x) { pre0 += v.x; pre1 += v.y; }
+    tot0 += v.x; tot1 += v.y;
   }
-  scan_buf[tid] = tot;
+  scan_buf[tid] = tot0 + tot1;
   __syncthreads();
-  for (int off = 1; off < 256; off <<= 1) {  // Hillis-Steele inclusive scan over 256 digits
-    uint32_t add = tid >= off ? scan_buf[tid - off] : 0u;
+  for (int off = 1; off < SORT_THREADS; off <<= 1) {  // Hillis-Steele inclusive scan over the 256 digit pairs
+    const uint32_t add = tid >= off ? scan_buf[tid - off] : 0u;
     __syncthreads();
     scan_buf[tid] += add;
     __syncthreads();
   }
-  const uint32_t excl = scan_buf[tid] - tot;
-  base[tid] = excl + pre;
-  if (pass == 0 && J.digit_start != nullptr && blockIdx.x == 0) {
-    J.digit_start[tid] = excl;
-    if (tid == 255) J.digit_start[256] = excl + tot;
+  const uint32_t excl0 = scan_buf[tid] - (tot0 + tot1), excl1 = excl0 + tot0;
+  base[2 * tid] = excl0 + pre0;
+  base[2 * tid + 1] = excl1 + pre1;
+  if (pass == 0 && J.digit_start != nullptr && blockIdx.x == 0 && tid < 128) {  // 8-bit ring keys: digits 0..255
+    J.digit_start[2 * tid] = excl0;
+    J.digit_start[2 * tid + 1] = excl1;
+    if (tid == 127) J.digit_start[256] = excl1 + tot1;
   }
   __syncthreads();
 
@@ -57,7 +60,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const SortJob* __
   const int end = min(n, beg + chunk);
 
   for (int tile = beg; tile < end; tile += SORT_TILE) {
-    for (int i = tid; i < 8 * 256; i += SORT_THREADS) (&wcnt[0][0])[i] = 0;
+    for (int i = tid; i < 8 * SORT_RADIX; i += SORT_THREADS) (&wcnt[0][0])[i] = 0;
     __syncthreads();
     uint32_t k[4], v[4], r[4], d[4];
     bool ok[4];
@@ -81,15 +84,17 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const SortJob* __
       __syncwarp();
     }
     __syncthreads();
-    {  // exclusive prefix over the 8 warps for digit `tid`, on top of the running base
-      uint32_t run = base[tid];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {  // exclusive prefix over the 8 warps for digits tid and tid + 256, on top of the running base
+      const int dg = tid + h * SORT_THREADS;
+      uint32_t run = base[dg];
 #pragma unroll
       for (int ww = 0; ww < 8; ++ww) {
-        uint32_t c = wcnt[ww][tid];
-        wcnt[ww][tid] = run;
+        const uint32_t c = wcnt[ww][dg];
+        wcnt[ww][dg] = run;
         run += c;
       }
-      base[tid] = run;
+      base[dg] = run;
     }
     __syncthreads();
 #pragma unroll
@@ -98,6 +103,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const SortJob* __
         const uint32_t pos = wcnt[warp][d[it]] + r[it];
         kout[pos] = k[it];
         vout[pos] = v[it];
+        if (count_next) atomicAdd(sort_hist(J, pass + 1, (int)(pos / (uint32_t)chunk)) + ((k[it] >> shift_next) & mask), 1u);
       }
     }
     __syncthreads();
@@ -108,13 +114,6 @@ void launch_sort_scatter(const Launch& L, const SortJob* jobs_dev, int njobs, in
   dim3 grid(SORT_G, njobs);
   k_sort_scatter<<<grid, SORT_THREADS, 0, L.st>>>(jobs_dev, pass);
   L.tick(K_SORT_SCATTER);
-}
-
-void launch_sort_pass(const Launch& L, const SortJob* jobs_dev, int njobs, int pass) {
-  dim3 grid(SORT_G, njobs);
-  k_sort_hist<KeyGenNone, false><<<grid, SORT_THREADS, 0, L.st>>>(jobs_dev, pass, KeyGenNone());
-  L.tick(K_SORT_HIST);
-  launch_sort_scatter(L, jobs_dev, njobs, pass);
 }
 
 }  // namespace vilf

@@ -2,9 +2,9 @@
 // the scan features and EM:347-350 for the local maps) and pcl::CropBox (EM:335-344), batched over jobs.
 //
 //   k_vox_bbox      crop-box test (closed AABB, bounds cast to fp32) + getMinMax3D over the kept points
-//   k_sort_hist<KeyGenVoxel>  min_b/div_b, PCL's int32 guard, fp32 voxel index per point (cropped-out points get
+//   k_sort_keyhist<KeyGenVoxel>  min_b/div_b, PCL's int32 guard, fp32 voxel index per point (cropped-out points get
 //                   the sentinel key dx*dy*dz and sort to the tail), pass-0 digit histogram
-//   3 x (hist, scatter) + scatter of pass 0     stable radix sort by voxel index (k_sort.cu)
+//   k_sort_scatter x 3-4   stable radix sort by voxel index, next-pass histogram fused (k_sort.cu)
 //   k_vox_heads     first point of every occupied voxel, counted per CTA chunk
 //   k_vox_centroid  one thread per occupied voxel walks its points in input order and accumulates
 //                   x, y, z, intensity in fp32 exactly like PCL's `centroid += ...; centroid /= count`;
@@ -13,21 +13,10 @@
 //   k_map_init      localMapInited (EM:105-115)
 //
 // Algorithmic bytes per point: 16 B read + 16 B/voxel written; the sort's (key,index) traffic
-// (4 passes x 24 B) is implementation overhead.
-#include "k_sort.cuh"
+// (3-4 passes x 16 B) is implementation overhead.
+#include "k_voxel.cuh"
 
 namespace vilf {
-
-__device__ __forceinline__ bool in_crop(const VoxJob& J, const float4 p, const float lo[3], const float hi[3]) {
-  return !(p.x < lo[0] || p.y < lo[1] || p.z < lo[2] || p.x > hi[0] || p.y > hi[1] || p.z > hi[2]);
-}
-__device__ __forceinline__ void crop_bounds(const VoxJob& J, float lo[3], float hi[3]) {
-  for (int a = 0; a < 3; ++a) {
-    if (J.crop == 2) { lo[a] = J.crop_lo[a]; hi[a] = J.crop_hi[a]; continue; }
-    lo[a] = (float)dsub(J.crop_center[a], J.crop_half);  // EM:327-336: bounds in fp64, stored in an Eigen::Vector4f
-    hi[a] = (float)dadd(J.crop_center[a], J.crop_half);
-  }
-}
 
 __global__ void __launch_bounds__(256) k_vox_bbox(const VoxJob* __restrict__ jobs) {
   const VoxJob& J = jobs[blockIdx.y];
@@ -38,88 +27,15 @@ __global__ void __launch_bounds__(256) k_vox_bbox(const VoxJob* __restrict__ job
   int cnt = 0;
   for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
     const float4 p = J.in[i];
-    if (J.crop && !in_crop(J, p, lo, hi)) continue;
+    if (J.crop && outside(p, lo, hi)) continue;
     ++cnt;
     mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
     mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
     mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
   }
-  for (int off = 16; off > 0; off >>= 1) {
-    for (int a = 0; a < 3; ++a) {
-      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], off));
-      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], off));
-    }
-    cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
-  }
-  if ((threadIdx.x & 31) == 0 && cnt > 0) {
-    for (int a = 0; a < 3; ++a) {
-      atomicMin(&J.vv->bbox[a], f2ord(mn[a]));
-      atomicMax(&J.vv->bbox[3 + a], f2ord(mx[a]));
-    }
-    atomicAdd(&J.vv->n_valid, cnt);
-  }
+  __shared__ float bb_sm[7 * 8];
+  bbox_commit(J.vv, mn, mx, cnt, bb_sm);
 }
-
-struct KeyGenVoxel {
-  const VoxJob* jobs;
-  // per-CTA state (set by prepare)
-  float inv;
-  float lo[3], hi[3];
-  int min_b[3], mul[3], total, guard, crop;
-  const float4* in;
-
-  __device__ int prepare(int job) {
-    const VoxJob& J = jobs[job];
-    const VoxVars& V = *J.vv;
-    in = J.in;
-    crop = J.crop;
-    if (crop) crop_bounds(J, lo, hi);
-    inv = 1.0f / J.leaf;  // inverse_leaf_size_ = Array4f::Ones() / leaf_size_.array()
-    int bits = 1;
-    guard = 0; total = 1;
-    min_b[0] = min_b[1] = min_b[2] = 0; mul[0] = mul[1] = mul[2] = 0;
-    int div_b[3] = {1, 1, 1};
-    if (J.passthrough) {
-      // pcl::CropBox::filter alone (test entry point): kept points get key 0, the rest the sentinel 1; the
-      // stable sort then is an order-preserving compaction and every kept point is its own output.
-      guard = 1;
-    } else if (V.n_valid > 0) {
-      float mn[3], mx[3];
-      for (int a = 0; a < 3; ++a) { mn[a] = ord2f(V.bbox[a]); mx[a] = ord2f(V.bbox[3 + a]); }
-      const long long dx = (long long)(fmul(fsub(mx[0], mn[0]), inv)) + 1;
-      const long long dy = (long long)(fmul(fsub(mx[1], mn[1]), inv)) + 1;
-      const long long dz = (long long)(fmul(fsub(mx[2], mn[2]), inv)) + 1;
-      if (dx * dy * dz > (long long)INT_MAX) {
-        guard = 1;  // "Leaf size is too small for the input dataset": PCL returns the input cloud
-        total = 1;
-      } else {
-        for (int a = 0; a < 3; ++a) {
-          min_b[a] = (int)floorf(fmul(mn[a], inv));
-          const int max_b = (int)floorf(fmul(mx[a], inv));
-          div_b[a] = max_b - min_b[a] + 1;
-        }
-        mul[0] = 1; mul[1] = div_b[0]; mul[2] = div_b[0] * div_b[1];
-        total = div_b[0] * div_b[1] * div_b[2];
-      }
-      bits = 32 - __clz(total);  // keys are 0..total (total = sentinel)
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-      VoxVars& W = *J.vv;
-      for (int a = 0; a < 3; ++a) { W.min_b[a] = min_b[a]; W.div_b[a] = div_b[a]; }
-      W.bits = bits; W.guard = guard; W.total = total;
-    }
-    return bits;
-  }
-  __device__ uint32_t key(int, int i) const {
-    const float4 p = in[i];
-    if (crop && (p.x < lo[0] || p.y < lo[1] || p.z < lo[2] || p.x > hi[0] || p.y > hi[1] || p.z > hi[2])) return (uint32_t)total;
-    if (guard) return 0u;
-    const int i0 = (int)fsub(floorf(fmul(p.x, inv)), (float)min_b[0]);
-    const int i1 = (int)fsub(floorf(fmul(p.y, inv)), (float)min_b[1]);
-    const int i2 = (int)fsub(floorf(fmul(p.z, inv)), (float)min_b[2]);
-    return (uint32_t)(i0 * mul[0] + i1 * mul[1] + i2 * mul[2]);
-  }
-};
 
 __device__ __forceinline__ void vox_chunk(int n, int b, int& beg, int& end) {
   int chunk = (n + VOX_G - 1) / VOX_G;
@@ -132,7 +48,7 @@ __global__ void __launch_bounds__(256) k_vox_heads(const VoxJob* __restrict__ jo
   const VoxJob& J = jobs[blockIdx.y];
   const int n = J.vv->n_valid;
   const int guard = J.vv->guard;
-  const uint32_t* key = J.sort.key[0];
+  const uint32_t* key = J.sort.key[sort_passes(J.vv->bits, J.sort.npass) & 1];
   int beg, end;
   vox_chunk(n, blockIdx.x, beg, end);
   int cnt = 0;
@@ -152,11 +68,13 @@ __global__ void __launch_bounds__(256) k_vox_centroid(const VoxJob* __restrict__
   const VoxJob& J = jobs[blockIdx.y];
   const int n = J.vv->n_valid;
   const int guard = J.vv->guard;
-  const uint32_t* __restrict__ key = J.sort.key[0];
-  const uint32_t* __restrict__ val = J.sort.val[0];
+  const int res = sort_passes(J.vv->bits, J.sort.npass) & 1;
+  const uint32_t* __restrict__ key = J.sort.key[res];
+  const uint32_t* __restrict__ val = J.sort.val[res];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   __shared__ int red[256];
   __shared__ int wsum[8];
+  __shared__ float4 stage[8][32];
   // heads in the chunks before this CTA, and in total
   int pre = 0, tot = 0;
   for (int b = tid; b < VOX_G; b += 256) { const int c = J.head_cnt[b]; if (b < (int)blockIdx.x) pre += c; tot += c; }
@@ -188,40 +106,24 @@ __global__ void __launch_bounds__(256) k_vox_centroid(const VoxJob* __restrict__
     int off = 0, total = 0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) { const int c = wsum[w]; if (w < warp) off += c; total += c; }
-    if (head) {
-      const int dst = run + off + __popc(b & ((1u << lane) - 1u));
-      if (dst < J.cap_out) {
-        const uint32_t k0 = key[i];
-        float4 c = J.in[val[i]];
-        int cnt = 1;
-        if (!guard) {
-          for (int j = i + 1; j < n && key[j] == k0; ++j) {  // input order inside the voxel (stable sort)
-            const float4 p = J.in[val[j]];
-            c.x = fadd(c.x, p.x); c.y = fadd(c.y, p.y); c.z = fadd(c.z, p.z); c.w = fadd(c.w, p.w);
-            ++cnt;
-          }
-          const float fc = (float)cnt;
-          c.x = __fdiv_rn(c.x, fc); c.y = __fdiv_rn(c.y, fc); c.z = __fdiv_rn(c.z, fc); c.w = __fdiv_rn(c.w, fc);
-        }
-        J.out[dst] = c;
-      }
-    }
+    emit_centroids(J, key, val, n, guard, i, head, run + off + __popc(b & ((1u << lane) - 1u)), stage[warp]);
     run += total;
     __syncthreads();
   }
 }
 
-void launch_voxel(const Launch& L, const VoxJob* jobs_dev, int njobs, const SortJob* sort_jobs_dev) {
+void launch_voxel(const Launch& L, const VoxJob* jobs_dev, int njobs, const SortJob* sort_jobs_dev, bool bbox_done) {
   dim3 gv(VOX_G, njobs);
-  k_vox_bbox<<<gv, 256, 0, L.st>>>(jobs_dev);
-  L.tick(K_VOX_BBOX);
+  if (!bbox_done) {  // otherwise the producer of the input cloud already reduced the bounding box (k_compact_features / k_map_append)
+    k_vox_bbox<<<gv, 256, 0, L.st>>>(jobs_dev);
+    L.tick(K_VOX_BBOX);
+  }
   KeyGenVoxel gen;
   gen.jobs = jobs_dev;
   dim3 gs(SORT_G, njobs);
-  k_sort_hist<KeyGenVoxel, true><<<gs, SORT_THREADS, 0, L.st>>>(sort_jobs_dev, 0, gen);
+  k_sort_keyhist<KeyGenVoxel><<<gs, SORT_THREADS, 0, L.st>>>(sort_jobs_dev, gen);
   L.tick(K_VOX_KEYHIST);
-  launch_sort_scatter(L, sort_jobs_dev, njobs, 0);
-  for (int pass = 1; pass < 4; ++pass) launch_sort_pass(L, sort_jobs_dev, njobs, pass);
+  for (int pass = 0; pass < 4; ++pass) launch_sort_scatter(L, sort_jobs_dev, njobs, pass);
   k_vox_heads<<<gv, 256, 0, L.st>>>(jobs_dev);
   L.tick(K_VOX_HEADS);
   k_vox_centroid<<<gv, 256, 0, L.st>>>(jobs_dev);
@@ -231,22 +133,44 @@ void launch_voxel(const Launch& L, const VoxJob* jobs_dev, int njobs, const Sort
 // ------------------------------------------------------------------------------------------------
 // map maintenance helpers
 // ------------------------------------------------------------------------------------------------
+// createSubMap step 1 (EM:308-324) fused with the crop-box test and getMinMax3D of step 2-4's input: the voxel-filtered
+// scan features are transformed with the final pose and appended; every point of map + appended (old and new) that lies
+// inside the crop box (EM:327-344) contributes to the bounding box the voxel filter needs.
 __global__ void __launch_bounds__(256) k_map_append(LaneDev* lanes, int lane0, int cur, ConfigDev cfg) {
   const LaneDev& L = lanes[lane0 + blockIdx.y];
   LaneVars& V = *L.v;
-  const int ne = V.n_ds[0], ns = V.n_ds[1];
-  const int me = V.n_map[0], ms = V.n_map[1];
   const int cap = cfg.cap_map + cfg.cap_scan;
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < ne + ns; i += gridDim.x * 256) {
-    const int w = i < ne ? 0 : 1;
-    const int k = i < ne ? i : i - ne;
-    const int dst = (w ? ms : me) + k;
-    if (dst < cap) L.map[w][cur][dst] = associate(V.x, L.ds[w][k]);  // EM:313-314, :321-322
+  float lo[3], hi[3];
+  for (int a = 0; a < 3; ++a) {
+    lo[a] = (float)dsub(V.x[4 + a], cfg.crop_half);
+    hi[a] = (float)dadd(V.x[4 + a], cfg.crop_half);
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    V.n_cat[0] = min(cap, me + ne);
-    V.n_cat[1] = min(cap, ms + ns);
-    if (me + ne > cap || ms + ns > cap) atomicOr(&V.status, ST_MAP_CAPACITY);
+  __shared__ float bb_sm[7 * 8];
+  for (int w = 0; w < 2; ++w) {
+    const int nd = V.n_ds[w], m = V.n_map[w];
+    const int tot = min(cap, m + nd);
+    float4* map = L.map[w][cur];
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    int cnt = 0;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < tot; i += gridDim.x * 256) {
+      float4 p;
+      if (i < m) {
+        p = map[i];
+      } else {
+        p = associate(V.x, L.ds[w][i - m]);  // EM:313-314, :321-322
+        map[i] = p;
+      }
+      if (p.x < lo[0] || p.y < lo[1] || p.z < lo[2] || p.x > hi[0] || p.y > hi[1] || p.z > hi[2]) continue;
+      ++cnt;
+      mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
+      mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
+      mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
+    }
+    bbox_commit(L.vv + 2 + w, mn, mx, cnt, bb_sm);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      V.n_cat[w] = tot;
+      if (m + nd > cap) atomicOr(&V.status, ST_MAP_CAPACITY);
+    }
   }
 }
 
@@ -277,7 +201,7 @@ __global__ void k_map_init_commit(LaneDev* lanes, int lane0, ConfigDev cfg) {
 }
 
 void launch_map_append(const Launch& L, LaneDev* lanes, int lane0, int nlanes, int cur, const ConfigDev& cfg) {
-  dim3 g(64, nlanes);
+  dim3 g(148, nlanes);
   k_map_append<<<g, 256, 0, L.st>>>(lanes, lane0, cur, cfg);
   L.tick(K_MAP_APPEND);
 }

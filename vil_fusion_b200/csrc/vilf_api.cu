@@ -120,9 +120,9 @@ int alloc_sort(Ctx* C, SortJob& S, const int* n, const int* bits, int fixed_bits
     CK(dalloc(C, &S.key[b], (size_t)cap));
     CK(dalloc(C, &S.val[b], (size_t)cap));
   }
-  CK(dalloc(C, &S.hist, (size_t)SORT_G * 256));
+  CK(dalloc(C, &S.hist, (size_t)4 * SORT_G * SORT_RADIX));
   S.digit_start = nullptr;
-  if (digit_start) CK(dalloc(C, &S.digit_start, 260));
+  if (digit_start) CK(dalloc(C, &S.digit_start, 264));
   return VILF_OK;
 }
 
@@ -152,6 +152,12 @@ int build_ctx(Ctx* C) {
   while ((double)cell * (double)cell < u.knn_gate) cell *= 2.0f;  // power of two >= sqrt(gate)
   c.inv_cell = 1.0f / cell;
   c.outer_iters = u.outer_iters; c.lm_max_iters = u.lm_max_iters;
+  {
+    int ring_pts = u.max_ring_points > 0 ? u.max_ring_points : 6 * MAX_SECTOR + 10;
+    int ms = (ring_pts - 10) / SECTORS + 8;  // FE:205-214: the last sector takes the remainder (< 6 more)
+    ms = (ms + 7) / 8 * 8;
+    c.max_sector = ms < 64 ? 64 : (ms > MAX_SECTOR ? MAX_SECTOR : ms);
+  }
   c.cap_scan = u.max_scan_points; c.cap_map = u.max_map_points;
   const int NL = C->nlanes;
   const int capS = c.cap_scan, capM = c.cap_map + c.cap_scan;
@@ -185,6 +191,7 @@ int build_ctx(Ctx* C) {
     LaneDev& L = C->lanes_host[l];
     memset(&L, 0, sizeof(L));
     L.v = C->vars_dev + l;
+    L.vv = C->vv_dev + (size_t)l * VV_PER_LANE;
     L.trace = C->trace_dev + (size_t)l * MAX_OUTER;
     for (int b = 0; b < 2; ++b) {
       CK(dalloc(C, &L.scan[b], (size_t)capS));
@@ -353,7 +360,7 @@ int enqueue_frame(Ctx* C, int lane0, int nl, bool first, bool with_extract, int 
     launch_grid_build(L, C->grid_dev[cur] + lane0 * 2, nl * 2, cfg);
   } else {
     phase(1);
-    launch_voxel(L, C->vox_scan_dev + lane0 * 2, nl * 2, C->vox_scan_sort_dev + lane0 * 2);
+    launch_voxel(L, C->vox_scan_dev + lane0 * 2, nl * 2, C->vox_scan_sort_dev + lane0 * 2, with_extract);
     phase(2);
     for (int it = 0; it < cfg.outer_iters; ++it) {
       launch_knn_fit(L, C->lanes_dev, C->grid_dev[cur], lane0, nl, cur, cfg, nullptr, 0);
@@ -361,7 +368,7 @@ int enqueue_frame(Ctx* C, int lane0, int nl, bool first, bool with_extract, int 
     }
     phase(3);
     launch_map_append(L, C->lanes_dev, lane0, nl, cur, cfg);
-    launch_voxel(L, C->vox_map_dev[cur] + lane0 * 2, nl * 2, C->vox_map_sort_dev[cur] + lane0 * 2);
+    launch_voxel(L, C->vox_map_dev[cur] + lane0 * 2, nl * 2, C->vox_map_sort_dev[cur] + lane0 * 2, true);
     phase(4);
     launch_grid_build(L, C->grid_dev[cur ^ 1] + lane0 * 2, nl * 2, cfg);
     for (int l = lane0; l < lane0 + nl; ++l) C->cur[l] = cur ^ 1;
@@ -494,7 +501,7 @@ int run_aux_voxel(Ctx* C, const float* pts, int n, float leaf, int crop, const d
   vv.bbox[3] = vv.bbox[4] = vv.bbox[5] = INT_MIN;
   CK(cudaMemcpyAsync(J.vv, &vv, sizeof(vv), cudaMemcpyHostToDevice, C->st));
   CK(cudaStreamSynchronize(C->st));  // the staged host structs above live on this stack frame
-  launch_voxel(mk(C), C->aux_vox_dev, 1, C->aux_sort_dev);
+  launch_voxel(mk(C), C->aux_vox_dev, 1, C->aux_sort_dev, false);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(hdr, C->aux_n, sizeof(hdr), cudaMemcpyDeviceToHost, C->st));
   CK(cudaMemcpyAsync(&vv, J.vv, sizeof(vv), cudaMemcpyDeviceToHost, C->st));
@@ -553,7 +560,7 @@ int vilf_default_config(vilf_config* c) {
   c->lidar_min = 3.0; c->lidar_max = 90.0; c->edge_threshold = 0.1;
   c->edge_leaf = 0.4; c->surf_leaf = 0.8; c->crop_half = 100.0; c->knn_gate = 1.0; c->huber = 0.1;
   c->outer_iters = 2; c->lm_max_iters = 4;
-  c->max_scan_points = 300000; c->max_map_points = 1 << 20;
+  c->max_scan_points = 300000; c->max_map_points = 1 << 20; c->max_ring_points = 0;
   return VILF_OK;
 }
 
@@ -961,10 +968,10 @@ int vilf_profile_read_kernels(vilf_handle* h, double* ms_out, int64_t* launches_
   return VILF_OK;
 }
 const char* vilf_profile_kernel_name(int kernel) {
-  static const char* names[K_COUNT] = {"k_frame_reset", "k_sort_hist<KeyGenRing>", "k_sort_hist", "k_sort_scatter", "k_sector_select", "k_compact_features",
-                                       "k_vox_bbox", "k_sort_hist<KeyGenVoxel>", "k_vox_heads", "k_vox_centroid", "k_map_append", "k_map_init",
-                                       "k_grid_zero", "k_grid_count", "k_grid_scan_partial", "k_grid_scan_final", "k_grid_scatter", "k_knn_fit",
-                                       "k_knn_only", "k_solve"};
+  static const char* names[K_COUNT] = {"k_frame_reset", "k_sort_keyhist<KeyGenRing>", "k_sort_hist", "k_sort_scatter", "k_sector_select", "k_compact_features",
+                                       "k_vox_bbox", "k_sort_keyhist<KeyGenVoxel>", "k_vox_heads", "k_vox_centroid", "k_map_append", "k_map_init",
+                                       "k_grid_zero", "k_grid_count", "k_grid_scan_partial", "k_grid_scan_final", "k_grid_scatter", "k_knn_assoc",
+                                       "k_knn_only", "k_solve", "k_fit"};
   return (kernel >= 0 && kernel < K_COUNT) ? names[kernel] : "";
 }
 int vilf_launch_count(vilf_handle* h, int64_t* launches) {

@@ -19,10 +19,14 @@ constexpr int SORT_G = 128;          // max CTAs per radix-sort job
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_TILE = 1024;      // 256 threads x 4 keys
 constexpr int SORT_MIN_CHUNK = 2048;
+constexpr int SORT_RADIX_BITS = 9;   // digit width limit; tables are [4 passes][SORT_G][512]
+constexpr int SORT_RADIX = 1 << SORT_RADIX_BITS;
 constexpr int VOX_G = 148;           // CTAs per voxel job for the bbox / head / centroid kernels
 constexpr int GRID_G = 148;          // CTAs per hash-grid job
-constexpr int KNN_G = 148 * 4;       // CTAs (8 warps each) of the kNN + fit kernel per lane
-constexpr int LM_THREADS = 512;
+constexpr int KNN_G = 148 * 4;       // CTAs (8 warps each) of the kNN kernel per lane
+constexpr int FIT_G = 148;           // CTAs (128 threads) of the fit kernel per lane
+constexpr int LM_THREADS = 256;     // per CTA of the solve cluster
+constexpr int LM_CLUSTER = 8;       // CTAs (SMs) per sequence in the solve kernel
 constexpr int MAX_TRACE_ROWS = 8;
 constexpr int MAX_OUTER = 4;
 
@@ -36,6 +40,7 @@ struct ConfigDev {
   double lidar_min, lidar_max, edge_threshold, knn_gate, huber, crop_half;
   float edge_leaf, surf_leaf;
   float inv_cell;  // 1 / hash-grid cell edge (a power of two >= sqrt(knn_gate))
+  int max_sector;  // elements per (ring, sector) the selection kernel stages in shared memory (<= MAX_SECTOR)
   int outer_iters, lm_max_iters;
   int cap_scan, cap_map;
 };
@@ -71,10 +76,10 @@ struct SortJob {
   const int* n;           // element count
   const int* bits;        // significant key bits (device) or null -> fixed_bits
   int fixed_bits;
-  int npass;              // 1 or 4; digit width = ceil(bits / npass) <= 8
-  uint32_t* key[2];
+  int npass;              // pass limit: 1 (ring ids) or 4; P = min(npass, ceil(bits / 9)) passes of ceil(bits / P) bits
+  uint32_t* key[2];       // result in key[P & 1] / val[P & 1]
   uint32_t* val[2];
-  uint32_t* hist;         // [SORT_G][256]
+  uint32_t* hist;         // [4][SORT_G][SORT_RADIX]
   uint32_t* digit_start;  // optional [257]: exclusive digit offsets of pass 0 (+ total)
 };
 
@@ -119,6 +124,7 @@ struct GridJob {
 // Per-lane device pointers.
 struct LaneDev {
   LaneVars* v;
+  VoxVars* vv;                       // [4]: scan edge, scan surf, map edge, map surf voxel jobs
   SolveTraceDev* trace;              // [MAX_OUTER]
   float4* scan[2]; uint16_t* ring_in[2];  // double buffered: H2D of frame t+1 overlaps the kernels of frame t
   // stage 1
@@ -141,6 +147,43 @@ struct LaneDev {
 // ---- ordered-int float mapping for atomicMin/atomicMax ----
 __device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7FFFFFFF; }
 __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
+
+// Block-reduce a bounding box + count and merge it into a voxel job's VoxVars with 7 atomics per CTA (getMinMax3D is
+// order independent).  Every thread of the CTA must call it; sm = 7 * (blockDim.x / 32) floats of shared memory.
+__device__ __forceinline__ void bbox_commit(VoxVars* vv, float mn[3], float mx[3], int cnt, float* sm) {
+  for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], off));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], off));
+    }
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+  }
+  const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();  // sm may still be in use by a previous call
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { sm[warp * 7 + a] = mn[a]; sm[warp * 7 + 3 + a] = mx[a]; }
+    sm[warp * 7 + 6] = __int_as_float(cnt);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int total = 0;
+    for (int w = 0; w < nw; ++w) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { mn[a] = fminf(mn[a], sm[w * 7 + a]); mx[a] = fmaxf(mx[a], sm[w * 7 + 3 + a]); }
+      total += __float_as_int(sm[w * 7 + 6]);
+    }
+    if (total > 0) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        atomicMin(&vv->bbox[a], f2ord(mn[a]));
+        atomicMax(&vv->bbox[3 + a], f2ord(mx[a]));
+      }
+      atomicAdd(&vv->n_valid, total);
+    }
+  }
+}
 
 // fp32 arithmetic that must round exactly like the reference's scalar SSE code (no contraction).
 __device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
@@ -180,7 +223,7 @@ __device__ __forceinline__ float4 associate(const double* x, float4 p) {
 enum KernelId {
   K_RESET = 0, K_RING_KEYHIST, K_SORT_HIST, K_SORT_SCATTER, K_SECTOR, K_COMPACT, K_VOX_BBOX, K_VOX_KEYHIST, K_VOX_HEADS, K_VOX_CENTROID,
   K_MAP_APPEND, K_MAP_INIT, K_GRID_ZERO, K_GRID_COUNT, K_GRID_SCAN_PARTIAL, K_GRID_SCAN_FINAL, K_GRID_SCATTER, K_KNN_FIT, K_KNN_ONLY,
-  K_SOLVE, K_COUNT
+  K_SOLVE, K_FIT, K_COUNT
 };
 constexpr int PROF_PHASES = 5;      // 0 extract, 1 scan downsample, 2 association + solve, 3 map update, 4 grid build
 constexpr int PROF_TAGS = PROF_PHASES * 32;
@@ -206,13 +249,12 @@ struct Launch {
 };
 
 // k_sort.cu
-void launch_sort_pass(const Launch& L, const SortJob* jobs_dev, int njobs, int pass);  // hist + scatter on stored keys
 void launch_sort_scatter(const Launch& L, const SortJob* jobs_dev, int njobs, int pass);
 // k_extract.cu
 void launch_frame_reset(const Launch& L, LaneDev* lanes, int lane0, int nlanes, VoxVars* vv, int vv_per_lane, int predict);
 void launch_extract(const Launch& L, LaneDev* lanes, const SortJob* ring_jobs, int lane0, int nlanes, int sel, const ConfigDev& cfg);
 // k_voxel.cu
-void launch_voxel(const Launch& L, const VoxJob* jobs_dev, int njobs, const SortJob* sort_jobs_dev);
+void launch_voxel(const Launch& L, const VoxJob* jobs_dev, int njobs, const SortJob* sort_jobs_dev, bool bbox_done);
 void launch_map_append(const Launch& L, LaneDev* lanes, int lane0, int nlanes, int cur, const ConfigDev& cfg);
 void launch_map_init(const Launch& L, LaneDev* lanes, int lane0, int nlanes, int cur, const ConfigDev& cfg);
 // k_knn.cu
