@@ -104,6 +104,14 @@ int vilf_update(vilf_handle* h, double pose_out[7]);
 int vilf_update_points(vilf_handle* h, const float* edge, int n_edge, const float* surf, int n_surf, double pose_out[7]);
 /* globalOdom (EM:387): pose as quaternion + translation, and optionally the 3x3 rotation (row-major) + t. */
 int vilf_get_pose(vilf_handle* h, double pose_out[7], double* rt12_or_null);
+/* Overwrite parameter_opti (EM:383; q_w_c / t_w_c alias it) and, when update_odom != 0, globalOdom as EM:291-293 does. */
+int vilf_set_pose(vilf_handle* h, const double pose[7], int update_odom);
+/* The constant-velocity prediction that opens optimation_processing (EM:238-243): globalOdom <- globalOdom *
+ * (globalOdom_last^-1 * globalOdom), globalOdom_last <- old globalOdom, parameter_opti <- predicted pose. */
+int vilf_predict(vilf_handle* h, double pose_out[7]);
+/* EstimationMapping::createSubMap (EM:298-352) on explicit voxel-filtered scan features at the current parameter_opti:
+ * transform + append to both local maps, crop box +-crop_half about the pose, voxel filter, rebuild the search grids. */
+int vilf_create_submap(vilf_handle* h, const float* edge_ds, int n_edge, const float* surf_ds, int n_surf);
 /* Clouds owned by the object. which: 0 localMapEdge, 1 localMapSurf (EM:394-395), 2/3 the voxel-filtered
  * scan edge/surf features (EM:246-251), 4 cloudRegistered, 5 cloudNoRegistered (EM:391-392; getMapCloud
  * EM:365-375 returns 4+5 or 5). */

@@ -1,0 +1,134 @@
+// Drives the host-side mirror classes (include/vilf/featureExtraction.hpp, include/vilf/EstimationMapping.hpp) the way
+// the reference's ROS node does (feature_tracker_node.cpp:339-389), three ways over the same scans:
+//   A  node order, ONE shared device session (features stay resident between the two classes)
+//   B  node order, independent objects exactly as the reference declares them (features cross the host)
+//   C  the public pieces one by one: predictPose, voxelFilter, 2 x (ProblemReset, EdgeCostFactor, SurfCostFactor,
+//      SolveProblem), createSubMap  — the body of optimation_processing (EM:235-296) spelled out by the caller
+// and writes the per-frame poses of A; A == B bit for bit, C == A to 1e-9 (the factor list of C is compacted, so the
+// reduction order of the normal equations differs).  The Python test compares A with the CPU oracle.
+//
+// usage: shim_test <scans.bin> <n_scan> <poses_out.bin>
+//   scans.bin: int32 frames, then per frame: int32 n, float32[n][4]
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <vector>
+
+#include "vilf/EstimationMapping.hpp"
+
+using vilf::Cloud;
+using vilf::CloudPtr;
+
+static std::vector<CloudPtr> read_scans(const char* path) {
+  std::vector<CloudPtr> out;
+  FILE* f = std::fopen(path, "rb");
+  if (!f) { std::perror(path); std::exit(2); }
+  int frames = 0;
+  if (std::fread(&frames, 4, 1, f) != 1) std::exit(2);
+  for (int i = 0; i < frames; ++i) {
+    int n = 0;
+    if (std::fread(&n, 4, 1, f) != 1) std::exit(2);
+    std::vector<float> buf((size_t)n * 4);
+    if (n && std::fread(buf.data(), 16, (size_t)n, f) != (size_t)n) std::exit(2);
+    CloudPtr c = vilf::make_cloud();
+    vilf::append_cloud(*c, buf.data(), (size_t)n);
+    out.push_back(c);
+  }
+  std::fclose(f);
+  return out;
+}
+
+static void node_loop(featureExtraction& fe, EstimationMapping& est, const std::vector<CloudPtr>& scans, std::vector<double>& poses) {
+  bool init_pub = false;
+  for (size_t i = 0; i < scans.size(); ++i) {
+    CloudPtr MapCloud = vilf::make_cloud(), edge = vilf::make_cloud(), surf = vilf::make_cloud();
+    fe.extractFeature(scans[i], edge, surf);              // NODE:346
+    if (!init_pub) {
+      init_pub = true;
+      est.localMapInited(edge, surf);                     // NODE:373
+    } else {
+      est.optimation_processing(edge, surf);              // NODE:384
+      est.getMapCloud(MapCloud);                          // NODE:385
+      if (MapCloud->points.empty()) { std::fprintf(stderr, "empty /GlobalMap cloud at frame %zu\n", i); std::exit(1); }
+    }
+    for (int k = 0; k < 7; ++k) poses.push_back(est.parameter_opti[k]);
+  }
+}
+
+int main(int argc, char** argv) {
+  if (argc < 4) { std::fprintf(stderr, "usage: shim_test scans.bin n_scan poses_out.bin\n"); return 2; }
+  try {
+    std::vector<CloudPtr> scans = read_scans(argv[1]);
+    vilf::ParamMap nh;  // config/kitti/velodyne_param_64.yaml:9-23
+    nh.set("/N_SCAN", std::atof(argv[2]));
+    nh.set("/lidarMinRange", 3.0); nh.set("/lidarMaxRange", 90.0); nh.set("/edgeThreshold", 0.1); nh.set("/surfThreshold", 0.1);
+    nh.set("/EdgeLeafSize", 0.4); nh.set("/SurfLeafSize", 0.8);
+
+    // A: shared session
+    std::vector<double> pa, pb, pc;
+    {
+      featureExtraction featureExtractFactor;   // NODE:18
+      EstimationMapping Estimator;              // NODE:19
+      featureExtractFactor.initParam(nh);       // NODE:509
+      Estimator.initParameter(nh);              // NODE:510
+      Estimator.shareSession(featureExtractFactor);
+      node_loop(featureExtractFactor, Estimator, scans, pa);
+    }
+    // B: independent objects
+    {
+      featureExtraction featureExtractFactor;
+      EstimationMapping Estimator;
+      featureExtractFactor.initParam(nh);
+      Estimator.initParameter(nh);
+      node_loop(featureExtractFactor, Estimator, scans, pb);
+    }
+    // C: F-LOAM names + the pieces one by one
+    {
+      vilf::LaserProcessingClass laserProcessing;
+      vilf::OdomEstimationClass odomEstimation;
+      laserProcessing.initParam(nh);
+      odomEstimation.init(0.4, 0.8);
+      for (size_t i = 0; i < scans.size(); ++i) {
+        CloudPtr edge = vilf::make_cloud(), surf = vilf::make_cloud();
+        laserProcessing.featureExtraction(scans[i], edge, surf);
+        if (i == 0) {
+          odomEstimation.initMapWithPoints(edge, surf);
+        } else {
+          odomEstimation.predictPose();
+          CloudPtr de = vilf::make_cloud(), ds = vilf::make_cloud();
+          odomEstimation.downSamplingToMap(edge, de, surf, ds);
+          for (int it = 0; it < 2; ++it) {
+            odomEstimation.ProblemReset();
+            odomEstimation.addEdgeCostFactor(de);
+            odomEstimation.addSurfCostFactor(ds);
+            odomEstimation.SolveProblem(4);
+          }
+          odomEstimation.addPointsToMap(de, ds);
+        }
+        for (int k = 0; k < 7; ++k) pc.push_back(odomEstimation.parameter_opti[k]);
+      }
+      CloudPtr m = vilf::make_cloud();
+      odomEstimation.getMap(m);
+      if (m->points.empty()) { std::fprintf(stderr, "empty map\n"); return 1; }
+      vilf::PointType pi = scans[0]->points[0], po;
+      odomEstimation.pointAssociateToMap(&pi, &po);
+      if (!(std::isfinite(po.x) && std::isfinite(po.y) && std::isfinite(po.z))) return 1;
+    }
+    double dab = 0, dac = 0;
+    for (size_t i = 0; i < pa.size(); ++i) {
+      dab = std::fmax(dab, std::fabs(pa[i] - pb[i]));
+      dac = std::fmax(dac, std::fabs(pa[i] - pc[i]));
+    }
+    std::printf("frames %zu  max|A-B| %.3e  max|A-C| %.3e\n", scans.size(), dab, dac);
+    FILE* f = std::fopen(argv[3], "wb");
+    if (!f) { std::perror(argv[3]); return 2; }
+    std::fwrite(pa.data(), sizeof(double), pa.size(), f);
+    std::fclose(f);
+    if (dab != 0.0) { std::fprintf(stderr, "shared-session and host-round-trip runs differ\n"); return 1; }
+    if (!(dac < 1e-9)) { std::fprintf(stderr, "piecewise run differs from optimation_processing\n"); return 1; }
+    return 0;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "shim_test: %s\n", e.what());
+    return 3;
+  }
+}

@@ -38,7 +38,7 @@ SYMBOLS = [
     "vilf_default_config", "vilf_create", "vilf_create_batch", "vilf_destroy", "vilf_last_error", "vilf_host_alloc", "vilf_host_free",
     "vilf_process_scan", "vilf_submit_scan", "vilf_wait", "vilf_submit_scan_batch", "vilf_wait_batch", "vilf_submit_scan_batch_dev",
     "vilf_feature_extract", "vilf_get_features", "vilf_map_init", "vilf_map_init_points", "vilf_update", "vilf_update_points",
-    "vilf_get_pose", "vilf_get_cloud", "vilf_voxel_downsample", "vilf_crop_voxel_downsample", "vilf_crop_box", "vilf_knn5",
+    "vilf_get_pose", "vilf_set_pose", "vilf_predict", "vilf_create_submap", "vilf_get_cloud", "vilf_voxel_downsample", "vilf_crop_voxel_downsample", "vilf_crop_box", "vilf_knn5",
     "vilf_factors", "vilf_normal_equations", "vilf_solve", "vilf_get_solves", "vilf_state_export", "vilf_state_import",
     "vilf_profile_enable", "vilf_profile_read", "vilf_profile_read_kernels", "vilf_profile_kernel_name", "vilf_launch_count", "vilf_get_stream", "vilf_get_counts",
 ]
@@ -169,6 +169,19 @@ class Odometry:
         rt = np.zeros(12)
         self._ck(lib().vilf_get_pose(self._h, _p(pose, C.c_double), _p(rt, C.c_double)))
         return pose, rt
+
+    def set_pose(self, pose, update_odom: bool = True):
+        pose = _f64(pose)
+        self._ck(lib().vilf_set_pose(self._h, _p(pose, C.c_double), int(update_odom)))
+
+    def predict(self):
+        pose = np.zeros(7)
+        self._ck(lib().vilf_predict(self._h, _p(pose, C.c_double)))
+        return pose
+
+    def create_submap(self, edge_ds, surf_ds):
+        e, s = _f32(edge_ds), _f32(surf_ds)
+        self._ck(lib().vilf_create_submap(self._h, _p(e, C.c_float), e.shape[0], _p(s, C.c_float), s.shape[0]))
 
     def cloud(self, which: int):
         n = C.c_int()

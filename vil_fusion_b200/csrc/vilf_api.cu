@@ -336,6 +336,17 @@ int status_to_rc(Ctx* C, int status) {
   return VILF_OK;
 }
 
+// createSubMap (EM:298-352) for lanes [lane0, lane0+nl): append the voxel-filtered scan features at the current pose,
+// crop + voxel-filter both maps into the other buffer, rebuild the search grids, flip the buffers.
+void enqueue_submap(Ctx* C, const Launch& L, int lane0, int nl, ProfSink* sink) {
+  const int cur = C->cur[lane0];
+  launch_map_append(L, C->lanes_dev, lane0, nl, cur, C->cfg);
+  launch_voxel(L, C->vox_map_dev[cur] + lane0 * 2, nl * 2, C->vox_map_sort_dev[cur] + lane0 * 2, true);
+  if (sink) sink->phase = 4;
+  launch_grid_build(L, C->grid_dev[cur ^ 1] + lane0 * 2, nl * 2, C->cfg);
+  for (int l = lane0; l < lane0 + nl; ++l) C->cur[l] = cur ^ 1;
+}
+
 // The per-frame launch sequence for lanes [lane0, lane0+nl), which all share `cur`, `first` and the scan slot.
 // with_extract = 0: features were uploaded by the caller (vilf_update_points / vilf_map_init_points).
 int enqueue_frame(Ctx* C, int lane0, int nl, bool first, bool with_extract, int sel, Slot* S) {
@@ -367,11 +378,7 @@ int enqueue_frame(Ctx* C, int lane0, int nl, bool first, bool with_extract, int 
       launch_solve(L, C->lanes_dev, lane0, nl, it, it == cfg.outer_iters - 1 ? 1 : 0, cfg, cfg.lm_max_iters);
     }
     phase(3);
-    launch_map_append(L, C->lanes_dev, lane0, nl, cur, cfg);
-    launch_voxel(L, C->vox_map_dev[cur] + lane0 * 2, nl * 2, C->vox_map_sort_dev[cur] + lane0 * 2, true);
-    phase(4);
-    launch_grid_build(L, C->grid_dev[cur ^ 1] + lane0 * 2, nl * 2, cfg);
-    for (int l = lane0; l < lane0 + nl; ++l) C->cur[l] = cur ^ 1;
+    enqueue_submap(C, L, lane0, nl, sink);
   }
   for (int l = lane0; l < lane0 + nl; ++l) {
     C->have_map[l] = 1; C->have_feat[l] = 1; C->last_init[l] = first ? 1 : 0; C->frame_no[l] += 1;
@@ -720,6 +727,59 @@ int vilf_update_points(vilf_handle* h, const float* edge, int n_edge, const floa
   if (rc) return rc;
   C->have_feat[h->lane] = 1;
   return update_impl(C, h->lane, pose_out);
+}
+
+int vilf_set_pose(vilf_handle* h, const double pose[7], int update_odom) {
+  HCHECK(h);
+  CK(cudaSetDevice(C->device));
+  if (!pose) return VILF_ERR_INVALID;
+  LaneVars V;
+  int rc = read_vars(C, h->lane, &V);
+  if (rc) return rc;
+  memcpy(V.x, pose, 7 * sizeof(double));
+  if (update_odom) {  // EM:291-293: globalOdom.linear() = q_w_c.toRotationMatrix(); translation = t_w_c (Eigen operation order)
+    const double* x = V.x;
+    const double tx = 2 * x[0], ty = 2 * x[1], tz = 2 * x[2];
+    const double twx = tx * x[3], twy = ty * x[3], twz = tz * x[3];
+    const double txx = tx * x[0], txy = ty * x[0], txz = tz * x[0];
+    const double tyy = ty * x[1], tyz = tz * x[1], tzz = tz * x[2];
+    double* o = V.odom;
+    o[0] = 1 - (tyy + tzz); o[1] = txy - twz; o[2] = txz + twy;
+    o[3] = txy + twz; o[4] = 1 - (txx + tzz); o[5] = tyz - twx;
+    o[6] = txz - twy; o[7] = tyz + twx; o[8] = 1 - (txx + tyy);
+    o[9] = x[4]; o[10] = x[5]; o[11] = x[6];
+  }
+  CK(cudaMemcpyAsync(C->vars_dev + h->lane, &V, sizeof(V), cudaMemcpyHostToDevice, C->st));
+  CK(cudaStreamSynchronize(C->st));
+  return VILF_OK;
+}
+
+int vilf_predict(vilf_handle* h, double pose_out[7]) {
+  HCHECK(h);
+  CK(cudaSetDevice(C->device));
+  launch_frame_reset(mk(C), C->lanes_dev, h->lane, 1, C->vv_dev, VV_PER_LANE, 1);
+  CK(cudaGetLastError());
+  return finish_sync(C, h->lane, pose_out);
+}
+
+int vilf_create_submap(vilf_handle* h, const float* edge_ds, int n_edge, const float* surf_ds, int n_surf) {
+  HCHECK(h);
+  CK(cudaSetDevice(C->device));
+  const int lane = h->lane;
+  if (n_edge < 0 || n_surf < 0 || (n_edge && !edge_ds) || (n_surf && !surf_ds)) return fail(C, VILF_ERR_INVALID, "bad feature clouds");
+  if (n_edge > C->cfg.cap_scan || n_surf > C->cfg.cap_scan) return fail(C, VILF_ERR_CAPACITY, "feature cloud exceeds max_scan_points");
+  LaneDev& L = C->lanes_host[lane];
+  if (n_edge) CK(cudaMemcpyAsync(L.ds[0], edge_ds, (size_t)n_edge * 16, cudaMemcpyHostToDevice, C->st));
+  if (n_surf) CK(cudaMemcpyAsync(L.ds[1], surf_ds, (size_t)n_surf * 16, cudaMemcpyHostToDevice, C->st));
+  int cnt[2] = {n_edge, n_surf};
+  CK(cudaMemcpyAsync(&L.v->n_ds[0], cnt, sizeof(cnt), cudaMemcpyHostToDevice, C->st));  // n_ds[0], n_ds[1] are adjacent
+  CK(cudaStreamSynchronize(C->st));
+  const Launch Ln = mk(C);
+  launch_frame_reset(Ln, C->lanes_dev, lane, 1, C->vv_dev, VV_PER_LANE, 0);  // bounding boxes / status of this map update
+  enqueue_submap(C, Ln, lane, 1, nullptr);
+  CK(cudaGetLastError());
+  C->have_map[lane] = 1; C->last_init[lane] = 0;
+  return finish_sync(C, lane, nullptr);
 }
 
 int vilf_get_pose(vilf_handle* h, double pose_out[7], double* rt12) {
