@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--cpu-frames", type=int, default=60, help="frames per core of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--map-cap", type=int, default=1 << 18, help="capacity of each local map (points); overflow is an error, not a truncation")
     return ap.parse_args()
 
 
@@ -204,7 +205,8 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
     dev_ring.copy_(torch.from_numpy(host_ring.view(np.int16)), non_blocking=False)
     torch.cuda.synchronize()
 
-    cfg = cabi.default_config(n_scan=w["n_scan"], n_rings=w["n_rings"], max_scan_points=max(cap, 1024))
+    cfg = cabi.default_config(n_scan=w["n_scan"], n_rings=w["n_rings"], max_scan_points=max(cap, 1024), max_map_points=args.map_cap,
+                              max_ring_points=seqs[0].sensor.n_az + 64)
 
     barrier = replicas.barrier
 

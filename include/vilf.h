@@ -57,8 +57,11 @@ typedef struct vilf_config {
   int32_t max_scan_points; /* capacity: points per scan */
   int32_t max_map_points;  /* capacity: points per local map (edge and surf each) */
   int32_t max_ring_points; /* capacity: returns per ring (sizes the selection kernel's shared memory); 0 = 12298, the kernel's limit */
-  int32_t reserved_;
+  int32_t flags;           /* VILF_FLAG_* bits; 0 by default */
 } vilf_config;
+
+/* Implementation-selection flags (results are bit-identical either way; used by the parity tests and for profiling). */
+#define VILF_FLAG_NO_CLUSTER 1 /* never take the one-cluster-per-cloud kernels; always the grid-wide multi-launch path */
 
 int vilf_default_config(vilf_config* cfg);
 
@@ -168,6 +171,9 @@ const char* vilf_profile_kernel_name(int kernel);
 int vilf_launch_count(vilf_handle* h, int64_t* launches);
 /* The CUDA stream all work of this handle is issued on (for external cudaEvent timing). */
 int vilf_get_stream(vilf_handle* h, void** cuda_stream);
+/* Cluster-path voxel filter of the last frame: %globaltimer (ns) at its phase boundaries (start, keys, heads, centroids,
+ * grid build, end). job: 0 scan edge, 1 scan surf, 2 map edge, 3 map surf. */
+int vilf_debug_voxel_phases(vilf_handle* h, int job, int64_t out8[8]);
 /* Counts on the device after the last frame: n_edge, n_surf, n_ds_edge, n_ds_surf, n_map_edge, n_map_surf, status bits, frames. */
 int vilf_get_counts(vilf_handle* h, int32_t out8[8]);
 

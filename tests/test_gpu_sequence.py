@@ -198,3 +198,33 @@ def test_map_capacity_overflow_is_reported(cabi, synth):
         g.process_scan(seq[1][0])
     assert e.value.code == 3
     g.close()
+
+
+def test_cluster_and_grid_wide_paths_are_bit_identical(cabi, synth):
+    """One-cluster-per-cloud kernels (k_cluster.cu) vs the grid-wide multi-launch path: same poses, maps and stage outputs, bit for bit."""
+    frames = 10
+    seq = synth.Sequence("hdl64", frames, seed=11)
+    kw = dict(max_scan_points=116000, max_map_points=1 << 18)
+    a = cabi.Odometry(cabi.default_config(**kw))
+    b = cabi.Odometry(cabi.default_config(flags=cabi.FLAG_NO_CLUSTER, **kw))
+    for i in range(frames):
+        x, _ = seq[i]
+        pa, pb = a.process_scan(x), b.process_scan(x)
+        assert np.array_equal(pa, pb), i
+        for which in (cabi.DS_EDGE, cabi.DS_SURF, cabi.MAP_EDGE, cabi.MAP_SURF, cabi.REGISTERED):
+            assert np.array_equal(a.cloud(which), b.cloud(which)), (i, which)
+    # stage-level entry points take the cluster path for small clouds as well
+    rng = np.random.default_rng(5)
+    pts = (rng.random((50000, 4), dtype=np.float32) - 0.5) * np.float32(60.0)
+    for leaf in (0.4, 0.8, 0.05):
+        va, ga = a.voxel_downsample(pts, leaf)
+        vb, gb = b.voxel_downsample(pts, leaf)
+        assert ga == gb and np.array_equal(va, vb)
+    ca = a.crop_voxel_downsample(pts, [1.0, -2.0, 0.5], 20.0, 0.4)
+    cb = b.crop_voxel_downsample(pts, [1.0, -2.0, 0.5], 20.0, 0.4)
+    assert np.array_equal(ca, cb)
+    q = pts[:2000]
+    ia, da = a.knn5(pts, q)
+    ib, db = b.knn5(pts, q)
+    assert np.array_equal(ia, ib) and np.array_equal(da, db)
+    a.close(); b.close()

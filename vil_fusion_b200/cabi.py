@@ -29,7 +29,7 @@ class Config(C.Structure):
         ("edge_leaf", C.c_double), ("surf_leaf", C.c_double), ("crop_half", C.c_double),
         ("knn_gate", C.c_double), ("huber", C.c_double),
         ("outer_iters", C.c_int32), ("lm_max_iters", C.c_int32),
-        ("max_scan_points", C.c_int32), ("max_map_points", C.c_int32), ("max_ring_points", C.c_int32), ("reserved_", C.c_int32),
+        ("max_scan_points", C.c_int32), ("max_map_points", C.c_int32), ("max_ring_points", C.c_int32), ("flags", C.c_int32),
     ]
 
 
@@ -40,7 +40,7 @@ SYMBOLS = [
     "vilf_feature_extract", "vilf_get_features", "vilf_map_init", "vilf_map_init_points", "vilf_update", "vilf_update_points",
     "vilf_get_pose", "vilf_set_pose", "vilf_predict", "vilf_create_submap", "vilf_get_cloud", "vilf_voxel_downsample", "vilf_crop_voxel_downsample", "vilf_crop_box", "vilf_knn5",
     "vilf_factors", "vilf_normal_equations", "vilf_solve", "vilf_get_solves", "vilf_state_export", "vilf_state_import",
-    "vilf_profile_enable", "vilf_profile_read", "vilf_profile_read_kernels", "vilf_profile_kernel_name", "vilf_launch_count", "vilf_get_stream", "vilf_get_counts",
+    "vilf_profile_enable", "vilf_profile_read", "vilf_profile_read_kernels", "vilf_profile_kernel_name", "vilf_launch_count", "vilf_get_stream", "vilf_get_counts", "vilf_debug_voxel_phases",
 ]
 
 _lib = None
@@ -80,6 +80,7 @@ def _p(a, t):
     return None if a is None else a.ctypes.data_as(C.POINTER(t))
 
 
+FLAG_NO_CLUSTER = 1
 MAP_EDGE, MAP_SURF, DS_EDGE, DS_SURF, REGISTERED, NO_REGISTERED = range(6)
 
 
@@ -292,6 +293,11 @@ class Odometry:
         p = C.c_void_p()
         self._ck(lib().vilf_get_stream(self._h, C.byref(p)))
         return p.value or 0
+
+    def voxel_phases(self, job: int):
+        t = np.zeros(8, np.int64)
+        self._ck(lib().vilf_debug_voxel_phases(self._h, job, _p(t, C.c_int64)))
+        return t
 
     def counts(self):
         c = np.zeros(8, np.int32)

@@ -1,0 +1,465 @@
+// One thread-block CLUSTER per cloud: the latency-optimised path for clouds of up to CLUSTER_MAX_POINTS points (every
+// per-frame cloud of an HDL-64 / 128-beam sequence).  The grid-wide kernels of k_voxel.cu / k_knn.cu need 1 + 7 + 5
+// dependent launches for map append + voxel filter + grid build, and at these sizes they are launch / tail / atomics
+// bound (profiles/r1b_frame_S16.txt: 377 us of a 1275 us frame).  Here the phases of one job run inside ONE kernel on 8
+// SMs, separated by cluster barriers instead of kernel boundaries, and the CTAs exchange digit histograms / head counts
+// / partial sums through distributed shared memory instead of global tables.  Independent jobs (edge + surf cloud of
+// every sequence of a batch) are separate clusters of the same launch (blockIdx.y), so a batch still fills the GPU.
+//
+//   k_voxel_cluster   [createSubMap append (EM:308-324)] -> pcl::CropBox + getMinMax3D -> PCL voxel keys -> P stable
+//                     radix passes (<= 9-bit digits) -> heads -> centroids (EM:248-251, :327-350)
+//                     [-> spatial-hash build of the filtered map for the 5-NN search (EM:256-257)].
+//                     Same key generator, same stable order and same centroid emitter as the grid-wide path, hence
+//                     bit-identical output.
+//   k_grid_cluster    the spatial-hash build alone (first frame, state import).
+#include "k_voxel.cuh"
+#include <cooperative_groups.h>
+
+namespace vilf {
+
+namespace cg = cooperative_groups;
+
+constexpr int CL = 8;              // CTAs per cluster (portable maximum)
+constexpr int CT = 512;            // threads per CTA (== SORT_RADIX: one thread per digit)
+constexpr int CW = CT / 32;        // warps per CTA
+
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define PHASE_MARK(k) do { if (rank == 0 && tid == 0) J.vv->t[k] = gtimer(); } while (0)
+
+struct VoxShared {
+  uint32_t wcnt[CW][SORT_RADIX];   // per-warp digit counters (histogram, then running scatter offsets)
+  uint32_t cta_hist[SORT_RADIX];   // this CTA's digit totals; read by the peers over DSMEM
+  uint32_t scan[CW];
+  float4 stage[CW][32];
+  float bb[8];                     // partial bounding box + count of this CTA
+  int heads;                       // heads in this CTA's chunk
+  int wsum[CW];
+  uint32_t part;                   // grid build: this CTA's bucket-count total
+};
+
+// Exclusive scan of one value per thread over the CTA (CT threads); every thread gets the CTA total.  Ends synchronised.
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* buf, uint32_t* total) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t inc = v;
+  for (int off = 1; off < 32; off <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, off); if (lane >= off) inc += t; }
+  __syncthreads();  // buf may still be read from a previous call
+  if (lane == 31) buf[warp] = inc;
+  __syncthreads();
+  uint32_t woff = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < CW; ++w) { const uint32_t c = buf[w]; if (w < warp) woff += c; tot += c; }
+  if (total) *total = tot;
+  return woff + inc - v;
+}
+
+__device__ __forceinline__ uint32_t cell_hash_c(int x, int y, int z) {
+  return ((uint32_t)x * 73856093u) ^ ((uint32_t)y * 19349663u) ^ ((uint32_t)z * 83492791u);
+}
+
+// Spatial-hash build (same table layout as k_knn.cu's grid-wide build) by the whole cluster.  `S` = this CTA's shared block.
+__device__ void grid_build_cluster(cg::cluster_group& cluster, const GridJob& G, int n, float inv_cell, VoxShared& S) {
+  const int rank = (int)cluster.block_rank();
+  const int tid = threadIdx.x;
+  int H = 1024;
+  while (H < 2 * n && H < G.hcap) H <<= 1;
+  const uint32_t hm = (uint32_t)H - 1u;
+  const int total = H + 1;
+  const int gtid = rank * CT + tid, gstride = CL * CT;
+  for (int i = gtid; i < total; i += gstride) G.start[i] = 0;
+  if (gtid == 0) *G.hvar = H;
+  cluster.sync();
+  for (int i = gtid; i < n; i += gstride) {
+    const float4 p = __ldcg(G.pts + i);
+    const int cx = (int)floorf(fmul(p.x, inv_cell)), cy = (int)floorf(fmul(p.y, inv_cell)), cz = (int)floorf(fmul(p.z, inv_cell));
+    G.rank[i] = atomicAdd(&G.start[cell_hash_c(cx, cy, cz) & hm], 1u);
+  }
+  cluster.sync();
+  // exclusive scan of the bucket counts: CTA `rank` owns one contiguous chunk
+  int chunk = (total + CL - 1) / CL;
+  chunk = (chunk + CT - 1) / CT * CT;
+  const int beg = min(total, rank * chunk), end = min(total, beg + chunk);
+  {
+    uint32_t s = 0;
+    for (int i = beg + tid; i < end; i += CT) s += __ldcg(G.start + i);
+    uint32_t tot = 0;
+    block_excl_scan(s, S.scan, &tot);
+    if (tid == 0) S.part = tot;
+  }
+  cluster.sync();
+  uint32_t run = 0;
+  for (int c = 0; c < rank; ++c) run += cluster.map_shared_rank(&S, c)->part;
+  for (int base = beg; base < end; base += CT) {
+    const int i = base + tid;
+    const uint32_t v = i < end ? __ldcg(G.start + i) : 0u;
+    uint32_t tot = 0;
+    const uint32_t ex = block_excl_scan(v, S.scan, &tot);
+    if (i < end) G.start[i] = run + ex;
+    run += tot;
+  }
+  cluster.sync();
+  for (int i = gtid; i < n; i += gstride) {
+    const float4 p = __ldcg(G.pts + i);
+    const int cx = (int)floorf(fmul(p.x, inv_cell)), cy = (int)floorf(fmul(p.y, inv_cell)), cz = (int)floorf(fmul(p.z, inv_cell));
+    const uint32_t pos = __ldcg(G.start + (cell_hash_c(cx, cy, cz) & hm)) + G.rank[i];
+    G.sorted[pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+  }
+}
+
+// Centroids of the voxels whose first sorted element ("head") lies in [beg, end), by ONE warp, 32 sorted positions per
+// step: coalesced (key, index) loads and the gathered points of the NEXT step are in flight while the current 32 points,
+// staged in shared memory, are summed — every run by the lane at its first element, sequentially in input order, i.e.
+// PCL's `centroid += point; ...; centroid /= count` in fp32 (same order as the grid-wide emitter => identical bits).  A run
+// that is still open at the end of a step is carried into the next one (also past `end`: it still belongs to this warp).
+// `dst0` = output index of the first run that starts in the range.  All loads are ld.global.ca (see k_voxel.cuh).
+__device__ void emit_range(const VoxJob& J, const uint32_t* key, const uint32_t* val, int nv, int guard, int beg, int end, int dst0, float4* stage) {
+  if (beg >= end) return;  // uniform over the warp
+  const int lane = threadIdx.x & 31;
+  const unsigned FULL = 0xffffffffu;
+  int dst = dst0;
+  bool open = false;  // carried run (all of this is uniform over the warp)
+  float4 cacc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int ccnt = 0, cdst = 0;
+  uint32_t prevk = beg > 0 ? __ldca(key + beg - 1) : 0u;
+  uint32_t k = 0;
+  float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+  bool valid = beg + lane < nv;
+  if (valid) { k = __ldca(key + beg + lane); p = __ldca(J.in + __ldca(val + beg + lane)); }
+  for (int base = beg;; base += 32) {
+    // next step's loads first
+    const int ni = base + 32 + lane;
+    const bool nvalid = ni < nv;
+    uint32_t nk = 0;
+    float4 np = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (nvalid) { nk = __ldca(key + ni); np = __ldca(J.in + __ldca(val + ni)); }
+    // heads of this step
+    uint32_t kl = __shfl_up_sync(FULL, k, 1);
+    if (lane == 0) kl = prevk;
+    const bool head = valid && (guard || base + lane == 0 || k != kl);
+    const unsigned hm = __ballot_sync(FULL, head);
+    const unsigned beyond = __ballot_sync(FULL, head && base + lane >= end);  // heads of the next warp's range
+    const int nval = __popc(__ballot_sync(FULL, valid));                      // valid lanes are a prefix
+    const int lim = min(beyond ? __ffs(beyond) - 1 : 32, nval);               // lanes [0, lim) are in play
+    const unsigned starts = lim >= 32 ? hm : (hm & ((1u << lim) - 1u));
+    const bool cont0 = open && lim > 0 && !(starts & 1u);                     // the carried run continues at lane 0
+    if (open && !cont0) {                                                     // ... or it ended with the previous step
+      if (lane == 0 && cdst < J.cap_out) {
+        const float fc = (float)ccnt;
+        J.out[cdst] = make_float4(__fdiv_rn(cacc.x, fc), __fdiv_rn(cacc.y, fc), __fdiv_rn(cacc.z, fc), __fdiv_rn(cacc.w, fc));
+      }
+      open = false;
+    }
+    stage[lane] = p;
+    __syncwarp();
+    const unsigned all_starts = starts | (cont0 ? 1u : 0u);
+    const bool is_start = lane < lim && ((all_starts >> lane) & 1u);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cnt = 0, e = 0, my_dst = 0;
+    if (is_start) {
+      const unsigned higher = lane == 31 ? 0u : (all_starts & ~((2u << lane) - 1u));
+      e = higher ? min(__ffs(higher) - 1, lim) : lim;  // exclusive end of my run inside this step
+      if (lane == 0 && cont0) { acc = cacc; cnt = ccnt; my_dst = cdst; }
+      else my_dst = dst + __popc(starts & ((1u << lane) - 1u));
+      for (int t = lane; t < e; ++t) {
+        const float4 q = stage[t];
+        acc.x = fadd(acc.x, q.x); acc.y = fadd(acc.y, q.y); acc.z = fadd(acc.z, q.z); acc.w = fadd(acc.w, q.w);
+        ++cnt;
+      }
+    }
+    // a run reaching the end of a FULL step may continue: carry it; every other run is complete
+    const bool carry = is_start && e == 32 && lim == 32;
+    if (is_start && !carry && my_dst < J.cap_out) {
+      const float fc = (float)cnt;
+      J.out[my_dst] = make_float4(__fdiv_rn(acc.x, fc), __fdiv_rn(acc.y, fc), __fdiv_rn(acc.z, fc), __fdiv_rn(acc.w, fc));
+    }
+    __syncwarp();  // stage is rewritten in the next step
+    dst += __popc(starts);
+    if (lim < 32) break;
+    const unsigned cm = __ballot_sync(FULL, carry);  // the last run of a full step, if this warp owns any run in it
+    if (cm == 0u) {                                  // nothing owned yet (the step continues a previous warp's run)
+      if (base + 32 >= end) break;                   // ... and no head of this range is left
+      prevk = __shfl_sync(FULL, k, 31);
+      k = nk; p = np; valid = nvalid;
+      continue;
+    }
+    const int cl = __ffs(cm) - 1;
+    cacc.x = __shfl_sync(FULL, acc.x, cl); cacc.y = __shfl_sync(FULL, acc.y, cl); cacc.z = __shfl_sync(FULL, acc.z, cl); cacc.w = __shfl_sync(FULL, acc.w, cl);
+    ccnt = __shfl_sync(FULL, cnt, cl);
+    cdst = __shfl_sync(FULL, my_dst, cl);
+    open = true;
+    prevk = __shfl_sync(FULL, k, 31);
+    k = nk; p = np; valid = nvalid;
+  }
+}
+
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CT, 2) k_voxel_cluster(const VoxJob* __restrict__ jobs, int bbox_done, float inv_cell) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const VoxJob& J = jobs[blockIdx.y];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ VoxShared S;
+
+  PHASE_MARK(0);
+  // ---- input size; map jobs first append the voxel-filtered scan features at the final pose (EM:308-324) ----
+  int n, m_old = 0;
+  if (J.app_src != nullptr) {
+    m_old = *J.app_n_map;
+    const int nd = *J.app_n;
+    n = min(J.app_cap, m_old + nd);
+    if (rank == 0 && tid == 0) {
+      *const_cast<int*>(J.n_in) = n;
+      if (m_old + nd > J.app_cap) atomicOr(J.status, ST_MAP_CAPACITY);
+    }
+  } else {
+    n = *J.n_in;
+  }
+
+  // ---- geometry: CTA `rank` owns one contiguous chunk, each of its warps one contiguous sub-chunk (stable order) ----
+  int cchunk = (n + CL - 1) / CL;
+  cchunk = (cchunk + CT - 1) / CT * CT;
+  const int wchunk = cchunk / CW;  // multiple of 32
+  const int cbeg = min(n, rank * cchunk);
+  const int cend = min(n, cbeg + cchunk);
+  const int wbeg = min(cend, cbeg + warp * wchunk);
+  const int wend = min(cend, wbeg + wchunk);
+
+  // ---- phase 0: [append] + bounding box of the points inside the crop box (getMinMax3D) ----
+  float mn[3], mx[3];
+  int n_valid;
+  if (bbox_done && J.app_src == nullptr) {
+    for (int a = 0; a < 3; ++a) { mn[a] = ord2f(J.vv->bbox[a]); mx[a] = ord2f(J.vv->bbox[3 + a]); }
+    n_valid = J.vv->n_valid;
+  } else {
+    float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+    if (J.crop) crop_bounds(J, lo, hi);
+    double x[7];
+    if (J.app_src != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 7; ++i) x[i] = J.app_pose[i];
+    }
+    for (int a = 0; a < 3; ++a) { mn[a] = FLT_MAX; mx[a] = -FLT_MAX; }
+    int cnt = 0;
+    float4* inw = const_cast<float4*>(J.in);
+    for (int i = cbeg + tid; i < cend; i += CT) {
+      float4 p;
+      if (i < m_old || J.app_src == nullptr) {
+        p = J.in[i];
+      } else {
+        p = associate(x, J.app_src[i - m_old]);  // EM:313-314, :321-322
+        inw[i] = p;
+      }
+      if (J.crop && outside(p, lo, hi)) continue;
+      ++cnt;
+      mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
+      mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
+      mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], off));
+        mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], off));
+      }
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+    }
+    float* sm = reinterpret_cast<float*>(&S.wcnt[0][0]);  // scratch, free until the first pass
+    if (lane == 0) {
+      for (int a = 0; a < 3; ++a) { sm[warp * 7 + a] = mn[a]; sm[warp * 7 + 3 + a] = mx[a]; }
+      sm[warp * 7 + 6] = __int_as_float(cnt);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int total = 0;
+      for (int w = 0; w < CW; ++w) {
+        for (int a = 0; a < 3; ++a) { mn[a] = fminf(mn[a], sm[w * 7 + a]); mx[a] = fmaxf(mx[a], sm[w * 7 + 3 + a]); }
+        total += __float_as_int(sm[w * 7 + 6]);
+      }
+      for (int a = 0; a < 3; ++a) { S.bb[a] = mn[a]; S.bb[3 + a] = mx[a]; }
+      S.bb[6] = __int_as_float(total);
+    }
+    cluster.sync();  // partial boxes visible; appended points visible to the whole cluster
+    n_valid = 0;
+    for (int a = 0; a < 3; ++a) { mn[a] = FLT_MAX; mx[a] = -FLT_MAX; }
+    for (int c = 0; c < CL; ++c) {
+      const float* rb = cluster.map_shared_rank(&S, c)->bb;
+      for (int a = 0; a < 3; ++a) { mn[a] = fminf(mn[a], rb[a]); mx[a] = fmaxf(mx[a], rb[3 + a]); }
+      n_valid += __float_as_int(rb[6]);
+    }
+    if (rank == 0 && tid == 0) {
+      for (int a = 0; a < 3; ++a) { J.vv->bbox[a] = f2ord(mn[a]); J.vv->bbox[3 + a] = f2ord(mx[a]); }
+      J.vv->n_valid = n_valid;
+    }
+    __syncthreads();  // S.wcnt scratch is reused below
+  }
+
+  PHASE_MARK(1);
+  // ---- phase 1: voxel keys + stable radix sort ----
+  KeyGenVoxel gen;
+  gen.jobs = jobs;
+  const int bits = gen.setup(J, mn, mx, n_valid, rank == 0 && tid == 0);
+  const int guard = gen.guard;
+  const int P = sort_passes(bits, J.sort.npass);
+  const int w = sort_width(bits, P);
+  const uint32_t mask = (1u << w) - 1u;
+  const int nd_used = 1 << w;  // digits in use (<= SORT_RADIX)
+  for (int pass = 0; pass < P; ++pass) {
+    const int shift = pass * w;
+    const uint32_t* __restrict__ kin = J.sort.key[pass & 1];
+    const uint32_t* __restrict__ vin = J.sort.val[pass & 1];
+    uint32_t* __restrict__ kout = J.sort.key[(pass + 1) & 1];
+    uint32_t* __restrict__ vout = J.sort.val[(pass + 1) & 1];
+    // sweep 1: warp-private digit histogram (pass 0 also materialises the keys); 4 x 32 keys in flight per warp
+    for (int i = tid; i < CW * SORT_RADIX; i += CT) (&S.wcnt[0][0])[i] = 0;
+    __syncthreads();
+    for (int base = wbeg; base < wend; base += 128) {
+      uint32_t k[4];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int i = base + it * 32 + lane;
+        k[it] = 0;
+        if (i < wend) {
+          if (pass == 0) { k[it] = gen.key(0, i); J.sort.key[0][i] = k[it]; }
+          else k[it] = __ldcg(kin + i);  // written by other CTAs in the previous pass: L2, and no L1 allocation (see k_voxel.cuh)
+        }
+      }
+#pragma unroll
+      for (int it = 0; it < 4; ++it)
+        if (base + it * 32 + lane < wend) atomicAdd(&S.wcnt[warp][(k[it] >> shift) & mask], 1u);
+    }
+    __syncthreads();
+    {
+      uint32_t s = 0;
+      if (tid < nd_used) {
+#pragma unroll
+        for (int ww = 0; ww < CW; ++ww) s += S.wcnt[ww][tid];
+      }
+      S.cta_hist[tid] = s;
+    }
+    cluster.sync();
+    // offsets of digit `tid`: exclusive scan over digits + same-digit counts of lower-rank CTAs and lower warps
+    {
+      uint32_t tot = 0, pre = 0;
+      if (tid < nd_used) {
+        for (int c = 0; c < CL; ++c) {
+          const uint32_t v = cluster.map_shared_rank(&S, c)->cta_hist[tid];
+          if (c < rank) pre += v;
+          tot += v;
+        }
+      }
+      uint32_t run = block_excl_scan(tot, S.scan, nullptr) + pre;
+      if (tid < nd_used) {
+#pragma unroll
+        for (int ww = 0; ww < CW; ++ww) {
+          const uint32_t c = S.wcnt[ww][tid];
+          S.wcnt[ww][tid] = run;
+          run += c;
+        }
+      }
+    }
+    __syncthreads();
+    // sweep 2: stable rank inside the warp's sub-chunk, 32 keys at a time in order (4 x 32 loaded ahead), and scatter
+    for (int base = wbeg; base < wend; base += 128) {
+      uint32_t k[4], v[4];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int i = base + it * 32 + lane;
+        k[it] = 0; v[it] = (uint32_t)i;
+        if (i < wend) {
+          k[it] = __ldcg(J.sort.key[pass & 1] + i);
+          if (pass != 0) v[it] = __ldcg(vin + i);
+        }
+      }
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const bool ok = base + it * 32 + lane < wend;
+        const uint32_t d = (k[it] >> shift) & mask;
+        const unsigned act = __ballot_sync(0xffffffffu, ok);
+        unsigned peers = 0, lower = 0;
+        uint32_t before = 0;
+        if (ok) {
+          peers = __match_any_sync(act, d);
+          lower = peers & ((1u << lane) - 1u);
+          before = S.wcnt[warp][d];
+        }
+        __syncwarp();
+        if (ok) {
+          if (lower == 0) S.wcnt[warp][d] = before + __popc(peers);
+          const uint32_t pos = before + __popc(lower);
+          kout[pos] = k[it];
+          vout[pos] = v[it];
+        }
+        __syncwarp();
+      }
+    }
+    cluster.sync();  // scattered pairs visible to the whole cluster; cta_hist may be overwritten
+  }
+
+  PHASE_MARK(2);
+  // ---- phase 2: heads (first point of every occupied voxel) and centroids, in ascending voxel order ----
+  const uint32_t* key = J.sort.key[P & 1];  // first L1-allocating reads of these buffers in this kernel: ld.global.ca is coherent here
+  const uint32_t* val = J.sort.val[P & 1];
+  const int nv = n_valid;  // cropped-out points carry the sentinel key and sit behind the valid ones
+  int hchunk = (nv + CL - 1) / CL;
+  hchunk = (hchunk + CT - 1) / CT * CT;
+  const int hwchunk = hchunk / CW;
+  const int hbeg = min(nv, rank * hchunk), hend = min(nv, hbeg + hchunk);
+  const int hwbeg = min(hend, hbeg + warp * hwchunk), hwend = min(hend, hwbeg + hwchunk);
+  {
+    int cnt = 0;
+    for (int i = hwbeg + lane; i < hwend; i += 32) cnt += (guard || i == 0 || __ldca(key + i) != __ldca(key + i - 1)) ? 1 : 0;
+    for (int off = 16; off > 0; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+    if (lane == 0) S.wsum[warp] = cnt;
+    __syncthreads();
+    if (tid == 0) {
+      int s = 0;
+      for (int ww = 0; ww < CW; ++ww) s += S.wsum[ww];
+      S.heads = s;
+    }
+  }
+  cluster.sync();
+  int run = 0, total_heads = 0;
+  for (int c = 0; c < CL; ++c) {
+    const int h = cluster.map_shared_rank(&S, c)->heads;
+    if (c < rank) run += h;
+    total_heads += h;
+  }
+  for (int ww = 0; ww < warp; ++ww) run += S.wsum[ww];
+  int n_out = total_heads;
+  if (n_out > J.cap_out) n_out = J.cap_out;
+  if (rank == 0 && tid == 0) {
+    if (total_heads > J.cap_out) atomicOr(J.status, ST_MAP_CAPACITY);
+    *J.n_out = n_out;
+  }
+  PHASE_MARK(3);
+  emit_range(J, key, val, nv, guard, hwbeg, hwend, run, S.stage[warp]);  // warps run independently
+
+  // ---- phase 3 (map jobs): spatial hash of the filtered map for the next frame's 5-NN search ----
+  if (J.grid != nullptr) {
+    cluster.sync();  // all centroids written
+    PHASE_MARK(4);
+    grid_build_cluster(cluster, *J.grid, n_out, inv_cell, S);
+  }
+  cluster.sync();  // no CTA may exit while a peer can still read its shared memory
+  PHASE_MARK(5);
+}
+
+void launch_voxel_cluster(const Launch& L, const VoxJob* jobs_dev, int njobs, bool bbox_done, const ConfigDev& cfg) {
+  dim3 g(CL, njobs);
+  k_voxel_cluster<<<g, CT, 0, L.st>>>(jobs_dev, bbox_done ? 1 : 0, cfg.inv_cell);
+  L.tick(K_VOX_CLUSTER);
+}
+
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CT, 2) k_grid_cluster(const GridJob* __restrict__ jobs, float inv_cell) {
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ VoxShared S;
+  const GridJob& G = jobs[blockIdx.y];
+  grid_build_cluster(cluster, G, *G.n, inv_cell, S);
+  cluster.sync();
+}
+
+void launch_grid_cluster(const Launch& L, const GridJob* jobs_dev, int njobs, const ConfigDev& cfg) {
+  dim3 g(CL, njobs);
+  k_grid_cluster<<<g, CT, 0, L.st>>>(jobs_dev, cfg.inv_cell);
+  L.tick(K_GRID_CLUSTER);
+}
+
+}  // namespace vilf

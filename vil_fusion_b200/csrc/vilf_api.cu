@@ -48,6 +48,7 @@ struct Ctx {
   VoxJob* vox_map_dev[2] = {nullptr, nullptr}; SortJob* vox_map_sort_dev[2] = {nullptr, nullptr};  // [cur][nlanes*2]
   GridJob* grid_dev[2] = {nullptr, nullptr};                                  // [buf][nlanes*2]
   // aux (stage-level entry points)
+  bool cluster_scan = false, cluster_map = false;  // one-cluster-per-cloud path (k_cluster.cu) for scan / map clouds
   int cap_aux = 0;
   float4* aux_in = nullptr; float4* aux_out = nullptr;
   int* aux_n = nullptr;      // [4] n_in, n_out, nq, spare
@@ -111,6 +112,12 @@ int fail(Ctx* C, int code, const char* msg) {
 }
 
 Launch mk(Ctx* C, ProfSink* sink = nullptr) { Launch L; L.st = C->st; L.counter = &C->launches; L.prof = sink; return L; }
+
+// Spatial-hash build of `njobs` maps: one cluster per map for clouds of up to CLUSTER_MAX_POINTS, grid-wide otherwise.
+void build_grids(Ctx* C, const Launch& L, const GridJob* jobs_dev, int njobs, bool small) {
+  if (small) launch_grid_cluster(L, jobs_dev, njobs, C->cfg);
+  else launch_grid_build(L, jobs_dev, njobs, C->cfg);
+}
 
 int pow2_ge(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
@@ -181,6 +188,10 @@ int build_ctx(Ctx* C) {
   CK(dalloc(C, &C->trace_dev, (size_t)NL * MAX_OUTER));
   CK(dalloc(C, &C->vv_dev, (size_t)NL * VV_PER_LANE + 1));
   CK(dalloc(C, &C->lanes_dev, (size_t)NL));
+  for (int b = 0; b < 2; ++b) CK(dalloc(C, &C->grid_dev[b], (size_t)NL * 2));
+  const bool allow_cluster = !(u.flags & VILF_FLAG_NO_CLUSTER);
+  C->cluster_scan = allow_cluster && capS <= CLUSTER_MAX_POINTS;
+  C->cluster_map = allow_cluster && capM <= CLUSTER_MAX_POINTS;
   C->lanes_host.resize(NL);
   std::vector<SortJob> ring_jobs[2] = {std::vector<SortJob>(NL), std::vector<SortJob>(NL)};
   std::vector<VoxJob> vox_scan(NL * 2), vox_map[2] = {std::vector<VoxJob>(NL * 2), std::vector<VoxJob>(NL * 2)};
@@ -246,6 +257,10 @@ int build_ctx(Ctx* C) {
         J.crop = 1; J.passthrough = 0; J.crop_center = &L.v->x[4]; J.crop_half = c.crop_half;
         J.out = L.map[w][b ^ 1]; J.n_out = &L.v->n_map[w]; J.cap_out = c.cap_map; J.status = &L.v->status;
         J.vv = vv; J.head_cnt = head_cnt; J.sort = srt;
+        if (C->cluster_map) {  // append + filter + grid build in one cluster kernel (k_cluster.cu)
+          J.app_src = L.ds[w]; J.app_n = &L.v->n_ds[w]; J.app_n_map = &L.v->n_map[w]; J.app_pose = L.v->x; J.app_cap = capM;
+          J.grid = C->grid_dev[b ^ 1] + l * 2 + w;
+        }
       }
       vox_map_sort[l * 2 + w] = srt;
     }
@@ -279,7 +294,6 @@ int build_ctx(Ctx* C) {
     CK(cudaMemcpy(C->vox_map_dev[b], vox_map[b].data(), sizeof(VoxJob) * NL * 2, cudaMemcpyHostToDevice));
     CK(dalloc(C, &C->vox_map_sort_dev[b], (size_t)NL * 2));
     CK(cudaMemcpy(C->vox_map_sort_dev[b], vox_map_sort.data(), sizeof(SortJob) * NL * 2, cudaMemcpyHostToDevice));
-    CK(dalloc(C, &C->grid_dev[b], (size_t)NL * 2));
     CK(cudaMemcpy(C->grid_dev[b], grid[b].data(), sizeof(GridJob) * NL * 2, cudaMemcpyHostToDevice));
   }
   // aux
@@ -340,10 +354,14 @@ int status_to_rc(Ctx* C, int status) {
 // crop + voxel-filter both maps into the other buffer, rebuild the search grids, flip the buffers.
 void enqueue_submap(Ctx* C, const Launch& L, int lane0, int nl, ProfSink* sink) {
   const int cur = C->cur[lane0];
-  launch_map_append(L, C->lanes_dev, lane0, nl, cur, C->cfg);
-  launch_voxel(L, C->vox_map_dev[cur] + lane0 * 2, nl * 2, C->vox_map_sort_dev[cur] + lane0 * 2, true);
-  if (sink) sink->phase = 4;
-  launch_grid_build(L, C->grid_dev[cur ^ 1] + lane0 * 2, nl * 2, C->cfg);
+  if (C->cluster_map) {
+    launch_voxel_cluster(L, C->vox_map_dev[cur] + lane0 * 2, nl * 2, false, C->cfg);
+  } else {
+    launch_map_append(L, C->lanes_dev, lane0, nl, cur, C->cfg);
+    launch_voxel(L, C->vox_map_dev[cur] + lane0 * 2, nl * 2, C->vox_map_sort_dev[cur] + lane0 * 2, true);
+    if (sink) sink->phase = 4;
+    launch_grid_build(L, C->grid_dev[cur ^ 1] + lane0 * 2, nl * 2, C->cfg);
+  }
   for (int l = lane0; l < lane0 + nl; ++l) C->cur[l] = cur ^ 1;
 }
 
@@ -368,10 +386,11 @@ int enqueue_frame(Ctx* C, int lane0, int nl, bool first, bool with_extract, int 
     phase(3);
     launch_map_init(L, C->lanes_dev, lane0, nl, cur, cfg);
     phase(4);
-    launch_grid_build(L, C->grid_dev[cur] + lane0 * 2, nl * 2, cfg);
+    build_grids(C, L, C->grid_dev[cur] + lane0 * 2, nl * 2, C->cluster_map);
   } else {
     phase(1);
-    launch_voxel(L, C->vox_scan_dev + lane0 * 2, nl * 2, C->vox_scan_sort_dev + lane0 * 2, with_extract);
+    if (C->cluster_scan) launch_voxel_cluster(L, C->vox_scan_dev + lane0 * 2, nl * 2, with_extract, cfg);
+    else launch_voxel(L, C->vox_scan_dev + lane0 * 2, nl * 2, C->vox_scan_sort_dev + lane0 * 2, with_extract);
     phase(2);
     for (int it = 0; it < cfg.outer_iters; ++it) {
       launch_knn_fit(L, C->lanes_dev, C->grid_dev[cur], lane0, nl, cur, cfg, nullptr, 0);
@@ -508,7 +527,8 @@ int run_aux_voxel(Ctx* C, const float* pts, int n, float leaf, int crop, const d
   vv.bbox[3] = vv.bbox[4] = vv.bbox[5] = INT_MIN;
   CK(cudaMemcpyAsync(J.vv, &vv, sizeof(vv), cudaMemcpyHostToDevice, C->st));
   CK(cudaStreamSynchronize(C->st));  // the staged host structs above live on this stack frame
-  launch_voxel(mk(C), C->aux_vox_dev, 1, C->aux_sort_dev, false);
+  if (!(C->ucfg.flags & VILF_FLAG_NO_CLUSTER) && n <= CLUSTER_MAX_POINTS) launch_voxel_cluster(mk(C), C->aux_vox_dev, 1, false, C->cfg);
+  else launch_voxel(mk(C), C->aux_vox_dev, 1, C->aux_sort_dev, false);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(hdr, C->aux_n, sizeof(hdr), cudaMemcpyDeviceToHost, C->st));
   CK(cudaMemcpyAsync(&vv, J.vv, sizeof(vv), cudaMemcpyDeviceToHost, C->st));
@@ -567,7 +587,7 @@ int vilf_default_config(vilf_config* c) {
   c->lidar_min = 3.0; c->lidar_max = 90.0; c->edge_threshold = 0.1;
   c->edge_leaf = 0.4; c->surf_leaf = 0.8; c->crop_half = 100.0; c->knn_gate = 1.0; c->huber = 0.1;
   c->outer_iters = 2; c->lm_max_iters = 4;
-  c->max_scan_points = 300000; c->max_map_points = 1 << 20; c->max_ring_points = 0;
+  c->max_scan_points = 300000; c->max_map_points = 1 << 20; c->max_ring_points = 0; c->flags = 0;
   return VILF_OK;
 }
 
@@ -688,7 +708,7 @@ int vilf_get_features(vilf_handle* h, int which, float* pts, int32_t* src, int c
 static int map_init_impl(Ctx* C, int lane) {
   const Launch L = mk(C);
   launch_map_init(L, C->lanes_dev, lane, 1, C->cur[lane], C->cfg);
-  launch_grid_build(L, C->grid_dev[C->cur[lane]] + lane * 2, 2, C->cfg);
+  build_grids(C, L, C->grid_dev[C->cur[lane]] + lane * 2, 2, C->cluster_map);
   CK(cudaGetLastError());
   C->have_map[lane] = 1; C->last_init[lane] = 1;
   return finish_sync(C, lane, nullptr);
@@ -848,7 +868,7 @@ int vilf_knn5(vilf_handle* h, const float* map, int m, const float* q, int nq, i
   CK(cudaMemcpyAsync(C->aux_n, hdr, sizeof(hdr), cudaMemcpyHostToDevice, C->st));
   CK(cudaStreamSynchronize(C->st));
   const Launch L = mk(C);
-  launch_grid_build(L, C->aux_grid_dev, 1, C->cfg);
+  build_grids(C, L, C->aux_grid_dev, 1, !(C->ucfg.flags & VILF_FLAG_NO_CLUSTER) && m <= CLUSTER_MAX_POINTS);
   launch_knn_only(L, C->aux_grid_dev, C->aux_out, C->aux_n + 2, C->aux_idx, C->aux_d2, C->cfg);
   CK(cudaGetLastError());
   if (nq) {
@@ -987,7 +1007,7 @@ int vilf_state_import(vilf_handle* h, const double s[31], const float* map_edge,
   CK(cudaMemcpyAsync(C->vars_dev + lane, &V, sizeof(V), cudaMemcpyHostToDevice, C->st));
   if (n_edge) CK(cudaMemcpyAsync(L.map[0][cur], map_edge, (size_t)n_edge * 16, cudaMemcpyHostToDevice, C->st));
   if (n_surf) CK(cudaMemcpyAsync(L.map[1][cur], map_surf, (size_t)n_surf * 16, cudaMemcpyHostToDevice, C->st));
-  launch_grid_build(mk(C), C->grid_dev[cur] + lane * 2, 2, C->cfg);
+  build_grids(C, mk(C), C->grid_dev[cur] + lane * 2, 2, C->cluster_map);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(C->st));
   C->have_map[lane] = 1;
@@ -1031,7 +1051,7 @@ const char* vilf_profile_kernel_name(int kernel) {
   static const char* names[K_COUNT] = {"k_frame_reset", "k_sort_keyhist<KeyGenRing>", "k_sort_hist", "k_sort_scatter", "k_sector_select", "k_compact_features",
                                        "k_vox_bbox", "k_sort_keyhist<KeyGenVoxel>", "k_vox_heads", "k_vox_centroid", "k_map_append", "k_map_init",
                                        "k_grid_zero", "k_grid_count", "k_grid_scan_partial", "k_grid_scan_final", "k_grid_scatter", "k_knn_assoc",
-                                       "k_knn_only", "k_solve", "k_fit"};
+                                       "k_knn_only", "k_solve", "k_fit", "k_voxel_cluster", "k_grid_cluster"};
   return (kernel >= 0 && kernel < K_COUNT) ? names[kernel] : "";
 }
 int vilf_launch_count(vilf_handle* h, int64_t* launches) {
@@ -1044,6 +1064,16 @@ int vilf_get_stream(vilf_handle* h, void** cuda_stream) {
   HCHECK(h);
   if (!cuda_stream) return VILF_ERR_INVALID;
   *cuda_stream = (void*)C->st;
+  return VILF_OK;
+}
+int vilf_debug_voxel_phases(vilf_handle* h, int job, int64_t out8[8]) {
+  HCHECK(h);
+  CK(cudaSetDevice(C->device));
+  if (job < 0 || job >= VV_PER_LANE || !out8) return VILF_ERR_INVALID;
+  VoxVars vv;
+  CK(cudaStreamSynchronize(C->st));
+  CK(cudaMemcpy(&vv, C->vv_dev + (size_t)h->lane * VV_PER_LANE + job, sizeof(vv), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 8; ++i) out8[i] = (int64_t)vv.t[i];
   return VILF_OK;
 }
 int vilf_get_counts(vilf_handle* h, int32_t out8[8]) {

@@ -90,6 +90,8 @@ struct VoxVars {
   int bits;       // significant bits of (voxel index | sentinel)
   int guard;      // PCL "leaf size too small" guard fired: output = input
   int total;      // dx*dy*dz (sentinel key of cropped-out points)
+  int pad_;
+  unsigned long long t[8];  // cluster path: %globaltimer at the phase boundaries (ns), written by the leader thread
 };
 
 struct VoxJob {
@@ -108,6 +110,14 @@ struct VoxJob {
   VoxVars* vv;
   int* head_cnt;            // [VOX_G]
   SortJob sort;
+  // cluster path only (k_cluster.cu).  Map jobs: createSubMap's append (EM:308-324) runs inside the voxel kernel:
+  // in[app_n_map .. ) <- associate(app_pose, app_src[0 .. *app_n)), n_in <- min(app_cap, *app_n_map + *app_n).
+  const float4* app_src;
+  const int* app_n;
+  const int* app_n_map;
+  const double* app_pose;
+  int app_cap;
+  const struct GridJob* grid;  // spatial hash to build over `out` after the filter (map jobs) or null
 };
 
 struct GridJob {
@@ -223,7 +233,7 @@ __device__ __forceinline__ float4 associate(const double* x, float4 p) {
 enum KernelId {
   K_RESET = 0, K_RING_KEYHIST, K_SORT_HIST, K_SORT_SCATTER, K_SECTOR, K_COMPACT, K_VOX_BBOX, K_VOX_KEYHIST, K_VOX_HEADS, K_VOX_CENTROID,
   K_MAP_APPEND, K_MAP_INIT, K_GRID_ZERO, K_GRID_COUNT, K_GRID_SCAN_PARTIAL, K_GRID_SCAN_FINAL, K_GRID_SCATTER, K_KNN_FIT, K_KNN_ONLY,
-  K_SOLVE, K_FIT, K_COUNT
+  K_SOLVE, K_FIT, K_VOX_CLUSTER, K_GRID_CLUSTER, K_COUNT
 };
 constexpr int PROF_PHASES = 5;      // 0 extract, 1 scan downsample, 2 association + solve, 3 map update, 4 grid build
 constexpr int PROF_TAGS = PROF_PHASES * 32;
@@ -257,6 +267,10 @@ void launch_extract(const Launch& L, LaneDev* lanes, const SortJob* ring_jobs, i
 void launch_voxel(const Launch& L, const VoxJob* jobs_dev, int njobs, const SortJob* sort_jobs_dev, bool bbox_done);
 void launch_map_append(const Launch& L, LaneDev* lanes, int lane0, int nlanes, int cur, const ConfigDev& cfg);
 void launch_map_init(const Launch& L, LaneDev* lanes, int lane0, int nlanes, int cur, const ConfigDev& cfg);
+// k_cluster.cu
+constexpr int CLUSTER_MAX_POINTS = 1 << 19;  // clouds up to this size take the one-cluster-per-cloud path
+void launch_voxel_cluster(const Launch& L, const VoxJob* jobs_dev, int njobs, bool bbox_done, const ConfigDev& cfg);
+void launch_grid_cluster(const Launch& L, const GridJob* jobs_dev, int njobs, const ConfigDev& cfg);
 // k_knn.cu
 void launch_grid_build(const Launch& L, const GridJob* jobs_dev, int njobs, const ConfigDev& cfg);
 void launch_knn_fit(const Launch& L, LaneDev* lanes, const GridJob* grid_jobs, int lane0, int nlanes, int cur, const ConfigDev& cfg,
