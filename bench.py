@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--workload", default="hdl64", choices=sorted(WORKLOADS))
     ap.add_argument("--seqs", type=int, default=8, help="independent sequences per GPU, stepped in lock-step")
     ap.add_argument("--depth", type=int, default=3, help="frames in flight (submit ahead of wait)")
+    ap.add_argument("--groups", type=int, default=1, help="split the sequences of a GPU into this many lock-step batches, each on its own CUDA stream")
     ap.add_argument("--cpu-frames", type=int, default=60, help="frames per core of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-roofline", action="store_true")
@@ -210,62 +211,81 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
 
     barrier = replicas.barrier
 
+    G = max(1, min(args.groups, S))
+    bounds = [round(g * S / G) for g in range(G + 1)]  # group g owns sequences [bounds[g], bounds[g+1])
+
     def run_pass(mode: str, profile: bool = False):
-        """One full pass (W warm-up + K timed steps) on fresh sequences. mode: 'dev' | 'host'. Returns (ms, launches, batch)."""
-        b = cabi.Batch(cfg, S, device=local_rank)
-        stream = torch.cuda.ExternalStream(b.seqs[0].stream())
+        """One full pass (W warm-up + K timed steps) on fresh sequences. mode: 'dev' | 'host'. Returns (ms, wall_ms, launches, batches, poses).
+        profile=True runs group 0 alone (one stream) with an event after every kernel, so kernel durations are not mixed with other streams' work."""
+        ng = 1 if profile else G
+        bs = [cabi.Batch(cfg, bounds[g + 1] - bounds[g], device=local_rank) for g in range(ng)]
+        stream = torch.cuda.ExternalStream(bs[0].seqs[0].stream())
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         tickets = []
 
         def submit(f):
-            if mode == "dev":
-                ptrs = [dev[s, f].data_ptr() for s in range(S)]
-                rp = [dev_ring[s, f].data_ptr() for s in range(S)] if use_ring else None
-                return b.submit_dev(ptrs, [int(counts[s, f]) for s in range(S)], rp)
-            return b.submit([host[s, f, : counts[s, f]] for s in range(S)], [host_ring[s, f, : counts[s, f]] for s in range(S)] if use_ring else None)
+            ts = []
+            for g, b in enumerate(bs):
+                rng = range(bounds[g], bounds[g + 1])
+                if mode == "dev":
+                    ptrs = [dev[s, f].data_ptr() for s in rng]
+                    rp = [dev_ring[s, f].data_ptr() for s in rng] if use_ring else None
+                    ts.append(b.submit_dev(ptrs, [int(counts[s, f]) for s in rng], rp))
+                else:
+                    ts.append(b.submit([host[s, f, : counts[s, f]] for s in rng], [host_ring[s, f, : counts[s, f]] for s in rng] if use_ring else None))
+            return ts
+
+        def wait(ts):
+            return np.concatenate([b.wait(t) for b, t in zip(bs, ts)], axis=0)
 
         poses = None
         for f in range(W):
-            poses = b.wait(submit(f))
+            poses = wait(submit(f))
         if profile:
-            b.seqs[0].profile(True)
+            bs[0].seqs[0].profile(True)
+        torch.cuda.synchronize()
         barrier()
-        l0 = b.seqs[0].launch_count()
+        l0 = sum(b.seqs[0].launch_count() for b in bs)
         ev0.record(stream)
         t0 = time.perf_counter()
         for f in range(W, F):
             tickets.append(submit(f))
             if len(tickets) >= D:
-                poses = b.wait(tickets.pop(0))
+                poses = wait(tickets.pop(0))
         while tickets:
-            poses = b.wait(tickets.pop(0))
-        ev1.record(stream)
+            poses = wait(tickets.pop(0))
+        ev1.record(stream)  # every ticket of every group has been waited for: this closes the device interval of the whole pass
+        torch.cuda.synchronize()
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3
         ms = ev0.elapsed_time(ev1)
-        launches = b.seqs[0].launch_count() - l0
-        return ms, wall_ms, launches, b, poses
+        launches = sum(b.seqs[0].launch_count() for b in bs) - l0
+        return ms, wall_ms, launches, bs, poses
+
+    def close_all(bs):
+        for b in bs:
+            b.close()
 
     clocks = Clocks(local_rank)
     clocks.start()
     ms_dev, wall_dev, launches, b_dev, poses_dev = run_pass("dev")
     clk = clocks.stop()
-    cnt = [b_dev.seqs[s].counts() for s in range(S)]
-    b_dev.close()
+    cnt = [sq.counts() for b in b_dev for sq in b.seqs]
+    close_all(b_dev)
     ms_host, wall_host, _, b_host, poses_host = run_pass("host")
-    b_host.close()
+    close_all(b_host)
     same = bool(np.array_equal(poses_dev, poses_host))
 
     roof = None
     kern_table = None
     if not args.no_roofline:
         ms_p, _, _, b_p, _ = run_pass("dev", profile=True)
-        kt = b_p.seqs[0].profile_kernels()
-        stage, frames = b_p.seqs[0].profile_read(reset=False)
-        b_p.close()
+        kt = b_p[0].seqs[0].profile_kernels()
+        stage, frames = b_p[0].seqs[0].profile_read(reset=False)
+        close_all(b_p)
         mean_counts = dict(
             n_scan=float(counts[:, W:].mean()), n_edge=float(np.mean([c["n_edge"] for c in cnt])), n_surf=float(np.mean([c["n_surf"] for c in cnt])),
-            n_ds=float(np.mean([c["n_ds_edge"] + c["n_ds_surf"] for c in cnt])), n_map=float(np.mean([c["n_map_edge"] + c["n_map_surf"] for c in cnt])), seqs=S)
+            n_ds=float(np.mean([c["n_ds_edge"] + c["n_ds_surf"] for c in cnt])), n_map=float(np.mean([c["n_map_edge"] + c["n_map_surf"] for c in cnt])), seqs=bounds[1] - bounds[0])
         tot = sum(v[0] for v in kt.values()) or 1.0
         kern_table = sorted(([f"{p}/{k}", v[0], v[1]] for (p, k), v in kt.items()), key=lambda r: -r[1])
         (dp, dk), (dms, dn) = max(kt.items(), key=lambda kv: kv[1][0])
@@ -292,7 +312,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32 geometry / f64 solve", data="synthetic",
         config=dict(workload=w["desc"], sequences_per_gpu=S, scans_per_step=S * world, points_per_scan=int(counts[:, W:].mean()),
                     frames_in_flight=D, l2="inputs of one step are distinct frames (S x 1.8 MB) and all K steps use fresh scans; no cache flush needed",
-                    parallelism=f"{world} replica(s) x {S} lock-step sequences, no collective"),
+                    parallelism=f"{world} replica(s) x {S} independent sequences in {G} lock-step batch(es) on {G} stream(s), no collective"),
         e2e=dict(value=scans / (ms_host_max * 1e-3), unit="scans/s", h2d_bytes_per_step=int(counts[:, W:].mean() * 16 * S), d2h_bytes_per_step=int(S * 7 * 8),
                  ms_per_step=ms_host_max / K, poses_equal_to_device_resident_run=same),
         gpu_launches=int(launches), clocks=clk,

@@ -145,10 +145,12 @@ struct KeyGenRing {
 // ------------------------------------------------------------------------------------------------
 // per-(ring, sector) selection
 // ------------------------------------------------------------------------------------------------
-// dynamic shared memory of the selection kernel for sectors of up to ms elements (ms + 10 staged points)
+// dynamic shared memory of the selection kernel for sectors of up to ms elements (ms + 10 staged points; the sort
+// network runs over np = the power of two >= ms)
+static inline int sector_pow2(int ms) { int p = 64; while (p < ms) p <<= 1; return p; }
 static inline size_t sector_smem(int ms) {
-  const size_t pts = (size_t)ms + 10;
-  return sizeof(float4) * pts + sizeof(double) * ms + sizeof(uint32_t) * pts + sizeof(uint16_t) * ms + (pts + 15) / 16 * 16 + 16;
+  const size_t pts = (size_t)ms + 10, np = (size_t)sector_pow2(ms);
+  return sizeof(float4) * pts + sizeof(unsigned long long) * ms + sizeof(uint32_t) * pts + sizeof(uint16_t) * np + (pts + 15) / 16 * 16 + 16;
 }
 
 __device__ __forceinline__ bool sector_range(int n_r, int s, int& start, int& m) {
@@ -182,10 +184,10 @@ __global__ void __launch_bounds__(256) k_sector_select(LaneDev* lanes, int lane0
   }
   extern __shared__ __align__(16) unsigned char smem[];
   float4* pts = reinterpret_cast<float4*>(smem);                              // ring points start .. start+m+9
-  double* val = reinterpret_cast<double*>(smem + sizeof(float4) * (MS + 10)); // curvature of element e
+  unsigned long long* val = reinterpret_cast<unsigned long long*>(smem + sizeof(float4) * (MS + 10));  // curvature bits of element e
   uint32_t* srcs = reinterpret_cast<uint32_t*>(val + MS);                     // scan index of each staged point
-  uint16_t* sorted = reinterpret_cast<uint16_t*>(srcs + MS + 10);             // elements in ascending (curvature, index)
-  uint8_t* picked = reinterpret_cast<uint8_t*>(sorted + MS);                  // cloudNeighborPicked as flags
+  uint16_t* sorted = reinterpret_cast<uint16_t*>(srcs + MS + 10);             // elements in ascending (curvature, index); NP entries
+  uint8_t* picked = reinterpret_cast<uint8_t*>(sorted + cfg.sector_np);       // cloudNeighborPicked as flags
 
   const uint32_t* perm = L.ring_sort.val[1];  // scan indices in (ring, arrival) order after the single pass
   for (int k = tid; k < m + 10; k += 256) {
@@ -196,6 +198,7 @@ __global__ void __launch_bounds__(256) k_sector_select(LaneDev* lanes, int lane0
   }
   __syncthreads();
   // FE:190-200: fp32 left-to-right 11-tap sums, squared in fp64.  Element e <-> ring index 5+start+e <-> pts[e+5].
+  // The curvature is a non-negative double, so its bit pattern orders like the value: kept as a 64-bit integer key.
   for (int e = tid; e < m; e += 256) {
     const float4* p = pts + e + 5;
     float fx = fadd(fadd(fadd(fadd(p[-5].x, p[-4].x), p[-3].x), p[-2].x), p[-1].x);
@@ -208,20 +211,31 @@ __global__ void __launch_bounds__(256) k_sector_select(LaneDev* lanes, int lane0
     fz = fsub(fz, fmul(10.0f, p[0].z));
     fz = fadd(fadd(fadd(fadd(fadd(fz, p[1].z), p[2].z), p[3].z), p[4].z), p[5].z);
     const double dx = fx, dy = fy, dz = fz;
-    val[e] = dadd(dadd(dmul(dx, dx), dmul(dy, dy)), dmul(dz, dz));
+    const double c = dadd(dadd(dmul(dx, dx), dmul(dy, dy)), dmul(dz, dz));
+    val[e] = (unsigned long long)__double_as_longlong(c == 0.0 ? 0.0 : c);  // -0.0 cannot occur (sum of squares); NaN-free input
   }
+  // std::sort ascending by curvature (FE:115); equal curvatures ordered by index (tie class T1 made canonical): a bitonic
+  // network over the element INDICES (keys stay in place), NP = power of two >= m, padding entries sort to the end.
+  // O(NP log^2 NP) compare-exchanges instead of the m^2 comparisons of a rank sort (profiles/r1b: 23 k warp instructions
+  // per sector); steps with partner distance <= 32 stay inside one warp's 64-element block and need only __syncwarp.
+  int NP = 64;
+  while (NP < m) NP <<= 1;
+  for (int e = tid; e < NP; e += 256) sorted[e] = e < m ? (uint16_t)e : (uint16_t)0xffffu;
   __syncthreads();
-  // std::sort ascending by curvature (FE:115); equal curvatures ordered by index (tie class T1 made canonical).
-  for (int e = tid; e < m; e += 256) {
-    const double v = val[e];
-    int rank = 0;
-    for (int k = 0; k < m; ++k) {
-      const double vk = val[k];
-      rank += (vk < v || (vk == v && k < e)) ? 1 : 0;
+  for (int k = 2; k <= NP; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = tid; t < (NP >> 1); t += 256) {
+        const int i = 2 * t - (t & (j - 1));
+        const int l = i + j;
+        const uint32_t ea = sorted[i], eb = sorted[l];
+        const unsigned long long ka = ea == 0xffffu ? ~0ull : val[ea], kb = eb == 0xffffu ? ~0ull : val[eb];
+        const bool gt = ka > kb || (ka == kb && ea > eb);
+        if (gt == ((i & k) == 0)) { sorted[i] = (uint16_t)eb; sorted[l] = (uint16_t)ea; }
+      }
+      if (j > 32) __syncthreads(); else __syncwarp();
     }
-    sorted[rank] = (uint16_t)e;
+    __syncthreads();
   }
-  __syncthreads();
 
   int n_edge = 0;
   if (warp == 0) {  // FE:120-163, serial in pick order, 32 candidates examined per step
@@ -236,7 +250,7 @@ __global__ void __launch_bounds__(256) k_sector_select(LaneDev* lanes, int lane0
       if (msk == 0) { i -= 32; continue; }
       const int l = __ffs(msk) - 1;
       const int esel = __shfl_sync(0xffffffffu, e, l);
-      if (val[esel] <= cfg.edge_threshold) break;  // FE:125
+      if (__longlong_as_double((long long)val[esel]) <= cfg.edge_threshold) break;  // FE:125
       ++cnt;                                        // FE:128
       const int li = esel + 5;
       if (lane == 0) picked[li] = 1;                // FE:129
@@ -290,49 +304,248 @@ __global__ void __launch_bounds__(256) k_sector_select(LaneDev* lanes, int lane0
   if (tid == 0) L.sec_cnt[blockIdx.x] = make_int2(n_edge, run);
 }
 
-__global__ void __launch_bounds__(256) k_compact_features(LaneDev* lanes, int lane0, ConfigDev cfg) {
+// ------------------------------------------------------------------------------------------------
+// warp-per-sector selection (sectors of up to 32 * EPL elements): no CTA barrier anywhere
+// ------------------------------------------------------------------------------------------------
+// The sort keys live in REGISTERS: lane l holds the EPL consecutive network positions l*EPL .. l*EPL+EPL-1 as
+// (curvature bits hi, lo, element index).  Bitonic steps with partner distance < EPL are register compare-exchanges,
+// larger distances are warp shuffles; ~5 k warp instructions per sector against ~17 k for the shared-memory network
+// and ~23 k for the rank sort (profiles/r1d).  The greedy pick and the surf compaction are warp-serial as before.
+constexpr int SEC_WPC = 4;  // sectors (warps) per CTA
+__host__ __device__ constexpr size_t sec_warp_bytes(int ms, int np) {  // shared memory of one warp: sectors of <= ms elements, network of np
+  return ((sizeof(float4) * (ms + 10) + sizeof(double) * ms + sizeof(uint32_t) * (ms + 10) + sizeof(uint16_t) * np + (ms + 16)) + 15) / 16 * 16;
+}
+
+struct SortReg { unsigned long long k; uint32_t id; };
+// (curvature, index) lexicographic, branch-free: bitwise predicate logic + selects (short-circuit && / || compiled to
+// ~37 instructions and several branches per compare-exchange, profiles/r1e)
+__device__ __forceinline__ bool sr_gt(const SortReg& a, const SortReg& b) { return (a.k > b.k) | ((a.k == b.k) & (a.id > b.id)); }
+__device__ __forceinline__ void sr_cswap(SortReg& a, SortReg& b, bool asc) {  // afterwards a <= b when asc
+  const bool sw = sr_gt(a, b) == asc;
+  const unsigned long long ak = sw ? b.k : a.k, bk = sw ? a.k : b.k;
+  const uint32_t ai = sw ? b.id : a.id, bi = sw ? a.id : b.id;
+  a.k = ak; b.k = bk; a.id = ai; b.id = bi;
+}
+template <int EPL, int J>
+__device__ __forceinline__ void sr_local_step(SortReg (&v)[EPL], int lane, int k) {
+#pragma unroll
+  for (int r = 0; r < EPL; ++r)
+    if ((r & J) == 0) sr_cswap(v[r], v[r | J], ((lane * EPL + r) & k) == 0);
+}
+
+template <int EPL>
+__global__ void __launch_bounds__(32 * SEC_WPC) k_sector_warp(LaneDev* lanes, int lane0, int sel, ConfigDev cfg, int n_sectors) {
   const LaneDev& L = lanes[lane0 + blockIdx.y];
-  const int tid = threadIdx.x;
-  __shared__ int red_e[256], red_s[256];
-  int se = 0, ss = 0;
-  for (int i = tid; i < (int)blockIdx.x; i += 256) { const int2 c = L.sec_cnt[i]; se += c.x; ss += c.y; }
-  red_e[tid] = se; red_s[tid] = ss;
-  __syncthreads();
-  for (int off = 128; off > 0; off >>= 1) {
-    if (tid < off) { red_e[tid] += red_e[tid + off]; red_s[tid] += red_s[tid + off]; }
-    __syncthreads();
-  }
-  const int oe = red_e[0], os = red_s[0];
-  const int2 c = L.sec_cnt[blockIdx.x];
-  const int r = blockIdx.x / SECTORS, s = blockIdx.x % SECTORS;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sec = blockIdx.x * SEC_WPC + warp;
+  if (sec >= n_sectors) return;
+  const int r = sec / SECTORS, s = sec % SECTORS;
   const uint32_t* rs = L.ring_sort.digit_start;
   const int ring_beg = (int)rs[r];
+  const int n_r = (int)rs[r + 1] - ring_beg;
   int start = 0, m = 0;
-  sector_range((int)rs[r + 1] - ring_beg, s, start, m);
+  bool ok = sector_range(n_r, s, start, m);
+  constexpr int NP = 32 * EPL;
+  if (ok && m > min(cfg.max_sector, NP)) {
+    if (lane == 0) atomicOr(&L.v->status, ST_SECTOR_TOO_LONG);
+    ok = false;
+  }
+  if (!ok) {
+    if (lane == 0) L.sec_cnt[sec] = make_int2(0, 0);
+    return;
+  }
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int MS = min(cfg.max_sector, NP);  // multiple of 8
+  unsigned char* base_sm = smem + (size_t)warp * sec_warp_bytes(MS, NP);
+  float4* pts = reinterpret_cast<float4*>(base_sm);                        // ring points start .. start+m+9
+  double* val = reinterpret_cast<double*>(base_sm + sizeof(float4) * (MS + 10));  // curvature of element e
+  uint32_t* srcs = reinterpret_cast<uint32_t*>(val + MS);                  // scan index of each staged point
+  uint16_t* sorted = reinterpret_cast<uint16_t*>(srcs + MS + 10);          // elements in ascending (curvature, index)
+  uint8_t* picked = reinterpret_cast<uint8_t*>(sorted + NP);               // cloudNeighborPicked as flags
+
+  const uint32_t* perm = L.ring_sort.val[1];  // scan indices in (ring, arrival) order after the single pass
+  for (int k = lane; k < m + 10; k += 32) {
+    const uint32_t src = perm[ring_beg + start + k];
+    srcs[k] = src;
+    pts[k] = L.scan[sel][src];
+    picked[k] = 0;
+  }
+  __syncwarp();
+  // FE:190-200: fp32 left-to-right 11-tap sums, squared in fp64.  Element e <-> ring index 5+start+e <-> pts[e+5].
+  for (int e = lane; e < m; e += 32) {
+    const float4* p = pts + e + 5;
+    float fx = fadd(fadd(fadd(fadd(p[-5].x, p[-4].x), p[-3].x), p[-2].x), p[-1].x);
+    fx = fsub(fx, fmul(10.0f, p[0].x));
+    fx = fadd(fadd(fadd(fadd(fadd(fx, p[1].x), p[2].x), p[3].x), p[4].x), p[5].x);
+    float fy = fadd(fadd(fadd(fadd(p[-5].y, p[-4].y), p[-3].y), p[-2].y), p[-1].y);
+    fy = fsub(fy, fmul(10.0f, p[0].y));
+    fy = fadd(fadd(fadd(fadd(fadd(fy, p[1].y), p[2].y), p[3].y), p[4].y), p[5].y);
+    float fz = fadd(fadd(fadd(fadd(p[-5].z, p[-4].z), p[-3].z), p[-2].z), p[-1].z);
+    fz = fsub(fz, fmul(10.0f, p[0].z));
+    fz = fadd(fadd(fadd(fadd(fadd(fz, p[1].z), p[2].z), p[3].z), p[4].z), p[5].z);
+    const double dx = fx, dy = fy, dz = fz;
+    const double c = dadd(dadd(dmul(dx, dx), dmul(dy, dy)), dmul(dz, dz));
+    val[e] = c == 0.0 ? 0.0 : c;  // (+0.0; the input is NaN-free, FE:56-57)
+  }
+  __syncwarp();
+  // std::sort ascending by curvature (FE:115); equal curvatures ordered by index (tie class T1 made canonical).
+  // A non-negative double orders like its bit pattern; padding positions (>= m) carry the maximal key.
+  SortReg v[EPL];
+#pragma unroll
+  for (int q = 0; q < EPL; ++q) {
+    const int p = lane * EPL + q;
+    if (p < m) { v[q].k = (unsigned long long)__double_as_longlong(val[p]); v[q].id = (uint32_t)p; }
+    else { v[q].k = ~0ull; v[q].id = 0xffff0000u + (uint32_t)p; }
+  }
+  for (int k = 2; k <= NP; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= EPL) {  // partner position p ^ j lives in lane ^ (j / EPL), same register
+        const int lj = j / EPL;
+        const bool lower = (lane & lj) == 0;
+#pragma unroll
+        for (int q = 0; q < EPL; ++q) {
+          SortReg o;
+          o.k = __shfl_xor_sync(0xffffffffu, v[q].k, lj);
+          o.id = __shfl_xor_sync(0xffffffffu, v[q].id, lj);
+          const bool asc = ((lane * EPL + q) & k) == 0;
+          const bool take = sr_gt(v[q], o) == (asc == lower);  // keys are distinct (the index is part of the key)
+          v[q].k = take ? o.k : v[q].k;
+          v[q].id = take ? o.id : v[q].id;
+        }
+      } else {
+        if (EPL > 1 && j == 1) sr_local_step<EPL, 1>(v, lane, k);
+        if (EPL > 2 && j == 2) sr_local_step<EPL, (EPL > 2 ? 2 : 1)>(v, lane, k);
+        if (EPL > 4 && j == 4) sr_local_step<EPL, (EPL > 4 ? 4 : 1)>(v, lane, k);
+        if (EPL > 8 && j == 8) sr_local_step<EPL, (EPL > 8 ? 8 : 1)>(v, lane, k);
+        if (EPL > 16 && j == 16) sr_local_step<EPL, (EPL > 16 ? 16 : 1)>(v, lane, k);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < EPL; ++q) sorted[lane * EPL + q] = (uint16_t)v[q].id;  // padding sorts behind the m elements
+  __syncwarp();
+
+  int n_edge = 0;
+  {  // FE:120-163, serial in pick order, 32 candidates examined per step
+    int i = m - 1;
+    int cnt = 0;
+    while (i >= 0) {
+      const int pos = i - lane;
+      int e = 0;
+      bool un = false;
+      if (pos >= 0) { e = sorted[pos]; un = picked[e + 5] == 0; }
+      const unsigned msk = __ballot_sync(0xffffffffu, un);
+      if (msk == 0) { i -= 32; continue; }
+      const int l = __ffs(msk) - 1;
+      const int esel = __shfl_sync(0xffffffffu, e, l);
+      if (val[esel] <= cfg.edge_threshold) break;  // FE:125
+      ++cnt;                                        // FE:128
+      const int li = esel + 5;
+      if (lane == 0) picked[li] = 1;                // FE:129
+      if (cnt > EDGES_PER_SECTOR) break;            // FE:131-136: the 21st is consumed, not emitted
+      if (lane == 0) {
+        L.sec_edge[sec * EDGES_PER_SECTOR + cnt - 1] = pts[li];
+        L.sec_edge_src[sec * EDGES_PER_SECTOR + cnt - 1] = (int)srcs[li];
+      }
+      n_edge = cnt;
+      bool stop = false;  // FE:138-160: gap^2 between consecutive ring points, fp32 difference squared in fp64
+      if (lane < 5 || (lane >= 8 && lane < 13)) {
+        const int k = lane < 5 ? lane + 1 : -(lane - 8 + 1);
+        const float4 a = pts[li + k];
+        const float4 b = lane < 5 ? pts[li + k - 1] : pts[li + k + 1];
+        const double gx = fsub(a.x, b.x), gy = fsub(a.y, b.y), gz = fsub(a.z, b.z);
+        stop = dadd(dadd(dmul(gx, gx), dmul(gy, gy)), dmul(gz, gz)) > 0.05;
+      }
+      const unsigned sm = __ballot_sync(0xffffffffu, stop);
+      const unsigned f = sm & 0x1fu, bk = (sm >> 8) & 0x1fu;
+      const int nf = f ? __ffs(f) - 1 : 5, nbk = bk ? __ffs(bk) - 1 : 5;
+      if (lane < nf) picked[li + lane + 1] = 1;
+      if (lane >= 8 && lane - 8 < nbk) picked[li - (lane - 8 + 1)] = 1;
+      __syncwarp();
+      i = i - l - 1;
+    }
+  }
+  __syncwarp();
+  // FE:165-172: everything not picked, in ascending-curvature order -> surf
   const int sbase = ring_beg + 5 + start;
-  // copy + getMinMax3D of both feature clouds for the voxel filter that follows (EM:248-251)
-  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-  int cnt = 0;
-  for (int k = tid; k < c.x; k += 256) {
-    const float4 p = L.sec_edge[blockIdx.x * EDGES_PER_SECTOR + k];
-    L.feat[0][oe + k] = p;
-    L.feat_src[0][oe + k] = L.sec_edge_src[blockIdx.x * EDGES_PER_SECTOR + k];
-    mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x); mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
-    mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z); ++cnt;
+  int run = 0;
+  for (int base = 0; base < m; base += 32) {
+    const int i = base + lane;
+    int e = 0;
+    bool keep = false;
+    if (i < m) { e = sorted[i]; keep = picked[e + 5] == 0; }
+    const unsigned b = __ballot_sync(0xffffffffu, keep);
+    if (keep) {
+      const int dst = sbase + run + __popc(b & ((1u << lane) - 1u));
+      L.sec_surf[dst] = pts[e + 5];
+      L.sec_surf_src[dst] = (int)srcs[e + 5];
+    }
+    run += __popc(b);
   }
+  if (lane == 0) L.sec_cnt[sec] = make_int2(n_edge, run);
+}
+
+template <int EPL>
+static void launch_sector_warp(const Launch& L, LaneDev* lanes, int lane0, int nlanes, int sel, const ConfigDev& cfg) {
+  constexpr int NP = 32 * EPL;
+  const size_t PER_WARP = sec_warp_bytes(cfg.max_sector < NP ? cfg.max_sector : NP, NP);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_sector_warp<EPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sec_warp_bytes(NP, NP) * SEC_WPC));
+    attr_set = true;
+  }
+  const int n_sectors = cfg.rings_total * SECTORS;
+  dim3 g((n_sectors + SEC_WPC - 1) / SEC_WPC, nlanes);
+  k_sector_warp<EPL><<<g, 32 * SEC_WPC, PER_WARP * SEC_WPC, L.st>>>(lanes, lane0, sel, cfg, n_sectors);
+  L.tick(K_SECTOR);
+}
+
+// One CTA per ring: concatenates its 6 per-sector lists behind those of the lower rings = the reference's push_back
+// order of cloud_Edge / cloud_Surf (FE:133, :170), and reduces getMinMax3D of both clouds for the voxel filter (EM:248-251).
+__global__ void __launch_bounds__(256) k_compact_features(LaneDev* lanes, int lane0, ConfigDev cfg) {
+  const LaneDev& L = lanes[lane0 + blockIdx.y];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int r = blockIdx.x, sec0 = r * SECTORS;
+  __shared__ int s_off[2];
   __shared__ float bb_sm[7 * 8];
-  bbox_commit(L.vv + 0, mn, mx, cnt, bb_sm);
-  for (int a = 0; a < 3; ++a) { mn[a] = FLT_MAX; mx[a] = -FLT_MAX; }
-  cnt = 0;
-  for (int k = tid; k < c.y; k += 256) {
-    const float4 p = L.sec_surf[sbase + k];
-    L.feat[1][os + k] = p;
-    L.feat_src[1][os + k] = L.sec_surf_src[sbase + k];
-    mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x); mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
-    mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z); ++cnt;
+  if (tid < 32) {  // features emitted by the sectors of the lower rings
+    int se = 0, ss = 0;
+    for (int i = lane; i < sec0; i += 32) { const int2 c = L.sec_cnt[i]; se += c.x; ss += c.y; }
+    for (int off = 16; off > 0; off >>= 1) { se += __shfl_xor_sync(0xffffffffu, se, off); ss += __shfl_xor_sync(0xffffffffu, ss, off); }
+    if (lane == 0) { s_off[0] = se; s_off[1] = ss; }
   }
-  bbox_commit(L.vv + 1, mn, mx, cnt, bb_sm);
-  if (blockIdx.x == gridDim.x - 1 && tid == 0) { L.v->n_edge = oe + c.x; L.v->n_surf = os + c.y; }
+  __syncthreads();
+  int oe = s_off[0], os = s_off[1];
+  const uint32_t* rs = L.ring_sort.digit_start;
+  const int ring_beg = (int)rs[r];
+  const int n_r = (int)rs[r + 1] - ring_beg;
+  float emn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, emx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  float smn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, smx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  int ecnt = 0, scnt = 0;
+  for (int s = 0; s < SECTORS; ++s) {
+    const int2 c = L.sec_cnt[sec0 + s];
+    int start = 0, m = 0;
+    sector_range(n_r, s, start, m);
+    const int sbase = ring_beg + 5 + start;
+    if (tid < c.x) {  // <= 20 edges
+      const float4 p = L.sec_edge[(sec0 + s) * EDGES_PER_SECTOR + tid];
+      L.feat[0][oe + tid] = p;
+      L.feat_src[0][oe + tid] = L.sec_edge_src[(sec0 + s) * EDGES_PER_SECTOR + tid];
+      emn[0] = fminf(emn[0], p.x); emx[0] = fmaxf(emx[0], p.x); emn[1] = fminf(emn[1], p.y); emx[1] = fmaxf(emx[1], p.y);
+      emn[2] = fminf(emn[2], p.z); emx[2] = fmaxf(emx[2], p.z); ++ecnt;
+    }
+    for (int k = tid; k < c.y; k += 256) {
+      const float4 p = L.sec_surf[sbase + k];
+      L.feat[1][os + k] = p;
+      L.feat_src[1][os + k] = L.sec_surf_src[sbase + k];
+      smn[0] = fminf(smn[0], p.x); smx[0] = fmaxf(smx[0], p.x); smn[1] = fminf(smn[1], p.y); smx[1] = fmaxf(smx[1], p.y);
+      smn[2] = fminf(smn[2], p.z); smx[2] = fmaxf(smx[2], p.z); ++scnt;
+    }
+    oe += c.x; os += c.y;
+  }
+  bbox_commit(L.vv + 0, emn, emx, ecnt, bb_sm);
+  bbox_commit(L.vv + 1, smn, smx, scnt, bb_sm);
+  if (blockIdx.x == gridDim.x - 1 && tid == 0) { L.v->n_edge = oe; L.v->n_surf = os; }
 }
 
 void launch_extract(const Launch& L, LaneDev* lanes, const SortJob* ring_jobs, int lane0, int nlanes, int sel, const ConfigDev& cfg) {
@@ -348,10 +561,16 @@ void launch_extract(const Launch& L, LaneDev* lanes, const SortJob* ring_jobs, i
   k_sort_keyhist<KeyGenRing><<<gs, SORT_THREADS, 0, L.st>>>(ring_jobs + lane0, gen);
   L.tick(K_RING_KEYHIST);
   launch_sort_scatter(L, ring_jobs + lane0, nlanes, 0);
-  dim3 g2(cfg.rings_total * SECTORS, nlanes);
-  k_sector_select<<<g2, 256, SEC_SMEM, L.st>>>(lanes, lane0, sel, cfg);
-  L.tick(K_SECTOR);
-  k_compact_features<<<g2, 256, 0, L.st>>>(lanes, lane0, cfg);
+  if (cfg.max_sector <= 128) launch_sector_warp<4>(L, lanes, lane0, nlanes, sel, cfg);
+  else if (cfg.max_sector <= 256) launch_sector_warp<8>(L, lanes, lane0, nlanes, sel, cfg);
+  else if (cfg.max_sector <= 512) launch_sector_warp<16>(L, lanes, lane0, nlanes, sel, cfg);
+  else {  // very long rings: one CTA per sector with the sort network in shared memory
+    dim3 g2(cfg.rings_total * SECTORS, nlanes);
+    k_sector_select<<<g2, 256, SEC_SMEM, L.st>>>(lanes, lane0, sel, cfg);
+    L.tick(K_SECTOR);
+  }
+  dim3 g3(cfg.rings_total, nlanes);
+  k_compact_features<<<g3, 256, 0, L.st>>>(lanes, lane0, cfg);
   L.tick(K_COMPACT);
 }
 

@@ -164,6 +164,8 @@ int build_ctx(Ctx* C) {
     int ms = (ring_pts - 10) / SECTORS + 8;  // FE:205-214: the last sector takes the remainder (< 6 more)
     ms = (ms + 7) / 8 * 8;
     c.max_sector = ms < 64 ? 64 : (ms > MAX_SECTOR ? MAX_SECTOR : ms);
+    c.sector_np = 64;
+    while (c.sector_np < c.max_sector) c.sector_np <<= 1;
   }
   c.cap_scan = u.max_scan_points; c.cap_map = u.max_map_points;
   const int NL = C->nlanes;

@@ -41,6 +41,7 @@ struct ConfigDev {
   float edge_leaf, surf_leaf;
   float inv_cell;  // 1 / hash-grid cell edge (a power of two >= sqrt(knn_gate))
   int max_sector;  // elements per (ring, sector) the selection kernel stages in shared memory (<= MAX_SECTOR)
+  int sector_np;   // power of two >= max_sector: size of the selection kernel's sort network
   int outer_iters, lm_max_iters;
   int cap_scan, cap_map;
 };
