@@ -8,14 +8,12 @@
 // map point + 8 B per bucket.  The reordered copy carries the original map index in .w, so neighbour indices
 // are reported in the reference's map order.
 //
-// Query: one warp per feature point.  Lanes 0..26 look up the 27 buckets around the query cell, the candidate
-// lists are flattened with a warp scan and read 32 at a time (one coalesced float4 each); a candidate counts
-// only for the lane whose cell it really lies in (hash collisions are filtered by recomputing the cell).
-// Every point closer than c is inside those 27 cells, hence every neighbour with d^2 < knn_gate is found:
-// the result is exact wherever the reference uses it (EM:129/:189 reject the feature when d^2[4] >= 1); candidates
-// at or beyond the gate are dropped on sight (their slots stay idx -1, d^2 FLT_MAX).
-// Distances: ((dx*dx)+dy*dy)+dz*dz in fp32 without contraction = FLANN L2_Simple<float>.  Top-5 kept
-// replicated in registers, ordered by (d^2, index): deterministic tie break (tie class T2).
+// Query: one thread per feature point walks the 27 buckets around its cell (float4 loads through the read-only path; the
+// lanes of a warp are spatial neighbours and share buckets).  Every point closer than c is inside those 27 cells, hence
+// every neighbour with d^2 < knn_gate is found: the result is exact wherever the reference uses it (EM:129/:189 reject the
+// feature when d^2[4] >= 1); candidates at or beyond the gate are dropped on sight (their slots stay idx -1, d^2 FLT_MAX).
+// Distances: ((dx*dx)+dy*dy)+dz*dz in fp32 without contraction = FLANN L2_Simple<float>.  Top-5 kept in registers,
+// ordered by (d^2, index): deterministic tie break (tie class T2).
 #include "vilf_internal.cuh"
 
 namespace vilf {
@@ -135,83 +133,82 @@ void launch_grid_build(const Launch& L, const GridJob* jobs_dev, int njobs, cons
 }
 
 // ------------------------------------------------------------------------------------------------
-// warp-cooperative 5-NN
+// 5-NN, one THREAD per query
 // ------------------------------------------------------------------------------------------------
+// The first version gave every query a whole warp (27 lanes looked up one bucket each, candidates were read 32 at a time
+// and inserted through warp shuffles): 231 warp instructions per query, issue bound (profiles/r1b, r1d).  With ~30
+// candidates per query there is not enough work to amortise the warp-wide bookkeeping, so each thread now walks its own 27
+// buckets.  Consecutive queries are spatial neighbours (the voxel filter emits them in voxel order), hence the lanes of a
+// warp read the same buckets and points: the loads hit L1 and the per-lane trip counts are similar.
+//
+// Exactness: a bucket holds every point of its cell (plus, rarely, points of cells that hash alike; those are farther than
+// one cell edge >= sqrt(gate), unless the colliding cell is itself one of the 27 — then the same bucket is visited twice and
+// the duplicate is rejected by index).  So every map point with d^2 < gate is seen at least once and kept at most once.
 struct Top5 {
   float d[5];
   int id[5];
 };
-__device__ __forceinline__ bool closer(float d, int id, float bd, int bid) { return d < bd || (d == bd && id < bid); }
+// (d^2, index) lexicographic order, evaluated without branches
+__device__ __forceinline__ bool closer(float d, int id, float bd, int bid) { return (d < bd) | ((d == bd) & (id < bid)); }
 
-__device__ __forceinline__ void top5_insert(Top5& t, float cd, int ci) {
-  bool placed = false;
+__device__ __forceinline__ void top5_insert(Top5& t, float cd, int ci) {  // precondition: (cd, ci) is closer than t[4] and not in t
+  t.d[4] = cd; t.id[4] = ci;
 #pragma unroll
   for (int k = 4; k > 0; --k) {
-    if (!placed) {
-      if (closer(cd, ci, t.d[k - 1], t.id[k - 1])) { t.d[k] = t.d[k - 1]; t.id[k] = t.id[k - 1]; }
-      else { t.d[k] = cd; t.id[k] = ci; placed = true; }
-    }
+    const bool sw = closer(t.d[k], t.id[k], t.d[k - 1], t.id[k - 1]);
+    const float dk = sw ? t.d[k - 1] : t.d[k], dk1 = sw ? t.d[k] : t.d[k - 1];
+    const int ik = sw ? t.id[k - 1] : t.id[k], ik1 = sw ? t.id[k] : t.id[k - 1];
+    t.d[k] = dk; t.d[k - 1] = dk1; t.id[k] = ik; t.id[k - 1] = ik1;
   }
-  if (!placed) { t.d[0] = cd; t.id[0] = ci; }
 }
 
-// All 32 lanes of a warp call this with the same query; the result is replicated in every lane.
-__device__ __forceinline__ void warp_knn5(const GridJob& G, float inv_cell, double gate, float qx, float qy, float qz, Top5& best) {
-  const int lane = threadIdx.x & 31;
+__device__ __forceinline__ void knn_consider(Top5& best, float gate_f, float qx, float qy, float qz, const float4 c) {
+  const float ddx = fsub(qx, c.x), ddy = fsub(qy, c.y), ddz = fsub(qz, c.z);
+  const float cd = fadd(fadd(fmul(ddx, ddx), fmul(ddy, ddy)), fmul(ddz, ddz));  // FLANN L2_Simple<float>
+  const int ci = __float_as_int(c.w);
+  // neighbours at or beyond the gate can never be used (EM:129 / :189 reject the feature), so they never enter the list
+  if ((cd < gate_f) & closer(cd, ci, best.d[4], best.id[4])) {
+    const bool dup = (ci == best.id[0]) | (ci == best.id[1]) | (ci == best.id[2]) | (ci == best.id[3]);  // (ci != id[4]: strictly closer)
+    if (!dup) top5_insert(best, cd, ci);
+  }
+}
+
+// The walk is latency bound (every bucket costs a dependent pair of loads), so the loads of one row of three cells are
+// issued together: 6 bucket bounds, then the first PF candidates of each of the three buckets, then the (rare) rest.
+// (A single flattened loop over all candidates of a query, fed from a per-thread bucket list in shared memory, was
+// measured slower: 111 us against 77 us per launch at 16 sequences — the longest lane of the warp then dictates ~80
+// dependent L2 round trips.)
+__device__ __forceinline__ void thread_knn5(const GridJob& G, float inv_cell, float gate_f, float qx, float qy, float qz, Top5& best) {
+  constexpr int PF = 3;
 #pragma unroll
   for (int k = 0; k < 5; ++k) { best.d[k] = FLT_MAX; best.id[k] = INT_MAX; }
   const uint32_t hm = (uint32_t)(*G.hvar) - 1u;
   int qcx, qcy, qcz;
   cell_of(make_float4(qx, qy, qz, 0.f), inv_cell, qcx, qcy, qcz);
-  // lane < 27 owns neighbour cell (lane%3-1, (lane/3)%3-1, lane/9-1)
-  int cx = 0, cy = 0, cz = 0;
-  uint32_t s = 0, cnt = 0;
-  if (lane < 27) {
-    cx = qcx + (lane % 3) - 1; cy = qcy + ((lane / 3) % 3) - 1; cz = qcz + (lane / 9) - 1;
-    const uint32_t h = cell_hash(cx, cy, cz) & hm;
-    s = G.start[h];
-    cnt = G.start[h + 1] - s;
-  }
-  uint32_t inc = cnt;
-  for (int off = 1; off < 32; off <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, off); if (lane >= off) inc += t; }
-  const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
-  for (uint32_t base = 0; base < total; base += 32) {
-    const uint32_t t = base + lane;
-    // owner = first lane whose inclusive prefix exceeds t (binary search over the replicated prefix)
-    int lo = 0, hi = 31;
+  const uint32_t* __restrict__ start = G.start;
+  const float4* __restrict__ sorted = G.sorted;
+#pragma unroll 1
+  for (int row = 0; row < 9; ++row) {
+    const int dy = row % 3 - 1, dz = row / 3 - 1;
+    uint32_t s[3], e[3];
 #pragma unroll
-    for (int step = 0; step < 5; ++step) {
-      const int mid = (lo + hi) >> 1;
-      const uint32_t v = __shfl_sync(0xffffffffu, inc, mid);
-      if (v > t) hi = mid; else lo = mid + 1;
+    for (int dx = 0; dx < 3; ++dx) {
+      const uint32_t h = cell_hash(qcx + dx - 1, qcy + dy, qcz + dz) & hm;
+      s[dx] = __ldg(start + h);
+      e[dx] = __ldg(start + h + 1);
     }
-    const int owner = lo;
-    const uint32_t o_inc = __shfl_sync(0xffffffffu, inc, owner);
-    const uint32_t o_cnt = __shfl_sync(0xffffffffu, cnt, owner);
-    const uint32_t o_s = __shfl_sync(0xffffffffu, s, owner);
-    const int ocx = __shfl_sync(0xffffffffu, cx, owner), ocy = __shfl_sync(0xffffffffu, cy, owner), ocz = __shfl_sync(0xffffffffu, cz, owner);
-    float cd = FLT_MAX;
-    int ci = INT_MAX;
-    bool have = false;
-    if (t < total) {
-      const float4 p = G.sorted[o_s + (t - (o_inc - o_cnt))];
-      int pcx, pcy, pcz;
-      cell_of(p, inv_cell, pcx, pcy, pcz);
-      if (pcx == ocx && pcy == ocy && pcz == ocz) {
-        const float dx = fsub(qx, p.x), dy = fsub(qy, p.y), dz = fsub(qz, p.z);
-        cd = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
-        ci = __float_as_int(p.w);
-        // neighbours at or beyond the gate can never be used (EM:129 / :189 reject the feature), so they never enter the list
-        have = (double)cd < gate && closer(cd, ci, best.d[4], best.id[4]);
-      }
-    }
-    unsigned m = __ballot_sync(0xffffffffu, have);
-    while (m) {
-      const int l = __ffs(m) - 1;
-      m &= m - 1;
-      const float d = __shfl_sync(0xffffffffu, cd, l);
-      const int id = __shfl_sync(0xffffffffu, ci, l);
-      if (closer(d, id, best.d[4], best.id[4])) top5_insert(best, d, id);
+    float4 c[3][PF];
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+      for (int i = 0; i < PF; ++i)
+        if (s[dx] + i < e[dx]) c[dx][i] = __ldg(sorted + s[dx] + i);
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+      for (int i = 0; i < PF; ++i)
+        if (s[dx] + i < e[dx]) knn_consider(best, gate_f, qx, qy, qz, c[dx][i]);
+      for (uint32_t p = s[dx] + PF; p < e[dx]; ++p) knn_consider(best, gate_f, qx, qy, qz, __ldg(sorted + p));
     }
   }
 }
@@ -337,8 +334,8 @@ __device__ D3 lstsq5x3(const double Ain[5][3]) {
   return d3(n[0], n[1], n[2]);
 }
 
-// Association, kernel 1: one warp per voxel-filtered feature point: transform (EM:355-363) + 5-NN (EM:128 / :185).
-__global__ void __launch_bounds__(256) k_knn_assoc(LaneDev* lanes, const GridJob* __restrict__ grid_jobs, int lane0, ConfigDev cfg,
+// Association, kernel 1: one thread per voxel-filtered feature point: transform (EM:355-363) + 5-NN (EM:128 / :185).
+__global__ void __launch_bounds__(128) k_knn_assoc(LaneDev* lanes, const GridJob* __restrict__ grid_jobs, int lane0, ConfigDev cfg,
                                                     const double* pose_override) {
   const int ln = lane0 + blockIdx.y;
   const LaneDev& L = lanes[ln];
@@ -346,25 +343,20 @@ __global__ void __launch_bounds__(256) k_knn_assoc(LaneDev* lanes, const GridJob
   const int me = V.n_map[0], ms = V.n_map[1];
   if (!(me > 10 && ms > 50)) return;  // EM:254
   const int ne = V.n_ds[0], ns = V.n_ds[1];
-  const int lane = threadIdx.x & 31;
-  const int wid = (blockIdx.x * 256 + threadIdx.x) >> 5;
-  const int nw = (gridDim.x * 256) >> 5;
   double x[7];
 #pragma unroll
   for (int i = 0; i < 7; ++i) x[i] = pose_override ? pose_override[i] : V.x[i];
   if (blockIdx.x == 0 && threadIdx.x == 0) V.opt_ran = 1;
-  for (int q = wid; q < ne + ns; q += nw) {
+  for (int q = blockIdx.x * 128 + threadIdx.x; q < ne + ns; q += gridDim.x * 128) {
     const int w = q < ne ? 0 : 1;
     const int k = q < ne ? q : q - ne;
     const float4 pw = associate(x, L.ds[w][k]);
     Top5 best;
-    warp_knn5(grid_jobs[ln * 2 + w], cfg.inv_cell, cfg.knn_gate, pw.x, pw.y, pw.z, best);
-    if (lane < 5) {
-      float d = best.d[0]; int id = best.id[0];
+    thread_knn5(grid_jobs[ln * 2 + w], cfg.inv_cell, cfg.knn_gate_f, pw.x, pw.y, pw.z, best);
 #pragma unroll
-      for (int j = 1; j < 5; ++j) if (lane == j) { d = best.d[j]; id = best.id[j]; }
-      L.nn_idx[w][k * 5 + lane] = id == INT_MAX ? -1 : id;
-      L.nn_d2[w][k * 5 + lane] = d;
+    for (int j = 0; j < 5; ++j) {
+      L.nn_idx[w][k * 5 + j] = best.id[j] == INT_MAX ? -1 : best.id[j];
+      L.nn_d2[w][k * 5 + j] = best.d[j];
     }
   }
 }
@@ -440,7 +432,7 @@ void launch_knn_fit(const Launch& L, LaneDev* lanes, const GridJob* grid_jobs, i
                     const double* pose_override, int want_nn) {
   (void)want_nn;
   dim3 g(KNN_G, nlanes);
-  k_knn_assoc<<<g, 256, 0, L.st>>>(lanes, grid_jobs, lane0, cfg, pose_override);
+  k_knn_assoc<<<g, 128, 0, L.st>>>(lanes, grid_jobs, lane0, cfg, pose_override);
   L.tick(K_KNN_FIT);
   dim3 g2(FIT_G, nlanes);
   k_fit<<<g2, 128, 0, L.st>>>(lanes, lane0, cur, cfg);
@@ -448,28 +440,23 @@ void launch_knn_fit(const Launch& L, LaneDev* lanes, const GridJob* grid_jobs, i
 }
 
 // nearestKSearch alone against an explicit map (test entry point vilf_knn5).
-__global__ void __launch_bounds__(256) k_knn_only(const GridJob* __restrict__ job, const float4* __restrict__ q, const int* nq_dev, int* idx,
-                                                   float* d2, float inv_cell, double gate) {
+__global__ void __launch_bounds__(128) k_knn_only(const GridJob* __restrict__ job, const float4* __restrict__ q, const int* nq_dev, int* idx,
+                                                   float* d2, float inv_cell, float gate_f) {
   const int nq = *nq_dev;
-  const int lane = threadIdx.x & 31;
-  const int wid = (blockIdx.x * 256 + threadIdx.x) >> 5;
-  const int nw = (gridDim.x * 256) >> 5;
-  for (int i = wid; i < nq; i += nw) {
+  for (int i = blockIdx.x * 128 + threadIdx.x; i < nq; i += gridDim.x * 128) {
     const float4 p = q[i];
     Top5 best;
-    warp_knn5(*job, inv_cell, gate, p.x, p.y, p.z, best);
-    if (lane < 5) {
-      float d = best.d[0]; int id = best.id[0];
+    thread_knn5(*job, inv_cell, gate_f, p.x, p.y, p.z, best);
 #pragma unroll
-      for (int j = 1; j < 5; ++j) if (lane == j) { d = best.d[j]; id = best.id[j]; }
-      idx[i * 5 + lane] = id == INT_MAX ? -1 : id;
-      d2[i * 5 + lane] = d;
+    for (int j = 0; j < 5; ++j) {
+      idx[i * 5 + j] = best.id[j] == INT_MAX ? -1 : best.id[j];
+      d2[i * 5 + j] = best.d[j];
     }
   }
 }
 
 void launch_knn_only(const Launch& L, const GridJob* job_dev, const float4* q, const int* nq_dev, int* idx, float* d2, const ConfigDev& cfg) {
-  k_knn_only<<<KNN_G, 256, 0, L.st>>>(job_dev, q, nq_dev, idx, d2, cfg.inv_cell, cfg.knn_gate);
+  k_knn_only<<<KNN_G, 128, 0, L.st>>>(job_dev, q, nq_dev, idx, d2, cfg.inv_cell, cfg.knn_gate_f);
   L.tick(K_KNN_ONLY);
 }
 

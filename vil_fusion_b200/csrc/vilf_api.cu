@@ -158,6 +158,8 @@ int build_ctx(Ctx* C) {
   float cell = 1.0f / 1024.0f;
   while ((double)cell * (double)cell < u.knn_gate) cell *= 2.0f;  // power of two >= sqrt(gate)
   c.inv_cell = 1.0f / cell;
+  c.knn_gate_f = (float)u.knn_gate;
+  if ((double)c.knn_gate_f < u.knn_gate) c.knn_gate_f = nextafterf(c.knn_gate_f, INFINITY);
   c.outer_iters = u.outer_iters; c.lm_max_iters = u.lm_max_iters;
   {
     int ring_pts = u.max_ring_points > 0 ? u.max_ring_points : 6 * MAX_SECTOR + 10;

@@ -23,7 +23,7 @@ constexpr int SORT_RADIX_BITS = 9;   // digit width limit; tables are [4 passes]
 constexpr int SORT_RADIX = 1 << SORT_RADIX_BITS;
 constexpr int VOX_G = 148;           // CTAs per voxel job for the bbox / head / centroid kernels
 constexpr int GRID_G = 148;          // CTAs per hash-grid job
-constexpr int KNN_G = 148 * 4;       // CTAs (8 warps each) of the kNN kernel per lane
+constexpr int KNN_G = 148;           // CTAs (128 threads, one query each, grid-stride) of the kNN kernel per lane
 constexpr int FIT_G = 148;           // CTAs (128 threads) of the fit kernel per lane
 constexpr int LM_THREADS = 256;     // per CTA of the solve cluster
 constexpr int LM_CLUSTER = 8;       // CTAs (SMs) per sequence in the solve kernel
@@ -40,6 +40,7 @@ struct ConfigDev {
   double lidar_min, lidar_max, edge_threshold, knn_gate, huber, crop_half;
   float edge_leaf, surf_leaf;
   float inv_cell;  // 1 / hash-grid cell edge (a power of two >= sqrt(knn_gate))
+  float knn_gate_f;  // smallest float >= knn_gate: for a float d, d < knn_gate_f <=> (double)d < knn_gate
   int max_sector;  // elements per (ring, sector) the selection kernel stages in shared memory (<= MAX_SECTOR)
   int sector_np;   // power of two >= max_sector: size of the selection kernel's sort network
   int outer_iters, lm_max_iters;
