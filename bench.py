@@ -46,13 +46,13 @@ WORKLOADS = {
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="hdl64", choices=sorted(WORKLOADS))
-    ap.add_argument("--seqs", type=int, default=8, help="independent sequences per GPU, stepped in lock-step")
+    ap.add_argument("--seqs", type=int, default=32, help="independent sequences per GPU")
     ap.add_argument("--depth", type=int, default=3, help="frames in flight (submit ahead of wait)")
-    ap.add_argument("--groups", type=int, default=1, help="split the sequences of a GPU into this many lock-step batches, each on its own CUDA stream")
+    ap.add_argument("--groups", type=int, default=4, help="split the sequences of a GPU into this many lock-step batches, each on its own CUDA stream")
     ap.add_argument("--cpu-frames", type=int, default=60, help="frames per core of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-roofline", action="store_true")
