@@ -40,13 +40,13 @@ __device__ void se3_plus(const double* x, const double* delta, double* out) {
   const D3 omega = d3(delta[0], delta[1], delta[2]), ups = d3(delta[3], delta[4], delta[5]);
   const double theta = norm3(omega);
   const double half = dmul(0.5, theta);
-  double imag;
-  const double real = cos(half);
+  double imag, real, sin_half;
+  sincos(half, &sin_half, &real);
   if (theta < 1e-10) {
     const double t2 = dmul(theta, theta), t4 = dmul(t2, t2);
     imag = dadd(dsub(0.5, dmul(0.0208333, t2)), dmul(0.000260417, t4));
   } else {
-    imag = sin(half) / theta;
+    imag = sin_half / theta;
   }
   Q4 dq; dq.x = dmul(imag, omega.x); dq.y = dmul(imag, omega.y); dq.z = dmul(imag, omega.z); dq.w = real;
   double J[3][3];
@@ -63,8 +63,11 @@ __device__ void se3_plus(const double* x, const double* delta, double* out) {
     double Om2[3][3];
     for (int i = 0; i < 3; ++i)
       for (int j = 0; j < 3; ++j) Om2[i][j] = dadd(dadd(dmul(Om[i][0], Om[0][j]), dmul(Om[i][1], Om[1][j])), dmul(Om[i][2], Om[2][j]));
-    const double a = dsub(1, cos(theta)) / dmul(theta, theta);
-    const double b = dsub(theta, sin(theta)) / pow(theta, 3.0);
+    double sin_t, cos_t;
+    sincos(theta, &sin_t, &cos_t);
+    const double t2 = dmul(theta, theta);
+    const double a = dsub(1, cos_t) / t2;
+    const double b = dsub(theta, sin_t) / dmul(t2, theta);  // pow(theta, 3) in CM:170; the product differs by <= 1 ulp
     for (int i = 0; i < 3; ++i)
       for (int j = 0; j < 3; ++j) J[i][j] = dadd(dadd(i == j ? 1.0 : 0.0, dmul(a, Om[i][j])), dmul(b, Om2[i][j]));
   }
@@ -120,8 +123,8 @@ __device__ void evaluate(const LaneDev& L, int ne, int ns, const double* x, doub
       const D3 lp = qrot(q, p) + t;                    // LF:26
       const D3 nu = cross3(lp - a, lp - b);            // LF:28
       const D3 ab = a - b;
-      const double abn = norm3(ab);
-      double r[3] = {nu.x / abn, nu.y / abn, nu.z / abn};  // LF:31-33
+      const double inv_abn = 1.0 / norm3(ab);  // one division per factor; r and J below multiply by it (LF:31-33, :47 divide: <= 1 ulp apart)
+      double r[3] = {dmul(nu.x, inv_abn), dmul(nu.y, inv_abn), dmul(nu.z, inv_abn)};
       const double nsab[3][3] = {{0, ab.z, -ab.y}, {-ab.z, 0, ab.x}, {ab.y, -ab.x, 0}};  // -skew(ab)
       const double jse3[3][6] = {{0, lp.z, -lp.y, 1, 0, 0}, {-lp.z, 0, lp.x, 0, 1, 0}, {lp.y, -lp.x, 0, 0, 0, 1}};  // [-skew(lp) | I], LF:40-42
       double J[3][6];
@@ -129,7 +132,7 @@ __device__ void evaluate(const LaneDev& L, int ne, int ns, const double* x, doub
       for (int ii = 0; ii < 3; ++ii)
 #pragma unroll
         for (int jj = 0; jj < 6; ++jj)
-          J[ii][jj] = dadd(dadd(dmul(nsab[ii][0], jse3[0][jj]), dmul(nsab[ii][1], jse3[1][jj])), dmul(nsab[ii][2], jse3[2][jj])) / abn;  // LF:47
+          J[ii][jj] = dmul(dadd(dadd(dmul(nsab[ii][0], jse3[0][jj]), dmul(nsab[ii][1], jse3[1][jj])), dmul(nsab[ii][2], jse3[2][jj])), inv_abn);  // LF:47
       double rho0, sq;
       huber(dadd(dadd(dmul(r[0], r[0]), dmul(r[1], r[1])), dmul(r[2], r[2])), hub, rho0, sq);
       acc[27] += 0.5 * rho0;
@@ -215,28 +218,29 @@ __device__ bool lm_step(const LmShared& S, double* step) {
     A[i][i] += lm * lm;
     rhs[i] = S.g[i] * S.scale[i];
   }
-  double Lc[6][6];
-  for (int i = 0; i < 6; ++i)
-    for (int j = 0; j <= i; ++j) {
-      double s = A[i][j];
-      for (int k = 0; k < j; ++k) s -= Lc[i][k] * Lc[j][k];
-      if (i == j) {
-        if (!(s > 0)) return false;
-        Lc[i][i] = sqrt(s);
-      } else {
-        Lc[i][j] = s / Lc[j][j];
-      }
+  double Lc[6][6], inv[6];  // Cholesky with one reciprocal per column instead of a division per entry
+  for (int j = 0; j < 6; ++j) {
+    double d = A[j][j];
+    for (int k = 0; k < j; ++k) d -= Lc[j][k] * Lc[j][k];
+    if (!(d > 0)) return false;
+    Lc[j][j] = sqrt(d);
+    inv[j] = 1.0 / Lc[j][j];
+    for (int i = j + 1; i < 6; ++i) {
+      double sacc = A[i][j];
+      for (int k = 0; k < j; ++k) sacc -= Lc[i][k] * Lc[j][k];
+      Lc[i][j] = sacc * inv[j];
     }
+  }
   double z[6], y[6];
   for (int i = 0; i < 6; ++i) {
-    double s = rhs[i];
-    for (int k = 0; k < i; ++k) s -= Lc[i][k] * z[k];
-    z[i] = s / Lc[i][i];
+    double sacc = rhs[i];
+    for (int k = 0; k < i; ++k) sacc -= Lc[i][k] * z[k];
+    z[i] = sacc * inv[i];
   }
   for (int i = 5; i >= 0; --i) {
-    double s = z[i];
-    for (int k = i + 1; k < 6; ++k) s -= Lc[k][i] * y[k];
-    y[i] = s / Lc[i][i];
+    double sacc = z[i];
+    for (int k = i + 1; k < 6; ++k) sacc -= Lc[k][i] * y[k];
+    y[i] = sacc * inv[i];
   }
   bool finite = true;
   for (int i = 0; i < 6; ++i) { step[i] = -y[i]; if (!isfinite(step[i])) finite = false; }
@@ -245,7 +249,7 @@ __device__ bool lm_step(const LmShared& S, double* step) {
 
 }  // namespace
 
-__global__ void __cluster_dims__(LM_CLUSTER, 1, 1) __launch_bounds__(LM_THREADS, 1)
+__global__ void __cluster_dims__(LM_CLUSTER, 1, 1) __launch_bounds__(LM_THREADS, 2)
 k_solve(LaneDev* lanes, int lane0, int outer, int finalize, ConfigDev cfg, int max_iters) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
@@ -363,7 +367,7 @@ k_solve(LaneDev* lanes, int lane0, int outer, int finalize, ConfigDev cfg, int m
               S.x_norm = norm7(S.x);
               adopt_linearisation(S, false);
               S.step_successful = 1;
-              S.radius = S.radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * rel - 1.0, 3.0));
+              { const double c = 2.0 * rel - 1.0; S.radius = S.radius / fmax(1.0 / 3.0, 1.0 - c * c * c); }
               S.radius = fmin(1e16, S.radius);
               S.decrease_factor = 2.0;
               S.reuse_diagonal = 0;
