@@ -228,3 +228,37 @@ def test_cluster_and_grid_wide_paths_are_bit_identical(cabi, synth):
     ib, db = b.knn5(pts, q)
     assert np.array_equal(ia, ib) and np.array_equal(da, db)
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("sensor,n_scan,cap", [("vlp32", 32, 58000), ("hdl64", 64, 116000)])
+def test_1000_frames_free_running(cabi, orc, synth, sensor, n_scan, cap):
+    """BASELINE.json configs[1] / configs[2] and the north-star's parity clause: 1000-frame synthetic sequences, the GPU
+    free-running (never reset to the oracle's state), every frame within 1e-4 rad / 1e-3 m of the CPU oracle, final maps
+    within 1e-5 m.  Frames are submitted ahead of the waits (3 in flight) like bench.py does."""
+    frames = 1000
+    seq = synth.Sequence(sensor, frames, seed=21)
+    o = orc.Odometry(orc.config(n_scan=n_scan, n_rings=n_scan))
+    g = cabi.Odometry(cabi.default_config(n_scan=n_scan, n_rings=n_scan, max_scan_points=cap, max_map_points=1 << 18, max_ring_points=1864))
+    pend = []
+    worst = [0.0, 0.0]
+
+    def check(i, x, pg):
+        po, _, _ = o.process_scan(x)
+        e = pose_err(po, pg)
+        worst[0], worst[1] = max(worst[0], e[0]), max(worst[1], e[1])
+        assert e[0] <= TOL_ROT and e[1] <= TOL_TRANS, (i, e)
+
+    for i in range(frames):
+        x = np.ascontiguousarray(seq[i][0])
+        pend.append((i, x, g.submit_scan(x)))
+        if len(pend) >= 3:
+            j, xj, t = pend.pop(0)
+            check(j, xj, g.wait(t))
+    for j, xj, t in pend:
+        check(j, xj, g.wait(t))
+    maps_close(orc, cabi, o, g)
+    c = g.counts()
+    assert c["frames"] == frames - 1 and c["status"] == 0
+    # the trajectory really moved: ~1 m per frame
+    assert np.linalg.norm(g.pose()[0][4:]) > 500.0
+    g.close()

@@ -40,7 +40,7 @@ SYMBOLS = [
     "vilf_feature_extract", "vilf_get_features", "vilf_map_init", "vilf_map_init_points", "vilf_update", "vilf_update_points",
     "vilf_get_pose", "vilf_set_pose", "vilf_predict", "vilf_create_submap", "vilf_get_cloud", "vilf_voxel_downsample", "vilf_crop_voxel_downsample", "vilf_crop_box", "vilf_knn5",
     "vilf_factors", "vilf_normal_equations", "vilf_solve", "vilf_get_solves", "vilf_state_export", "vilf_state_import",
-    "vilf_profile_enable", "vilf_profile_read", "vilf_profile_read_kernels", "vilf_profile_kernel_name", "vilf_launch_count", "vilf_get_stream", "vilf_get_counts", "vilf_debug_voxel_phases",
+    "vilf_profile_enable", "vilf_profile_read", "vilf_profile_read_kernels", "vilf_profile_kernel_name", "vilf_launch_count", "vilf_get_stream", "vilf_get_counts", "vilf_debug_voxel_phases", "vilf_bench_stage",
 ]
 
 _lib = None
@@ -293,6 +293,14 @@ class Odometry:
         p = C.c_void_p()
         self._ck(lib().vilf_get_stream(self._h, C.byref(p)))
         return p.value or 0
+
+    def bench_stage(self, stage: int, mp, q=None, leaf: float = 0.4, iters: int = 10):
+        mp = _f32(mp)
+        q = None if q is None else _f32(q)
+        ms = np.zeros(4)
+        self._ck(lib().vilf_bench_stage(self._h, stage, _p(mp, C.c_float), mp.shape[0], _p(q, C.c_float), 0 if q is None else q.shape[0],
+                                        C.c_float(leaf), iters, _p(ms, C.c_double)))
+        return ms
 
     def voxel_phases(self, job: int):
         t = np.zeros(8, np.int64)

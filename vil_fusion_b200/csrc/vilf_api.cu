@@ -883,6 +883,66 @@ int vilf_knn5(vilf_handle* h, const float* map, int m, const float* q, int nq, i
   return VILF_OK;
 }
 
+int vilf_bench_stage(vilf_handle* h, int stage, const float* map, int m, const float* q, int nq, float leaf, int iters, double ms_out[4]) {
+  HCHECK(h);
+  CK(cudaSetDevice(C->device));
+  if (!map || m < 1 || iters < 1 || !ms_out || (stage != 0 && stage != 1) || (stage == 0 && (!q || nq < 1)) || (stage == 1 && !(leaf > 0)))
+    return fail(C, VILF_ERR_INVALID, "bad arguments");
+  if (m > C->cap_aux || nq > C->cap_aux) return fail(C, VILF_ERR_CAPACITY, "map or query set exceeds capacity");
+  const bool small = !(C->ucfg.flags & VILF_FLAG_NO_CLUSTER) && m <= CLUSTER_MAX_POINTS;
+  cudaEvent_t ev[3];
+  for (int i = 0; i < 3; ++i) CK(cudaEventCreate(&ev[i]));
+  CK(cudaMemcpyAsync(C->aux_in, map, (size_t)m * 16, cudaMemcpyHostToDevice, C->st));
+  int hdr[4] = {m, 0, nq, 0};
+  CK(cudaMemcpyAsync(C->aux_n, hdr, sizeof(hdr), cudaMemcpyHostToDevice, C->st));
+  double acc[2] = {0, 0};
+  const Launch L = mk(C);
+  if (stage == 0) {
+    CK(cudaMemcpyAsync(C->aux_out, q, (size_t)nq * 16, cudaMemcpyHostToDevice, C->st));
+    for (int it = -1; it < iters; ++it) {  // iteration -1 warms up
+      CK(cudaEventRecord(ev[0], C->st));
+      build_grids(C, L, C->aux_grid_dev, 1, small);
+      CK(cudaEventRecord(ev[1], C->st));
+      launch_knn_only(L, C->aux_grid_dev, C->aux_out, C->aux_n + 2, C->aux_idx, C->aux_d2, C->cfg);
+      CK(cudaEventRecord(ev[2], C->st));
+      CK(cudaStreamSynchronize(C->st));
+      CK(cudaGetLastError());
+      float a = 0, b = 0;
+      CK(cudaEventElapsedTime(&a, ev[0], ev[1]));
+      CK(cudaEventElapsedTime(&b, ev[1], ev[2]));
+      if (it >= 0) { acc[0] += a; acc[1] += b; }
+    }
+    ms_out[0] = acc[0] / iters; ms_out[1] = acc[1] / iters; ms_out[2] = 0; ms_out[3] = 0;
+  } else {
+    VoxJob J = C->aux_vox_host;
+    J.leaf = leaf; J.crop = 2; J.passthrough = 0;
+    for (int a = 0; a < 3; ++a) { J.crop_lo[a] = -100.0f; J.crop_hi[a] = 100.0f; }  // EM:327-336 about the origin
+    CK(cudaMemcpyAsync(C->aux_vox_dev, &J, sizeof(J), cudaMemcpyHostToDevice, C->st));
+    VoxVars vv;
+    memset(&vv, 0, sizeof(vv));
+    vv.bbox[0] = vv.bbox[1] = vv.bbox[2] = INT_MAX;
+    vv.bbox[3] = vv.bbox[4] = vv.bbox[5] = INT_MIN;
+    int n_out = 0;
+    for (int it = -1; it < iters; ++it) {
+      CK(cudaMemcpyAsync(J.vv, &vv, sizeof(vv), cudaMemcpyHostToDevice, C->st));
+      CK(cudaEventRecord(ev[0], C->st));
+      if (small) launch_voxel_cluster(L, C->aux_vox_dev, 1, false, C->cfg);
+      else launch_voxel(L, C->aux_vox_dev, 1, C->aux_sort_dev, false);
+      CK(cudaEventRecord(ev[1], C->st));
+      CK(cudaMemcpyAsync(hdr, C->aux_n, sizeof(hdr), cudaMemcpyDeviceToHost, C->st));
+      CK(cudaStreamSynchronize(C->st));
+      CK(cudaGetLastError());
+      float a = 0;
+      CK(cudaEventElapsedTime(&a, ev[0], ev[1]));
+      if (it >= 0) acc[0] += a;
+      n_out = hdr[1];
+    }
+    ms_out[0] = acc[0] / iters; ms_out[1] = 0; ms_out[2] = (double)n_out; ms_out[3] = 0;
+  }
+  for (int i = 0; i < 3; ++i) cudaEventDestroy(ev[i]);
+  return VILF_OK;
+}
+
 int vilf_factors(vilf_handle* h, const double pose[7], const float* edge, int n_edge, const float* surf, int n_surf, uint8_t* edge_valid,
                  double* edge_ab, int32_t* edge_nn, float* edge_d2, uint8_t* surf_valid, double* surf_nd, int32_t* surf_nn, float* surf_d2) {
   HCHECK(h);
