@@ -53,7 +53,7 @@ def parse():
     ap.add_argument("--seqs", type=int, default=32, help="independent sequences per GPU")
     ap.add_argument("--depth", type=int, default=3, help="frames in flight (submit ahead of wait)")
     ap.add_argument("--groups", type=int, default=4, help="split the sequences of a GPU into this many lock-step batches, each on its own CUDA stream")
-    ap.add_argument("--cpu-frames", type=int, default=60, help="frames per core of the bounded CPU sample")
+    ap.add_argument("--cpu-frames", type=int, default=300, help="frames per core of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--map-cap", type=int, default=1 << 18, help="capacity of each local map (points); overflow is an error, not a truncation")
@@ -163,12 +163,15 @@ def algorithmic_bytes(phase: str, kernel: str, c: dict) -> float | None:
     """Algorithmic bytes of ONE launch (all S sequences of the rank), SURVEY.md §8(d) figures; c = mean counts per sequence."""
     N, F, Q, M, S = c["n_scan"], c["n_edge"] + c["n_surf"], c["n_ds"], c["n_map"], c["seqs"]
     per = {
-        ("extract", "k_sort_hist<KeyGenRing>"): 16 * N,
+        ("extract", "k_sort_keyhist<KeyGenRing>"): 16 * N + 8 * N,
         ("extract", "k_sort_scatter"): 16 * N,
-        ("extract", "k_sector_select"): 16 * N + 16 * F,
-        ("extract", "k_compact_features"): 32 * F,
-        ("assoc_solve", "k_knn_fit"): 56 * Q + 16 * M + 96 * Q,
-        ("assoc_solve", "k_solve"): 96 * Q,
+        ("extract", "k_sector_select"): 4 * N + 16 * N + 20 * F,
+        ("extract", "k_compact_features"): 40 * F,
+        ("assoc_solve", "k_knn_assoc"): 136 * Q,            # 16 B query + 5 x 16 B neighbours + 40 B result
+        ("assoc_solve", "k_fit"): 40 * Q + 80 * Q + 64 * Q,  # result + gathered neighbours + factor record
+        ("assoc_solve", "k_solve"): 5 * 64 * Q,             # <= 5 evaluations of every factor record
+        ("scan_ds", "k_voxel_cluster"): 16 * F + 16 * Q,    # every feature read once, every voxel written once
+        ("map_update", "k_voxel_cluster"): 16 * (M + Q) + 16 * M + 32 * M,  # append + filter + hash build
         ("grid_build", None): 32 * M,
         ("scan_ds", None): 16 * F + 16 * Q,
         ("map_update", None): 16 * (M + Q) + 16 * M,
@@ -276,6 +279,29 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
     close_all(b_host)
     same = bool(np.array_equal(poses_dev, poses_host))
 
+    # ---- what the host link can do: the same pinned scans copied with nothing else running (the ceiling of e2e) ----
+    def h2d_copy_only():
+        frames = list(range(W, min(F, W + 20)))
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tgt = torch.empty((cap, 4), dtype=torch.float32, device="cuda")
+        st = torch.cuda.Stream()
+        nbytes = 0
+        with torch.cuda.stream(st):
+            for rep in range(2):  # first repetition warms up
+                if rep == 1:
+                    ev0.record(st)
+                for f in frames:
+                    for s_ in range(S):
+                        n = int(counts[s_, f])
+                        cabi.memcpy_h2d_async(tgt.data_ptr(), host[s_, f].ctypes.data, n * 16, st.cuda_stream)
+                        if rep == 1:
+                            nbytes += n * 16
+            ev1.record(st)
+        st.synchronize()
+        return nbytes / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
+
+    h2d_peak = h2d_copy_only()
+
     roof = None
     kern_table = None
     if not args.no_roofline:
@@ -314,7 +340,9 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
                     frames_in_flight=D, l2="inputs of one step are distinct frames (S x 1.8 MB) and all K steps use fresh scans; no cache flush needed",
                     parallelism=f"{world} replica(s) x {S} independent sequences in {G} lock-step batch(es) on {G} stream(s), no collective"),
         e2e=dict(value=scans / (ms_host_max * 1e-3), unit="scans/s", h2d_bytes_per_step=int(counts[:, W:].mean() * 16 * S), d2h_bytes_per_step=int(S * 7 * 8),
-                 ms_per_step=ms_host_max / K, poses_equal_to_device_resident_run=same),
+                 ms_per_step=ms_host_max / K, poses_equal_to_device_resident_run=same,
+                 h2d_gbs=float(counts[:, W:].sum()) * 16 / (ms_host * 1e-3) / 1e9, h2d_copy_only_gbs=h2d_peak,
+                 note="the step moves S packed scans (16 B per point, the payload of pcl::PointXYZI) over PCIe; h2d_copy_only_gbs is the same pinned buffers copied with the GPU idle"),
         gpu_launches=int(launches), clocks=clk,
         wall_ms=dict(dev=wall_dev, host=wall_host), gen_s=t_gen,
     )
@@ -327,6 +355,9 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
 
 def main():
     args = parse()
+    # torchrun pins OMP_NUM_THREADS to 1; the synthetic ray caster (OpenMP, host side, untimed) may use this rank's share of the cores
+    lws = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // max(lws, 1)))
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -74,6 +74,8 @@ const char* vilf_last_error(const vilf_handle* h);
 /* Pinned host memory for scan buffers (optional; makes the H2D copy asynchronous). */
 int vilf_host_alloc(void** p, uint64_t bytes);
 int vilf_host_free(void* p);
+/* cudaMemcpyAsync(HostToDevice) on a caller-supplied stream (bench.py measures the host link with it). */
+int vilf_memcpy_h2d_async(void* dst_dev, const void* src_host, uint64_t bytes, void* cuda_stream);
 
 /* ---- the per-frame path, as the node drives it (NODE:339-389) ---- */
 /* extractFeature (FE:223-232) + first frame ? localMapInited (EM:105-115) : optimation_processing

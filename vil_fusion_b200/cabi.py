@@ -35,7 +35,7 @@ class Config(C.Structure):
 
 # every symbol include/vilf.h declares (tests/test_abi.py checks the .so exports all of them)
 SYMBOLS = [
-    "vilf_default_config", "vilf_create", "vilf_create_batch", "vilf_destroy", "vilf_last_error", "vilf_host_alloc", "vilf_host_free",
+    "vilf_default_config", "vilf_create", "vilf_create_batch", "vilf_destroy", "vilf_last_error", "vilf_host_alloc", "vilf_host_free", "vilf_memcpy_h2d_async",
     "vilf_process_scan", "vilf_submit_scan", "vilf_wait", "vilf_submit_scan_batch", "vilf_wait_batch", "vilf_submit_scan_batch_dev",
     "vilf_feature_extract", "vilf_get_features", "vilf_map_init", "vilf_map_init_points", "vilf_update", "vilf_update_points",
     "vilf_get_pose", "vilf_set_pose", "vilf_predict", "vilf_create_submap", "vilf_get_cloud", "vilf_voxel_downsample", "vilf_crop_voxel_downsample", "vilf_crop_box", "vilf_knn5",
@@ -382,3 +382,10 @@ def host_alloc(nbytes: int) -> np.ndarray:
 
 def host_free(a: np.ndarray) -> None:
     lib().vilf_host_free(C.c_void_p(a.ctypes.data))
+
+
+def memcpy_h2d_async(dst_dev_ptr: int, src_host_ptr: int, nbytes: int, stream: int) -> None:
+    """cudaMemcpyAsync(HostToDevice) on `stream` through the CUDA runtime the library links (bench.py: link-speed probe)."""
+    rc = lib().vilf_memcpy_h2d_async(C.c_void_p(dst_dev_ptr), C.c_void_p(src_host_ptr), C.c_uint64(nbytes), C.c_void_p(stream))
+    if rc:
+        raise VilfError(rc, "cudaMemcpyAsync failed")

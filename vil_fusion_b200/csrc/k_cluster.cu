@@ -154,15 +154,40 @@ __device__ void emit_range(const VoxJob& J, const uint32_t* key, const uint32_t*
     const bool is_start = lane < lim && ((all_starts >> lane) & 1u);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int cnt = 0, e = 0, my_dst = 0;
-    if (is_start) {
+    if (all_starts == 1u && lim == 32) {
+      // the whole step lies inside ONE run (dense returns near the sensor: hundreds of points per voxel): lanes 0..3 sum
+      // one component each over the 32 staged points, loads first, then the dependent fp32 adds in input order
+      float a = 0.f;
+      if (lane < 4) {
+        if (cont0) a = lane == 0 ? cacc.x : lane == 1 ? cacc.y : lane == 2 ? cacc.z : cacc.w;
+        const float* sp = reinterpret_cast<const float*>(stage) + lane;
+        float vv[32];
+#pragma unroll
+        for (int t = 0; t < 32; ++t) vv[t] = sp[4 * t];
+#pragma unroll
+        for (int t = 0; t < 32; ++t) a = fadd(a, vv[t]);
+      }
+      acc.x = __shfl_sync(FULL, a, 0); acc.y = __shfl_sync(FULL, a, 1); acc.z = __shfl_sync(FULL, a, 2); acc.w = __shfl_sync(FULL, a, 3);
+      e = 32;
+      cnt = (cont0 ? ccnt : 0) + 32;
+      my_dst = cont0 ? cdst : dst;
+    } else if (is_start) {
       const unsigned higher = lane == 31 ? 0u : (all_starts & ~((2u << lane) - 1u));
       e = higher ? min(__ffs(higher) - 1, lim) : lim;  // exclusive end of my run inside this step
       if (lane == 0 && cont0) { acc = cacc; cnt = ccnt; my_dst = cdst; }
       else my_dst = dst + __popc(starts & ((1u << lane) - 1u));
-      for (int t = lane; t < e; ++t) {
+      cnt += e - lane;
+      int t = lane;
+      for (; t + 4 <= e; t += 4) {
+        const float4 q0 = stage[t], q1 = stage[t + 1], q2 = stage[t + 2], q3 = stage[t + 3];
+        acc.x = fadd(fadd(fadd(fadd(acc.x, q0.x), q1.x), q2.x), q3.x);
+        acc.y = fadd(fadd(fadd(fadd(acc.y, q0.y), q1.y), q2.y), q3.y);
+        acc.z = fadd(fadd(fadd(fadd(acc.z, q0.z), q1.z), q2.z), q3.z);
+        acc.w = fadd(fadd(fadd(fadd(acc.w, q0.w), q1.w), q2.w), q3.w);
+      }
+      for (; t < e; ++t) {
         const float4 q = stage[t];
         acc.x = fadd(acc.x, q.x); acc.y = fadd(acc.y, q.y); acc.z = fadd(acc.z, q.z); acc.w = fadd(acc.w, q.w);
-        ++cnt;
       }
     }
     // a run reaching the end of a FULL step may continue: carry it; every other run is complete

@@ -630,6 +630,9 @@ int vilf_destroy(vilf_handle* h) {
 const char* vilf_last_error(const vilf_handle* h) { return (h && h->ctx) ? h->ctx->err : "invalid handle"; }
 
 int vilf_host_alloc(void** p, uint64_t bytes) { return cudaMallocHost(p, bytes) == cudaSuccess ? VILF_OK : VILF_ERR_CUDA; }
+int vilf_memcpy_h2d_async(void* dst_dev, const void* src_host, uint64_t bytes, void* cuda_stream) {
+  return cudaMemcpyAsync(dst_dev, src_host, (size_t)bytes, cudaMemcpyHostToDevice, (cudaStream_t)cuda_stream) == cudaSuccess ? VILF_OK : VILF_ERR_CUDA;
+}
 int vilf_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? VILF_OK : VILF_ERR_CUDA; }
 
 int vilf_submit_scan(vilf_handle* h, const float* xyzi, int n, const uint16_t* ring, int64_t* ticket) {
