@@ -1,10 +1,10 @@
 #!/bin/bash
 # Run on the GPU box (via gpurun): plain run first, then the ncu launch list, then a --set full capture of ONE whole
-# steady-state frame (every kernel of the launch sequence once).
+# steady-state frame (every kernel of the launch sequence once).  One stream group, so launches are not interleaved.
 # usage: tools/profile_frame.sh <tag> <seqs> <launches_per_frame> [frame_to_capture]
 set -u
 TAG=$1; S=$2; LPF=$3; FR=${4:-20}
-ARGS="--steps 25 --warmup 3 --seqs $S --no-cpu --no-roofline"
+ARGS="--steps 25 --warmup 3 --seqs $S --groups 1 --no-cpu --no-roofline"
 mkdir -p gpurun_out
 python bench.py $ARGS > gpurun_out/${TAG}_plain.json 2> gpurun_out/${TAG}_plain.err || { echo "plain run failed"; tail -5 gpurun_out/${TAG}_plain.err; exit 1; }
 SKIP=$((LPF * FR))

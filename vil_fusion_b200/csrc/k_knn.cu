@@ -162,6 +162,16 @@ __device__ __forceinline__ void top5_insert(Top5& t, float cd, int ci) {  // pre
   }
 }
 
+// EIGHT lanes per query (four queries per warp).  A whole warp per query was issue bound (515 warp instructions per query
+// for ~30 candidates, profiles/r1b), one thread per query latency bound (27 x 2 dependent L2 round trips per thread, 9.7 of
+// 32 lanes active, profiles/r1f).  Here lane sl of a group owns buckets sl, sl+8, sl+16, sl+24 of the 27: their bounds
+// are 8 independent loads, the first two candidates of each of its buckets 8 more, so a query costs ~3 dependent round
+// trips.  Every lane keeps the best five of ITS candidates; five rounds of a group arg-min (xor shuffles over 8 lanes)
+// merge them, and every lane holding the winner pops it — which also removes duplicates that reach two lanes through
+// colliding buckets.  Same (d^2, index) order as before, so the result is bit-identical.
+constexpr int KNN_THREADS = 128;
+constexpr int KNN_GROUP = 8;
+
 __device__ __forceinline__ void knn_consider(Top5& best, float gate_f, float qx, float qy, float qz, const float4 c) {
   const float ddx = fsub(qx, c.x), ddy = fsub(qy, c.y), ddz = fsub(qz, c.z);
   const float cd = fadd(fadd(fmul(ddx, ddx), fmul(ddy, ddy)), fmul(ddz, ddz));  // FLANN L2_Simple<float>
@@ -173,43 +183,64 @@ __device__ __forceinline__ void knn_consider(Top5& best, float gate_f, float qx,
   }
 }
 
-// The walk is latency bound (every bucket costs a dependent pair of loads), so the loads of one row of three cells are
-// issued together: 6 bucket bounds, then the first PF candidates of each of the three buckets, then the (rare) rest.
-// (A single flattened loop over all candidates of a query, fed from a per-thread bucket list in shared memory, was
-// measured slower: 111 us against 77 us per launch at 16 sequences — the longest lane of the warp then dictates ~80
-// dependent L2 round trips.)
-__device__ __forceinline__ void thread_knn5(const GridJob& G, float inv_cell, float gate_f, float qx, float qy, float qz, Top5& best) {
-  constexpr int PF = 3;
+// Called by all 32 lanes; the lanes of a group (lane >> 3) pass the same query.  Returns in (rd, ri) of group lane sl < 5 the
+// sl-th nearest neighbour (FLT_MAX / INT_MAX when there are fewer than sl + 1 inside the gate).
+__device__ __forceinline__ void group_knn5(const GridJob& G, float inv_cell, float gate_f, float qx, float qy, float qz, bool active, float& rd, int& ri) {
+  constexpr int PF = 2;
+  const int sl = threadIdx.x & (KNN_GROUP - 1);
+  Top5 best;
 #pragma unroll
   for (int k = 0; k < 5; ++k) { best.d[k] = FLT_MAX; best.id[k] = INT_MAX; }
-  const uint32_t hm = (uint32_t)(*G.hvar) - 1u;
-  int qcx, qcy, qcz;
-  cell_of(make_float4(qx, qy, qz, 0.f), inv_cell, qcx, qcy, qcz);
-  const uint32_t* __restrict__ start = G.start;
-  const float4* __restrict__ sorted = G.sorted;
-#pragma unroll 1
-  for (int row = 0; row < 9; ++row) {
-    const int dy = row % 3 - 1, dz = row / 3 - 1;
-    uint32_t s[3], e[3];
+  if (active) {
+    const uint32_t hm = (uint32_t)(*G.hvar) - 1u;
+    int qcx, qcy, qcz;
+    cell_of(make_float4(qx, qy, qz, 0.f), inv_cell, qcx, qcy, qcz);
+    const uint32_t* __restrict__ start = G.start;
+    const float4* __restrict__ sorted = G.sorted;
+    uint32_t s[4], e[4];
 #pragma unroll
-    for (int dx = 0; dx < 3; ++dx) {
-      const uint32_t h = cell_hash(qcx + dx - 1, qcy + dy, qcz + dz) & hm;
-      s[dx] = __ldg(start + h);
-      e[dx] = __ldg(start + h + 1);
+    for (int j = 0; j < 4; ++j) {
+      const int c = sl + KNN_GROUP * j;  // cell (c % 3 - 1, (c / 3) % 3 - 1, c / 9 - 1)
+      s[j] = 0; e[j] = 0;
+      if (c < 27) {
+        const uint32_t h = cell_hash(qcx + c % 3 - 1, qcy + (c / 3) % 3 - 1, qcz + c / 9 - 1) & hm;
+        s[j] = __ldg(start + h);
+        e[j] = __ldg(start + h + 1);
+      }
     }
-    float4 c[3][PF];
+    float4 c[4][PF];
 #pragma unroll
-    for (int dx = 0; dx < 3; ++dx)
+    for (int j = 0; j < 4; ++j)
 #pragma unroll
       for (int i = 0; i < PF; ++i)
-        if (s[dx] + i < e[dx]) c[dx][i] = __ldg(sorted + s[dx] + i);
+        if (s[j] + i < e[j]) c[j][i] = __ldg(sorted + s[j] + i);
 #pragma unroll
-    for (int dx = 0; dx < 3; ++dx) {
+    for (int j = 0; j < 4; ++j) {
 #pragma unroll
       for (int i = 0; i < PF; ++i)
-        if (s[dx] + i < e[dx]) knn_consider(best, gate_f, qx, qy, qz, c[dx][i]);
-      for (uint32_t p = s[dx] + PF; p < e[dx]; ++p) knn_consider(best, gate_f, qx, qy, qz, __ldg(sorted + p));
+        if (s[j] + i < e[j]) knn_consider(best, gate_f, qx, qy, qz, c[j][i]);
+      for (uint32_t p = s[j] + PF; p < e[j]; ++p) knn_consider(best, gate_f, qx, qy, qz, __ldg(sorted + p));
     }
+  }
+  rd = FLT_MAX; ri = INT_MAX;
+#pragma unroll
+  for (int round = 0; round < 5; ++round) {
+    float wd = best.d[0];
+    int wi = best.id[0];
+#pragma unroll
+    for (int off = 1; off < KNN_GROUP; off <<= 1) {
+      const float od = __shfl_xor_sync(0xffffffffu, wd, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, wi, off);
+      const bool take = closer(od, oi, wd, wi);
+      wd = take ? od : wd;
+      wi = take ? oi : wi;
+    }
+    if (sl == round) { rd = wd; ri = wi; }
+    const bool pop = (best.id[0] == wi) & (wi != INT_MAX);  // every lane holding the winner drops it
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { best.d[k] = pop ? best.d[k + 1] : best.d[k]; best.id[k] = pop ? best.id[k + 1] : best.id[k]; }
+    best.d[4] = pop ? FLT_MAX : best.d[4];
+    best.id[4] = pop ? INT_MAX : best.id[4];
   }
 }
 
@@ -334,9 +365,9 @@ __device__ D3 lstsq5x3(const double Ain[5][3]) {
   return d3(n[0], n[1], n[2]);
 }
 
-// Association, kernel 1: one thread per voxel-filtered feature point: transform (EM:355-363) + 5-NN (EM:128 / :185).
-__global__ void __launch_bounds__(128) k_knn_assoc(LaneDev* lanes, const GridJob* __restrict__ grid_jobs, int lane0, ConfigDev cfg,
-                                                    const double* pose_override) {
+// Association, kernel 1: eight lanes per voxel-filtered feature point: transform (EM:355-363) + 5-NN (EM:128 / :185).
+__global__ void __launch_bounds__(KNN_THREADS) k_knn_assoc(LaneDev* lanes, const GridJob* __restrict__ grid_jobs, int lane0, ConfigDev cfg,
+                                                            const double* pose_override) {
   const int ln = lane0 + blockIdx.y;
   const LaneDev& L = lanes[ln];
   LaneVars& V = *L.v;
@@ -347,16 +378,22 @@ __global__ void __launch_bounds__(128) k_knn_assoc(LaneDev* lanes, const GridJob
 #pragma unroll
   for (int i = 0; i < 7; ++i) x[i] = pose_override ? pose_override[i] : V.x[i];
   if (blockIdx.x == 0 && threadIdx.x == 0) V.opt_ran = 1;
-  for (int q = blockIdx.x * 128 + threadIdx.x; q < ne + ns; q += gridDim.x * 128) {
-    const int w = q < ne ? 0 : 1;
-    const int k = q < ne ? q : q - ne;
-    const float4 pw = associate(x, L.ds[w][k]);
-    Top5 best;
-    thread_knn5(grid_jobs[ln * 2 + w], cfg.inv_cell, cfg.knn_gate_f, pw.x, pw.y, pw.z, best);
-#pragma unroll
-    for (int j = 0; j < 5; ++j) {
-      L.nn_idx[w][k * 5 + j] = best.id[j] == INT_MAX ? -1 : best.id[j];
-      L.nn_d2[w][k * 5 + j] = best.d[j];
+  const int sl = threadIdx.x & (KNN_GROUP - 1);
+  const int gpb = KNN_THREADS / KNN_GROUP;  // queries per CTA per sweep
+  const int nq = ne + ns;
+  for (int base = blockIdx.x * gpb; base < nq; base += gridDim.x * gpb) {  // whole warps iterate together (shuffles inside)
+    const int q = base + (threadIdx.x / KNN_GROUP);
+    const bool active = q < nq;
+    const int w = (active && q >= ne) ? 1 : 0;
+    const int k = active ? (q < ne ? q : q - ne) : 0;
+    float4 pw = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active) pw = associate(x, L.ds[w][k]);
+    float rd;
+    int ri;
+    group_knn5(grid_jobs[ln * 2 + w], cfg.inv_cell, cfg.knn_gate_f, pw.x, pw.y, pw.z, active, rd, ri);
+    if (active && sl < 5) {
+      L.nn_idx[w][k * 5 + sl] = ri == INT_MAX ? -1 : ri;
+      L.nn_d2[w][k * 5 + sl] = rd;
     }
   }
 }
@@ -431,8 +468,8 @@ __global__ void __launch_bounds__(128) k_fit(LaneDev* lanes, int lane0, int cur,
 void launch_knn_fit(const Launch& L, LaneDev* lanes, const GridJob* grid_jobs, int lane0, int nlanes, int cur, const ConfigDev& cfg,
                     const double* pose_override, int want_nn) {
   (void)want_nn;
-  dim3 g(KNN_G, nlanes);
-  k_knn_assoc<<<g, 128, 0, L.st>>>(lanes, grid_jobs, lane0, cfg, pose_override);
+  dim3 g(KNN_G * 4, nlanes);
+  k_knn_assoc<<<g, KNN_THREADS, 0, L.st>>>(lanes, grid_jobs, lane0, cfg, pose_override);
   L.tick(K_KNN_FIT);
   dim3 g2(FIT_G, nlanes);
   k_fit<<<g2, 128, 0, L.st>>>(lanes, lane0, cur, cfg);
@@ -440,23 +477,28 @@ void launch_knn_fit(const Launch& L, LaneDev* lanes, const GridJob* grid_jobs, i
 }
 
 // nearestKSearch alone against an explicit map (test entry point vilf_knn5).
-__global__ void __launch_bounds__(128) k_knn_only(const GridJob* __restrict__ job, const float4* __restrict__ q, const int* nq_dev, int* idx,
-                                                   float* d2, float inv_cell, float gate_f) {
+__global__ void __launch_bounds__(KNN_THREADS) k_knn_only(const GridJob* __restrict__ job, const float4* __restrict__ q, const int* nq_dev, int* idx,
+                                                           float* d2, float inv_cell, float gate_f) {
   const int nq = *nq_dev;
-  for (int i = blockIdx.x * 128 + threadIdx.x; i < nq; i += gridDim.x * 128) {
-    const float4 p = q[i];
-    Top5 best;
-    thread_knn5(*job, inv_cell, gate_f, p.x, p.y, p.z, best);
-#pragma unroll
-    for (int j = 0; j < 5; ++j) {
-      idx[i * 5 + j] = best.id[j] == INT_MAX ? -1 : best.id[j];
-      d2[i * 5 + j] = best.d[j];
+  const int sl = threadIdx.x & (KNN_GROUP - 1);
+  const int gpb = KNN_THREADS / KNN_GROUP;
+  for (int base = blockIdx.x * gpb; base < nq; base += gridDim.x * gpb) {
+    const int i = base + (threadIdx.x / KNN_GROUP);
+    const bool active = i < nq;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active) p = q[i];
+    float rd;
+    int ri;
+    group_knn5(*job, inv_cell, gate_f, p.x, p.y, p.z, active, rd, ri);
+    if (active && sl < 5) {
+      idx[i * 5 + sl] = ri == INT_MAX ? -1 : ri;
+      d2[i * 5 + sl] = rd;
     }
   }
 }
 
 void launch_knn_only(const Launch& L, const GridJob* job_dev, const float4* q, const int* nq_dev, int* idx, float* d2, const ConfigDev& cfg) {
-  k_knn_only<<<KNN_G, 128, 0, L.st>>>(job_dev, q, nq_dev, idx, d2, cfg.inv_cell, cfg.knn_gate_f);
+  k_knn_only<<<KNN_G * 4, KNN_THREADS, 0, L.st>>>(job_dev, q, nq_dev, idx, d2, cfg.inv_cell, cfg.knn_gate_f);
   L.tick(K_KNN_ONLY);
 }
 
