@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--cpu-frames", type=int, default=300, help="frames per core of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the large-map kNN / map-update stage timings")
     ap.add_argument("--map-cap", type=int, default=1 << 18, help="capacity of each local map (points); overflow is an error, not a truncation")
     return ap.parse_args()
 
@@ -329,6 +330,31 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
                     share_of_step=dms / tot, launches_timed=dn, avg_launch_us=dur_s * 1e6, algorithmic_bytes_per_launch=ab,
                     note="event-to-event interval (includes the launch gap); per-frame working set is L2-resident, so this path is latency-, not HBM-bound (DESIGN.md §6)")
 
+    # ---- the two stages the north star names, at a size where HBM matters (BASELINE configs[2]: ~1e6 map points) ----
+    large = None
+    if rank == 0 and not args.no_sweep:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import roofline_sweep as rs
+            rng = np.random.default_rng(7)
+            g = cabi.Odometry(cabi.default_config(max_scan_points=300000, max_map_points=(1 << 20) + 1024), device=local_rank)
+            mp = rs.make_map(1_000_000, rng)
+            nq = 260_000
+            q = mp[rng.integers(0, mp.shape[0], nq)].copy()
+            q[:, :3] += rng.normal(0, 0.03, (nq, 3)).astype(np.float32)
+            k = g.bench_stage(0, mp, q, iters=5)
+            u = g.bench_stage(1, mp, leaf=0.4, iters=5)
+            g.close()
+            pk = rs.peak
+            large = dict(map_points=int(mp.shape[0]), queries=nq, peak_gbs=pk,
+                         knn_build=dict(ms=k[0], gbs=32.0 * mp.shape[0] / (k[0] * 1e-3) / 1e9, frac=32.0 * mp.shape[0] / (k[0] * 1e-3) / 1e9 / pk),
+                         knn_query=dict(ms=k[1], queries_per_s=nq / (k[1] * 1e-3), gbs=136.0 * nq / (k[1] * 1e-3) / 1e9, frac=136.0 * nq / (k[1] * 1e-3) / 1e9 / pk),
+                         map_update=dict(ms=u[0], voxels_out=int(u[2]), points_per_s=mp.shape[0] / (u[0] * 1e-3),
+                                         gbs=(16.0 * mp.shape[0] + 16.0 * u[2]) / (u[0] * 1e-3) / 1e9, frac=(16.0 * mp.shape[0] + 16.0 * u[2]) / (u[0] * 1e-3) / 1e9 / pk),
+                         note="device-resident stage timings (vilf_bench_stage) on a synthetic 1e6-point map, algorithmic bytes: hash build 32 B/point, query 136 B, map update 16 B/point + 16 B/voxel")
+        except Exception as e:  # the headline numbers stand on their own
+            large = dict(error=repr(e))
+
     # ---- max over ranks ----
     ms_dev_max, ms_host_max = replicas.max_over_ranks([ms_dev, ms_host], device="cuda")
     scans = replicas.job_scans(world, S, K)
@@ -346,6 +372,8 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         gpu_launches=int(launches), clocks=clk,
         wall_ms=dict(dev=wall_dev, host=wall_host), gen_s=t_gen,
     )
+    if large:
+        out["large_map"] = large
     if roof:
         out["roofline"] = roof
         out["kernels_ms"] = kern_table[:12]

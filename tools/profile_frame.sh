@@ -4,7 +4,7 @@
 # usage: tools/profile_frame.sh <tag> <seqs> <launches_per_frame> [frame_to_capture]
 set -u
 TAG=$1; S=$2; LPF=$3; FR=${4:-20}
-ARGS="--steps 25 --warmup 3 --seqs $S --groups 1 --no-cpu --no-roofline"
+ARGS="--steps 25 --warmup 3 --seqs $S --groups 1 --no-cpu --no-sweep --no-roofline"
 mkdir -p gpurun_out
 python bench.py $ARGS > gpurun_out/${TAG}_plain.json 2> gpurun_out/${TAG}_plain.err || { echo "plain run failed"; tail -5 gpurun_out/${TAG}_plain.err; exit 1; }
 SKIP=$((LPF * FR))

@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 if [ "$K" = "all" ]; then python -m pytest tests -m gpu -x -q 2>&1 | tail -15
 elif [ "$K" != "none" ]; then python -m pytest tests -m gpu -x -q -k "$K" 2>&1 | tail -15; fi
 for s in $SEQS; do
-  python bench.py --steps 100 --warmup 5 --seqs $s --no-cpu > gpurun_out/c$s.json 2> gpurun_out/c$s.err || { echo "bench S=$s failed"; tail -5 gpurun_out/c$s.err; continue; }
+  python bench.py --steps 100 --warmup 5 --seqs $s --no-cpu --no-sweep > gpurun_out/c$s.json 2> gpurun_out/c$s.err || { echo "bench S=$s failed"; tail -5 gpurun_out/c$s.err; continue; }
   python - <<PY
 import json
 d=json.load(open("gpurun_out/c$s.json"))
