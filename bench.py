@@ -342,7 +342,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
             nq = 260_000
             q = mp[rng.integers(0, mp.shape[0], nq)].copy()
             q[:, :3] += rng.normal(0, 0.03, (nq, 3)).astype(np.float32)
-            k = g.bench_stage(0, mp, q, iters=5)
+            k = g.bench_stage(0, mp, q, leaf=0.2, iters=5)  # 0.24 m point spacing: the grid a 0.2 m voxel-filtered map gets
             u = g.bench_stage(1, mp, leaf=0.4, iters=5)
             g.close()
             pk = rs.peak

@@ -171,7 +171,8 @@ int vilf_profile_read_kernels(vilf_handle* h, double* ms_out, int64_t* launches_
 const char* vilf_profile_kernel_name(int kernel);
 /* Device-resident timing of one stage on an explicit cloud (roofline sweeps; the cloud is uploaded once, then the stage
  * runs `iters` times between CUDA events on the handle's stream, after one warm-up run).
- * stage 0: spatial-hash build over `map` + 5-NN of the nq queries -> ms_out[0] = build, ms_out[1] = query (per run).
+ * stage 0: spatial-hash build over `map` + 5-NN of the nq queries -> ms_out[0] = build, ms_out[1] = query (per run); the grid
+ *          cell is the one a map voxel-filtered at `leaf` gets (leaf <= 0: the handle's default), ms_out[2] = shells, ms_out[3] = cell.
  * stage 1: crop box (+-100 m about the origin) + voxel filter at `leaf` of `map` -> ms_out[0] per run, ms_out[2] = voxels out. */
 int vilf_bench_stage(vilf_handle* h, int stage, const float* map, int m, const float* q, int nq, float leaf, int iters, double ms_out[4]);
 /* Number of kernels this library has launched on the handle's context since creation. */

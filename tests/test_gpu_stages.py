@@ -318,3 +318,27 @@ def test_solve_random_problems_vs_oracle(g16, orc):
         assert termo == termg and tro.shape == trg.shape, trial
         assert np.array_equal(tro[:, :3], trg[:, :3])
         assert np.abs(po - pg).max() < 1e-9, trial
+
+
+@pytest.mark.parametrize("leaf,spacing", [(0.2, 0.2), (0.1, 0.12), (0.4, 0.4)])
+def test_knn5_dense_maps_fine_cells_early_exit(cabi, orc, leaf, spacing):
+    """Maps filtered at a fine leaf get search cells finer than the gate radius and a shell-by-shell walk with early exit
+    (k_knn.cu: group_knn5): the neighbours must still be exactly the oracle's (FLANN-order) five, index for index."""
+    rng = np.random.default_rng(int(leaf * 1000))
+    side = int(40.0 / spacing)
+    gx, gy = np.meshgrid(np.arange(side) * spacing - 20.0, np.arange(side) * spacing - 20.0)
+    ground = np.stack([gx.ravel(), gy.ravel(), np.full(side * side, -1.7)], 1)
+    ground += rng.uniform(-0.3, 0.3, ground.shape) * spacing
+    wall = np.stack([rng.uniform(-20, 20, 20000), np.full(20000, 7.0) + rng.normal(0, 0.02, 20000), rng.uniform(-1.7, 6.0, 20000)], 1)
+    sparse = rng.uniform(-20, 20, (300, 3))  # isolated points: queries near them need every shell or have fewer than 5 inside the gate
+    mp = np.concatenate([ground, wall, sparse]).astype(np.float32)
+    mp = np.concatenate([mp, rng.random((mp.shape[0], 1), dtype=np.float32)], 1)
+    q = np.concatenate([mp[rng.integers(0, mp.shape[0], 4000), :3] + rng.normal(0, 0.05, (4000, 3)), rng.uniform(-21, 21, (1000, 3))]).astype(np.float32)
+    q = np.concatenate([q, np.zeros((q.shape[0], 1), np.float32)], 1)
+    g = cabi.Odometry(cabi.default_config(edge_leaf=leaf, surf_leaf=2 * leaf, max_scan_points=20000, max_map_points=1 << 19))
+    gi, gd = g.knn5(mp, q)
+    oi, od = orc.knn(mp, q)
+    check_knn(gi, gd, oi, od)
+    full = od[:, 4] < 1.0
+    assert full.sum() > 3000 and (~full).sum() > 100  # both regimes are exercised
+    g.close()

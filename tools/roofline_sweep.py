@@ -43,13 +43,15 @@ def main():
         mp = make_map(m, rng)
         q = mp[rng.integers(0, mp.shape[0], nq)].copy()
         q[:, :3] += rng.normal(0, 0.03, (nq, 3)).astype(np.float32)
-        ms = g.bench_stage(0, mp, q, iters=10)
+        spacing = 200.0 / int(np.sqrt(int(m * 0.7)))
+        leaf = 0.8 if spacing >= 0.6 else 0.4 if spacing >= 0.3 else 0.2 if spacing >= 0.15 else 0.1  # the leaf such a map would be filtered at
+        ms = g.bench_stage(0, mp, q, leaf=leaf, iters=10)
         idx, d2 = g.knn5(mp[: min(m, 200000)], q[:1000])  # sanity: the stage returns real neighbours
         b_build, b_query = 32.0 * mp.shape[0], 136.0 * nq
         out = dict(case="knn", map_points=int(mp.shape[0]), queries=nq, build_ms=ms[0], query_ms=ms[1],
                    queries_per_s=nq / (ms[1] * 1e-3), build_gbs=b_build / (ms[0] * 1e-3) / 1e9, query_gbs=b_query / (ms[1] * 1e-3) / 1e9,
                    build_frac=b_build / (ms[0] * 1e-3) / 1e9 / peak, query_frac=b_query / (ms[1] * 1e-3) / 1e9 / peak, peak_gbs=peak,
-                   found5=float((idx[:, 4] >= 0).mean()))
+                   found5=float((idx[:, 4] >= 0).mean()), grid_leaf=leaf, grid_cell_m=ms[3], grid_shells=int(ms[2]))
         print(json.dumps(out), flush=True)
         for leaf in (0.4, 0.2):
             ms = g.bench_stage(1, mp, leaf=leaf, iters=10)

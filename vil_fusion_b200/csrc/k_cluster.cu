@@ -57,7 +57,8 @@ __device__ __forceinline__ uint32_t cell_hash_c(int x, int y, int z) {
 }
 
 // Spatial-hash build (same table layout as k_knn.cu's grid-wide build) by the whole cluster.  `S` = this CTA's shared block.
-__device__ void grid_build_cluster(cg::cluster_group& cluster, const GridJob& G, int n, float inv_cell, VoxShared& S) {
+__device__ void grid_build_cluster(cg::cluster_group& cluster, const GridJob& G, int n, VoxShared& S) {
+  const float inv_cell = G.inv_cell;
   const int rank = (int)cluster.block_rank();
   const int tid = threadIdx.x;
   int H = 1024;
@@ -216,7 +217,7 @@ __device__ void emit_range(const VoxJob& J, const uint32_t* key, const uint32_t*
   }
 }
 
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CT, 2) k_voxel_cluster(const VoxJob* __restrict__ jobs, int bbox_done, float inv_cell) {
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CT, 2) k_voxel_cluster(const VoxJob* __restrict__ jobs, int bbox_done) {
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const VoxJob& J = jobs[blockIdx.y];
@@ -461,29 +462,29 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CT, 2) k_voxel_clus
   if (J.grid != nullptr) {
     cluster.sync();  // all centroids written
     PHASE_MARK(4);
-    grid_build_cluster(cluster, *J.grid, n_out, inv_cell, S);
+    grid_build_cluster(cluster, *J.grid, n_out, S);
   }
   cluster.sync();  // no CTA may exit while a peer can still read its shared memory
   PHASE_MARK(5);
 }
 
-void launch_voxel_cluster(const Launch& L, const VoxJob* jobs_dev, int njobs, bool bbox_done, const ConfigDev& cfg) {
+void launch_voxel_cluster(const Launch& L, const VoxJob* jobs_dev, int njobs, bool bbox_done, const ConfigDev&) {
   dim3 g(CL, njobs);
-  k_voxel_cluster<<<g, CT, 0, L.st>>>(jobs_dev, bbox_done ? 1 : 0, cfg.inv_cell);
+  k_voxel_cluster<<<g, CT, 0, L.st>>>(jobs_dev, bbox_done ? 1 : 0);
   L.tick(K_VOX_CLUSTER);
 }
 
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CT, 2) k_grid_cluster(const GridJob* __restrict__ jobs, float inv_cell) {
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CT, 2) k_grid_cluster(const GridJob* __restrict__ jobs) {
   cg::cluster_group cluster = cg::this_cluster();
   __shared__ VoxShared S;
   const GridJob& G = jobs[blockIdx.y];
-  grid_build_cluster(cluster, G, *G.n, inv_cell, S);
+  grid_build_cluster(cluster, G, *G.n, S);
   cluster.sync();
 }
 
-void launch_grid_cluster(const Launch& L, const GridJob* jobs_dev, int njobs, const ConfigDev& cfg) {
+void launch_grid_cluster(const Launch& L, const GridJob* jobs_dev, int njobs, const ConfigDev&) {
   dim3 g(CL, njobs);
-  k_grid_cluster<<<g, CT, 0, L.st>>>(jobs_dev, cfg.inv_cell);
+  k_grid_cluster<<<g, CT, 0, L.st>>>(jobs_dev);
   L.tick(K_GRID_CLUSTER);
 }
 

@@ -39,8 +39,9 @@ __global__ void __launch_bounds__(256) k_grid_zero(const GridJob* __restrict__ j
   if (blockIdx.x == 0 && threadIdx.x == 0) *J.hvar = H;
 }
 
-__global__ void __launch_bounds__(256) k_grid_count(const GridJob* __restrict__ jobs, float inv_cell) {
+__global__ void __launch_bounds__(256) k_grid_count(const GridJob* __restrict__ jobs) {
   const GridJob& J = jobs[blockIdx.y];
+  const float inv_cell = J.inv_cell;
   const int n = *J.n;
   const uint32_t hm = (uint32_t)grid_buckets(n, J.hcap) - 1u;
   for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
@@ -105,8 +106,9 @@ __global__ void __launch_bounds__(256) k_grid_scan_final(const GridJob* __restri
   }
 }
 
-__global__ void __launch_bounds__(256) k_grid_scatter(const GridJob* __restrict__ jobs, float inv_cell) {
+__global__ void __launch_bounds__(256) k_grid_scatter(const GridJob* __restrict__ jobs) {
   const GridJob& J = jobs[blockIdx.y];
+  const float inv_cell = J.inv_cell;
   const int n = *J.n;
   const uint32_t hm = (uint32_t)grid_buckets(n, J.hcap) - 1u;
   for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
@@ -118,17 +120,17 @@ __global__ void __launch_bounds__(256) k_grid_scatter(const GridJob* __restrict_
   }
 }
 
-void launch_grid_build(const Launch& L, const GridJob* jobs_dev, int njobs, const ConfigDev& cfg) {
+void launch_grid_build(const Launch& L, const GridJob* jobs_dev, int njobs, const ConfigDev&) {
   dim3 g(GRID_G, njobs);
   k_grid_zero<<<g, 256, 0, L.st>>>(jobs_dev);
   L.tick(K_GRID_ZERO);
-  k_grid_count<<<g, 256, 0, L.st>>>(jobs_dev, cfg.inv_cell);
+  k_grid_count<<<g, 256, 0, L.st>>>(jobs_dev);
   L.tick(K_GRID_COUNT);
   k_grid_scan_partial<<<g, 256, 0, L.st>>>(jobs_dev);
   L.tick(K_GRID_SCAN_PARTIAL);
   k_grid_scan_final<<<g, 256, 0, L.st>>>(jobs_dev);
   L.tick(K_GRID_SCAN_FINAL);
-  k_grid_scatter<<<g, 256, 0, L.st>>>(jobs_dev, cfg.inv_cell);
+  k_grid_scatter<<<g, 256, 0, L.st>>>(jobs_dev);
   L.tick(K_GRID_SCATTER);
 }
 
@@ -183,20 +185,40 @@ __device__ __forceinline__ void knn_consider(Top5& best, float gate_f, float qx,
   }
 }
 
+// Walk one bucket: the first PF candidates were loaded by the caller, the rest follow.
+template <int PF>
+__device__ __forceinline__ void knn_bucket(Top5& best, float gate_f, float qx, float qy, float qz, const float4* __restrict__ sorted, uint32_t s, uint32_t e,
+                                           const float4 (&c)[PF]) {
+#pragma unroll
+  for (int i = 0; i < PF; ++i)
+    if (s + i < e) knn_consider(best, gate_f, qx, qy, qz, c[i]);
+  for (uint32_t p = s + PF; p < e; ++p) knn_consider(best, gate_f, qx, qy, qz, __ldg(sorted + p));
+}
+
 // Called by all 32 lanes; the lanes of a group (lane >> 3) pass the same query.  Returns in (rd, ri) of group lane sl < 5 the
 // sl-th nearest neighbour (FLT_MAX / INT_MAX when there are fewer than sl + 1 inside the gate).
-__device__ __forceinline__ void group_knn5(const GridJob& G, float inv_cell, float gate_f, float qx, float qy, float qz, bool active, float& rd, int& ri) {
+//
+// Cells of Chebyshev distance <= 1 (27 buckets) come first.  Grids of dense maps have cells finer than the gate radius
+// (G.rings > 1): further shells follow, and the walk stops as soon as the fifth-best distance is certainly smaller than the
+// distance to anything in an unvisited shell: after shell r every unseen point is farther than (r + f) * cell, f = the
+// query's distance to the nearest face of its own cell in cell units.  The test uses an upper bound of the group's true
+// fifth distance (the smallest fifth distance any single lane holds) and a 1e-5 relative margin for the fp32 rounding of
+// computed distances, so it can only stop late, never early: the result is the same exact 5-NN as the full walk.
+__device__ __forceinline__ void group_knn5(const GridJob& G, float gate_f, float qx, float qy, float qz, bool active, float& rd, int& ri) {
   constexpr int PF = 2;
   const int sl = threadIdx.x & (KNN_GROUP - 1);
   Top5 best;
 #pragma unroll
   for (int k = 0; k < 5; ++k) { best.d[k] = FLT_MAX; best.id[k] = INT_MAX; }
+  const float inv_cell = G.inv_cell;
+  const int rings = G.rings;
+  int qcx = 0, qcy = 0, qcz = 0;
+  uint32_t hm = 0;
+  const uint32_t* __restrict__ start = G.start;
+  const float4* __restrict__ sorted = G.sorted;
   if (active) {
-    const uint32_t hm = (uint32_t)(*G.hvar) - 1u;
-    int qcx, qcy, qcz;
+    hm = (uint32_t)(*G.hvar) - 1u;
     cell_of(make_float4(qx, qy, qz, 0.f), inv_cell, qcx, qcy, qcz);
-    const uint32_t* __restrict__ start = G.start;
-    const float4* __restrict__ sorted = G.sorted;
     uint32_t s[4], e[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -215,11 +237,35 @@ __device__ __forceinline__ void group_knn5(const GridJob& G, float inv_cell, flo
       for (int i = 0; i < PF; ++i)
         if (s[j] + i < e[j]) c[j][i] = __ldg(sorted + s[j] + i);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < 4; ++j) knn_bucket<PF>(best, gate_f, qx, qy, qz, sorted, s[j], e[j], c[j]);
+  }
+  // the groups of a warp may use different grids (edge / surf): the shell loop runs to the warp-wide maximum
+  const int rmax = __reduce_max_sync(0xffffffffu, active ? rings : 1);
+  if (rmax > 1) {
+    float fmin_cells = 0.f;
+    if (active) {
+      const float ux = fmul(qx, inv_cell), uy = fmul(qy, inv_cell), uz = fmul(qz, inv_cell);
+      const float fx = fsub(ux, floorf(ux)), fy = fsub(uy, floorf(uy)), fz = fsub(uz, floorf(uz));
+      fmin_cells = fminf(fminf(fminf(fx, 1.f - fx), fminf(fy, 1.f - fy)), fminf(fz, 1.f - fz));
+    }
+    const double cell = 1.0 / (double)inv_cell;
+    for (int r = 1; r < rmax; ++r) {  // shells 0..r are done; is shell r + 1 needed?
+      float ub = best.d[4];            // a lane's own fifth distance bounds the group's from above
 #pragma unroll
-      for (int i = 0; i < PF; ++i)
-        if (s[j] + i < e[j]) knn_consider(best, gate_f, qx, qy, qz, c[j][i]);
-      for (uint32_t p = s[j] + PF; p < e[j]; ++p) knn_consider(best, gate_f, qx, qy, qz, __ldg(sorted + p));
+      for (int off = 1; off < KNN_GROUP; off <<= 1) ub = fminf(ub, __shfl_xor_sync(0xffffffffu, ub, off));
+      const double reach = ((double)r + (double)fmin_cells) * cell;
+      const bool done = !active || r >= rings || (double)ub < reach * reach * (1.0 - 1e-5);
+      if (__all_sync(0xffffffffu, done)) break;
+      if (!done) {
+        const int R = r + 1, side = 2 * R + 1, ncell = side * side * side;
+        for (int t = sl; t < ncell; t += KNN_GROUP) {
+          const int dx = t % side - R, dy = (t / side) % side - R, dz = t / (side * side) - R;
+          if (max(max(abs(dx), abs(dy)), abs(dz)) != R) continue;  // interior: visited before
+          const uint32_t h = cell_hash(qcx + dx, qcy + dy, qcz + dz) & hm;
+          const uint32_t s0 = __ldg(start + h), e0 = __ldg(start + h + 1);
+          for (uint32_t p = s0; p < e0; ++p) knn_consider(best, gate_f, qx, qy, qz, __ldg(sorted + p));
+        }
+      }
     }
   }
   rd = FLT_MAX; ri = INT_MAX;
@@ -390,7 +436,7 @@ __global__ void __launch_bounds__(KNN_THREADS) k_knn_assoc(LaneDev* lanes, const
     if (active) pw = associate(x, L.ds[w][k]);
     float rd;
     int ri;
-    group_knn5(grid_jobs[ln * 2 + w], cfg.inv_cell, cfg.knn_gate_f, pw.x, pw.y, pw.z, active, rd, ri);
+    group_knn5(grid_jobs[ln * 2 + w], cfg.knn_gate_f, pw.x, pw.y, pw.z, active, rd, ri);
     if (active && sl < 5) {
       L.nn_idx[w][k * 5 + sl] = ri == INT_MAX ? -1 : ri;
       L.nn_d2[w][k * 5 + sl] = rd;
@@ -478,7 +524,7 @@ void launch_knn_fit(const Launch& L, LaneDev* lanes, const GridJob* grid_jobs, i
 
 // nearestKSearch alone against an explicit map (test entry point vilf_knn5).
 __global__ void __launch_bounds__(KNN_THREADS) k_knn_only(const GridJob* __restrict__ job, const float4* __restrict__ q, const int* nq_dev, int* idx,
-                                                           float* d2, float inv_cell, float gate_f) {
+                                                           float* d2, float gate_f) {
   const int nq = *nq_dev;
   const int sl = threadIdx.x & (KNN_GROUP - 1);
   const int gpb = KNN_THREADS / KNN_GROUP;
@@ -489,7 +535,7 @@ __global__ void __launch_bounds__(KNN_THREADS) k_knn_only(const GridJob* __restr
     if (active) p = q[i];
     float rd;
     int ri;
-    group_knn5(*job, inv_cell, gate_f, p.x, p.y, p.z, active, rd, ri);
+    group_knn5(*job, gate_f, p.x, p.y, p.z, active, rd, ri);
     if (active && sl < 5) {
       idx[i * 5 + sl] = ri == INT_MAX ? -1 : ri;
       d2[i * 5 + sl] = rd;
@@ -498,7 +544,7 @@ __global__ void __launch_bounds__(KNN_THREADS) k_knn_only(const GridJob* __restr
 }
 
 void launch_knn_only(const Launch& L, const GridJob* job_dev, const float4* q, const int* nq_dev, int* idx, float* d2, const ConfigDev& cfg) {
-  k_knn_only<<<KNN_G * 4, KNN_THREADS, 0, L.st>>>(job_dev, q, nq_dev, idx, d2, cfg.inv_cell, cfg.knn_gate_f);
+  k_knn_only<<<KNN_G * 4, KNN_THREADS, 0, L.st>>>(job_dev, q, nq_dev, idx, d2, cfg.knn_gate_f);
   L.tick(K_KNN_ONLY);
 }
 

@@ -56,6 +56,7 @@ struct Ctx {
   int* aux_idx = nullptr; float* aux_d2 = nullptr;
   VoxJob* aux_vox_dev = nullptr; SortJob* aux_sort_dev = nullptr; GridJob* aux_grid_dev = nullptr;
   VoxJob aux_vox_host;
+  GridJob aux_grid_host;
   int* aux_head_cnt = nullptr;
   // per-lane host state
   std::vector<int> cur;        // map buffer holding the current local maps
@@ -133,8 +134,20 @@ int alloc_sort(Ctx* C, SortJob& S, const int* n, const int* bits, int fixed_bits
   return VILF_OK;
 }
 
-int alloc_grid(Ctx* C, GridJob& G, const float4* pts, const int* n, int cap) {
+// Cell edge of a map's search grid: cmax = the power of two >= sqrt(knn_gate) (one shell of 27 cells covers the gate), halved
+// while the cell still spans >= 2.5 leaf sizes, so a voxel-filtered map keeps a handful of points per cell however fine its
+// leaf is (0.4 / 0.8 m leaves keep the 1 m cell; a 0.2 m leaf gets 0.5 m cells and two shells with early exit).
+void grid_geometry(const Ctx* C, double leaf, GridJob& G) {
+  float cell = 1.0f / C->cfg.inv_cell;
+  int rings = 1;
+  while (rings < 16 && (double)cell * 0.5 >= 2.5 * leaf) { cell *= 0.5f; rings *= 2; }
+  G.inv_cell = 1.0f / cell;
+  G.rings = rings;
+}
+
+int alloc_grid(Ctx* C, GridJob& G, const float4* pts, const int* n, int cap, double leaf) {
   G.pts = pts; G.n = n;
+  grid_geometry(C, leaf, G);
   G.hcap = pow2_ge(2 * cap);
   if (G.hcap < 1024) G.hcap = 1024;
   CK(dalloc(C, &G.start, (size_t)G.hcap + 8));
@@ -270,7 +283,7 @@ int build_ctx(Ctx* C) {
     }
     for (int w = 0; w < 2; ++w) {
       GridJob G0;
-      rc = alloc_grid(C, G0, L.map[w][0], &L.v->n_map[w], capM);
+      rc = alloc_grid(C, G0, L.map[w][0], &L.v->n_map[w], capM, w ? u.surf_leaf : u.edge_leaf);
       if (rc) return rc;
       grid[0][l * 2 + w] = G0;
       GridJob G1 = G0;  // the two buffers are never indexed at the same time: share the grid storage
@@ -321,7 +334,8 @@ int build_ctx(Ctx* C) {
     if (rc) return rc;
     CK(cudaMemcpy(C->aux_sort_dev, &J.sort, sizeof(SortJob), cudaMemcpyHostToDevice));
     GridJob G;
-    rc = alloc_grid(C, G, C->aux_in, C->aux_n, capM);
+    rc = alloc_grid(C, G, C->aux_in, C->aux_n, capM, u.edge_leaf < u.surf_leaf ? u.edge_leaf : u.surf_leaf);
+    C->aux_grid_host = G;
     if (rc) return rc;
     CK(cudaMemcpy(C->aux_grid_dev, &G, sizeof(GridJob), cudaMemcpyHostToDevice));
   }
@@ -901,6 +915,10 @@ int vilf_bench_stage(vilf_handle* h, int stage, const float* map, int m, const f
   double acc[2] = {0, 0};
   const Launch L = mk(C);
   if (stage == 0) {
+    GridJob Gb = C->aux_grid_host;
+    if (leaf > 0) grid_geometry(C, (double)leaf, Gb);  // search-grid cell sized for a map filtered at `leaf`
+    CK(cudaMemcpyAsync(C->aux_grid_dev, &Gb, sizeof(Gb), cudaMemcpyHostToDevice, C->st));
+    CK(cudaStreamSynchronize(C->st));
     CK(cudaMemcpyAsync(C->aux_out, q, (size_t)nq * 16, cudaMemcpyHostToDevice, C->st));
     for (int it = -1; it < iters; ++it) {  // iteration -1 warms up
       CK(cudaEventRecord(ev[0], C->st));
@@ -915,7 +933,8 @@ int vilf_bench_stage(vilf_handle* h, int stage, const float* map, int m, const f
       CK(cudaEventElapsedTime(&b, ev[1], ev[2]));
       if (it >= 0) { acc[0] += a; acc[1] += b; }
     }
-    ms_out[0] = acc[0] / iters; ms_out[1] = acc[1] / iters; ms_out[2] = 0; ms_out[3] = 0;
+    ms_out[0] = acc[0] / iters; ms_out[1] = acc[1] / iters; ms_out[2] = (double)Gb.rings; ms_out[3] = 1.0 / (double)Gb.inv_cell;
+    CK(cudaMemcpy(C->aux_grid_dev, &C->aux_grid_host, sizeof(GridJob), cudaMemcpyHostToDevice));
   } else {
     VoxJob J = C->aux_vox_host;
     J.leaf = leaf; J.crop = 2; J.passthrough = 0;

@@ -131,6 +131,8 @@ struct GridJob {
   int* hvar;          // buckets in use (power of two)
   uint32_t* partial;  // [GRID_G]
   int hcap;
+  float inv_cell;     // 1 / cell edge of THIS grid: cell = cmax / 2^k, cmax = the power of two >= sqrt(knn_gate)
+  int rings;          // 2^k: cells of Chebyshev distance <= rings around the query cell cover the gate radius
 };
 
 // Per-lane device pointers.
