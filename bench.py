@@ -354,6 +354,22 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
             q[:, :3] += rng.normal(0, 0.03, (nq, 3)).astype(np.float32)
             k = g.bench_stage(0, mp, q, leaf=0.2, iters=5)  # 0.24 m point spacing: the grid a 0.2 m voxel-filtered map gets
             u = g.bench_stage(1, mp, leaf=0.4, iters=5)
+            # the caller-side stage next to the path (DESIGN.md §0 row f): lidar depth for 150 visual features on an HDL-64 scan
+            from oracle import orc
+            x0 = np.ascontiguousarray(host[0, W, : counts[0, W]])
+            T = np.eye(4); T[:3, :3] = [[0, -1, 0], [0, 0, -1], [1, 0, 0]]
+            fts = np.stack([rng.uniform(-1.2, 1.2, 150), rng.uniform(-0.4, 0.12, 150), np.ones(150)], 1).astype(np.float32)
+            g.feature_extract(x0)
+            g.feature_depth(fts, T_lidar_cam=T)
+            t0 = time.perf_counter()
+            for _ in range(50):
+                dg, _, ncl = g.feature_depth(fts, T_lidar_cam=T)
+            gpu_ms = (time.perf_counter() - t0) / 50 * 1e3
+            t0 = time.perf_counter()
+            do, _ = orc.feature_depth(orc.camera_cloud(x0, T), fts)
+            cpu_ms = (time.perf_counter() - t0) * 1e3
+            depth_assoc = dict(features=150, cloud_points=int(ncl), gpu_ms_per_call=gpu_ms, cpu_port_ms=cpu_ms, identical_to_cpu_port=bool(np.array_equal(dg, do)),
+                               note="vilf_feature_depth on the resident scan: wall time of the blocking call (1.9 KB up, 0.6 KB down); cpu = oracle restatement of NODE:54-140, :348-361, one core")
             g.close()
             pk = rs.peak
             large = dict(map_points=int(mp.shape[0]), queries=nq, peak_gbs=pk,
@@ -361,6 +377,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
                          knn_query=dict(ms=k[1], queries_per_s=nq / (k[1] * 1e-3), gbs=136.0 * nq / (k[1] * 1e-3) / 1e9, frac=136.0 * nq / (k[1] * 1e-3) / 1e9 / pk),
                          map_update=dict(ms=u[0], voxels_out=int(u[2]), points_per_s=mp.shape[0] / (u[0] * 1e-3),
                                          gbs=(16.0 * mp.shape[0] + 16.0 * u[2]) / (u[0] * 1e-3) / 1e9, frac=(16.0 * mp.shape[0] + 16.0 * u[2]) / (u[0] * 1e-3) / 1e9 / pk),
+                         depth_association=depth_assoc,
                          note="device-resident stage timings (vilf_bench_stage) on a synthetic 1e6-point map, algorithmic bytes: hash build 32 B/point, query 136 B, map update 16 B/point + 16 B/voxel")
         except Exception as e:  # the headline numbers stand on their own
             large = dict(error=repr(e))

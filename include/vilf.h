@@ -122,6 +122,17 @@ int vilf_create_submap(vilf_handle* h, const float* edge_ds, int n_edge, const f
  * EM:365-375 returns 4+5 or 5). */
 int vilf_get_cloud(vilf_handle* h, int which, float* out, int cap, int* n);
 
+/* ---- next to the path: lidar depth for visual features ----
+ * getFeatureDepth steps 4.1-4.4 (NODE:54-140): features (normalised image coordinates x, y, 1) and cloud on the unit
+ * sphere, exact 3-NN, plane-ray intersection, the reference's range rules; depth_out[i] = -1 where no reliable depth
+ * exists.  cloud_cam != NULL: an explicit camera-frame cloud [n][4].  cloud_cam == NULL: the scan already resident from
+ * the last vilf_feature_extract / vilf_process_scan is used, after the reference's field-of-view filter and
+ * pcl::transformPointCloud(LIDAR_CAMERA_EX) (NODE:348-361), T_lidar_cam = that 4x4 matrix, row-major — no second upload.
+ * num_bins = 360 in the reference (NODE:51).  nn_out [m][3] (optional): indices of the three neighbours in the cloud
+ * (explicit cloud) / in the scan (resident scan).  n_cloud (optional): points that entered the search. */
+int vilf_feature_depth(vilf_handle* h, const float* cloud_cam, int n, const double T_lidar_cam[16], const float* feats, int m, int num_bins,
+                       float* depth_out, int32_t* nn_out, int* n_cloud);
+
 /* ---- stage-level entry points (unit parity against the oracle; they clobber per-frame scratch only) ---- */
 /* pcl::VoxelGrid<PointXYZI>::filter (EM:248-251, :347-350). Returns n_out; *guard = 1 when PCL's
  * "leaf size too small" int32 guard fired and the output is the input. */

@@ -19,7 +19,7 @@ _REF = os.path.join(_HERE, "_ref", "libref_nanoflann.so")
 def build(force: bool = False) -> None:
     """Compile the oracle (and oracle/_ref when /root/reference is present)."""
     if force or not os.path.exists(_LIB) or any(
-        os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB) for f in ("orc_capi.cpp", "orc_pipeline.hpp", "orc_math.hpp")
+        os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB) for f in ("orc_capi.cpp", "orc_pipeline.hpp", "orc_math.hpp", "orc_depth.hpp")
     ):
         subprocess.run(["make", "-C", _HERE, "_build/liborc.so"], check=True, capture_output=True)
     if os.path.isdir("/root/reference") and (force or not os.path.exists(_REF)):
@@ -135,6 +135,24 @@ def ref_knn(mp, q, k: int = 5):
     if r is None:
         raise RuntimeError("oracle/_ref/libref_nanoflann.so not built")
     return _knn(r.ref_nanoflann_knn, mp, q, k)
+
+
+def camera_cloud(scan, T):
+    """feature_tracker_node.cpp:348-361: camera field-of-view filter + pcl::transformPointCloud(LIDAR_CAMERA_EX)."""
+    scan = _f32(scan); T = _f64(np.asarray(T).reshape(16))
+    out = np.empty((max(scan.shape[0], 1), 4), np.float32)
+    no = C.c_int()
+    lib().orc_camera_cloud(_p(scan, C.c_float), scan.shape[0], _p(T, C.c_double), _p(out, C.c_float), C.byref(no))
+    return out[:no.value].copy()
+
+
+def feature_depth(cloud, feats, num_bins: int = 360):
+    """getFeatureDepth steps 4.1-4.4 (feature_tracker_node.cpp:54-140): (depth [m], 3-NN indices [m,3])."""
+    cloud = _f32(cloud); feats = np.ascontiguousarray(feats, dtype=np.float32)
+    m = feats.shape[0]
+    d = np.empty(max(m, 1), np.float32); nn = np.empty((max(m, 1), 3), np.int32)
+    lib().orc_feature_depth(_p(cloud, C.c_float), cloud.shape[0], _p(feats, C.c_float), m, num_bins, _p(d, C.c_float), _p(nn, C.c_int))
+    return d[:m].copy(), nn[:m].copy()
 
 
 def factors(cfg: Config, pose, edge, surf, map_e, map_s):

@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE — C entry points of the CPU oracle (loaded with ctypes by tests/ and by
 // bench.py's CPU-baseline legs only).  NOT product code; PARITY UNPINNED, see orc_pipeline.hpp.
 #include "orc_pipeline.hpp"
+#include "orc_depth.hpp"
 
 using namespace orc;
 
@@ -241,6 +242,17 @@ int orc_odom_get_solves(void* h, double* out, int max_rows) {
 void orc_odom_get_timing(void* h, double* out7) {
   Timing& t = ((Odometry*)h)->timing;
   out7[0] = t.extract; out7[1] = t.ds; out7[2] = t.kdbuild; out7[3] = t.assoc; out7[4] = t.solve; out7[5] = t.map; out7[6] = t.frames;
+}
+
+// Depth association of visual features (feature_tracker_node.cpp:54-140, :348-361).
+void orc_camera_cloud(const float* scan, int n, const double* T16, float* out, int* n_out) {
+  Cloud o;
+  camera_cloud((const P4*)scan, n, T16, o);
+  *n_out = (int)o.size();
+  if (!o.empty()) std::memcpy(out, o.data(), o.size() * sizeof(P4));
+}
+void orc_feature_depth(const float* cloud, int n, const float* feats, int m, int num_bins, float* depth_out, int* nn_out) {
+  feature_depth((const P4*)cloud, n, feats, m, num_bins, depth_out, nn_out);
 }
 
 }  // extern "C"

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "vilf/EstimationMapping.hpp"
+#include "vilf/featureDepth.hpp"
 
 using vilf::Cloud;
 using vilf::CloudPtr;
@@ -73,6 +74,32 @@ int main(int argc, char** argv) {
       Estimator.initParameter(nh);              // NODE:510
       Estimator.shareSession(featureExtractFactor);
       node_loop(featureExtractFactor, Estimator, scans, pa);
+      // depth for visual features (NODE:348-366): from the scan that is still resident, and from a host-prepared cloud
+      const double T[16] = {0, -1, 0, 0.05, 0, 0, -1, -0.1, 1, 0, 0, 0.02, 0, 0, 0, 1};  // LIDAR_CAMERA_EX, row-major
+      std::vector<vilf::Point32> feats;
+      for (int i = 0; i < 60; ++i) feats.push_back(vilf::Point32{-0.9f + 0.03f * i, -0.3f + 0.005f * i, 1.0f});
+      std::vector<float> d1 = vilf::getFeatureDepthFromScan(*featureExtractFactor.session(), T, feats);
+      CloudPtr cam = vilf::make_cloud();
+      const Cloud& full = *scans.back();
+      for (size_t i = 0; i < full.points.size(); ++i) {  // NODE:351-361 on the host
+        const vilf::PointType p = full.points[i];
+        if (p.x > 0 && std::fabs(p.y / p.x) <= 10 && std::fabs(p.z / p.x) <= 10) {
+          vilf::PointType q = p;
+          const double x = p.x, y = p.y, z = p.z;
+          q.x = (float)(T[0] * x + T[1] * y + T[2] * z + T[3]);
+          q.y = (float)(T[4] * x + T[5] * y + T[6] * z + T[7]);
+          q.z = (float)(T[8] * x + T[9] * y + T[10] * z + T[11]);
+          cam->push_back(q);
+        }
+      }
+      std::vector<float> d2 = vilf::getFeatureDepth(*featureExtractFactor.session(), cam, feats);
+      int with_depth = 0;
+      for (size_t i = 0; i < feats.size(); ++i) {
+        if (d1[i] != d2[i]) { std::fprintf(stderr, "depth from the resident scan and from the host-prepared cloud differ at %zu\n", i); return 1; }
+        with_depth += d1[i] > 0;
+      }
+      std::printf("depth association: %d of %zu features have lidar depth\n", with_depth, feats.size());
+      if (with_depth == 0) { std::fprintf(stderr, "no feature received a depth\n"); return 1; }
     }
     // B: independent objects
     {

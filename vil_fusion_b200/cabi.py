@@ -40,7 +40,7 @@ SYMBOLS = [
     "vilf_feature_extract", "vilf_get_features", "vilf_map_init", "vilf_map_init_points", "vilf_update", "vilf_update_points",
     "vilf_get_pose", "vilf_set_pose", "vilf_predict", "vilf_create_submap", "vilf_get_cloud", "vilf_voxel_downsample", "vilf_crop_voxel_downsample", "vilf_crop_box", "vilf_knn5",
     "vilf_factors", "vilf_normal_equations", "vilf_solve", "vilf_get_solves", "vilf_state_export", "vilf_state_import",
-    "vilf_profile_enable", "vilf_profile_read", "vilf_profile_read_kernels", "vilf_profile_kernel_name", "vilf_launch_count", "vilf_get_stream", "vilf_get_counts", "vilf_debug_voxel_phases", "vilf_bench_stage",
+    "vilf_profile_enable", "vilf_profile_read", "vilf_profile_read_kernels", "vilf_profile_kernel_name", "vilf_launch_count", "vilf_get_stream", "vilf_get_counts", "vilf_debug_voxel_phases", "vilf_bench_stage", "vilf_feature_depth",
 ]
 
 _lib = None
@@ -301,6 +301,17 @@ class Odometry:
         self._ck(lib().vilf_bench_stage(self._h, stage, _p(mp, C.c_float), mp.shape[0], _p(q, C.c_float), 0 if q is None else q.shape[0],
                                         C.c_float(leaf), iters, _p(ms, C.c_double)))
         return ms
+
+    def feature_depth(self, feats, cloud_cam=None, T_lidar_cam=None, num_bins: int = 360):
+        """(depth [m], nn [m,3], points searched).  cloud_cam=None: use the resident scan + T_lidar_cam (4x4)."""
+        feats = np.ascontiguousarray(feats, dtype=np.float32)
+        m = feats.shape[0]
+        d = np.empty(max(m, 1), np.float32); nn = np.empty((max(m, 1), 3), np.int32); cnt = C.c_int()
+        cl = None if cloud_cam is None else _f32(cloud_cam)
+        T = None if T_lidar_cam is None else _f64(np.asarray(T_lidar_cam).reshape(16))
+        self._ck(lib().vilf_feature_depth(self._h, _p(cl, C.c_float), 0 if cl is None else cl.shape[0], _p(T, C.c_double), _p(feats, C.c_float), m, num_bins,
+                                          _p(d, C.c_float), _p(nn, C.c_int32), C.byref(cnt)))
+        return d[:m].copy(), nn[:m].copy(), cnt.value
 
     def voxel_phases(self, job: int):
         t = np.zeros(8, np.int64)

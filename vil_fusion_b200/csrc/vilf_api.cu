@@ -14,6 +14,7 @@ using namespace vilf;
 namespace {
 
 constexpr int RING_SLOTS = 8;
+constexpr int DEPTH_MAX_FEATURES = 8192;
 constexpr int VV_PER_LANE = 4;  // scan edge, scan surf, map edge, map surf
 constexpr int N_STAGE = 7;
 constexpr int MAX_MARKS = PROF_MAX_EVENTS;
@@ -57,6 +58,8 @@ struct Ctx {
   VoxJob* aux_vox_dev = nullptr; SortJob* aux_sort_dev = nullptr; GridJob* aux_grid_dev = nullptr;
   VoxJob aux_vox_host;
   GridJob aux_grid_host;
+  float* depth_feat = nullptr; float* depth_out = nullptr; int* depth_nn = nullptr; double* depth_T = nullptr;  // [DEPTH_MAX_FEATURES] scratch
+  std::vector<int> last_sel;   // scan buffer holding the most recent scan of the lane
   int* aux_head_cnt = nullptr;
   // per-lane host state
   std::vector<int> cur;        // map buffer holding the current local maps
@@ -339,6 +342,11 @@ int build_ctx(Ctx* C) {
     if (rc) return rc;
     CK(cudaMemcpy(C->aux_grid_dev, &G, sizeof(GridJob), cudaMemcpyHostToDevice));
   }
+  CK(dalloc(C, &C->depth_feat, (size_t)DEPTH_MAX_FEATURES * 3));
+  CK(dalloc(C, &C->depth_out, (size_t)DEPTH_MAX_FEATURES));
+  CK(dalloc(C, &C->depth_nn, (size_t)DEPTH_MAX_FEATURES * 3));
+  CK(dalloc(C, &C->depth_T, 16));
+  C->last_sel.assign(NL, -1);
   C->cur.assign(NL, 0); C->have_map.assign(NL, 0); C->have_feat.assign(NL, 0); C->last_init.assign(NL, 0); C->frame_no.assign(NL, 0);
   CK(cudaDeviceSynchronize());
   return VILF_OK;
@@ -473,6 +481,7 @@ int submit_common(Ctx* C, int lane0, int nl, const float* const* xyzi, const int
   CK(cudaMemcpyAsync(S.vars_pin, C->vars_dev + lane0, sizeof(LaneVars) * nl, cudaMemcpyDeviceToHost, C->st));
   CK(cudaEventRecord(S.done, C->st));
   S.ticket = t; S.lane0 = lane0; S.nl = nl;
+  for (int l = lane0; l < lane0 + nl; ++l) C->last_sel[l] = sel;
   C->next_ticket++;
   *ticket = t;
   return VILF_OK;
@@ -705,6 +714,7 @@ int vilf_feature_extract(vilf_handle* h, const float* xyzi, int n, const uint16_
   int rc = read_vars(C, h->lane, &V);
   if (rc) return rc;
   C->have_feat[h->lane] = 1;
+  C->last_sel[h->lane] = 0;
   if (n_edge) *n_edge = V.n_edge;
   if (n_surf) *n_surf = V.n_surf;
   return status_to_rc(C, V.status);
@@ -965,6 +975,43 @@ int vilf_bench_stage(vilf_handle* h, int stage, const float* map, int m, const f
   return VILF_OK;
 }
 
+int vilf_feature_depth(vilf_handle* h, const float* cloud_cam, int n, const double T_lidar_cam[16], const float* feats, int m, int num_bins,
+                       float* depth_out, int32_t* nn_out, int* n_cloud) {
+  HCHECK(h);
+  CK(cudaSetDevice(C->device));
+  const int lane = h->lane;
+  if (m < 0 || m > DEPTH_MAX_FEATURES || (m > 0 && (!feats || !depth_out)) || num_bins < 1) return fail(C, VILF_ERR_INVALID, "bad arguments");
+  const float4* in = nullptr;
+  const int* n_dev = nullptr;
+  int from_scan = 0;
+  if (cloud_cam) {  // steps 4.1-4.4 on an explicit camera-frame cloud
+    if (n < 0 || n > C->cap_aux) return fail(C, VILF_ERR_CAPACITY, "cloud exceeds capacity");
+    if (n) CK(cudaMemcpyAsync(C->aux_in, cloud_cam, (size_t)n * 16, cudaMemcpyHostToDevice, C->st));
+    CK(cudaMemcpyAsync(C->aux_n, &n, sizeof(int), cudaMemcpyHostToDevice, C->st));
+    in = C->aux_in; n_dev = C->aux_n;
+  } else {          // NODE:348-361 on the scan that is resident from the last extractFeature / process_scan, then 4.1-4.4
+    if (!T_lidar_cam) return fail(C, VILF_ERR_INVALID, "no cloud and no extrinsic");
+    if (C->last_sel[lane] < 0) return fail(C, VILF_ERR_STATE, "no scan resident");
+    const int sel = C->last_sel[lane];
+    CK(cudaMemcpyAsync(C->depth_T, T_lidar_cam, 16 * sizeof(double), cudaMemcpyHostToDevice, C->st));
+    in = C->lanes_host[lane].scan[sel]; n_dev = &C->lanes_host[lane].v->n_scan[sel];
+    from_scan = 1;
+  }
+  if (m) CK(cudaMemcpyAsync(C->depth_feat, feats, (size_t)m * 12, cudaMemcpyHostToDevice, C->st));
+  const float bin_res = 180.0f / (float)num_bins;                                   // NODE:78
+  const float thr = (float)pow(sin(bin_res / 180.0 * M_PI) * 5.0, 2);               // NODE:103
+  CK(cudaStreamSynchronize(C->st));  // staged host values above live on this stack frame
+  launch_depth(mk(C), in, n_dev, from_scan, C->depth_T, C->aux_out, C->aux_idx, C->aux_n + 4, C->depth_feat, m, thr, C->depth_out, C->depth_nn);
+  CK(cudaGetLastError());
+  int cnt = 0;
+  if (m) CK(cudaMemcpyAsync(depth_out, C->depth_out, (size_t)m * 4, cudaMemcpyDeviceToHost, C->st));
+  if (m && nn_out) CK(cudaMemcpyAsync(nn_out, C->depth_nn, (size_t)m * 12, cudaMemcpyDeviceToHost, C->st));
+  CK(cudaMemcpyAsync(&cnt, C->aux_n + 4, sizeof(int), cudaMemcpyDeviceToHost, C->st));
+  CK(cudaStreamSynchronize(C->st));
+  if (n_cloud) *n_cloud = cnt;
+  return VILF_OK;
+}
+
 int vilf_factors(vilf_handle* h, const double pose[7], const float* edge, int n_edge, const float* surf, int n_surf, uint8_t* edge_valid,
                  double* edge_ab, int32_t* edge_nn, float* edge_d2, uint8_t* surf_valid, double* surf_nd, int32_t* surf_nn, float* surf_d2) {
   HCHECK(h);
@@ -1137,7 +1184,7 @@ const char* vilf_profile_kernel_name(int kernel) {
   static const char* names[K_COUNT] = {"k_frame_reset", "k_sort_keyhist<KeyGenRing>", "k_sort_hist", "k_sort_scatter", "k_sector_select", "k_compact_features",
                                        "k_vox_bbox", "k_sort_keyhist<KeyGenVoxel>", "k_vox_heads", "k_vox_centroid", "k_map_append", "k_map_init",
                                        "k_grid_zero", "k_grid_count", "k_grid_scan_partial", "k_grid_scan_final", "k_grid_scatter", "k_knn_assoc",
-                                       "k_knn_only", "k_solve", "k_fit", "k_voxel_cluster", "k_grid_cluster"};
+                                       "k_knn_only", "k_solve", "k_fit", "k_voxel_cluster", "k_grid_cluster", "k_depth_cloud", "k_depth_query"};
   return (kernel >= 0 && kernel < K_COUNT) ? names[kernel] : "";
 }
 int vilf_launch_count(vilf_handle* h, int64_t* launches) {

@@ -237,7 +237,7 @@ __device__ __forceinline__ float4 associate(const double* x, float4 p) {
 enum KernelId {
   K_RESET = 0, K_RING_KEYHIST, K_SORT_HIST, K_SORT_SCATTER, K_SECTOR, K_COMPACT, K_VOX_BBOX, K_VOX_KEYHIST, K_VOX_HEADS, K_VOX_CENTROID,
   K_MAP_APPEND, K_MAP_INIT, K_GRID_ZERO, K_GRID_COUNT, K_GRID_SCAN_PARTIAL, K_GRID_SCAN_FINAL, K_GRID_SCATTER, K_KNN_FIT, K_KNN_ONLY,
-  K_SOLVE, K_FIT, K_VOX_CLUSTER, K_GRID_CLUSTER, K_COUNT
+  K_SOLVE, K_FIT, K_VOX_CLUSTER, K_GRID_CLUSTER, K_DEPTH_CLOUD, K_DEPTH_QUERY, K_COUNT
 };
 constexpr int PROF_PHASES = 5;      // 0 extract, 1 scan downsample, 2 association + solve, 3 map update, 4 grid build
 constexpr int PROF_TAGS = PROF_PHASES * 32;
@@ -280,6 +280,9 @@ void launch_grid_build(const Launch& L, const GridJob* jobs_dev, int njobs, cons
 void launch_knn_fit(const Launch& L, LaneDev* lanes, const GridJob* grid_jobs, int lane0, int nlanes, int cur, const ConfigDev& cfg,
                     const double* pose_override, int want_nn);
 void launch_knn_only(const Launch& L, const GridJob* job_dev, const float4* q, const int* nq_dev, int* idx, float* d2, const ConfigDev& cfg);
+// k_depth.cu
+void launch_depth(const Launch& L, const float4* in, const int* n_dev, int from_scan, const double* T_dev, float4* sph, int* oidx, int* count,
+                  const float* feats_dev, int m, float thr, float* depth_dev, int* nn_dev);
 // k_solve.cu
 void launch_solve(const Launch& L, LaneDev* lanes, int lane0, int nlanes, int outer, int finalize, const ConfigDev& cfg, int max_iters);
 
