@@ -112,7 +112,7 @@ __device__ void grid_build_cluster(cg::cluster_group& cluster, const GridJob& G,
 // PCL's `centroid += point; ...; centroid /= count` in fp32 (same order as the grid-wide emitter => identical bits).  A run
 // that is still open at the end of a step is carried into the next one (also past `end`: it still belongs to this warp).
 // `dst0` = output index of the first run that starts in the range.  All loads are ld.global.ca (see k_voxel.cuh).
-__device__ void emit_range(const VoxJob& J, const uint32_t* key, const uint32_t* val, int nv, int guard, int beg, int end, int dst0, float4* stage) {
+__device__ void emit_range(const VoxJob& J, const uint2* kv, int nv, int guard, int beg, int end, int dst0, float4* stage) {
   if (beg >= end) return;  // uniform over the warp
   const int lane = threadIdx.x & 31;
   const unsigned FULL = 0xffffffffu;
@@ -120,18 +120,23 @@ __device__ void emit_range(const VoxJob& J, const uint32_t* key, const uint32_t*
   bool open = false;  // carried run (all of this is uniform over the warp)
   float4 cacc = make_float4(0.f, 0.f, 0.f, 0.f);
   int ccnt = 0, cdst = 0;
-  uint32_t prevk = beg > 0 ? __ldca(key + beg - 1) : 0u;
+  uint32_t prevk = beg > 0 ? __ldca(kv + beg - 1).x : 0u;
   uint32_t k = 0;
   float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
   bool valid = beg + lane < nv;
-  if (valid) { k = __ldca(key + beg + lane); p = __ldca(J.in + __ldca(val + beg + lane)); }
+  if (valid) { const uint2 e = __ldca(kv + beg + lane); k = e.x; p = __ldca(J.in + e.y); }
+  // software pipeline, two dependent loads deep: the (key, index) pair of step s + 2 and the gathered point of step s + 1 are
+  // in flight while step s is summed, so a step waits for one L2 round trip at most, not for the dependent pair
+  bool nvalid = beg + 32 + lane < nv;
+  uint2 ne = make_uint2(0u, 0u);
+  if (nvalid) ne = __ldca(kv + beg + 32 + lane);
   for (int base = beg;; base += 32) {
-    // next step's loads first
-    const int ni = base + 32 + lane;
-    const bool nvalid = ni < nv;
-    uint32_t nk = 0;
+    const uint32_t nk = ne.x;
     float4 np = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (nvalid) { nk = __ldca(key + ni); np = __ldca(J.in + __ldca(val + ni)); }
+    if (nvalid) np = __ldca(J.in + ne.y);
+    const bool nnvalid = base + 64 + lane < nv;
+    uint2 nne = make_uint2(0u, 0u);
+    if (nnvalid) nne = __ldca(kv + base + 64 + lane);
     // heads of this step
     uint32_t kl = __shfl_up_sync(FULL, k, 1);
     if (lane == 0) kl = prevk;
@@ -204,7 +209,7 @@ __device__ void emit_range(const VoxJob& J, const uint32_t* key, const uint32_t*
     if (cm == 0u) {                                  // nothing owned yet (the step continues a previous warp's run)
       if (base + 32 >= end) break;                   // ... and no head of this range is left
       prevk = __shfl_sync(FULL, k, 31);
-      k = nk; p = np; valid = nvalid;
+      k = nk; p = np; valid = nvalid; ne = nne; nvalid = nnvalid;
       continue;
     }
     const int cl = __ffs(cm) - 1;
@@ -213,7 +218,7 @@ __device__ void emit_range(const VoxJob& J, const uint32_t* key, const uint32_t*
     cdst = __shfl_sync(FULL, my_dst, cl);
     open = true;
     prevk = __shfl_sync(FULL, k, 31);
-    k = nk; p = np; valid = nvalid;
+    k = nk; p = np; valid = nvalid; ne = nne; nvalid = nnvalid;
   }
 }
 
@@ -329,10 +334,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CT, 2) k_voxel_clus
   const int nd_used = 1 << w;  // digits in use (<= SORT_RADIX)
   for (int pass = 0; pass < P; ++pass) {
     const int shift = pass * w;
-    const uint32_t* __restrict__ kin = J.sort.key[pass & 1];
-    const uint32_t* __restrict__ vin = J.sort.val[pass & 1];
-    uint32_t* __restrict__ kout = J.sort.key[(pass + 1) & 1];
-    uint32_t* __restrict__ vout = J.sort.val[(pass + 1) & 1];
+    const uint2* pin = J.sort.pair[pass & 1];   // (key, value) pairs, moved with one 8-byte access each
+    uint2* __restrict__ pout = J.sort.pair[(pass + 1) & 1];
     // sweep 1: warp-private digit histogram (pass 0 also materialises the keys); 4 x 32 keys in flight per warp
     for (int i = tid; i < CW * SORT_RADIX; i += CT) (&S.wcnt[0][0])[i] = 0;
     __syncthreads();
@@ -343,8 +346,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CT, 2) k_voxel_clus
         const int i = base + it * 32 + lane;
         k[it] = 0;
         if (i < wend) {
-          if (pass == 0) { k[it] = gen.key(0, i); J.sort.key[0][i] = k[it]; }
-          else k[it] = __ldcg(kin + i);  // written by other CTAs in the previous pass: L2, and no L1 allocation (see k_voxel.cuh)
+          if (pass == 0) { k[it] = gen.key(0, i); J.sort.pair[0][i] = make_uint2(k[it], (uint32_t)i); }
+          else k[it] = __ldcg(pin + i).x;  // written by other CTAs in the previous pass: L2, and no L1 allocation (see k_voxel.cuh)
         }
       }
 #pragma unroll
@@ -390,8 +393,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CT, 2) k_voxel_clus
         const int i = base + it * 32 + lane;
         k[it] = 0; v[it] = (uint32_t)i;
         if (i < wend) {
-          k[it] = __ldcg(J.sort.key[pass & 1] + i);
-          if (pass != 0) v[it] = __ldcg(vin + i);
+          const uint2 e = __ldcg(pin + i);
+          k[it] = e.x; v[it] = e.y;
         }
       }
 #pragma unroll
@@ -410,8 +413,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CT, 2) k_voxel_clus
         if (ok) {
           if (lower == 0) S.wcnt[warp][d] = before + __popc(peers);
           const uint32_t pos = before + __popc(lower);
-          kout[pos] = k[it];
-          vout[pos] = v[it];
+          pout[pos] = make_uint2(k[it], v[it]);
         }
         __syncwarp();
       }
@@ -421,8 +423,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CT, 2) k_voxel_clus
 
   PHASE_MARK(2);
   // ---- phase 2: heads (first point of every occupied voxel) and centroids, in ascending voxel order ----
-  const uint32_t* key = J.sort.key[P & 1];  // first L1-allocating reads of these buffers in this kernel: ld.global.ca is coherent here
-  const uint32_t* val = J.sort.val[P & 1];
+  const uint2* kv = J.sort.pair[P & 1];  // first L1-allocating reads of this buffer in this kernel: ld.global.ca is coherent here
   const int nv = n_valid;  // cropped-out points carry the sentinel key and sit behind the valid ones
   int hchunk = (nv + CL - 1) / CL;
   hchunk = (hchunk + CT - 1) / CT * CT;
@@ -431,7 +432,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CT, 2) k_voxel_clus
   const int hwbeg = min(hend, hbeg + warp * hwchunk), hwend = min(hend, hwbeg + hwchunk);
   {
     int cnt = 0;
-    for (int i = hwbeg + lane; i < hwend; i += 32) cnt += (guard || i == 0 || __ldca(key + i) != __ldca(key + i - 1)) ? 1 : 0;
+    for (int i = hwbeg + lane; i < hwend; i += 32) cnt += (guard || i == 0 || __ldca(kv + i).x != __ldca(kv + i - 1).x) ? 1 : 0;
     for (int off = 16; off > 0; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
     if (lane == 0) S.wsum[warp] = cnt;
     __syncthreads();
@@ -456,7 +457,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CT, 2) k_voxel_clus
     *J.n_out = n_out;
   }
   PHASE_MARK(3);
-  emit_range(J, key, val, nv, guard, hwbeg, hwend, run, S.stage[warp]);  // warps run independently
+  emit_range(J, kv, nv, guard, hwbeg, hwend, run, S.stage[warp]);  // warps run independently
 
   // ---- phase 3 (map jobs): spatial hash of the filtered map for the next frame's 5-NN search ----
   if (J.grid != nullptr) {

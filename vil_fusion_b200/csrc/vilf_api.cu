@@ -127,9 +127,11 @@ int pow2_ge(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 int alloc_sort(Ctx* C, SortJob& S, const int* n, const int* bits, int fixed_bits, int npass, int cap, bool digit_start) {
   S.n = n; S.bits = bits; S.fixed_bits = fixed_bits; S.npass = npass;
-  for (int b = 0; b < 2; ++b) {
-    CK(dalloc(C, &S.key[b], (size_t)cap));
-    CK(dalloc(C, &S.val[b], (size_t)cap));
+  for (int b = 0; b < 2; ++b) {  // one allocation per buffer: [cap] keys then [cap] values (grid-wide path) == [cap] pairs (cluster path)
+    const size_t capr = ((size_t)cap + 63) / 64 * 64;
+    CK(dalloc(C, &S.pair[b], capr));
+    S.key[b] = reinterpret_cast<uint32_t*>(S.pair[b]);
+    S.val[b] = S.key[b] + capr;
   }
   CK(dalloc(C, &S.hist, (size_t)4 * SORT_G * SORT_RADIX));
   S.digit_start = nullptr;

@@ -81,6 +81,7 @@ struct SortJob {
   int npass;              // pass limit: 1 (ring ids) or 4; P = min(npass, ceil(bits / 9)) passes of ceil(bits / P) bits
   uint32_t* key[2];       // result in key[P & 1] / val[P & 1]
   uint32_t* val[2];
+  uint2* pair[2];         // the same storage seen as (key, value) pairs: the cluster path moves a pair with one 8-byte access
   uint32_t* hist;         // [4][SORT_G][SORT_RADIX]
   uint32_t* digit_start;  // optional [257]: exclusive digit offsets of pass 0 (+ total)
 };
