@@ -123,6 +123,20 @@ struct KeyGenRing {
       const int r = (int)L.ring_in[sel][i];
       return (r < cfg.n_rings) ? (uint32_t)r : 255u;
     }
+    if (cfg.n_scan == 64) {
+      // Certified fp32 fast path: the ring id is a step function of the vertical angle; an fp32 angle (error < 1e-5 deg)
+      // decides it whenever the argument of every int() / comparison of FE:93-98 is farther than 1e-3 from a decision
+      // point (99.8 % of the returns); the rest take the reference's fp64 expression below.
+      const float af = atanf(__fdiv_rn(p.z, dxy)) * 57.29577951308232f;
+      const float u = af >= -8.83f ? (2.0f - af) * 3.0f + 0.5f : (-8.83f - af) * 2.0f + 0.5f;
+      const float fr = u - floorf(u);
+      const bool safe = fr > 1e-3f && fr < 1.0f - 1e-3f && fabsf(af + 8.83f) > 1e-3f && fabsf(af - 2.0f) > 1e-3f && fabsf(af + 24.33f) > 1e-3f;
+      if (safe) {
+        if (af > 2.0f || af < -24.33f) return 255u;
+        const int idf = af >= -8.83f ? (int)u : 32 + (int)u;
+        return (idf > 63 || idf < 0) ? 255u : (uint32_t)idf;
+      }
+    }
     const double angle = atan((double)p.z / distance) * 180 / M_PI;  // FE:73
     int id = 0;
     if (cfg.n_scan == 16) {
@@ -515,37 +529,53 @@ __global__ void __launch_bounds__(256) k_compact_features(LaneDev* lanes, int la
     if (lane == 0) { s_off[0] = se; s_off[1] = ss; }
   }
   __syncthreads();
-  int oe = s_off[0], os = s_off[1];
+  const int oe = s_off[0], os = s_off[1];
   const uint32_t* rs = L.ring_sort.digit_start;
   const int ring_beg = (int)rs[r];
   const int n_r = (int)rs[r + 1] - ring_beg;
+  // the ring's 6 sector lists as ONE flat index range each (edges, surfs): a single round of loads instead of six
+  __shared__ int s_cnt[2][SECTORS + 1], s_src[SECTORS];  // exclusive prefix of the per-sector counts; first staged surf element
+  if (tid == 0) {
+    int ae = 0, as = 0;
+    for (int s = 0; s < SECTORS; ++s) {
+      const int2 c = L.sec_cnt[sec0 + s];
+      int start = 0, m = 0;
+      sector_range(n_r, s, start, m);
+      s_cnt[0][s] = ae; s_cnt[1][s] = as; s_src[s] = ring_beg + 5 + start;
+      ae += c.x; as += c.y;
+    }
+    s_cnt[0][SECTORS] = ae; s_cnt[1][SECTORS] = as;
+  }
+  __syncthreads();
   float emn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, emx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   float smn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, smx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   int ecnt = 0, scnt = 0;
-  for (int s = 0; s < SECTORS; ++s) {
-    const int2 c = L.sec_cnt[sec0 + s];
-    int start = 0, m = 0;
-    sector_range(n_r, s, start, m);
-    const int sbase = ring_beg + 5 + start;
-    if (tid < c.x) {  // <= 20 edges
-      const float4 p = L.sec_edge[(sec0 + s) * EDGES_PER_SECTOR + tid];
-      L.feat[0][oe + tid] = p;
-      L.feat_src[0][oe + tid] = L.sec_edge_src[(sec0 + s) * EDGES_PER_SECTOR + tid];
-      emn[0] = fminf(emn[0], p.x); emx[0] = fmaxf(emx[0], p.x); emn[1] = fminf(emn[1], p.y); emx[1] = fmaxf(emx[1], p.y);
-      emn[2] = fminf(emn[2], p.z); emx[2] = fmaxf(emx[2], p.z); ++ecnt;
-    }
-    for (int k = tid; k < c.y; k += 256) {
-      const float4 p = L.sec_surf[sbase + k];
-      L.feat[1][os + k] = p;
-      L.feat_src[1][os + k] = L.sec_surf_src[sbase + k];
-      smn[0] = fminf(smn[0], p.x); smx[0] = fmaxf(smx[0], p.x); smn[1] = fminf(smn[1], p.y); smx[1] = fmaxf(smx[1], p.y);
-      smn[2] = fminf(smn[2], p.z); smx[2] = fmaxf(smx[2], p.z); ++scnt;
-    }
-    oe += c.x; os += c.y;
+  const int te = s_cnt[0][SECTORS], ts = s_cnt[1][SECTORS];
+  for (int k = tid; k < te; k += 256) {  // <= 120 edges
+    int s = 0;
+#pragma unroll
+    for (int q = 1; q < SECTORS; ++q) s += k >= s_cnt[0][q] ? 1 : 0;
+    const int src = (sec0 + s) * EDGES_PER_SECTOR + (k - s_cnt[0][s]);
+    const float4 p = L.sec_edge[src];
+    L.feat[0][oe + k] = p;
+    L.feat_src[0][oe + k] = L.sec_edge_src[src];
+    emn[0] = fminf(emn[0], p.x); emx[0] = fmaxf(emx[0], p.x); emn[1] = fminf(emn[1], p.y); emx[1] = fmaxf(emx[1], p.y);
+    emn[2] = fminf(emn[2], p.z); emx[2] = fmaxf(emx[2], p.z); ++ecnt;
+  }
+  for (int k = tid; k < ts; k += 256) {
+    int s = 0;
+#pragma unroll
+    for (int q = 1; q < SECTORS; ++q) s += k >= s_cnt[1][q] ? 1 : 0;
+    const int src = s_src[s] + (k - s_cnt[1][s]);
+    const float4 p = L.sec_surf[src];
+    L.feat[1][os + k] = p;
+    L.feat_src[1][os + k] = L.sec_surf_src[src];
+    smn[0] = fminf(smn[0], p.x); smx[0] = fmaxf(smx[0], p.x); smn[1] = fminf(smn[1], p.y); smx[1] = fmaxf(smx[1], p.y);
+    smn[2] = fminf(smn[2], p.z); smx[2] = fmaxf(smx[2], p.z); ++scnt;
   }
   bbox_commit(L.vv + 0, emn, emx, ecnt, bb_sm);
   bbox_commit(L.vv + 1, smn, smx, scnt, bb_sm);
-  if (blockIdx.x == gridDim.x - 1 && tid == 0) { L.v->n_edge = oe; L.v->n_surf = os; }
+  if (blockIdx.x == gridDim.x - 1 && tid == 0) { L.v->n_edge = oe + te; L.v->n_surf = os + ts; }
 }
 
 void launch_extract(const Launch& L, LaneDev* lanes, const SortJob* ring_jobs, int lane0, int nlanes, int sel, const ConfigDev& cfg) {
