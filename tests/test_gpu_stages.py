@@ -342,3 +342,43 @@ def test_knn5_dense_maps_fine_cells_early_exit(cabi, orc, leaf, spacing):
     full = od[:, 4] < 1.0
     assert full.sum() > 3000 and (~full).sum() > 100  # both regimes are exercised
     g.close()
+
+
+def test_voxel_fuzz_run_lengths_and_sizes(cabi, orc):
+    """Randomised clouds that stress the cluster path's centroid emitter (runs shorter / longer than a 32-position step, runs
+    crossing warp and CTA boundaries, one giant voxel, everything cropped but a corner) and its radix passes (1..4 passes,
+    sizes around the chunk / tile boundaries), on BOTH paths, bit-exact against the oracle's PCL restatement."""
+    rng = np.random.default_rng(99)
+    a = cabi.Odometry(cabi.default_config(max_scan_points=70000, max_map_points=1 << 16))
+    b = cabi.Odometry(cabi.default_config(max_scan_points=70000, max_map_points=1 << 16, flags=cabi.FLAG_NO_CLUSTER))
+    sizes = [1, 2, 31, 32, 33, 511, 512, 513, 4095, 4096, 4097, 8191, 12345, 32768, 60001]
+    for case, n in enumerate(sizes):
+        kind = case % 5
+        if kind == 0:    # uniform noise, mostly singletons
+            pts = rng.uniform(-30, 30, (n, 4))
+        elif kind == 1:  # a few giant voxels (hundreds to thousands of points each) + noise
+            centres = rng.uniform(-20, 20, (max(1, n // 1500), 3))
+            pts = np.concatenate([centres[rng.integers(0, len(centres), n)] + rng.uniform(0, 0.3, (n, 3)), rng.random((n, 1))], 1)
+        elif kind == 2:  # everything in ONE voxel
+            pts = np.concatenate([np.array([3.0, -7.0, 1.0]) + rng.uniform(0.05, 0.3, (n, 3)), rng.random((n, 1))], 1)
+        elif kind == 3:  # run lengths 1..70 in random order of arrival (runs straddle the 32-position steps)
+            reps = rng.integers(1, 70, n)
+            base = rng.uniform(-40, 40, (n, 3))
+            idx = np.repeat(np.arange(n), reps)[:n]
+            pts = np.concatenate([base[idx] + rng.uniform(0, 0.05, (n, 3)), rng.random((n, 1))], 1)
+            pts = pts[rng.permutation(n)]
+        else:            # thin wide slab: many key bits (4 passes at a fine leaf)
+            pts = np.concatenate([rng.uniform(-900, 900, (n, 2)), rng.uniform(-2, 2, (n, 1)), rng.random((n, 1))], 1)
+        pts = pts.astype(np.float32)
+        for leaf in (0.4, 0.05 if kind == 4 else 0.8):
+            o, ok = orc.voxel_grid(pts, leaf)
+            va, ga = a.voxel_downsample(pts, leaf)
+            vb, gb = b.voxel_downsample(pts, leaf)
+            assert ga == gb == (not ok), (n, kind, leaf)
+            assert np.array_equal(va, o) and np.array_equal(vb, o), (n, kind, leaf)
+        c = pts[rng.integers(0, n), :3].astype(np.float64)
+        oc = orc.crop_box(pts, c - 5.0, c + 5.0)
+        want = orc.voxel_grid(oc, 0.4)[0] if len(oc) else np.zeros((0, 4), np.float32)
+        assert np.array_equal(a.crop_voxel_downsample(pts, c, 5.0, 0.4), want), (n, kind)
+        assert np.array_equal(b.crop_voxel_downsample(pts, c, 5.0, 0.4), want), (n, kind)
+    a.close(); b.close()
