@@ -324,7 +324,8 @@ __global__ void __launch_bounds__(256) k_sector_select(LaneDev* lanes, int lane0
 // The sort keys live in REGISTERS: lane l holds the EPL consecutive network positions l*EPL .. l*EPL+EPL-1 as
 // (curvature bits hi, lo, element index).  Bitonic steps with partner distance < EPL are register compare-exchanges,
 // larger distances are warp shuffles; ~5 k warp instructions per sector against ~17 k for the shared-memory network
-// and ~23 k for the rank sort (profiles/r1d).  The greedy pick and the surf compaction are warp-serial as before.
+// and ~23 k for the rank sort (profiles/r1d).  (Packing (fp32 key << 32 | index) into one 64-bit word and sorting with 64-bit
+// min / max was tried: 34 M instead of 31 M warp instructions per launch — the selects dominate, not the compares.)  The greedy pick and the surf compaction are warp-serial as before.
 constexpr int SEC_WPC = 4;  // sectors (warps) per CTA
 __host__ __device__ constexpr size_t sec_warp_bytes(int ms, int np) {  // shared memory of one warp: sectors of <= ms elements, network of np
   return ((sizeof(float4) * (ms + 10) + sizeof(double) * ms + sizeof(uint32_t) * (ms + 10) + sizeof(uint16_t) * np + (ms + 16)) + 15) / 16 * 16;
@@ -503,11 +504,6 @@ template <int EPL>
 static void launch_sector_warp(const Launch& L, LaneDev* lanes, int lane0, int nlanes, int sel, const ConfigDev& cfg) {
   constexpr int NP = 32 * EPL;
   const size_t PER_WARP = sec_warp_bytes(cfg.max_sector < NP ? cfg.max_sector : NP, NP);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_sector_warp<EPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sec_warp_bytes(NP, NP) * SEC_WPC));
-    attr_set = true;
-  }
   const int n_sectors = cfg.rings_total * SECTORS;
   dim3 g((n_sectors + SEC_WPC - 1) / SEC_WPC, nlanes);
   k_sector_warp<EPL><<<g, 32 * SEC_WPC, PER_WARP * SEC_WPC, L.st>>>(lanes, lane0, sel, cfg, n_sectors);
@@ -578,12 +574,17 @@ __global__ void __launch_bounds__(256) k_compact_features(LaneDev* lanes, int la
   if (blockIdx.x == gridDim.x - 1 && tid == 0) { L.v->n_edge = oe + te; L.v->n_surf = os + ts; }
 }
 
+// Opt-in shared-memory sizes of the selection kernels.  Function attributes are per device: called once per context
+// (vilf_create*), never cached in a process-wide flag.
+cudaError_t init_extract_kernels() {
+  cudaError_t e = cudaFuncSetAttribute(k_sector_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_smem(MAX_SECTOR));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sector_warp<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sec_warp_bytes(128, 128) * SEC_WPC));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sector_warp<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sec_warp_bytes(256, 256) * SEC_WPC));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sector_warp<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sec_warp_bytes(512, 512) * SEC_WPC));
+  return e;
+}
+
 void launch_extract(const Launch& L, LaneDev* lanes, const SortJob* ring_jobs, int lane0, int nlanes, int sel, const ConfigDev& cfg) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_sector_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sector_smem(MAX_SECTOR));
-    attr_set = true;
-  }
   const size_t SEC_SMEM = sector_smem(cfg.max_sector);
   KeyGenRing gen;
   gen.lanes = lanes; gen.lane0 = lane0; gen.sel = sel; gen.cfg = cfg;

@@ -192,6 +192,7 @@ int build_ctx(Ctx* C) {
   const int capS = c.cap_scan, capM = c.cap_map + c.cap_scan;
 
   CK(cudaSetDevice(C->device));
+  CK(init_extract_kernels());
   CK(cudaStreamCreateWithFlags(&C->st, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&C->copy_st, cudaStreamNonBlocking));
   for (int i = 0; i < 2; ++i) {

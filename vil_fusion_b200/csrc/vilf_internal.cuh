@@ -266,6 +266,7 @@ struct Launch {
 // k_sort.cu
 void launch_sort_scatter(const Launch& L, const SortJob* jobs_dev, int njobs, int pass);
 // k_extract.cu
+cudaError_t init_extract_kernels();  // per-device function attributes; call once per context
 void launch_frame_reset(const Launch& L, LaneDev* lanes, int lane0, int nlanes, VoxVars* vv, int vv_per_lane, int predict);
 void launch_extract(const Launch& L, LaneDev* lanes, const SortJob* ring_jobs, int lane0, int nlanes, int sel, const ConfigDev& cfg);
 // k_voxel.cu
