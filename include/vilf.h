@@ -62,6 +62,7 @@ typedef struct vilf_config {
 
 /* Implementation-selection flags (results are bit-identical either way; used by the parity tests and for profiling). */
 #define VILF_FLAG_NO_CLUSTER 1 /* never take the one-cluster-per-cloud kernels; always the grid-wide multi-launch path */
+#define VILF_FLAG_NO_GRAPH 2   /* launch every kernel of a frame individually instead of replaying the captured CUDA graph */
 
 int vilf_default_config(vilf_config* cfg);
 

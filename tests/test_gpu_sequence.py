@@ -262,3 +262,20 @@ def test_1000_frames_free_running(cabi, orc, synth, sensor, n_scan, cap):
     # the trajectory really moved: ~1 m per frame
     assert np.linalg.norm(g.pose()[0][4:]) > 500.0
     g.close()
+
+
+def test_graph_replay_equals_individual_launches(cabi, synth):
+    """Steady-state frames are replayed as captured CUDA graphs (one per scan-buffer / map-buffer combination); the same
+    kernels launched one by one (VILF_FLAG_NO_GRAPH) must give identical poses, maps and launch counts."""
+    frames = 9
+    seq = synth.Sequence("hdl64", frames, seed=17)
+    kw = dict(max_scan_points=116000, max_map_points=1 << 18)
+    a = cabi.Odometry(cabi.default_config(**kw))
+    b = cabi.Odometry(cabi.default_config(flags=cabi.FLAG_NO_GRAPH, **kw))
+    for i in range(frames):
+        x, _ = seq[i]
+        assert np.array_equal(a.process_scan(x), b.process_scan(x)), i
+    for which in (cabi.MAP_EDGE, cabi.MAP_SURF, cabi.DS_SURF):
+        assert np.array_equal(a.cloud(which), b.cloud(which))
+    assert a.launch_count() == b.launch_count()
+    a.close(); b.close()

@@ -81,6 +81,7 @@ def _p(a, t):
 
 
 FLAG_NO_CLUSTER = 1
+FLAG_NO_GRAPH = 2
 MAP_EDGE, MAP_SURF, DS_EDGE, DS_SURF, REGISTERED, NO_REGISTERED = range(6)
 
 

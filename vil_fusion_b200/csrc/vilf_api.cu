@@ -7,6 +7,8 @@
 #include <cstring>
 #include <cmath>
 #include <new>
+#include <map>
+#include <tuple>
 #include <vector>
 
 using namespace vilf;
@@ -49,6 +51,10 @@ struct Ctx {
   VoxJob* vox_map_dev[2] = {nullptr, nullptr}; SortJob* vox_map_sort_dev[2] = {nullptr, nullptr};  // [cur][nlanes*2]
   GridJob* grid_dev[2] = {nullptr, nullptr};                                  // [buf][nlanes*2]
   // aux (stage-level entry points)
+  // steady-state frames replayed as CUDA graphs: one instantiated graph per (lane0, lanes, scan buffer, map buffer)
+  struct FrameGraph { cudaGraphExec_t exec = nullptr; int launches = 0; };
+  std::map<std::tuple<int, int, int, int>, FrameGraph> graphs;
+  bool use_graphs = true;
   bool cluster_scan = false, cluster_map = false;  // one-cluster-per-cloud path (k_cluster.cu) for scan / map clouds
   int cap_aux = 0;
   float4* aux_in = nullptr; float4* aux_out = nullptr;
@@ -213,6 +219,7 @@ int build_ctx(Ctx* C) {
   CK(dalloc(C, &C->lanes_dev, (size_t)NL));
   for (int b = 0; b < 2; ++b) CK(dalloc(C, &C->grid_dev[b], (size_t)NL * 2));
   const bool allow_cluster = !(u.flags & VILF_FLAG_NO_CLUSTER);
+  C->use_graphs = !(u.flags & VILF_FLAG_NO_GRAPH);
   C->cluster_scan = allow_cluster && capS <= CLUSTER_MAX_POINTS;
   C->cluster_map = allow_cluster && capM <= CLUSTER_MAX_POINTS;
   C->lanes_host.resize(NL);
@@ -359,6 +366,7 @@ void destroy_ctx(Ctx* C) {
   cudaSetDevice(C->device);
   if (C->st) cudaStreamSynchronize(C->st);
   if (C->copy_st) cudaStreamSynchronize(C->copy_st);
+  for (auto& kv : C->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   for (void* p : C->allocs) cudaFree(p);
   for (void* p : C->pinned) cudaFreeHost(p);
   for (int i = 0; i < 2; ++i) { if (C->extract_done[i]) cudaEventDestroy(C->extract_done[i]); if (C->h2d_done[i]) cudaEventDestroy(C->h2d_done[i]); }
@@ -381,8 +389,7 @@ int status_to_rc(Ctx* C, int status) {
 
 // createSubMap (EM:298-352) for lanes [lane0, lane0+nl): append the voxel-filtered scan features at the current pose,
 // crop + voxel-filter both maps into the other buffer, rebuild the search grids, flip the buffers.
-void enqueue_submap(Ctx* C, const Launch& L, int lane0, int nl, ProfSink* sink) {
-  const int cur = C->cur[lane0];
+void issue_submap(Ctx* C, const Launch& L, int lane0, int nl, int cur, ProfSink* sink) {
   if (C->cluster_map) {
     launch_voxel_cluster(L, C->vox_map_dev[cur] + lane0 * 2, nl * 2, false, C->cfg);
   } else {
@@ -391,11 +398,17 @@ void enqueue_submap(Ctx* C, const Launch& L, int lane0, int nl, ProfSink* sink) 
     if (sink) sink->phase = 4;
     launch_grid_build(L, C->grid_dev[cur ^ 1] + lane0 * 2, nl * 2, C->cfg);
   }
+}
+void enqueue_submap(Ctx* C, const Launch& L, int lane0, int nl, ProfSink* sink) {
+  const int cur = C->cur[lane0];
+  issue_submap(C, L, lane0, nl, cur, sink);
   for (int l = lane0; l < lane0 + nl; ++l) C->cur[l] = cur ^ 1;
 }
 
 // The per-frame launch sequence for lanes [lane0, lane0+nl), which all share `cur`, `first` and the scan slot.
 // with_extract = 0: features were uploaded by the caller (vilf_update_points / vilf_map_init_points).
+void issue_frame(Ctx* C, int lane0, int nl, bool first, bool with_extract, int sel, int cur, ProfSink* sink);
+
 int enqueue_frame(Ctx* C, int lane0, int nl, bool first, bool with_extract, int sel, Slot* S) {
   ProfSink* sink = nullptr;
   if (S && S->profiled) {
@@ -404,10 +417,44 @@ int enqueue_frame(Ctx* C, int lane0, int nl, bool first, bool with_extract, int 
     cudaEventRecord(sink->ev[0], C->st);  // frame start
     sink->tag[sink->n++] = -1;
   }
+  const int cur = C->cur[lane0];
+  if (C->use_graphs && !sink && !first && with_extract) {
+    // The steady-state frame is a fixed launch sequence whose arguments depend only on (lanes, scan buffer, map buffer): all
+    // element counts live in device memory.  It is captured once per combination and replayed with one cudaGraphLaunch.
+    Ctx::FrameGraph& G = C->graphs[std::make_tuple(lane0, nl, sel, cur)];
+    if (!G.exec) {
+      const int64_t before = C->launches;
+      cudaGraph_t graph = nullptr;
+      CK(cudaStreamBeginCapture(C->st, cudaStreamCaptureModeThreadLocal));
+      issue_frame(C, lane0, nl, first, with_extract, sel, cur, nullptr);
+      CK(cudaStreamEndCapture(C->st, &graph));
+      CK(cudaGraphInstantiate(&G.exec, graph, 0));
+      CK(cudaGraphDestroy(graph));
+      G.launches = (int)(C->launches - before);
+      C->launches = before;
+    }
+    CK(cudaGraphLaunch(G.exec, C->st));
+    C->launches += G.launches;
+  } else {
+    issue_frame(C, lane0, nl, first, with_extract, sel, cur, sink);
+  }
+  if (!first) for (int l = lane0; l < lane0 + nl; ++l) C->cur[l] = cur ^ 1;
+  for (int l = lane0; l < lane0 + nl; ++l) {
+    C->have_map[l] = 1; C->have_feat[l] = 1; C->last_init[l] = first ? 1 : 0; C->frame_no[l] += 1;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(C->err, sizeof(C->err), "kernel launch failed: %s", cudaGetErrorString(e));
+    return VILF_ERR_CUDA;
+  }
+  return VILF_OK;
+}
+
+// The launch sequence of one frame (no host-side state changes: it is also what a graph capture records).
+void issue_frame(Ctx* C, int lane0, int nl, bool first, bool with_extract, int sel, int cur, ProfSink* sink) {
   const Launch L = mk(C, sink);
   auto phase = [&](int p) { if (sink) sink->phase = p; };
   const ConfigDev& cfg = C->cfg;
-  const int cur = C->cur[lane0];
   phase(0);
   launch_frame_reset(L, C->lanes_dev, lane0, nl, C->vv_dev, VV_PER_LANE, first ? 0 : 1);
   if (with_extract) launch_extract(L, C->lanes_dev, C->ring_jobs_dev[sel], lane0, nl, sel, cfg);
@@ -426,17 +473,8 @@ int enqueue_frame(Ctx* C, int lane0, int nl, bool first, bool with_extract, int 
       launch_solve(L, C->lanes_dev, lane0, nl, it, it == cfg.outer_iters - 1 ? 1 : 0, cfg, cfg.lm_max_iters);
     }
     phase(3);
-    enqueue_submap(C, L, lane0, nl, sink);
+    issue_submap(C, L, lane0, nl, cur, sink);
   }
-  for (int l = lane0; l < lane0 + nl; ++l) {
-    C->have_map[l] = 1; C->have_feat[l] = 1; C->last_init[l] = first ? 1 : 0; C->frame_no[l] += 1;
-  }
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) {
-    snprintf(C->err, sizeof(C->err), "kernel launch failed: %s", cudaGetErrorString(e));
-    return VILF_ERR_CUDA;
-  }
-  return VILF_OK;
 }
 
 bool lanes_uniform(Ctx* C, int lane0, int nl) {
