@@ -189,6 +189,14 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
     w = WORKLOADS[args.workload]
     S, K, W, D = args.seqs, args.steps, max(args.warmup, 3), max(1, min(args.depth, 6))
     F = K + W
+    # every step consumes a fresh frame of every sequence, staged in pinned memory: bound that staging area (~1.85 MB per scan)
+    budget = 24e9
+    per_scan = {"hdl64": 64 * 1800, "vlp32": 32 * 1800, "beams128": 128 * 2048}[args.workload] * 18.0
+    if S * F * per_scan > budget:
+        S_fit = max(4, int(budget // (F * per_scan)))
+        if rank == 0:
+            print(f"bench.py: {S} sequences x {F} frames exceed the {budget / 1e9:.0f} GB pinned staging budget; using {S_fit} sequences per GPU", file=sys.stderr)
+        S = S_fit
     # ---- synthetic input: S independent sequences for this rank, staged in pinned host memory ----
     t_gen = time.time()
     seqs = [synth.Sequence(w["sensor"], F, seed=sd) for sd in replicas.sequence_seeds(rank, world, S)]

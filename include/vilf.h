@@ -75,6 +75,11 @@ const char* vilf_last_error(const vilf_handle* h);
 /* Pinned host memory for scan buffers (optional; makes the H2D copy asynchronous). */
 int vilf_host_alloc(void** p, uint64_t bytes);
 int vilf_host_free(void* p);
+/* sensor_msgs/PointCloud2 payload -> the packed float[n][4] every scan entry point takes (pcl::fromROSMsg at NODE:339-340):
+ * n_points = width * height, point_step and the byte offsets of the float32 fields x, y, z, intensity from msg.fields
+ * (off_intensity < 0: no such field, 0 is stored).  Host-side; write straight into a vilf_host_alloc buffer to keep the
+ * upload asynchronous. */
+int vilf_pack_pointcloud2(const uint8_t* data, int n_points, int point_step, int off_x, int off_y, int off_z, int off_intensity, float* xyzi_out);
 /* cudaMemcpyAsync(HostToDevice) on a caller-supplied stream (bench.py measures the host link with it). */
 int vilf_memcpy_h2d_async(void* dst_dev, const void* src_host, uint64_t bytes, void* cuda_stream);
 

@@ -14,6 +14,8 @@
 #include <string>
 #include <vector>
 
+#include "../vilf.h"
+
 #ifdef VILF_WITH_PCL
 #include <pcl/point_cloud.h>
 #include <pcl/point_types.h>
@@ -77,6 +79,25 @@ inline void append_cloud(CloudT& c, const float* xyzi, std::size_t n) {
     p.intensity = xyzi[4 * i + 3];
     c.push_back(p);
   }
+}
+
+// sensor_msgs::PointCloud2 (any type with .data, .width, .height, .point_step, .fields[i].{name, offset}) -> cloud, the
+// job of pcl::fromROSMsg at feature_tracker_node.cpp:339-340, through vilf_pack_pointcloud2.
+template <class MsgT, class CloudT>
+inline void from_pointcloud2(const MsgT& msg, CloudT& cloud) {
+  int ox = -1, oy = -1, oz = -1, oi = -1;
+  for (std::size_t f = 0; f < msg.fields.size(); ++f) {
+    if (msg.fields[f].name == "x") ox = (int)msg.fields[f].offset;
+    else if (msg.fields[f].name == "y") oy = (int)msg.fields[f].offset;
+    else if (msg.fields[f].name == "z") oz = (int)msg.fields[f].offset;
+    else if (msg.fields[f].name == "intensity") oi = (int)msg.fields[f].offset;
+  }
+  const int n = (int)(msg.width * msg.height);
+  std::vector<float> packed((std::size_t)(n > 0 ? n : 1) * 4);
+  if (vilf_pack_pointcloud2(msg.data.data(), n, (int)msg.point_step, ox, oy, oz, oi, packed.data()) != 0)
+    throw std::runtime_error("from_pointcloud2: the message has no float32 x / y / z fields");
+  cloud.clear();
+  append_cloud(cloud, packed.data(), (std::size_t)n);
 }
 
 #ifdef VILF_WITH_EIGEN

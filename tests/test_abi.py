@@ -67,3 +67,24 @@ def test_product_package_does_not_import_the_oracle():
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), f
                 assert "liborc" not in txt and "orc_capi" not in txt and "oracle/" not in txt, f
+
+
+def test_pack_pointcloud2(cabi):
+    """PointCloud2 -> packed float4 (feature_tracker_node.cpp:339-340, pcl::fromROSMsg): a velodyne-style layout
+    x y z intensity ring(u16) time(f32), point_step 22, and a layout without intensity."""
+    import numpy as np
+    rng = np.random.default_rng(1)
+    n = 1000
+    dt = np.dtype({"names": ["x", "y", "z", "intensity", "ring", "time"], "formats": ["<f4", "<f4", "<f4", "<f4", "<u2", "<f4"],
+                   "offsets": [0, 4, 8, 12, 16, 18], "itemsize": 22})
+    msg = np.zeros(n, dt)
+    for k in ("x", "y", "z", "intensity", "time"):
+        msg[k] = rng.normal(size=n).astype(np.float32)
+    msg["ring"] = rng.integers(0, 64, n)
+    raw = msg.view(np.uint8).reshape(-1)
+    out = cabi.pack_pointcloud2(raw, n, 22, 0, 4, 8, 12)
+    assert np.array_equal(out, np.stack([msg["x"], msg["y"], msg["z"], msg["intensity"]], 1))
+    out = cabi.pack_pointcloud2(raw, n, 22, 0, 4, 8, -1)
+    assert np.array_equal(out[:, :3], np.stack([msg["x"], msg["y"], msg["z"]], 1)) and (out[:, 3] == 0).all()
+    with pytest.raises(cabi.VilfError):
+        cabi.pack_pointcloud2(raw, n, 22, 0, 4, 20, 12)  # z would read past the point

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvilf_cuda.so")
+LIB_PATH = os.environ.get("VILF_LIB_PATH", os.path.join(_HERE, "libvilf_cuda.so"))  # the override is for A/B runs of kernel variants
 
 STATUS = {0: "OK", 1: "INVALID", 2: "CUDA", 3: "CAPACITY", 4: "UNSUPPORTED", 5: "STATE"}
 
@@ -35,7 +35,7 @@ class Config(C.Structure):
 
 # every symbol include/vilf.h declares (tests/test_abi.py checks the .so exports all of them)
 SYMBOLS = [
-    "vilf_default_config", "vilf_create", "vilf_create_batch", "vilf_destroy", "vilf_last_error", "vilf_host_alloc", "vilf_host_free", "vilf_memcpy_h2d_async",
+    "vilf_default_config", "vilf_create", "vilf_create_batch", "vilf_destroy", "vilf_last_error", "vilf_host_alloc", "vilf_host_free", "vilf_memcpy_h2d_async", "vilf_pack_pointcloud2",
     "vilf_process_scan", "vilf_submit_scan", "vilf_wait", "vilf_submit_scan_batch", "vilf_wait_batch", "vilf_submit_scan_batch_dev",
     "vilf_feature_extract", "vilf_get_features", "vilf_map_init", "vilf_map_init_points", "vilf_update", "vilf_update_points",
     "vilf_get_pose", "vilf_set_pose", "vilf_predict", "vilf_create_submap", "vilf_get_cloud", "vilf_voxel_downsample", "vilf_crop_voxel_downsample", "vilf_crop_box", "vilf_knn5",
@@ -401,3 +401,14 @@ def memcpy_h2d_async(dst_dev_ptr: int, src_host_ptr: int, nbytes: int, stream: i
     rc = lib().vilf_memcpy_h2d_async(C.c_void_p(dst_dev_ptr), C.c_void_p(src_host_ptr), C.c_uint64(nbytes), C.c_void_p(stream))
     if rc:
         raise VilfError(rc, "cudaMemcpyAsync failed")
+
+
+def pack_pointcloud2(data: np.ndarray, n_points: int, point_step: int, off_x: int, off_y: int, off_z: int, off_intensity: int = -1, out: np.ndarray | None = None):
+    """sensor_msgs/PointCloud2 payload (uint8 array) -> packed float32 [n, 4] (host side, no GPU needed)."""
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    if out is None:
+        out = np.empty((max(n_points, 1), 4), np.float32)
+    rc = lib().vilf_pack_pointcloud2(_p(data, C.c_uint8), n_points, point_step, off_x, off_y, off_z, off_intensity, _p(out, C.c_float))
+    if rc:
+        raise VilfError(rc, "bad PointCloud2 layout")
+    return out[:n_points]

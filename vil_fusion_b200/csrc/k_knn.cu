@@ -172,7 +172,11 @@ __device__ __forceinline__ void top5_insert(Top5& t, float cd, int ci) {  // pre
 // merge them, and every lane holding the winner pops it — which also removes duplicates that reach two lanes through
 // colliding buckets.  Same (d^2, index) order as before, so the result is bit-identical.
 constexpr int KNN_THREADS = 128;
-constexpr int KNN_GROUP = 8;
+#ifndef VILF_KNN_GROUP
+#define VILF_KNN_GROUP 8
+#endif
+constexpr int KNN_GROUP = VILF_KNN_GROUP;          // lanes per query (8: see above; 4 was measured)
+constexpr int KNN_SLOTS = (27 + KNN_GROUP - 1) / KNN_GROUP;  // buckets of the first 27 cells per lane
 
 __device__ __forceinline__ void knn_consider(Top5& best, float gate_f, float qx, float qy, float qz, const float4 c) {
   const float ddx = fsub(qx, c.x), ddy = fsub(qy, c.y), ddz = fsub(qz, c.z);
@@ -195,8 +199,8 @@ __device__ __forceinline__ void knn_bucket(Top5& best, float gate_f, float qx, f
   for (uint32_t p = s + PF; p < e; ++p) knn_consider(best, gate_f, qx, qy, qz, __ldg(sorted + p));
 }
 
-// Called by all 32 lanes; the lanes of a group (lane >> 3) pass the same query.  Returns in (rd, ri) of group lane sl < 5 the
-// sl-th nearest neighbour (FLT_MAX / INT_MAX when there are fewer than sl + 1 inside the gate).
+// Called by all 32 lanes; the lanes of a group (lane >> 3) pass the same query.  Returns, replicated in every lane of the group,
+// the five nearest neighbours in ascending (d^2, index) order (FLT_MAX / INT_MAX where fewer than five lie inside the gate).
 //
 // Cells of Chebyshev distance <= 1 (27 buckets) come first.  Grids of dense maps have cells finer than the gate radius
 // (G.rings > 1): further shells follow, and the walk stops as soon as the fifth-best distance is certainly smaller than the
@@ -204,8 +208,8 @@ __device__ __forceinline__ void knn_bucket(Top5& best, float gate_f, float qx, f
 // query's distance to the nearest face of its own cell in cell units.  The test uses an upper bound of the group's true
 // fifth distance (the smallest fifth distance any single lane holds) and a 1e-5 relative margin for the fp32 rounding of
 // computed distances, so it can only stop late, never early: the result is the same exact 5-NN as the full walk.
-__device__ __forceinline__ void group_knn5(const GridJob& G, float gate_f, float qx, float qy, float qz, bool active, float& rd, int& ri) {
-  constexpr int PF = 2;
+__device__ __forceinline__ void group_knn5(const GridJob& G, float gate_f, float qx, float qy, float qz, bool active, float (&rd)[5], int (&ri)[5]) {
+  constexpr int PF = KNN_GROUP >= 8 ? 2 : 1;
   const int sl = threadIdx.x & (KNN_GROUP - 1);
   Top5 best;
 #pragma unroll
@@ -219,9 +223,9 @@ __device__ __forceinline__ void group_knn5(const GridJob& G, float gate_f, float
   if (active) {
     hm = (uint32_t)(*G.hvar) - 1u;
     cell_of(make_float4(qx, qy, qz, 0.f), inv_cell, qcx, qcy, qcz);
-    uint32_t s[4], e[4];
+    uint32_t s[KNN_SLOTS], e[KNN_SLOTS];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < KNN_SLOTS; ++j) {
       const int c = sl + KNN_GROUP * j;  // cell (c % 3 - 1, (c / 3) % 3 - 1, c / 9 - 1)
       s[j] = 0; e[j] = 0;
       if (c < 27) {
@@ -230,14 +234,14 @@ __device__ __forceinline__ void group_knn5(const GridJob& G, float gate_f, float
         e[j] = __ldg(start + h + 1);
       }
     }
-    float4 c[4][PF];
+    float4 c[KNN_SLOTS][PF];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < KNN_SLOTS; ++j)
 #pragma unroll
       for (int i = 0; i < PF; ++i)
         if (s[j] + i < e[j]) c[j][i] = __ldg(sorted + s[j] + i);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) knn_bucket<PF>(best, gate_f, qx, qy, qz, sorted, s[j], e[j], c[j]);
+    for (int j = 0; j < KNN_SLOTS; ++j) knn_bucket<PF>(best, gate_f, qx, qy, qz, sorted, s[j], e[j], c[j]);
   }
   // the groups of a warp may use different grids (edge / surf): the shell loop runs to the warp-wide maximum
   const int rmax = __reduce_max_sync(0xffffffffu, active ? rings : 1);
@@ -268,7 +272,6 @@ __device__ __forceinline__ void group_knn5(const GridJob& G, float gate_f, float
       }
     }
   }
-  rd = FLT_MAX; ri = INT_MAX;
 #pragma unroll
   for (int round = 0; round < 5; ++round) {
     float wd = best.d[0];
@@ -281,7 +284,7 @@ __device__ __forceinline__ void group_knn5(const GridJob& G, float gate_f, float
       wd = take ? od : wd;
       wi = take ? oi : wi;
     }
-    if (sl == round) { rd = wd; ri = wi; }
+    rd[round] = wd; ri[round] = wi;  // known to every lane of the group
     const bool pop = (best.id[0] == wi) & (wi != INT_MAX);  // every lane holding the winner drops it
 #pragma unroll
     for (int k = 0; k < 4; ++k) { best.d[k] = pop ? best.d[k + 1] : best.d[k]; best.id[k] = pop ? best.id[k + 1] : best.id[k]; }
@@ -434,13 +437,15 @@ __global__ void __launch_bounds__(KNN_THREADS) k_knn_assoc(LaneDev* lanes, const
     const int k = active ? (q < ne ? q : q - ne) : 0;
     float4 pw = make_float4(0.f, 0.f, 0.f, 0.f);
     if (active) pw = associate(x, L.ds[w][k]);
-    float rd;
-    int ri;
+    float rd[5];
+    int ri[5];
     group_knn5(grid_jobs[ln * 2 + w], cfg.knn_gate_f, pw.x, pw.y, pw.z, active, rd, ri);
-    if (active && sl < 5) {
-      L.nn_idx[w][k * 5 + sl] = ri == INT_MAX ? -1 : ri;
-      L.nn_d2[w][k * 5 + sl] = rd;
-    }
+#pragma unroll
+    for (int j = 0; j < 5; ++j)
+      if (active && (j % KNN_GROUP) == sl) {
+        L.nn_idx[w][k * 5 + j] = ri[j] == INT_MAX ? -1 : ri[j];
+        L.nn_d2[w][k * 5 + j] = rd[j];
+      }
   }
 }
 
@@ -512,8 +517,7 @@ __global__ void __launch_bounds__(128) k_fit(LaneDev* lanes, int lane0, int cur,
 }
 
 void launch_knn_fit(const Launch& L, LaneDev* lanes, const GridJob* grid_jobs, int lane0, int nlanes, int cur, const ConfigDev& cfg,
-                    const double* pose_override, int want_nn) {
-  (void)want_nn;
+                    const double* pose_override) {
   dim3 g(KNN_G * 4, nlanes);
   k_knn_assoc<<<g, KNN_THREADS, 0, L.st>>>(lanes, grid_jobs, lane0, cfg, pose_override);
   L.tick(K_KNN_FIT);
@@ -533,13 +537,15 @@ __global__ void __launch_bounds__(KNN_THREADS) k_knn_only(const GridJob* __restr
     const bool active = i < nq;
     float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
     if (active) p = q[i];
-    float rd;
-    int ri;
+    float rd[5];
+    int ri[5];
     group_knn5(*job, gate_f, p.x, p.y, p.z, active, rd, ri);
-    if (active && sl < 5) {
-      idx[i * 5 + sl] = ri == INT_MAX ? -1 : ri;
-      d2[i * 5 + sl] = rd;
-    }
+#pragma unroll
+    for (int j = 0; j < 5; ++j)
+      if (active && (j % KNN_GROUP) == sl) {
+        idx[i * 5 + j] = ri[j] == INT_MAX ? -1 : ri[j];
+        d2[i * 5 + j] = rd[j];
+      }
   }
 }
 

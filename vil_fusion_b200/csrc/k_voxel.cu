@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256) k_vox_centroid(const VoxJob* __restrict__
     int off = 0, total = 0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) { const int c = wsum[w]; if (w < warp) off += c; total += c; }
-    emit_centroids<false>(J, key, val, n, guard, i, head, run + off + __popc(b & ((1u << lane) - 1u)), stage[warp]);
+    emit_centroids(J, key, val, n, guard, i, head, run + off + __popc(b & ((1u << lane) - 1u)), stage[warp]);
     run += total;
     __syncthreads();
   }

@@ -89,16 +89,7 @@ struct KeyGenVoxel {
 // points near the sensor) are walked by the whole warp: 32 coalesced (index, point) loads per step, prefetched one
 // step ahead, staged in shared memory, then lanes 0..3 each add one component sequentially — the same fp32 order.
 // Must be called by all 32 lanes; `stage` = 32 float4 of shared memory private to the warp.
-// CG = true (cluster path): the sorted pairs (and, for map jobs, the appended input points) were written by OTHER CTAs of
-// this same kernel.  They are read with explicit ld.global.ca — never ld.global.nc, whose "read-only for the kernel's
-// lifetime" contract would not hold — and that is safe because this SM cannot hold a stale L1 line of them: every
-// earlier access to those buffers in the kernel was a store or an ld.global.cg (no L1 allocation), see k_cluster.cu.
-template <bool CG>
-__device__ __forceinline__ uint32_t ld_u32(const uint32_t* p) { return CG ? __ldca(p) : *p; }
-template <bool CG>
-__device__ __forceinline__ float4 ld_f4(const float4* p) { return CG ? __ldca(p) : *p; }
-
-template <bool CG>
+// (Grid-wide path: the sorted pairs come from earlier kernels.  The cluster path has its own emitter, k_cluster.cu: emit_range.)
 __device__ __forceinline__ void emit_centroids(const VoxJob& J, const uint32_t* __restrict__ key, const uint32_t* __restrict__ val, int n, int guard,
                                                int i, bool head, int dst, float4* stage) {
   constexpr int SHORT_RUN = 8;
@@ -106,16 +97,16 @@ __device__ __forceinline__ void emit_centroids(const VoxJob& J, const uint32_t* 
   uint32_t k0 = 0;
   bool long_run = false;
   if (head && dst < J.cap_out) {
-    k0 = ld_u32<CG>(key + i);
-    if (!guard && i + SHORT_RUN < n && ld_u32<CG>(key + i + SHORT_RUN) == k0) {
+    k0 = key[i];
+    if (!guard && i + SHORT_RUN < n && key[i + SHORT_RUN] == k0) {
       long_run = true;
     } else if (guard) {
-      J.out[dst] = ld_f4<CG>(J.in + ld_u32<CG>(val + i));  // PCL's guard path returns the input points untouched
+      J.out[dst] = J.in[val[i]];  // PCL's guard path returns the input points untouched
     } else {
       float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
       int cnt = 0;
-      for (int j = i; j < n && (j == i || ld_u32<CG>(key + j) == k0); ++j) {
-        const float4 p = ld_f4<CG>(J.in + ld_u32<CG>(val + j));
+      for (int j = i; j < n && (j == i || key[j] == k0); ++j) {
+        const float4 p = J.in[val[j]];
         c.x = fadd(c.x, p.x); c.y = fadd(c.y, p.y); c.z = fadd(c.z, p.z); c.w = fadd(c.w, p.w);
         ++cnt;
       }
@@ -133,9 +124,9 @@ __device__ __forceinline__ void emit_centroids(const VoxJob& J, const uint32_t* 
     float acc = 0.f;  // lane c < 4 accumulates component c
     int cnt = 0;
     int j = start + lane;
-    bool valid = j < n && ld_u32<CG>(key + j) == ks;
+    bool valid = j < n && key[j] == ks;
     float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid) p = ld_f4<CG>(J.in + ld_u32<CG>(val + j));
+    if (valid) p = J.in[val[j]];
     for (;;) {
       const int len = __popc(__ballot_sync(0xffffffffu, valid));  // sorted keys: the valid lanes are a prefix
       stage[lane] = p;
@@ -144,8 +135,8 @@ __device__ __forceinline__ void emit_centroids(const VoxJob& J, const uint32_t* 
       float4 p2 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (len == 32) {
         j += 32;
-        valid2 = j < n && ld_u32<CG>(key + j) == ks;
-        if (valid2) p2 = ld_f4<CG>(J.in + ld_u32<CG>(val + j));
+        valid2 = j < n && key[j] == ks;
+        if (valid2) p2 = J.in[val[j]];
       }
       __syncwarp();
       if (lane < 4) {

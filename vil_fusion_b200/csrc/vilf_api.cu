@@ -469,7 +469,7 @@ void issue_frame(Ctx* C, int lane0, int nl, bool first, bool with_extract, int s
     else launch_voxel(L, C->vox_scan_dev + lane0 * 2, nl * 2, C->vox_scan_sort_dev + lane0 * 2, with_extract);
     phase(2);
     for (int it = 0; it < cfg.outer_iters; ++it) {
-      launch_knn_fit(L, C->lanes_dev, C->grid_dev[cur], lane0, nl, cur, cfg, nullptr, 0);
+      launch_knn_fit(L, C->lanes_dev, C->grid_dev[cur], lane0, nl, cur, cfg, nullptr);
       launch_solve(L, C->lanes_dev, lane0, nl, it, it == cfg.outer_iters - 1 ? 1 : 0, cfg, cfg.lm_max_iters);
     }
     phase(3);
@@ -696,6 +696,22 @@ const char* vilf_last_error(const vilf_handle* h) { return (h && h->ctx) ? h->ct
 int vilf_host_alloc(void** p, uint64_t bytes) { return cudaMallocHost(p, bytes) == cudaSuccess ? VILF_OK : VILF_ERR_CUDA; }
 int vilf_memcpy_h2d_async(void* dst_dev, const void* src_host, uint64_t bytes, void* cuda_stream) {
   return cudaMemcpyAsync(dst_dev, src_host, (size_t)bytes, cudaMemcpyHostToDevice, (cudaStream_t)cuda_stream) == cudaSuccess ? VILF_OK : VILF_ERR_CUDA;
+}
+int vilf_pack_pointcloud2(const uint8_t* data, int n_points, int point_step, int off_x, int off_y, int off_z, int off_intensity, float* xyzi_out) {
+  // sensor_msgs/PointCloud2 -> packed x, y, z, intensity (what pcl::fromROSMsg does for PointXYZI at NODE:339-340): a strided
+  // gather of four little-endian float32 fields per point; off_intensity < 0 = the message has no intensity field (0 is stored).
+  if (n_points < 0 || (n_points > 0 && (!data || !xyzi_out)) || point_step < 12 || off_x < 0 || off_y < 0 || off_z < 0) return VILF_ERR_INVALID;
+  if (off_x + 4 > point_step || off_y + 4 > point_step || off_z + 4 > point_step || off_intensity + 4 > point_step) return VILF_ERR_INVALID;
+  for (int i = 0; i < n_points; ++i) {
+    const uint8_t* p = data + (size_t)i * (size_t)point_step;
+    float* o = xyzi_out + (size_t)i * 4;
+    memcpy(o + 0, p + off_x, 4);
+    memcpy(o + 1, p + off_y, 4);
+    memcpy(o + 2, p + off_z, 4);
+    if (off_intensity >= 0) memcpy(o + 3, p + off_intensity, 4);
+    else o[3] = 0.0f;
+  }
+  return VILF_OK;
 }
 int vilf_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? VILF_OK : VILF_ERR_CUDA; }
 
@@ -1080,7 +1096,7 @@ int vilf_factors(vilf_handle* h, const double pose[7], const float* edge, int n_
   }
   CK(cudaMemsetAsync(L.edge_pab, 0, (size_t)(n_edge > 0 ? n_edge : 1) * 72, C->st));
   CK(cudaMemsetAsync(L.surf_pnd, 0, (size_t)(n_surf > 0 ? n_surf : 1) * 56, C->st));
-  launch_knn_fit(mk(C), C->lanes_dev, C->grid_dev[C->cur[lane]], lane, 1, C->cur[lane], C->cfg, C->aux_pose, 1);
+  launch_knn_fit(mk(C), C->lanes_dev, C->grid_dev[C->cur[lane]], lane, 1, C->cur[lane], C->cfg, C->aux_pose);
   CK(cudaGetLastError());
   std::vector<double> pab((size_t)(n_edge > 0 ? n_edge : 1) * 9), pnd((size_t)(n_surf > 0 ? n_surf : 1) * 7);
   if (n_edge) {

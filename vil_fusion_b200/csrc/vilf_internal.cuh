@@ -23,7 +23,7 @@ constexpr int SORT_RADIX_BITS = 9;   // digit width limit; tables are [4 passes]
 constexpr int SORT_RADIX = 1 << SORT_RADIX_BITS;
 constexpr int VOX_G = 148;           // CTAs per voxel job for the bbox / head / centroid kernels
 constexpr int GRID_G = 148;          // CTAs per hash-grid job
-constexpr int KNN_G = 148;           // CTAs (128 threads, one query each, grid-stride) of the kNN kernel per lane
+constexpr int KNN_G = 148;           // the kNN kernels launch 4 x KNN_G CTAs per lane (128 threads = 16 queries of 8 lanes each, grid-stride)
 constexpr int FIT_G = 148;           // CTAs (128 threads) of the fit kernel per lane
 constexpr int LM_THREADS = 256;     // per CTA of the solve cluster
 constexpr int LM_CLUSTER = 8;       // CTAs (SMs) per sequence in the solve kernel
@@ -280,7 +280,7 @@ void launch_grid_cluster(const Launch& L, const GridJob* jobs_dev, int njobs, co
 // k_knn.cu
 void launch_grid_build(const Launch& L, const GridJob* jobs_dev, int njobs, const ConfigDev& cfg);
 void launch_knn_fit(const Launch& L, LaneDev* lanes, const GridJob* grid_jobs, int lane0, int nlanes, int cur, const ConfigDev& cfg,
-                    const double* pose_override, int want_nn);
+                    const double* pose_override);
 void launch_knn_only(const Launch& L, const GridJob* job_dev, const float4* q, const int* nq_dev, int* idx, float* d2, const ConfigDev& cfg);
 // k_depth.cu
 void launch_depth(const Launch& L, const float4* in, const int* n_dev, int from_scan, const double* T_dev, float4* sph, int* oidx, int* count,
