@@ -30,7 +30,6 @@ struct VoxShared {
   uint32_t wcnt[CW][SORT_RADIX];   // per-warp digit counters (histogram, then running scatter offsets)
   uint32_t cta_hist[SORT_RADIX];   // this CTA's digit totals; read by the peers over DSMEM
   uint32_t scan[CW];
-  float4 stage[CW][32];
   float bb[8];                     // partial bounding box + count of this CTA
   int heads;                       // heads in this CTA's chunk
   int wsum[CW];
@@ -112,6 +111,14 @@ __device__ void grid_build_cluster(cg::cluster_group& cluster, const GridJob& G,
 // PCL's `centroid += point; ...; centroid /= count` in fp32 (same order as the grid-wide emitter => identical bits).  A run
 // that is still open at the end of a step is carried into the next one (also past `end`: it still belongs to this warp).
 // `dst0` = output index of the first run that starts in the range.  All loads are ld.global.ca (see k_voxel.cuh).
+// centroid /= count.  A voxel with one point (most voxels of a local map) keeps the point: (0 + p) / 1 == p bit for bit, and
+// skipping four IEEE divisions matters because this phase is instruction bound (150 warp instructions per 32 positions).
+__device__ __forceinline__ float4 centroid_of(const float4 acc, int cnt) {
+  if (cnt == 1) return acc;
+  const float fc = (float)cnt;
+  return make_float4(__fdiv_rn(acc.x, fc), __fdiv_rn(acc.y, fc), __fdiv_rn(acc.z, fc), __fdiv_rn(acc.w, fc));
+}
+
 __device__ void emit_range(const VoxJob& J, const uint2* kv, int nv, int guard, int beg, int end, int dst0, float4* stage) {
   if (beg >= end) return;  // uniform over the warp
   const int lane = threadIdx.x & 31;
@@ -130,7 +137,17 @@ __device__ void emit_range(const VoxJob& J, const uint2* kv, int nv, int guard, 
   bool nvalid = beg + 32 + lane < nv;
   uint2 ne = make_uint2(0u, 0u);
   if (nvalid) ne = __ldca(kv + beg + 32 + lane);
+  float4* const stage_base = stage;
+  int buf = 0;
   for (int base = beg;; base += 32) {
+    // The staged points go to the buffer the PREVIOUS step did not use, so one warp barrier per step suffices (the barrier of
+    // step s + 1 orders the reads of step s before the writes of step s + 2).  The barrier also waits for this warp's
+    // outstanding global loads and stores (measured: two L2 round trips per step when loads were issued before it and
+    // stores sat before a second barrier), hence: stage, barrier, THEN issue the next step's loads, sum, store.
+    stage = stage_base + 32 * buf;
+    buf ^= 1;
+    stage[lane] = p;
+    __syncwarp();
     const uint32_t nk = ne.x;
     float4 np = make_float4(0.f, 0.f, 0.f, 0.f);
     if (nvalid) np = __ldca(J.in + ne.y);
@@ -148,14 +165,9 @@ __device__ void emit_range(const VoxJob& J, const uint2* kv, int nv, int guard, 
     const unsigned starts = lim >= 32 ? hm : (hm & ((1u << lim) - 1u));
     const bool cont0 = open && lim > 0 && !(starts & 1u);                     // the carried run continues at lane 0
     if (open && !cont0) {                                                     // ... or it ended with the previous step
-      if (lane == 0 && cdst < J.cap_out) {
-        const float fc = (float)ccnt;
-        J.out[cdst] = make_float4(__fdiv_rn(cacc.x, fc), __fdiv_rn(cacc.y, fc), __fdiv_rn(cacc.z, fc), __fdiv_rn(cacc.w, fc));
-      }
+      if (lane == 0 && cdst < J.cap_out) J.out[cdst] = centroid_of(cacc, ccnt);
       open = false;
     }
-    stage[lane] = p;
-    __syncwarp();
     const unsigned all_starts = starts | (cont0 ? 1u : 0u);
     const bool is_start = lane < lim && ((all_starts >> lane) & 1u);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -198,11 +210,7 @@ __device__ void emit_range(const VoxJob& J, const uint2* kv, int nv, int guard, 
     }
     // a run reaching the end of a FULL step may continue: carry it; every other run is complete
     const bool carry = is_start && e == 32 && lim == 32;
-    if (is_start && !carry && my_dst < J.cap_out) {
-      const float fc = (float)cnt;
-      J.out[my_dst] = make_float4(__fdiv_rn(acc.x, fc), __fdiv_rn(acc.y, fc), __fdiv_rn(acc.z, fc), __fdiv_rn(acc.w, fc));
-    }
-    __syncwarp();  // stage is rewritten in the next step
+    if (is_start && !carry && my_dst < J.cap_out) J.out[my_dst] = centroid_of(acc, cnt);
     dst += __popc(starts);
     if (lim < 32) break;
     const unsigned cm = __ballot_sync(FULL, carry);  // the last run of a full step, if this warp owns any run in it
@@ -457,7 +465,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CT, 2) k_voxel_clus
     *J.n_out = n_out;
   }
   PHASE_MARK(3);
-  emit_range(J, kv, nv, guard, hwbeg, hwend, run, S.stage[warp]);  // warps run independently
+  // staging of the centroid emitter: two 32-point buffers per warp, in the digit-counter table the sort no longer needs
+  emit_range(J, kv, nv, guard, hwbeg, hwend, run, reinterpret_cast<float4*>(&S.wcnt[0][0]) + warp * 64);  // warps run independently
 
   // ---- phase 3 (map jobs): spatial hash of the filtered map for the next frame's 5-NN search ----
   if (J.grid != nullptr) {
