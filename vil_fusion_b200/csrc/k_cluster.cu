@@ -22,6 +22,7 @@ namespace cg = cooperative_groups;
 constexpr int CL = 8;              // CTAs per cluster (portable maximum)
 constexpr int CT = 512;            // threads per CTA (== SORT_RADIX: one thread per digit)
 constexpr int CW = CT / 32;        // warps per CTA
+constexpr int NB = 8;              // 32-key groups a warp loads ahead in the sort sweeps (every batch costs one exposed L2 round trip)
 
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define PHASE_MARK(k) do { if (rank == 0 && tid == 0) J.vv->t[k] = gtimer(); } while (0)
@@ -344,13 +345,13 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CT, 2) k_voxel_clus
     const int shift = pass * w;
     const uint2* pin = J.sort.pair[pass & 1];   // (key, value) pairs, moved with one 8-byte access each
     uint2* __restrict__ pout = J.sort.pair[(pass + 1) & 1];
-    // sweep 1: warp-private digit histogram (pass 0 also materialises the keys); 4 x 32 keys in flight per warp
+    // sweep 1: warp-private digit histogram (pass 0 also materialises the keys); NB x 32 keys in flight per warp
     for (int i = tid; i < CW * SORT_RADIX; i += CT) (&S.wcnt[0][0])[i] = 0;
     __syncthreads();
-    for (int base = wbeg; base < wend; base += 128) {
-      uint32_t k[4];
+    for (int base = wbeg; base < wend; base += 32 * NB) {
+      uint32_t k[NB];
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
+      for (int it = 0; it < NB; ++it) {
         const int i = base + it * 32 + lane;
         k[it] = 0;
         if (i < wend) {
@@ -359,7 +360,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CT, 2) k_voxel_clus
         }
       }
 #pragma unroll
-      for (int it = 0; it < 4; ++it)
+      for (int it = 0; it < NB; ++it)
         if (base + it * 32 + lane < wend) atomicAdd(&S.wcnt[warp][(k[it] >> shift) & mask], 1u);
     }
     __syncthreads();
@@ -393,11 +394,11 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CT, 2) k_voxel_clus
       }
     }
     __syncthreads();
-    // sweep 2: stable rank inside the warp's sub-chunk, 32 keys at a time in order (4 x 32 loaded ahead), and scatter
-    for (int base = wbeg; base < wend; base += 128) {
-      uint32_t k[4], v[4];
+    // sweep 2: stable rank inside the warp's sub-chunk, 32 keys at a time in order (NB x 32 loaded ahead), and scatter
+    for (int base = wbeg; base < wend; base += 32 * NB) {
+      uint32_t k[NB], v[NB];
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
+      for (int it = 0; it < NB; ++it) {
         const int i = base + it * 32 + lane;
         k[it] = 0; v[it] = (uint32_t)i;
         if (i < wend) {
@@ -406,7 +407,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CT, 2) k_voxel_clus
         }
       }
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
+      for (int it = 0; it < NB; ++it) {
         const bool ok = base + it * 32 + lane < wend;
         const uint32_t d = (k[it] >> shift) & mask;
         const unsigned act = __ballot_sync(0xffffffffu, ok);
