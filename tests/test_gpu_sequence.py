@@ -279,3 +279,25 @@ def test_graph_replay_equals_individual_launches(cabi, synth):
         assert np.array_equal(a.cloud(which), b.cloud(which))
     assert a.launch_count() == b.launch_count()
     a.close(); b.close()
+
+
+def test_config5_128_beams_fine_voxels(cabi, orc, synth):
+    """BASELINE.json configs[4]: dense 128-beam scans (explicit ring ids) with a 0.2 m edge / 0.4 m surf map voxel.  The edge
+    map then gets 0.5 m search cells and the two-shell 5-NN walk with early exit, the surf map keeps 1 m cells — both kinds
+    of grid are queried by the same warps of k_knn_assoc.  Free-running against the oracle, maps compared at the end."""
+    frames = 8
+    seq = synth.Sequence("beams128", frames, seed=31)
+    o = orc.Odometry(orc.config(n_scan=0, n_rings=128, edge_leaf=0.2, surf_leaf=0.4))
+    g = cabi.Odometry(cabi.default_config(n_scan=0, n_rings=128, edge_leaf=0.2, surf_leaf=0.4, max_scan_points=263000, max_map_points=1 << 18,
+                                          max_ring_points=2048 + 64))
+    for i in range(frames):
+        x, r = seq[i]
+        po, _, _ = o.process_scan(x, r)
+        pg = g.process_scan(x, r)
+        e = pose_err(po, pg)
+        assert e[0] <= TOL_ROT and e[1] <= TOL_TRANS, (i, e)
+    maps_close(orc, cabi, o, g)
+    assert np.array_equal(o.solves()[:, :4], g.solves()[:, :4])  # same factor counts, terminations and iteration counts
+    c = g.counts()
+    assert c["status"] == 0 and c["n_map_edge"] > 5000
+    g.close()
