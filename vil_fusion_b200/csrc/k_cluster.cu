@@ -19,7 +19,10 @@ namespace vilf {
 
 namespace cg = cooperative_groups;
 
-constexpr int CL = 8;              // CTAs per cluster (portable maximum)
+#ifndef VILF_VOX_CLUSTER
+#define VILF_VOX_CLUSTER 8
+#endif
+constexpr int CL = VILF_VOX_CLUSTER;  // CTAs per cluster (8 = portable maximum)
 constexpr int CT = 512;            // threads per CTA (== SORT_RADIX: one thread per digit)
 constexpr int CW = CT / 32;        // warps per CTA
 constexpr int NB = 8;              // 32-key groups a warp loads ahead in the sort sweeps (every batch costs one exposed L2 round trip)

@@ -25,8 +25,14 @@ constexpr int VOX_G = 148;           // CTAs per voxel job for the bbox / head /
 constexpr int GRID_G = 148;          // CTAs per hash-grid job
 constexpr int KNN_G = 148;           // the kNN kernels launch 4 x KNN_G CTAs per lane (128 threads = 16 queries of 8 lanes each, grid-stride)
 constexpr int FIT_G = 148;           // CTAs (128 threads) of the fit kernel per lane
-constexpr int LM_THREADS = 256;     // per CTA of the solve cluster
-constexpr int LM_CLUSTER = 8;       // CTAs (SMs) per sequence in the solve kernel
+#ifndef VILF_LM_THREADS
+#define VILF_LM_THREADS 256
+#endif
+#ifndef VILF_LM_CLUSTER
+#define VILF_LM_CLUSTER 8
+#endif
+constexpr int LM_THREADS = VILF_LM_THREADS;  // per CTA of the solve cluster
+constexpr int LM_CLUSTER = VILF_LM_CLUSTER;  // CTAs (SMs) per sequence in the solve kernel
 constexpr int MAX_TRACE_ROWS = 8;
 constexpr int MAX_OUTER = 4;
 
