@@ -321,31 +321,99 @@ __global__ void __launch_bounds__(256) k_sector_select(LaneDev* lanes, int lane0
 // ------------------------------------------------------------------------------------------------
 // warp-per-sector selection (sectors of up to 32 * EPL elements): no CTA barrier anywhere
 // ------------------------------------------------------------------------------------------------
-// The sort keys live in REGISTERS: lane l holds the EPL consecutive network positions l*EPL .. l*EPL+EPL-1 as
-// (curvature bits hi, lo, element index).  Bitonic steps with partner distance < EPL are register compare-exchanges,
-// larger distances are warp shuffles; ~5 k warp instructions per sector against ~17 k for the shared-memory network
-// and ~23 k for the rank sort (profiles/r1d).  (Packing (fp32 key << 32 | index) into one 64-bit word and sorting with 64-bit
-// min / max was tried: 34 M instead of 31 M warp instructions per launch — the selects dominate, not the compares.)  The greedy pick and the surf compaction are warp-serial as before.
+// The sort keys live in REGISTERS: lane l holds the EPL consecutive network positions l*EPL .. l*EPL+EPL-1 as ONE 32-bit
+// word each (23-bit curvature prefix, 9-bit element index).  Bitonic steps with partner distance < EPL are register min / max
+// pairs, larger distances are warp shuffles.  History (warp instructions per sector, the kernel is issue bound): rank sort
+// in shared memory 23 k, bitonic network in shared memory 17 k, register network on (u64 key, index) with short-circuit
+// compares 18 k, the same branch-free 10 k, 32-bit keys + tie fix-up ~6 k (profiles/r1d, r1e, r1h).  Packing (fp32 key << 32 |
+// index) into one 64-bit word did not help: the selects dominate, not the compares.  The greedy pick and the surf
+// compaction are warp-serial as before.
 constexpr int SEC_WPC = 4;  // sectors (warps) per CTA
 __host__ __device__ constexpr size_t sec_warp_bytes(int ms, int np) {  // shared memory of one warp: sectors of <= ms elements, network of np
   return ((sizeof(float4) * (ms + 10) + sizeof(double) * ms + sizeof(uint32_t) * (ms + 10) + sizeof(uint16_t) * np + (ms + 16)) + 15) / 16 * 16;
 }
 
-struct SortReg { unsigned long long k; uint32_t id; };
-// (curvature, index) lexicographic, branch-free: bitwise predicate logic + selects (short-circuit && / || compiled to
-// ~37 instructions and several branches per compare-exchange, profiles/r1e)
-__device__ __forceinline__ bool sr_gt(const SortReg& a, const SortReg& b) { return (a.k > b.k) | ((a.k == b.k) & (a.id > b.id)); }
-__device__ __forceinline__ void sr_cswap(SortReg& a, SortReg& b, bool asc) {  // afterwards a <= b when asc
-  const bool sw = sr_gt(a, b) == asc;
-  const unsigned long long ak = sw ? b.k : a.k, bk = sw ? a.k : b.k;
-  const uint32_t ai = sw ? b.id : a.id, bi = sw ? a.id : b.id;
-  a.k = ak; b.k = bk; a.id = ai; b.id = bi;
-}
+// 32-bit keys: (top 23 bits of the fp32-rounded curvature) << 9 | index.  Rounding and truncation are monotone, so two
+// elements whose 23-bit prefixes differ are ordered exactly like their fp64 curvatures, and a compare-exchange is one
+// min + one max (4-5 instructions instead of ~20 for the (u64, index) pair: this kernel is instruction-issue bound).
+// Elements with EQUAL prefixes end up adjacent, ordered by index only; fix_tie_runs() then orders every such run by the
+// exact (fp64 curvature, index) key with an odd-even transposition inside the run (runs are 2-3 elements long; roughly
+// every second sector has one).
 template <int EPL, int J>
-__device__ __forceinline__ void sr_local_step(SortReg (&v)[EPL], int lane, int k) {
+__device__ __forceinline__ void k32_local_step(uint32_t (&v)[EPL], int lane, int k) {
 #pragma unroll
   for (int r = 0; r < EPL; ++r)
-    if ((r & J) == 0) sr_cswap(v[r], v[r | J], ((lane * EPL + r) & k) == 0);
+    if ((r & J) == 0) {
+      const uint32_t lo = min(v[r], v[r | J]), hi = max(v[r], v[r | J]);
+      const bool asc = ((lane * EPL + r) & k) == 0;
+      v[r] = asc ? lo : hi;
+      v[r | J] = asc ? hi : lo;
+    }
+}
+template <int EPL>
+__device__ __forceinline__ void k32_sort(uint32_t (&v)[EPL], int lane) {
+  constexpr int NP = 32 * EPL;
+  for (int k = 2; k <= NP; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= EPL) {
+        const int lj = j / EPL;
+        const bool lower = (lane & lj) == 0;
+#pragma unroll
+        for (int q = 0; q < EPL; ++q) {
+          const uint32_t o = __shfl_xor_sync(0xffffffffu, v[q], lj);
+          const bool keep_min = (((lane * EPL + q) & k) == 0) == lower;
+          v[q] = keep_min ? min(v[q], o) : max(v[q], o);
+        }
+      } else {
+        if (EPL > 1 && j == 1) k32_local_step<EPL, 1>(v, lane, k);
+        if (EPL > 2 && j == 2) k32_local_step<EPL, (EPL > 2 ? 2 : 1)>(v, lane, k);
+        if (EPL > 4 && j == 4) k32_local_step<EPL, (EPL > 4 ? 4 : 1)>(v, lane, k);
+        if (EPL > 8 && j == 8) k32_local_step<EPL, (EPL > 8 ? 8 : 1)>(v, lane, k);
+        if (EPL > 16 && j == 16) k32_local_step<EPL, (EPL > 16 ? 16 : 1)>(v, lane, k);
+      }
+    }
+  }
+}
+__device__ __forceinline__ uint32_t curv_prefix(double c) { return __float_as_uint(__double2float_rn(c)) >> 8; }  // 23 bits (sign is 0)
+
+// sorted[0..m): elements ordered by (23-bit prefix, index).  Order every run of equal prefixes by (fp64 value, index).
+// Returns false when a run is too long for the transposition passes (the caller then falls back to an exact rank sort).
+__device__ __forceinline__ bool fix_tie_runs(const double* val, uint16_t* sorted, int m, int lane) {
+  constexpr int MAX_RUN = 8;
+  // pair (p, p+1) is "tied" when both elements share the prefix
+  bool any = false, too_long = false;
+  for (int p = lane; p + 1 < m; p += 32) {
+    const uint32_t a = curv_prefix(val[sorted[p]]), b = curv_prefix(val[sorted[p + 1]]);
+    if (a == b) {
+      any = true;
+      if (p + MAX_RUN < m && curv_prefix(val[sorted[p + MAX_RUN]]) == a) too_long = true;
+    }
+  }
+  if (__any_sync(0xffffffffu, too_long)) return false;
+  if (!__any_sync(0xffffffffu, any)) return true;
+  for (int round = 0; round < MAX_RUN; ++round) {  // odd-even transposition sorts runs of up to MAX_RUN elements in MAX_RUN rounds
+    const int par = round & 1;
+    for (int p = 2 * lane + par; p + 1 < m; p += 64) {
+      const int ea = sorted[p], eb = sorted[p + 1];
+      const double va = val[ea], vb = val[eb];
+      if (curv_prefix(va) == curv_prefix(vb) && ((va > vb) | ((va == vb) & (ea > eb)))) { sorted[p] = (uint16_t)eb; sorted[p + 1] = (uint16_t)ea; }
+    }
+    __syncwarp();
+  }
+  return true;
+}
+
+// Exact fallback for a sector with a long run of equal prefixes: rank sort on the fp64 curvatures, (value, index) order.
+__device__ __noinline__ void exact_rank_sort(const double* val, int m, int lane, uint16_t* sorted) {
+  for (int e = lane; e < m; e += 32) {
+    const double v = val[e];
+    int rank = 0;
+    for (int k = 0; k < m; ++k) {
+      const double vk = val[k];
+      rank += ((vk < v) | ((vk == v) & (k < e))) ? 1 : 0;
+    }
+    sorted[rank] = (uint16_t)e;
+  }
 }
 
 template <int EPL>
@@ -404,40 +472,21 @@ __global__ void __launch_bounds__(32 * SEC_WPC) k_sector_warp(LaneDev* lanes, in
   }
   __syncwarp();
   // std::sort ascending by curvature (FE:115); equal curvatures ordered by index (tie class T1 made canonical).
-  // A non-negative double orders like its bit pattern; padding positions (>= m) carry the maximal key.
-  SortReg v[EPL];
+  static_assert(EPL <= 16, "the element index must fit the 9 low bits of the 32-bit sort key");
+  uint32_t v[EPL];
 #pragma unroll
   for (int q = 0; q < EPL; ++q) {
     const int p = lane * EPL + q;
-    if (p < m) { v[q].k = (unsigned long long)__double_as_longlong(val[p]); v[q].id = (uint32_t)p; }
-    else { v[q].k = ~0ull; v[q].id = 0xffff0000u + (uint32_t)p; }
+    v[q] = p < m ? ((curv_prefix(val[p]) << 9) | (uint32_t)p) : 0xffffffffu;  // padding sorts behind the m elements
   }
-  for (int k = 2; k <= NP; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      if (j >= EPL) {  // partner position p ^ j lives in lane ^ (j / EPL), same register
-        const int lj = j / EPL;
-        const bool lower = (lane & lj) == 0;
+  k32_sort<EPL>(v, lane);
 #pragma unroll
-        for (int q = 0; q < EPL; ++q) {
-          SortReg o;
-          o.k = __shfl_xor_sync(0xffffffffu, v[q].k, lj);
-          o.id = __shfl_xor_sync(0xffffffffu, v[q].id, lj);
-          const bool asc = ((lane * EPL + q) & k) == 0;
-          const bool take = sr_gt(v[q], o) == (asc == lower);  // keys are distinct (the index is part of the key)
-          v[q].k = take ? o.k : v[q].k;
-          v[q].id = take ? o.id : v[q].id;
-        }
-      } else {
-        if (EPL > 1 && j == 1) sr_local_step<EPL, 1>(v, lane, k);
-        if (EPL > 2 && j == 2) sr_local_step<EPL, (EPL > 2 ? 2 : 1)>(v, lane, k);
-        if (EPL > 4 && j == 4) sr_local_step<EPL, (EPL > 4 ? 4 : 1)>(v, lane, k);
-        if (EPL > 8 && j == 8) sr_local_step<EPL, (EPL > 8 ? 8 : 1)>(v, lane, k);
-        if (EPL > 16 && j == 16) sr_local_step<EPL, (EPL > 16 ? 16 : 1)>(v, lane, k);
-      }
-    }
+  for (int q = 0; q < EPL; ++q) sorted[lane * EPL + q] = (uint16_t)(v[q] & 0x1ffu);  // (padding entries are never read: positions >= m)
+  __syncwarp();
+  if (!fix_tie_runs(val, sorted, m, lane)) {
+    __syncwarp();
+    exact_rank_sort(val, m, lane, sorted);
   }
-#pragma unroll
-  for (int q = 0; q < EPL; ++q) sorted[lane * EPL + q] = (uint16_t)v[q].id;  // padding sorts behind the m elements
   __syncwarp();
 
   int n_edge = 0;
