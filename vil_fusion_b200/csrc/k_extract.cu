@@ -1,14 +1,15 @@
 // Stage 1 — featureExtraction::extractFeature (FE:223-232) on the device.
 //
 //   k_frame_reset        per-frame scratch reset + constant-velocity pose prediction (EM:238-243)
-//   k_sort_keyhist<KeyGenRing>  getLaserCloud (FE:54-110): range gate + vertical-angle -> ring id, as the
-//                        8-bit key of a single stable radix pass (arrival order kept inside a ring, FE:108)
+//   k_ring_partition     getLaserCloud (FE:54-110): range gate + vertical-angle -> ring id, and the stable partition of
+//                        the scan by ring (arrival order kept inside a ring, FE:108), one cluster per sequence
 //   k_sector_select      featureEdge_Surf + featureExtractionFromSector (FE:112-220): one CTA per
 //                        (ring, sector): 11-tap fp32 curvature, rank-sort in shared memory, warp-serial
 //                        greedy edge pick with +-5 neighbour suppression, surf = everything not picked
 //   k_compact_features   concatenates the per-sector lists in (ring, sector) order = the reference's
 //                        push_back order of cloud_Edge / cloud_Surf
 #include "k_sort.cuh"
+#include <cooperative_groups.h>
 
 namespace vilf {
 
@@ -155,6 +156,129 @@ struct KeyGenRing {
     return (uint32_t)id;
   }
 };
+
+// ------------------------------------------------------------------------------------------------
+// ring partition in one cluster kernel
+// ------------------------------------------------------------------------------------------------
+// getLaserCloud's "push_back to ring cloud r in arrival order" (FE:75-108) is a stable partition of the scan by an 8-bit
+// key.  The generic radix machinery (k_sort_keyhist + k_sort_scatter: 512-digit tables, a 256-thread Hillis-Steele scan, an
+// O(CTAs^2) histogram read, 160 instructions per point) is far more than this needs.  One 8-CTA cluster per sequence:
+// every warp owns a contiguous slice of the scan, counts its ring ids (keys kept in global memory as one byte per point),
+// the CTAs exchange their 256-bin histograms through distributed shared memory, and the warps then write the scan indices
+// to their ring's range in arrival order.  Outputs: ring_sort.val[1] (indices in (ring, arrival) order), digit_start[257].
+namespace cgx = cooperative_groups;
+constexpr int RP_CL = 8, RP_CT = 512, RP_CW = RP_CT / 32;
+
+struct RingShared {
+  uint32_t wcnt[RP_CW][256];
+  uint32_t cta_hist[256];
+  uint32_t scan[RP_CW];
+};
+
+__global__ void __cluster_dims__(RP_CL, 1, 1) __launch_bounds__(RP_CT, 2) k_ring_partition(LaneDev* lanes, int lane0, int sel, ConfigDev cfg) {
+  cgx::cluster_group cluster = cgx::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const LaneDev& L = lanes[lane0 + blockIdx.y];
+  const int n = L.v->n_scan[sel];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ RingShared S;
+  KeyGenRing gen;
+  gen.lanes = lanes; gen.lane0 = lane0; gen.sel = sel; gen.cfg = cfg;
+  uint8_t* keys = reinterpret_cast<uint8_t*>(L.ring_sort.key[0]);  // one byte per point (scratch of the generic sort job)
+  uint32_t* __restrict__ perm = L.ring_sort.val[1];
+  int cchunk = (n + RP_CL - 1) / RP_CL;
+  cchunk = (cchunk + RP_CT - 1) / RP_CT * RP_CT;
+  const int wchunk = cchunk / RP_CW;  // multiple of 32
+  const int cbeg = min(n, rank * cchunk), cend = min(n, cbeg + cchunk);
+  const int wbeg = min(cend, cbeg + warp * wchunk), wend = min(cend, wbeg + wchunk);
+  for (int i = tid; i < RP_CW * 256; i += RP_CT) (&S.wcnt[0][0])[i] = 0;
+  __syncthreads();
+  constexpr int RB = 4;  // 32-point groups in flight per warp (every batch costs one exposed L2 round trip)
+  for (int base = wbeg; base < wend; base += 32 * RB) {
+    uint32_t k[RB];
+#pragma unroll
+    for (int it = 0; it < RB; ++it) {
+      const int i = base + it * 32 + lane;
+      k[it] = i < wend ? gen.key(blockIdx.y, i) : 0u;
+    }
+#pragma unroll
+    for (int it = 0; it < RB; ++it) {
+      const int i = base + it * 32 + lane;
+      if (i < wend) { keys[i] = (uint8_t)k[it]; atomicAdd(&S.wcnt[warp][k[it]], 1u); }
+    }
+  }
+  __syncthreads();
+  if (tid < 256) {
+    uint32_t s = 0;
+#pragma unroll
+    for (int w = 0; w < RP_CW; ++w) s += S.wcnt[w][tid];
+    S.cta_hist[tid] = s;
+  }
+  cluster.sync();
+  {  // ring start = rings below; this CTA's first slot in ring `tid` = ring start + same ring in lower-rank CTAs
+    uint32_t tot = 0, pre = 0;
+    if (tid < 256) {
+#pragma unroll
+      for (int c = 0; c < RP_CL; ++c) {
+        const uint32_t v = cluster.map_shared_rank(&S, c)->cta_hist[tid];
+        if (c < rank) pre += v;
+        tot += v;
+      }
+    }
+    // exclusive scan over the 256 rings (threads >= 256 contribute 0)
+    uint32_t inc = tot;
+    for (int off = 1; off < 32; off <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, off); if (lane >= off) inc += t; }
+    if (lane == 31) S.scan[warp] = inc;
+    __syncthreads();
+    uint32_t woff = 0;
+#pragma unroll
+    for (int w = 0; w < RP_CW; ++w) woff += w < warp ? S.scan[w] : 0u;
+    const uint32_t start = woff + inc - tot;
+    if (tid < 256) {
+      if (rank == 0) {
+        L.ring_sort.digit_start[tid] = start;
+        if (tid == 255) L.ring_sort.digit_start[256] = start + tot;
+      }
+      uint32_t run = start + pre;
+#pragma unroll
+      for (int w = 0; w < RP_CW; ++w) {
+        const uint32_t c = S.wcnt[w][tid];
+        S.wcnt[w][tid] = run;
+        run += c;
+      }
+    }
+  }
+  __syncthreads();
+  for (int base = wbeg; base < wend; base += 32 * RB) {  // in arrival order, 32 points at a time, RB groups loaded ahead
+    uint32_t dk[RB];
+#pragma unroll
+    for (int it = 0; it < RB; ++it) {
+      const int i = base + it * 32 + lane;
+      dk[it] = i < wend ? (uint32_t)keys[i] : 0u;
+    }
+#pragma unroll
+    for (int it = 0; it < RB; ++it) {
+      const int i = base + it * 32 + lane;
+      const bool ok = i < wend;
+      const uint32_t d = dk[it];
+      const unsigned act = __ballot_sync(0xffffffffu, ok);
+      unsigned peers = 0, lower = 0;
+      uint32_t before = 0;
+      if (ok) {
+        peers = __match_any_sync(act, d);
+        lower = peers & ((1u << lane) - 1u);
+        before = S.wcnt[warp][d];
+      }
+      __syncwarp();
+      if (ok) {
+        if (lower == 0) S.wcnt[warp][d] = before + __popc(peers);
+        perm[before + __popc(lower)] = (uint32_t)i;
+      }
+      __syncwarp();
+    }
+  }
+  cluster.sync();  // no CTA may exit while a peer can still read its shared memory
+}
 
 // ------------------------------------------------------------------------------------------------
 // per-(ring, sector) selection
@@ -637,10 +761,16 @@ void launch_extract(const Launch& L, LaneDev* lanes, const SortJob* ring_jobs, i
   const size_t SEC_SMEM = sector_smem(cfg.max_sector);
   KeyGenRing gen;
   gen.lanes = lanes; gen.lane0 = lane0; gen.sel = sel; gen.cfg = cfg;
-  dim3 gs(SORT_G, nlanes);
-  k_sort_keyhist<KeyGenRing><<<gs, SORT_THREADS, 0, L.st>>>(ring_jobs + lane0, gen);
-  L.tick(K_RING_KEYHIST);
-  launch_sort_scatter(L, ring_jobs + lane0, nlanes, 0);
+  if (cfg.flags_no_cluster) {  // generic radix machinery (also the reference implementation of the partition for the tests)
+    dim3 gs(SORT_G, nlanes);
+    k_sort_keyhist<KeyGenRing><<<gs, SORT_THREADS, 0, L.st>>>(ring_jobs + lane0, gen);
+    L.tick(K_RING_KEYHIST);
+    launch_sort_scatter(L, ring_jobs + lane0, nlanes, 0);
+  } else {
+    dim3 gr(RP_CL, nlanes);
+    k_ring_partition<<<gr, RP_CT, 0, L.st>>>(lanes, lane0, sel, cfg);
+    L.tick(K_RING_PARTITION);
+  }
   if (cfg.max_sector <= 128) launch_sector_warp<4>(L, lanes, lane0, nlanes, sel, cfg);
   else if (cfg.max_sector <= 256) launch_sector_warp<8>(L, lanes, lane0, nlanes, sel, cfg);
   else if (cfg.max_sector <= 512) launch_sector_warp<16>(L, lanes, lane0, nlanes, sel, cfg);

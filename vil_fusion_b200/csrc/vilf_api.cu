@@ -220,6 +220,7 @@ int build_ctx(Ctx* C) {
   for (int b = 0; b < 2; ++b) CK(dalloc(C, &C->grid_dev[b], (size_t)NL * 2));
   const bool allow_cluster = !(u.flags & VILF_FLAG_NO_CLUSTER);
   C->use_graphs = !(u.flags & VILF_FLAG_NO_GRAPH);
+  c.flags_no_cluster = (u.flags & VILF_FLAG_NO_CLUSTER) ? 1 : 0;
   C->cluster_scan = allow_cluster && capS <= CLUSTER_MAX_POINTS;
   C->cluster_map = allow_cluster && capM <= CLUSTER_MAX_POINTS;
   C->lanes_host.resize(NL);
@@ -1241,7 +1242,7 @@ const char* vilf_profile_kernel_name(int kernel) {
   static const char* names[K_COUNT] = {"k_frame_reset", "k_sort_keyhist<KeyGenRing>", "k_sort_hist", "k_sort_scatter", "k_sector_select", "k_compact_features",
                                        "k_vox_bbox", "k_sort_keyhist<KeyGenVoxel>", "k_vox_heads", "k_vox_centroid", "k_map_append", "k_map_init",
                                        "k_grid_zero", "k_grid_count", "k_grid_scan_partial", "k_grid_scan_final", "k_grid_scatter", "k_knn_assoc",
-                                       "k_knn_only", "k_solve", "k_fit", "k_voxel_cluster", "k_grid_cluster", "k_depth_cloud", "k_depth_query"};
+                                       "k_knn_only", "k_solve", "k_fit", "k_voxel_cluster", "k_grid_cluster", "k_depth_cloud", "k_depth_query", "k_ring_partition"};
   return (kernel >= 0 && kernel < K_COUNT) ? names[kernel] : "";
 }
 int vilf_launch_count(vilf_handle* h, int64_t* launches) {

@@ -51,6 +51,7 @@ struct ConfigDev {
   int sector_np;   // power of two >= max_sector: size of the selection kernel's sort network
   int outer_iters, lm_max_iters;
   int cap_scan, cap_map;
+  int flags_no_cluster;  // VILF_FLAG_NO_CLUSTER: grid-wide multi-launch kernels everywhere
 };
 
 // One iteration row of the trust-region trace (same columns as the oracle's LmIter).
@@ -244,7 +245,7 @@ __device__ __forceinline__ float4 associate(const double* x, float4 p) {
 enum KernelId {
   K_RESET = 0, K_RING_KEYHIST, K_SORT_HIST, K_SORT_SCATTER, K_SECTOR, K_COMPACT, K_VOX_BBOX, K_VOX_KEYHIST, K_VOX_HEADS, K_VOX_CENTROID,
   K_MAP_APPEND, K_MAP_INIT, K_GRID_ZERO, K_GRID_COUNT, K_GRID_SCAN_PARTIAL, K_GRID_SCAN_FINAL, K_GRID_SCATTER, K_KNN_FIT, K_KNN_ONLY,
-  K_SOLVE, K_FIT, K_VOX_CLUSTER, K_GRID_CLUSTER, K_DEPTH_CLOUD, K_DEPTH_QUERY, K_COUNT
+  K_SOLVE, K_FIT, K_VOX_CLUSTER, K_GRID_CLUSTER, K_DEPTH_CLOUD, K_DEPTH_QUERY, K_RING_PARTITION, K_COUNT
 };
 constexpr int PROF_PHASES = 5;      // 0 extract, 1 scan downsample, 2 association + solve, 3 map update, 4 grid build
 constexpr int PROF_TAGS = PROF_PHASES * 32;
