@@ -28,11 +28,14 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const SortJob* __
   __shared__ uint32_t scan_buf[SORT_THREADS];
 
   // 1. digit offsets of this CTA: exclusive scan of the digit totals + counts of the CTAs before it (digits 2t, 2t+1).
+  const int nd = 1 << w;  // digits in use (<= SORT_RADIX): everything below touches only those
   uint32_t tot0 = 0, tot1 = 0, pre0 = 0, pre1 = 0;
-  for (int b = 0; b < geff; ++b) {
-    const uint2 v = *reinterpret_cast<const uint2*>(sort_hist(J, pass, b) + 2 * tid);
-    if (b < (int)blockIdx.x) { pre0 += v.x; pre1 += v.y; }
-    tot0 += v.x; tot1 += v.y;
+  if (2 * tid < nd) {
+    for (int b = 0; b < geff; ++b) {
+      const uint2 v = *reinterpret_cast<const uint2*>(sort_hist(J, pass, b) + 2 * tid);
+      if (b < (int)blockIdx.x) { pre0 += v.x; pre1 += v.y; }
+      tot0 += v.x; tot1 += v.y;
+    }
   }
   scan_buf[tid] = tot0 + tot1;
   __syncthreads();
@@ -60,7 +63,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const SortJob* __
   const int end = min(n, beg + chunk);
 
   for (int tile = beg; tile < end; tile += SORT_TILE) {
-    for (int i = tid; i < 8 * SORT_RADIX; i += SORT_THREADS) (&wcnt[0][0])[i] = 0;
+    for (int i = tid; i < 8 * nd; i += SORT_THREADS) wcnt[i >> w][i & (int)mask] = 0;
     __syncthreads();
     uint32_t k[4], v[4], r[4], d[4];
     bool ok[4];
@@ -87,6 +90,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const SortJob* __
 #pragma unroll
     for (int h = 0; h < 2; ++h) {  // exclusive prefix over the 8 warps for digits tid and tid + 256, on top of the running base
       const int dg = tid + h * SORT_THREADS;
+      if (dg >= nd) break;
       uint32_t run = base[dg];
 #pragma unroll
       for (int ww = 0; ww < 8; ++ww) {

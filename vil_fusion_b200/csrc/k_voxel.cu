@@ -6,8 +6,8 @@
 //                   the sentinel key dx*dy*dz and sort to the tail), pass-0 digit histogram
 //   k_sort_scatter x 3-4   stable radix sort by voxel index, next-pass histogram fused (k_sort.cu)
 //   k_vox_heads     first point of every occupied voxel, counted per CTA chunk
-//   k_vox_centroid  one thread per occupied voxel walks its points in input order and accumulates
-//                   x, y, z, intensity in fp32 exactly like PCL's `centroid += ...; centroid /= count`;
+//   k_vox_centroid  every warp walks a contiguous range of the sorted points 32 at a time and accumulates x, y, z,
+//                   intensity of every voxel in input order in fp32, exactly like PCL's `centroid += ...; centroid /= count`;
 //                   output order = ascending voxel index = PCL's output order
 //   k_map_append    createSubMap step 1 (EM:308-324): world-transform the filtered scan features and append
 //   k_map_init      localMapInited (EM:105-115)
@@ -44,72 +44,64 @@ __device__ __forceinline__ void vox_chunk(int n, int b, int& beg, int& end) {
   end = min(n, beg + chunk);
 }
 
+// Sorted positions are split into VOX_G CTA chunks of 8 contiguous warp ranges each (multiples of 32 positions).
+__device__ __forceinline__ void vox_warp_range(int n, int cta, int warp, int& beg, int& end) {
+  int cb, ce;
+  vox_chunk(n, cta, cb, ce);
+  int chunk = (n + VOX_G - 1) / VOX_G;
+  chunk = (chunk + 255) / 256 * 256;
+  const int wchunk = chunk / 8;
+  beg = min(ce, cb + warp * wchunk);
+  end = min(ce, beg + wchunk);
+}
+
 __global__ void __launch_bounds__(256) k_vox_heads(const VoxJob* __restrict__ jobs) {
   const VoxJob& J = jobs[blockIdx.y];
   const int n = J.vv->n_valid;
   const int guard = J.vv->guard;
   const uint32_t* key = J.sort.key[sort_passes(J.vv->bits, J.sort.npass) & 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int beg, end;
-  vox_chunk(n, blockIdx.x, beg, end);
+  vox_warp_range(n, blockIdx.x, warp, beg, end);
   int cnt = 0;
-  for (int i = beg + threadIdx.x; i < end; i += 256) cnt += (guard || i == 0 || key[i] != key[i - 1]) ? 1 : 0;
-  __shared__ int red[8];
+  for (int i = beg + lane; i < end; i += 32) cnt += (guard || i == 0 || key[i] != key[i - 1]) ? 1 : 0;
   for (int off = 16; off > 0; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = cnt;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int s = 0;
-    for (int w = 0; w < 8; ++w) s += red[w];
-    J.head_cnt[blockIdx.x] = s;
-  }
+  if (lane == 0) J.head_cnt[blockIdx.x * 8 + warp] = cnt;  // heads (first points of occupied voxels) per warp range
 }
 
+// Every warp emits the centroids of the voxels whose head lies in its range (k_voxel.cuh: emit_range — the same
+// warp-collective, software-pipelined emitter as the cluster path, hence identical bits), at the output index given by
+// the number of heads in all earlier ranges.
 __global__ void __launch_bounds__(256) k_vox_centroid(const VoxJob* __restrict__ jobs) {
   const VoxJob& J = jobs[blockIdx.y];
   const int n = J.vv->n_valid;
   const int guard = J.vv->guard;
   const int res = sort_passes(J.vv->bits, J.sort.npass) & 1;
-  const uint32_t* __restrict__ key = J.sort.key[res];
-  const uint32_t* __restrict__ val = J.sort.val[res];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  __shared__ int red[256];
-  __shared__ int wsum[8];
-  __shared__ float4 stage[8][32];
-  // heads in the chunks before this CTA, and in total
+  __shared__ int red[8];
+  __shared__ __align__(16) float4 stage[8][64];
+  const int first = blockIdx.x * 8;  // index of this CTA's first warp range
   int pre = 0, tot = 0;
-  for (int b = tid; b < VOX_G; b += 256) { const int c = J.head_cnt[b]; if (b < (int)blockIdx.x) pre += c; tot += c; }
-  red[tid] = pre;
+  for (int b = tid; b < VOX_G * 8; b += 256) { const int c = J.head_cnt[b]; if (b < first) pre += c; tot += c; }
+  // block sums of `pre` (heads before this CTA) and `tot` (all heads)
+  for (int off = 16; off > 0; off >>= 1) { pre += __shfl_xor_sync(0xffffffffu, pre, off); tot += __shfl_xor_sync(0xffffffffu, tot, off); }
+  __shared__ int rp[8], rt[8];
+  if (lane == 0) { rp[warp] = pre; rt[warp] = tot; }
   __syncthreads();
-  for (int off = 128; off > 0; off >>= 1) { if (tid < off) red[tid] += red[tid + off]; __syncthreads(); }
-  pre = red[0];
+  pre = 0; tot = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) { pre += rp[w]; tot += rt[w]; }
+  if (tid < 8) red[tid] = J.head_cnt[first + tid];
   __syncthreads();
-  if (blockIdx.x == 0) {
-    red[tid] = tot;
-    __syncthreads();
-    for (int off = 128; off > 0; off >>= 1) { if (tid < off) red[tid] += red[tid + off]; __syncthreads(); }
-    if (tid == 0) {
-      int total = red[0];
-      if (total > J.cap_out) { atomicOr(J.status, ST_MAP_CAPACITY); total = J.cap_out; }
-      *J.n_out = total;
-    }
-    __syncthreads();
+  for (int w = 0; w < warp; ++w) pre += red[w];
+  if (blockIdx.x == 0 && tid == 0) {
+    int total = tot;
+    if (total > J.cap_out) { atomicOr(J.status, ST_MAP_CAPACITY); total = J.cap_out; }
+    *J.n_out = total;
   }
   int beg, end;
-  vox_chunk(n, blockIdx.x, beg, end);
-  int run = pre;
-  for (int base = beg; base < end; base += 256) {
-    const int i = base + tid;
-    const bool head = i < end && (guard || i == 0 || key[i] != key[i - 1]);
-    const unsigned b = __ballot_sync(0xffffffffu, head);
-    if (lane == 0) wsum[warp] = __popc(b);
-    __syncthreads();
-    int off = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) { const int c = wsum[w]; if (w < warp) off += c; total += c; }
-    emit_centroids(J, key, val, n, guard, i, head, run + off + __popc(b & ((1u << lane) - 1u)), stage[warp]);
-    run += total;
-    __syncthreads();
-  }
+  vox_warp_range(n, blockIdx.x, warp, beg, end);
+  emit_range(J, KvSplit{J.sort.key[res], J.sort.val[res]}, n, guard, beg, end, pre, &stage[warp][0]);
 }
 
 void launch_voxel(const Launch& L, const VoxJob* jobs_dev, int njobs, const SortJob* sort_jobs_dev, bool bbox_done) {

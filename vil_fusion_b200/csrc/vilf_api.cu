@@ -267,7 +267,7 @@ int build_ctx(Ctx* C) {
       J.crop = 0; J.passthrough = 0; J.crop_center = nullptr; J.crop_half = 0;
       J.out = L.ds[w]; J.n_out = &L.v->n_ds[w]; J.cap_out = capS; J.status = &L.v->status;
       J.vv = C->vv_dev + l * VV_PER_LANE + w;
-      CK(dalloc(C, &J.head_cnt, (size_t)VOX_G));
+      CK(dalloc(C, &J.head_cnt, (size_t)VOX_G * 8));
       rc = alloc_sort(C, J.sort, J.n_in, &J.vv->bits, 0, 4, capS, false);
       if (rc) return rc;
       vox_scan_sort[l * 2 + w] = J.sort;
@@ -279,7 +279,7 @@ int build_ctx(Ctx* C) {
       rc = alloc_sort(C, srt, &L.v->n_cat[w], &vv->bits, 0, 4, capM, false);
       if (rc) return rc;
       int* head_cnt = nullptr;
-      CK(dalloc(C, &head_cnt, (size_t)VOX_G));
+      CK(dalloc(C, &head_cnt, (size_t)VOX_G * 8));
       for (int b = 0; b < 2; ++b) {
         VoxJob& J = vox_map[b][l * 2 + w];
         memset(&J, 0, sizeof(J));
@@ -343,7 +343,7 @@ int build_ctx(Ctx* C) {
     memset(&J, 0, sizeof(J));
     J.in = C->aux_in; J.n_in = C->aux_n; J.out = C->aux_out; J.n_out = C->aux_n + 1; J.cap_out = capM;
     J.status = C->aux_n + 3; J.vv = C->vv_dev + NL * VV_PER_LANE; J.crop_center = C->aux_pose;
-    CK(dalloc(C, &J.head_cnt, (size_t)VOX_G));
+    CK(dalloc(C, &J.head_cnt, (size_t)VOX_G * 8));
     int rc = alloc_sort(C, J.sort, J.n_in, &J.vv->bits, 0, 4, capM, false);
     if (rc) return rc;
     CK(cudaMemcpy(C->aux_sort_dev, &J.sort, sizeof(SortJob), cudaMemcpyHostToDevice));

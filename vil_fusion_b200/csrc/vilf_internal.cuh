@@ -118,7 +118,7 @@ struct VoxJob {
   int cap_out;
   int* status;              // lane status word (capacity overflow)
   VoxVars* vv;
-  int* head_cnt;            // [VOX_G]
+  int* head_cnt;            // [VOX_G * 8]: heads per warp range of the sorted points (grid-wide path)
   SortJob sort;
   // cluster path only (k_cluster.cu).  Map jobs: createSubMap's append (EM:308-324) runs inside the voxel kernel:
   // in[app_n_map .. ) <- associate(app_pose, app_src[0 .. *app_n)), n_in <- min(app_cap, *app_n_map + *app_n).
