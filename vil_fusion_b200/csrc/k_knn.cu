@@ -44,10 +44,26 @@ __global__ void __launch_bounds__(256) k_grid_count(const GridJob* __restrict__ 
   const float inv_cell = J.inv_cell;
   const int n = *J.n;
   const uint32_t hm = (uint32_t)grid_buckets(n, J.hcap) - 1u;
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
-    int cx, cy, cz;
-    cell_of(J.pts[i], inv_cell, cx, cy, cz);
-    J.rank[i] = atomicAdd(&J.start[cell_hash(cx, cy, cz) & hm], 1u);
+  // the atomic returns the point's slot inside its bucket, so a thread waits for a full L2 round trip per point:
+  // four independent points in flight per thread
+  const int stride = gridDim.x * 256;
+  for (int i0 = blockIdx.x * 256 + threadIdx.x; i0 < n; i0 += 4 * stride) {
+    uint32_t r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * stride;
+      r[u] = 0;
+      if (i < n) {
+        int cx, cy, cz;
+        cell_of(J.pts[i], inv_cell, cx, cy, cz);
+        r[u] = atomicAdd(&J.start[cell_hash(cx, cy, cz) & hm], 1u);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * stride;
+      if (i < n) J.rank[i] = r[u];
+    }
   }
 }
 
@@ -90,17 +106,28 @@ __global__ void __launch_bounds__(256) k_grid_scan_final(const GridJob* __restri
   uint32_t run = red[0];
   int beg, end;
   grid_chunk(total, blockIdx.x, beg, end);
-  for (int base = beg; base < end; base += 256) {
-    const int i = base + tid;
-    const uint32_t v = i < end ? J.start[i] : 0u;
-    uint32_t inc = v;  // inclusive warp scan
+  // tiles of 2048 counters: every thread scans 8 consecutive ones serially, the 256 thread sums are scanned by the block
+  for (int base = beg; base < end; base += 2048) {
+    const int i0 = base + tid * 8;
+    uint32_t v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = i0 + u < end ? J.start[i0 + u] : 0u;
+    uint32_t sum = 0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) sum += v[u];
+    uint32_t inc = sum;  // inclusive warp scan of the thread sums
     for (int off = 1; off < 32; off <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, off); if (lane >= off) inc += t; }
     if (lane == 31) wsum[warp] = inc;
     __syncthreads();
     uint32_t woff = 0, tot = 0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) { const uint32_t c = wsum[w]; if (w < warp) woff += c; tot += c; }
-    if (i < end) J.start[i] = run + woff + inc - v;
+    uint32_t ex = run + woff + inc - sum;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (i0 + u < end) J.start[i0 + u] = ex;
+      ex += v[u];
+    }
     run += tot;
     __syncthreads();
   }
@@ -111,12 +138,26 @@ __global__ void __launch_bounds__(256) k_grid_scatter(const GridJob* __restrict_
   const float inv_cell = J.inv_cell;
   const int n = *J.n;
   const uint32_t hm = (uint32_t)grid_buckets(n, J.hcap) - 1u;
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
-    const float4 p = J.pts[i];
-    int cx, cy, cz;
-    cell_of(p, inv_cell, cx, cy, cz);
-    const uint32_t pos = J.start[cell_hash(cx, cy, cz) & hm] + J.rank[i];
-    J.sorted[pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+  const int stride = gridDim.x * 256;
+  for (int i0 = blockIdx.x * 256 + threadIdx.x; i0 < n; i0 += 4 * stride) {  // four dependent (bucket start, slot) lookups in flight
+    float4 p[4];
+    uint32_t pos[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * stride;
+      pos[u] = 0;
+      if (i < n) {
+        p[u] = J.pts[i];
+        int cx, cy, cz;
+        cell_of(p[u], inv_cell, cx, cy, cz);
+        pos[u] = J.start[cell_hash(cx, cy, cz) & hm] + J.rank[i];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * stride;
+      if (i < n) J.sorted[pos[u]] = make_float4(p[u].x, p[u].y, p[u].z, __int_as_float(i));
+    }
   }
 }
 
