@@ -570,12 +570,19 @@ __global__ void __launch_bounds__(32 * SEC_WPC) k_sector_warp(LaneDev* lanes, in
   uint16_t* sorted = reinterpret_cast<uint16_t*>(srcs + MS + 10);          // elements in ascending (curvature, index)
   uint8_t* picked = reinterpret_cast<uint8_t*>(sorted + NP);               // cloudNeighborPicked as flags
 
-  const uint32_t* perm = L.ring_sort.val[1];  // scan indices in (ring, arrival) order after the single pass
-  for (int k = lane; k < m + 10; k += 32) {
-    const uint32_t src = perm[ring_beg + start + k];
-    srcs[k] = src;
-    pts[k] = L.scan[sel][src];
-    picked[k] = 0;
+  const uint32_t* perm = L.ring_sort.val[1];  // scan indices in (ring, arrival) order after the partition
+  for (int k0 = lane; k0 < m + 10; k0 += 32 * 6) {  // index, then point: two dependent loads; six of each in flight per lane
+    uint32_t src[6];
+    float4 pt[6];
+#pragma unroll
+    for (int u = 0; u < 6; ++u) src[u] = k0 + 32 * u < m + 10 ? perm[ring_beg + start + k0 + 32 * u] : 0u;
+#pragma unroll
+    for (int u = 0; u < 6; ++u) if (k0 + 32 * u < m + 10) pt[u] = L.scan[sel][src[u]];
+#pragma unroll
+    for (int u = 0; u < 6; ++u) {
+      const int k = k0 + 32 * u;
+      if (k < m + 10) { srcs[k] = src[u]; pts[k] = pt[u]; picked[k] = 0; }
+    }
   }
   __syncwarp();
   // FE:190-200: fp32 left-to-right 11-tap sums, squared in fp64.  Element e <-> ring index 5+start+e <-> pts[e+5].
@@ -731,16 +738,31 @@ __global__ void __launch_bounds__(256) k_compact_features(LaneDev* lanes, int la
     emn[0] = fminf(emn[0], p.x); emx[0] = fmaxf(emx[0], p.x); emn[1] = fminf(emn[1], p.y); emx[1] = fmaxf(emx[1], p.y);
     emn[2] = fminf(emn[2], p.z); emx[2] = fmaxf(emx[2], p.z); ++ecnt;
   }
-  for (int k = tid; k < ts; k += 256) {
-    int s = 0;
+  for (int k0 = tid; k0 < ts; k0 += 256 * 4) {  // four points in flight per thread (the loads are L2 round trips)
+    float4 p[4];
+    int si[4];
 #pragma unroll
-    for (int q = 1; q < SECTORS; ++q) s += k >= s_cnt[1][q] ? 1 : 0;
-    const int src = s_src[s] + (k - s_cnt[1][s]);
-    const float4 p = L.sec_surf[src];
-    L.feat[1][os + k] = p;
-    L.feat_src[1][os + k] = L.sec_surf_src[src];
-    smn[0] = fminf(smn[0], p.x); smx[0] = fmaxf(smx[0], p.x); smn[1] = fminf(smn[1], p.y); smx[1] = fmaxf(smx[1], p.y);
-    smn[2] = fminf(smn[2], p.z); smx[2] = fmaxf(smx[2], p.z); ++scnt;
+    for (int u = 0; u < 4; ++u) {
+      const int k = k0 + 256 * u;
+      if (k < ts) {
+        int s = 0;
+#pragma unroll
+        for (int q = 1; q < SECTORS; ++q) s += k >= s_cnt[1][q] ? 1 : 0;
+        const int src = s_src[s] + (k - s_cnt[1][s]);
+        p[u] = L.sec_surf[src];
+        si[u] = L.sec_surf_src[src];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = k0 + 256 * u;
+      if (k < ts) {
+        L.feat[1][os + k] = p[u];
+        L.feat_src[1][os + k] = si[u];
+        smn[0] = fminf(smn[0], p[u].x); smx[0] = fmaxf(smx[0], p[u].x); smn[1] = fminf(smn[1], p[u].y); smx[1] = fmaxf(smx[1], p[u].y);
+        smn[2] = fminf(smn[2], p[u].z); smx[2] = fmaxf(smx[2], p[u].z); ++scnt;
+      }
+    }
   }
   bbox_commit(L.vv + 0, emn, emx, ecnt, bb_sm);
   bbox_commit(L.vv + 1, smn, smx, scnt, bb_sm);
