@@ -117,9 +117,10 @@ __device__ void evaluate(const LaneDev& L, int ne, int ns, const double* x, doub
   const D3 t = d3(x[4], x[5], x[6]);
   for (int i = first; i < ne + ns; i += stride) {
     if (i < ne) {
-      if (!L.fvalid[0][i]) continue;
+      // the record is read before the validity flag is tested (every slot < ne exists): one L2 round trip, not two
       const double* f = L.edge_pab + (size_t)i * 9;
       const D3 p = d3(f[0], f[1], f[2]), a = d3(f[3], f[4], f[5]), b = d3(f[6], f[7], f[8]);
+      if (!L.fvalid[0][i]) continue;
       const D3 lp = qrot(q, p) + t;                    // LF:26
       const D3 nu = cross3(lp - a, lp - b);            // LF:28
       const D3 ab = a - b;
@@ -146,11 +147,12 @@ __device__ void evaluate(const LaneDev& L, int ne, int ns, const double* x, doub
       }
     } else {
       const int k = i - ne;
-      if (!L.fvalid[1][k]) continue;
       const double* f = L.surf_pnd + (size_t)k * 7;
       const D3 p = d3(f[0], f[1], f[2]), n = d3(f[3], f[4], f[5]);
+      const double f6 = f[6];
+      if (!L.fvalid[1][k]) continue;
       const D3 pw = qrot(q, p) + t;                 // LF:83
-      double r = dadd(dot3(n, pw), f[6]);           // LF:84
+      double r = dadd(dot3(n, pw), f6);             // LF:84
       const double jse3[3][6] = {{0, pw.z, -pw.y, 1, 0, 0}, {-pw.z, 0, pw.x, 0, 1, 0}, {pw.y, -pw.x, 0, 0, 0, 1}};
       double J[6];
 #pragma unroll
@@ -165,11 +167,27 @@ __device__ void evaluate(const LaneDev& L, int ne, int ns, const double* x, doub
       accumulate_row(acc, J, r);
     }
   }
+  // Warp reduction of the 30 sums by transposition: in the round with lane distance o every lane keeps one half of its
+  // current values and adds the partner's copies of that half, so 16 + 8 + 4 + 2 + 1 = 31 exchanges replace 30 x 5, and
+  // lane l ends up with the warp total of sum number rev5(l) (fixed order: deterministic).
+  double a32[32];
 #pragma unroll
-  for (int i = 0; i < NACC; ++i) {
-    double v = acc[i];
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-    if (lane == 0) wred[warp][i] = v;
+  for (int i = 0; i < 32; ++i) a32[i] = i < NACC ? acc[i] : 0.0;
+#pragma unroll
+  for (int o = 16, n = 32; o > 0; o >>= 1, n >>= 1) {
+    const bool hi = (lane & o) != 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (j < n / 2) {
+        const double send = hi ? a32[j] : a32[j + n / 2];
+        const double keep = hi ? a32[j + n / 2] : a32[j];
+        a32[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+      }
+    }
+  }
+  {  // lane l holds sum index: bit 4 of l selected the half of 32, bit 3 the half of 16, ...
+    const int idx = ((lane >> 4) & 1) * 16 + ((lane >> 3) & 1) * 8 + ((lane >> 2) & 1) * 4 + ((lane >> 1) & 1) * 2 + (lane & 1);
+    if (idx < NACC) wred[warp][idx] = a32[0];
   }
   __syncthreads();
   if (tid < NACC) {
@@ -352,7 +370,7 @@ k_solve(LaneDev* lanes, int lane0, int outer, int finalize, ConfigDev cfg, int m
         evaluate(L, ne, ns, xl, cfg.huber, S, wred, first, stride);
         cluster.sync();
         gather();
-        if (leader && tid == 0) {
+          if (leader && tid == 0) {
           S.candidate_cost = S.acc[27];
           double sn = 0;
           for (int i = 0; i < 7; ++i) sn += (S.x[i] - S.cand[i]) * (S.x[i] - S.cand[i]);
@@ -411,3 +429,4 @@ void launch_solve(const Launch& L, LaneDev* lanes, int lane0, int nlanes, int ou
 }
 
 }  // namespace vilf
+
