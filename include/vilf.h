@@ -80,6 +80,16 @@ int vilf_host_free(void* p);
  * (off_intensity < 0: no such field, 0 is stored).  Host-side; write straight into a vilf_host_alloc buffer to keep the
  * upload asynchronous. */
 int vilf_pack_pointcloud2(const uint8_t* data, int n_points, int point_step, int off_x, int off_y, int off_z, int off_intensity, float* xyzi_out);
+/* The inverse: packed float[n][4] -> PointCloud2 data bytes, the job of pcl::toROSMsg on the /GlobalMap cloud (NODE:439-440).
+ * For pcl::PointXYZI the wire layout is point_step 32, x / y / z at 0 / 4 / 8, intensity at 16; bytes no field covers are
+ * zeroed.  off_intensity < 0 drops the intensity. */
+int vilf_unpack_pointcloud2(const float* xyzi, int n_points, int point_step, int off_x, int off_y, int off_z, int off_intensity, uint8_t* data_out);
+/* What the node publishes after optimation_processing (NODE:388-446), host-side arithmetic in Eigen's operation order:
+ * q_estimator = Quaterniond(globalOdom.rotation()), t_estimator = globalOdom.translation() (NODE:388-389) from vilf_get_pose's
+ * rt12 -> path_pose_out {qx,qy,qz,qw,tx,ty,tz} (the /path and tf pose, NODE:391-436); the /Odometry message carries the
+ * RELATIVE pose q_last^-1 * q_estimator, q_last^-1 * (t_estimator - t_last) (NODE:400-401) -> relative_out; then
+ * last <- current (NODE:445-446).  `last` is the caller's q_last / t_last, {0,0,0,1,0,0,0} after the first frame (NODE:376-377). */
+int vilf_node_outputs(const double rt12[12], double last[7], double relative_out[7], double path_pose_out[7]);
 /* cudaMemcpyAsync(HostToDevice) on a caller-supplied stream (bench.py measures the host link with it). */
 int vilf_memcpy_h2d_async(void* dst_dev, const void* src_host, uint64_t bytes, void* cuda_stream);
 

@@ -109,6 +109,12 @@ inline void iso_from_rt12(Isometry3d& T, const double rt[12]) {
     T.translation()(i) = rt[9 + i];
   }
 }
+inline void iso_to_rt12(const Isometry3d& T, double rt[12]) {
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) rt[3 * i + j] = T.linear()(i, j);
+    rt[9 + i] = T.translation()(i);
+  }
+}
 #else
 // Stand-in for Eigen::Isometry3d as the node reads it (feature_tracker_node.cpp:388-389): rotation + translation.
 struct Isometry3d {
@@ -126,6 +132,10 @@ struct Isometry3d {
 inline void iso_from_rt12(Isometry3d& T, const double rt[12]) {
   std::memcpy(T.R, rt, 9 * sizeof(double));
   std::memcpy(T.t, rt + 9, 3 * sizeof(double));
+}
+inline void iso_to_rt12(const Isometry3d& T, double rt[12]) {
+  std::memcpy(rt, T.R, 9 * sizeof(double));
+  std::memcpy(rt + 9, T.t, 3 * sizeof(double));
 }
 #endif
 

@@ -155,6 +155,14 @@ def feature_depth(cloud, feats, num_bins: int = 360):
     return d[:m].copy(), nn[:m].copy()
 
 
+def node_outputs(rt12, last):
+    """feature_tracker_node.cpp:388-401, :445-446: (relative pose [7], path pose [7], new last [7])."""
+    rt12 = _f64(rt12); last = _f64(last).copy()
+    rel = np.empty(7); path = np.empty(7)
+    lib().orc_node_outputs(_p(rt12, C.c_double), _p(last, C.c_double), _p(rel, C.c_double), _p(path, C.c_double))
+    return rel, path, last
+
+
 def factors(cfg: Config, pose, edge, surf, map_e, map_s):
     """Data association at `pose` -> dict of per-point outputs for edge and surf features."""
     pose = _f64(pose); edge = _f32(edge); surf = _f32(surf); map_e = _f32(map_e); map_s = _f32(map_s)

@@ -255,4 +255,25 @@ void orc_feature_depth(const float* cloud, int n, const float* feats, int m, int
   feature_depth((const P4*)cloud, n, feats, m, num_bins, depth_out, nn_out);
 }
 
+// Node outputs after optimation_processing (feature_tracker_node.cpp:388-401, :445-446): q_estimator from the rotation
+// matrix, the relative pose published on /Odometry, then last <- current.  rt12 = row-major R, then t.
+void orc_node_outputs(const double* rt12, double* last7, double* rel7, double* path7) {
+  M3 R;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) R.m[i][j] = rt12[3 * i + j];
+  const Quat q = mat2q(R);
+  const V3 t{rt12[9], rt12[10], rt12[11]};
+  const Quat ql{last7[0], last7[1], last7[2], last7[3]};
+  const V3 tl{last7[4], last7[5], last7[6]};
+  const double n2 = ql.x * ql.x + ql.y * ql.y + ql.z * ql.z + ql.w * ql.w;  // Quaternion::inverse(): conjugate / squaredNorm
+  Quat qi{0, 0, 0, 0};
+  if (n2 > 0) qi = {-ql.x / n2, -ql.y / n2, -ql.z / n2, ql.w / n2};
+  const Quat qr = qmul(qi, q);
+  const V3 tr = qrot(qi, t - tl);
+  rel7[0] = qr.x; rel7[1] = qr.y; rel7[2] = qr.z; rel7[3] = qr.w; rel7[4] = tr.x; rel7[5] = tr.y; rel7[6] = tr.z;
+  path7[0] = q.x; path7[1] = q.y; path7[2] = q.z; path7[3] = q.w; path7[4] = t.x; path7[5] = t.y; path7[6] = t.z;
+  last7[0] = q.x; last7[1] = q.y; last7[2] = q.z; last7[3] = q.w; last7[4] = t.x; last7[5] = t.y; last7[6] = t.z;
+}
+
+
 }  // extern "C"

@@ -16,6 +16,7 @@
 
 #include "vilf/EstimationMapping.hpp"
 #include "vilf/featureDepth.hpp"
+#include "vilf/nodeOutputs.hpp"
 
 using vilf::Cloud;
 using vilf::CloudPtr;
@@ -39,18 +40,61 @@ static std::vector<CloudPtr> read_scans(const char* path) {
   return out;
 }
 
+// The payloads the node publishes (NODE:385-446): chaining the /Odometry relative poses must reproduce the /path pose, and
+// the /GlobalMap message must decode to the cloud it was made from.
+static void check_outputs(vilf::NodeOutputs& out, const EstimationMapping& est, const CloudPtr& MapCloud, double chain[7]) {
+  out.update(est.globalOdom);
+  const vilf::PoseMsg& r = out.odometry;
+  const vilf::PoseMsg& a = out.pathPose;
+  const double q[4] = {chain[0], chain[1], chain[2], chain[3]}, t[3] = {chain[4], chain[5], chain[6]};
+  // chain <- chain * relative
+  const double v[3] = {r.x, r.y, r.z};
+  double uv[3] = {q[1] * v[2] - q[2] * v[1], q[2] * v[0] - q[0] * v[2], q[0] * v[1] - q[1] * v[0]};
+  for (int c = 0; c < 3; ++c) uv[c] *= 2;
+  const double w[3] = {q[1] * uv[2] - q[2] * uv[1], q[2] * uv[0] - q[0] * uv[2], q[0] * uv[1] - q[1] * uv[0]};
+  for (int c = 0; c < 3; ++c) chain[4 + c] = t[c] + v[c] + q[3] * uv[c] + w[c];
+  chain[0] = q[3] * r.qx + q[0] * r.qw + q[1] * r.qz - q[2] * r.qy;
+  chain[1] = q[3] * r.qy + q[1] * r.qw + q[2] * r.qx - q[0] * r.qz;
+  chain[2] = q[3] * r.qz + q[2] * r.qw + q[0] * r.qy - q[1] * r.qx;
+  chain[3] = q[3] * r.qw - q[0] * r.qx - q[1] * r.qy - q[2] * r.qz;
+  const double ref[7] = {a.qx, a.qy, a.qz, a.qw, a.x, a.y, a.z};
+  const double sgn = (chain[3] * ref[3] + chain[0] * ref[0] + chain[1] * ref[1] + chain[2] * ref[2]) < 0 ? -1.0 : 1.0;
+  for (int c = 0; c < 7; ++c) {
+    const double d = std::fabs((c < 4 ? sgn : 1.0) * chain[c] - ref[c]);
+    if (!(d < 1e-9)) { std::fprintf(stderr, "chained /Odometry differs from /path by %.3e in component %d\n", d, c); std::exit(1); }
+  }
+  const double* po = est.parameter_opti;
+  const double sgn2 = (po[0] * ref[0] + po[1] * ref[1] + po[2] * ref[2] + po[3] * ref[3]) < 0 ? -1.0 : 1.0;
+  for (int c = 0; c < 7; ++c) {
+    if (!(std::fabs(ref[c] - (c < 4 ? sgn2 : 1.0) * po[c]) < 1e-12)) { std::fprintf(stderr, "/path pose differs from parameter_opti in component %d\n", c); std::exit(1); }
+  }
+  vilf::PointCloud2 msg;
+  vilf::to_pointcloud2(*MapCloud, msg);
+  CloudPtr back = vilf::make_cloud();
+  vilf::from_pointcloud2(msg, *back);
+  if (msg.point_step != 32 || msg.width != MapCloud->points.size() || back->points.size() != MapCloud->points.size()) { std::fprintf(stderr, "bad /GlobalMap message\n"); std::exit(1); }
+  for (size_t i = 0; i < back->points.size(); ++i) {
+    const vilf::PointType &p = back->points[i], &o = MapCloud->points[i];
+    if (p.x != o.x || p.y != o.y || p.z != o.z || p.intensity != o.intensity) { std::fprintf(stderr, "/GlobalMap message does not decode to MapCloud\n"); std::exit(1); }
+  }
+}
+
 static void node_loop(featureExtraction& fe, EstimationMapping& est, const std::vector<CloudPtr>& scans, std::vector<double>& poses) {
   bool init_pub = false;
+  vilf::NodeOutputs outputs;
+  double chain[7] = {0, 0, 0, 1, 0, 0, 0};
   for (size_t i = 0; i < scans.size(); ++i) {
     CloudPtr MapCloud = vilf::make_cloud(), edge = vilf::make_cloud(), surf = vilf::make_cloud();
     fe.extractFeature(scans[i], edge, surf);              // NODE:346
     if (!init_pub) {
       init_pub = true;
       est.localMapInited(edge, surf);                     // NODE:373
+      outputs.reset();                                    // NODE:376-377
     } else {
       est.optimation_processing(edge, surf);              // NODE:384
       est.getMapCloud(MapCloud);                          // NODE:385
       if (MapCloud->points.empty()) { std::fprintf(stderr, "empty /GlobalMap cloud at frame %zu\n", i); std::exit(1); }
+      check_outputs(outputs, est, MapCloud, chain);      // NODE:388-446
     }
     for (int k = 0; k < 7; ++k) poses.push_back(est.parameter_opti[k]);
   }

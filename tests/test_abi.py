@@ -88,3 +88,50 @@ def test_pack_pointcloud2(cabi):
     assert np.array_equal(out[:, :3], np.stack([msg["x"], msg["y"], msg["z"]], 1)) and (out[:, 3] == 0).all()
     with pytest.raises(cabi.VilfError):
         cabi.pack_pointcloud2(raw, n, 22, 0, 4, 20, 12)  # z would read past the point
+
+
+def test_unpack_pointcloud2_round_trip(cabi):
+    """packed float4 -> PointCloud2 bytes in pcl::toROSMsg's PointXYZI layout (feature_tracker_node.cpp:439-440) and back."""
+    import numpy as np
+    rng = np.random.default_rng(2)
+    pts = rng.normal(size=(777, 4)).astype(np.float32)
+    raw = cabi.unpack_pointcloud2(pts)
+    assert raw.size == 777 * 32
+    rec = raw.view(np.dtype({"names": ["x", "y", "z", "intensity"], "formats": ["<f4"] * 4, "offsets": [0, 4, 8, 16], "itemsize": 32}))
+    assert np.array_equal(np.stack([rec["x"], rec["y"], rec["z"], rec["intensity"]], 1), pts)
+    pad = raw.reshape(-1, 32)
+    assert not pad[:, 12:16].any() and not pad[:, 20:].any()
+    assert np.array_equal(cabi.pack_pointcloud2(raw, 777, 32, 0, 4, 8, 16), pts)
+    assert cabi.unpack_pointcloud2(np.zeros((0, 4), np.float32)).size == 0
+    with pytest.raises(cabi.VilfError):
+        cabi.unpack_pointcloud2(pts, 16, 0, 4, 8, 16)  # intensity would land past the point
+
+
+def test_node_outputs_match_the_oracle_and_scipy(cabi):
+    """/Odometry relative pose and /path pose (feature_tracker_node.cpp:388-401): the library's host arithmetic against the
+    oracle bit for bit, and against scipy's rotation algebra to rounding, over a random walk that includes rotations
+    beyond 120 degrees (the non-trace branches of the matrix -> quaternion conversion)."""
+    import numpy as np
+    from scipy.spatial.transform import Rotation as Rot
+    from oracle import orc
+    rng = np.random.default_rng(3)
+    last_a = np.array([0, 0, 0, 1, 0, 0, 0], np.float64)
+    last_b = last_a.copy()
+    Rprev, tprev = np.eye(3), np.zeros(3)
+    R, t = np.eye(3), np.zeros(3)
+    branches = set()
+    for k in range(400):
+        R = R @ Rot.from_rotvec(rng.normal(size=3) * (0.02 if k % 7 else 1.5)).as_matrix()
+        t = t + rng.normal(size=3)
+        rt12 = np.concatenate([R.reshape(-1), t])
+        rel_a, path_a, last_a = cabi.node_outputs(rt12, last_a)
+        rel_b, path_b, last_b = orc.node_outputs(rt12, last_b)
+        assert np.array_equal(rel_a, rel_b) and np.array_equal(path_a, path_b) and np.array_equal(last_a, last_b)
+        branches.add(bool(np.trace(R) > 0))
+        q = Rot.from_matrix(R).as_quat()
+        assert min(np.abs(path_a[:4] - q).max(), np.abs(path_a[:4] + q).max()) < 1e-12 and np.array_equal(path_a[4:], t)
+        qr = Rot.from_matrix(Rprev.T @ R).as_quat()
+        assert min(np.abs(rel_a[:4] - qr).max(), np.abs(rel_a[:4] + qr).max()) < 1e-12
+        assert np.abs(rel_a[4:] - Rprev.T @ (t - tprev)).max() < 1e-11
+        Rprev, tprev = R.copy(), t.copy()
+    assert branches == {True, False}

@@ -35,7 +35,7 @@ class Config(C.Structure):
 
 # every symbol include/vilf.h declares (tests/test_abi.py checks the .so exports all of them)
 SYMBOLS = [
-    "vilf_default_config", "vilf_create", "vilf_create_batch", "vilf_destroy", "vilf_last_error", "vilf_host_alloc", "vilf_host_free", "vilf_memcpy_h2d_async", "vilf_pack_pointcloud2",
+    "vilf_default_config", "vilf_create", "vilf_create_batch", "vilf_destroy", "vilf_last_error", "vilf_host_alloc", "vilf_host_free", "vilf_memcpy_h2d_async", "vilf_pack_pointcloud2", "vilf_unpack_pointcloud2", "vilf_node_outputs",
     "vilf_process_scan", "vilf_submit_scan", "vilf_wait", "vilf_submit_scan_batch", "vilf_wait_batch", "vilf_submit_scan_batch_dev",
     "vilf_feature_extract", "vilf_get_features", "vilf_map_init", "vilf_map_init_points", "vilf_update", "vilf_update_points",
     "vilf_get_pose", "vilf_set_pose", "vilf_predict", "vilf_create_submap", "vilf_get_cloud", "vilf_voxel_downsample", "vilf_crop_voxel_downsample", "vilf_crop_box", "vilf_knn5",
@@ -412,3 +412,25 @@ def pack_pointcloud2(data: np.ndarray, n_points: int, point_step: int, off_x: in
     if rc:
         raise VilfError(rc, "bad PointCloud2 layout")
     return out[:n_points]
+
+
+def unpack_pointcloud2(xyzi: np.ndarray, point_step: int = 32, off_x: int = 0, off_y: int = 4, off_z: int = 8, off_intensity: int = 16):
+    """Packed float32 [n, 4] -> PointCloud2 data bytes; the defaults are pcl::toROSMsg's layout of pcl::PointXYZI."""
+    xyzi = np.ascontiguousarray(xyzi, dtype=np.float32).reshape(-1, 4)
+    n = xyzi.shape[0]
+    out = np.empty(max(n, 1) * point_step, np.uint8)
+    rc = lib().vilf_unpack_pointcloud2(_p(xyzi, C.c_float), n, point_step, off_x, off_y, off_z, off_intensity, _p(out, C.c_uint8))
+    if rc:
+        raise VilfError(rc, "bad PointCloud2 layout")
+    return out[:n * point_step]
+
+
+def node_outputs(rt12, last):
+    """feature_tracker_node.cpp:388-401, :445-446 from get_pose()'s rt12: (relative pose [7], path pose [7], new last [7])."""
+    rt12 = np.ascontiguousarray(rt12, dtype=np.float64).reshape(12)
+    last = np.array(last, dtype=np.float64).reshape(7)
+    rel = np.empty(7); path = np.empty(7)
+    rc = lib().vilf_node_outputs(_p(rt12, C.c_double), _p(last, C.c_double), _p(rel, C.c_double), _p(path, C.c_double))
+    if rc:
+        raise VilfError(rc, "vilf_node_outputs")
+    return rel, path, last

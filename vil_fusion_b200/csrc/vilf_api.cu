@@ -714,6 +714,72 @@ int vilf_pack_pointcloud2(const uint8_t* data, int n_points, int point_step, int
   }
   return VILF_OK;
 }
+int vilf_unpack_pointcloud2(const float* xyzi, int n_points, int point_step, int off_x, int off_y, int off_z, int off_intensity, uint8_t* data_out) {
+  // packed x, y, z, intensity -> PointCloud2 bytes (pcl::toROSMsg at NODE:439-440 is a memcpy of PointXYZI[n], whose padding
+  // this zero-fills): a strided scatter of four float32 fields per point.
+  if (n_points < 0 || (n_points > 0 && (!xyzi || !data_out)) || point_step < 12 || off_x < 0 || off_y < 0 || off_z < 0) return VILF_ERR_INVALID;
+  if (off_x + 4 > point_step || off_y + 4 > point_step || off_z + 4 > point_step || off_intensity + 4 > point_step) return VILF_ERR_INVALID;
+  for (int i = 0; i < n_points; ++i) {
+    uint8_t* p = data_out + (size_t)i * (size_t)point_step;
+    const float* s = xyzi + (size_t)i * 4;
+    memset(p, 0, (size_t)point_step);
+    memcpy(p + off_x, s + 0, 4);
+    memcpy(p + off_y, s + 1, 4);
+    memcpy(p + off_z, s + 2, 4);
+    if (off_intensity >= 0) memcpy(p + off_intensity, s + 3, 4);
+  }
+  return VILF_OK;
+}
+
+int vilf_node_outputs(const double rt12[12], double last[7], double relative_out[7], double path_pose_out[7]) {
+  if (!rt12 || !last) return VILF_ERR_INVALID;
+  // NODE:388: Eigen::Quaterniond(Matrix3d) -- the trace / largest-diagonal branches of Eigen's rotation-matrix assignment.
+  const double* R = rt12;  // row-major
+  double q[4];             // x y z w
+  double t = R[0] + R[4] + R[8];
+  if (t > 0.0) {
+    t = sqrt(t + 1.0);
+    q[3] = 0.5 * t;
+    t = 0.5 / t;
+    q[0] = (R[7] - R[5]) * t;
+    q[1] = (R[2] - R[6]) * t;
+    q[2] = (R[3] - R[1]) * t;
+  } else {
+    int i = 0;
+    if (R[4] > R[0]) i = 1;
+    if (R[8] > R[4 * i]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = sqrt(R[4 * i] - R[4 * j] - R[4 * k] + 1.0);
+    q[i] = 0.5 * t;
+    t = 0.5 / t;
+    q[3] = (R[3 * k + j] - R[3 * j + k]) * t;
+    q[j] = (R[3 * j + i] + R[3 * i + j]) * t;
+    q[k] = (R[3 * k + i] + R[3 * i + k]) * t;
+  }
+  const double tt[3] = {rt12[9], rt12[10], rt12[11]};
+  if (path_pose_out) {
+    for (int c = 0; c < 4; ++c) path_pose_out[c] = q[c];
+    for (int c = 0; c < 3; ++c) path_pose_out[4 + c] = tt[c];
+  }
+  if (relative_out) {
+    // NODE:400-401.  Quaternion::inverse() = conjugate / squaredNorm; product and vector rotation as Eigen evaluates them.
+    const double n2 = last[0] * last[0] + last[1] * last[1] + last[2] * last[2] + last[3] * last[3];
+    double a[4] = {0, 0, 0, 0};  // inverse of q_last (Eigen returns the zero quaternion for a zero input)
+    if (n2 > 0.0) { a[0] = -last[0] / n2; a[1] = -last[1] / n2; a[2] = -last[2] / n2; a[3] = last[3] / n2; }
+    relative_out[0] = a[3] * q[0] + a[0] * q[3] + a[1] * q[2] - a[2] * q[1];
+    relative_out[1] = a[3] * q[1] + a[1] * q[3] + a[2] * q[0] - a[0] * q[2];
+    relative_out[2] = a[3] * q[2] + a[2] * q[3] + a[0] * q[1] - a[1] * q[0];
+    relative_out[3] = a[3] * q[3] - a[0] * q[0] - a[1] * q[1] - a[2] * q[2];
+    const double v[3] = {tt[0] - last[4], tt[1] - last[5], tt[2] - last[6]};
+    double uv[3] = {a[1] * v[2] - a[2] * v[1], a[2] * v[0] - a[0] * v[2], a[0] * v[1] - a[1] * v[0]};
+    for (int c = 0; c < 3; ++c) uv[c] += uv[c];
+    const double w[3] = {a[1] * uv[2] - a[2] * uv[1], a[2] * uv[0] - a[0] * uv[2], a[0] * uv[1] - a[1] * uv[0]};
+    for (int c = 0; c < 3; ++c) relative_out[4 + c] = v[c] + a[3] * uv[c] + w[c];
+  }
+  for (int c = 0; c < 4; ++c) last[c] = q[c];  // NODE:445-446
+  for (int c = 0; c < 3; ++c) last[4 + c] = tt[c];
+  return VILF_OK;
+}
 int vilf_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? VILF_OK : VILF_ERR_CUDA; }
 
 int vilf_submit_scan(vilf_handle* h, const float* xyzi, int n, const uint16_t* ring, int64_t* ticket) {
