@@ -5,8 +5,10 @@
 // J^T r, cost) with warp shuffles + a fixed-order shared-memory tree; the leader CTA gathers the 8 partials
 // over distributed shared memory (fixed order -> deterministic) and its thread 0 runs Ceres' trust-region
 // bookkeeping (Jacobi scaling fixed at iteration 0, LM diagonal clamp, radius update, parameter / function /
-// gradient tolerance exits, step rejection) on the 6x6 system; the candidate pose is broadcast back through
-// DSMEM, so the pose never leaves the SMs between iterations.  (The FP64 work of one evaluation, ~6 k factors
+// gradient tolerance exits, step rejection) on the 6x6 system -- accept / reject of the evaluated candidate and the
+// next step in ONE serial section, with the projected-gradient norm computed beside it by a second thread, so an
+// LM iteration costs two cluster barriers; the candidate pose is broadcast back through DSMEM, so the pose never
+// leaves the SMs between iterations.  (The FP64 work of one evaluation, ~6 k factors
 // x ~300 instructions, is what bounds this kernel: one SM took 27 us per evaluation, 8 SMs take ~4.)
 //
 // Ceres solves [J S; D] y = [r; 0] by QR; here the same minimiser is obtained from the normal equations
@@ -23,6 +25,7 @@ constexpr int NACC = 30;  // 21 H + 6 g + cost + n_edge + n_surf
 
 struct LmShared {
   double x[7], cand[7], params[7];
+  double grad_spec;  // projected-gradient max-norm at the point just evaluated (adopted with the step)
   double H[21], g[6], cost;
   double acc[NACC];   // cluster-wide sums (leader only)
   double part[NACC];  // this CTA's partial sums (read by the leader over DSMEM)
@@ -97,17 +100,28 @@ __device__ __forceinline__ void huber(double s, double a, double& rho0, double& 
   }
 }
 
+// acc += [J^T J (upper triangle), J^T r] of one residual row.  Z = index of a Jacobian entry that is structurally zero
+// (-1: none): its products are +-0 and are skipped.  The sums are FMA-accumulated: the reference has no counterpart of
+// this summation (Ceres factorises J itself), only its value matters.
+template <int Z>
 __device__ __forceinline__ void accumulate_row(double* acc, const double* J, double r) {
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
+    if (i == Z) continue;
 #pragma unroll
-    for (int j = i; j < 6; ++j) acc[hidx(i, j)] += J[i] * J[j];
-    acc[21 + i] += J[i] * r;
+    for (int j = i; j < 6; ++j)
+      if (j != Z) acc[hidx(i, j)] = fma(J[i], J[j], acc[hidx(i, j)]);
+    acc[21 + i] = fma(J[i], r, acc[21 + i]);
   }
 }
 
 // Robustified cost / gradient / normal matrix of every valid factor at pose x; result in S.acc (all threads sync).
 // Partial sums of this CTA (factor slots first, first + stride, ...) into S.part; ends with a CTA barrier.
+//
+// The Jacobians are the reference's products -skew(a-b) * [-skew(lp) | I] / |a-b| (LF:39-47) and n^T * [-skew(pw) | I]
+// (LF:90-97) with the structural zeros of the two skew matrices and of the identity block multiplied out by hand: the
+// terms left are the same roundings in the same order (x * 0 + y == y, (-x) * (-y) == x * y), 24 instead of 126 FP64
+// operations for a line factor and 9 instead of 30 for a plane factor.
 __device__ void evaluate(const LaneDev& L, int ne, int ns, const double* x, double hub, LmShared& S, double (*wred)[NACC], int first, int stride) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double acc[NACC];
@@ -126,25 +140,27 @@ __device__ void evaluate(const LaneDev& L, int ne, int ns, const double* x, doub
       const D3 ab = a - b;
       const double inv_abn = 1.0 / norm3(ab);  // one division per factor; r and J below multiply by it (LF:31-33, :47 divide: <= 1 ulp apart)
       double r[3] = {dmul(nu.x, inv_abn), dmul(nu.y, inv_abn), dmul(nu.z, inv_abn)};
-      const double nsab[3][3] = {{0, ab.z, -ab.y}, {-ab.z, 0, ab.x}, {ab.y, -ab.x, 0}};  // -skew(ab)
-      const double jse3[3][6] = {{0, lp.z, -lp.y, 1, 0, 0}, {-lp.z, 0, lp.x, 0, 1, 0}, {lp.y, -lp.x, 0, 0, 0, 1}};  // [-skew(lp) | I], LF:40-42
-      double J[3][6];
-#pragma unroll
-      for (int ii = 0; ii < 3; ++ii)
-#pragma unroll
-        for (int jj = 0; jj < 6; ++jj)
-          J[ii][jj] = dmul(dadd(dadd(dmul(nsab[ii][0], jse3[0][jj]), dmul(nsab[ii][1], jse3[1][jj])), dmul(nsab[ii][2], jse3[2][jj])), inv_abn);  // LF:47
+      const double pxx = dmul(ab.x, lp.x), pyy = dmul(ab.y, lp.y), pzz = dmul(ab.z, lp.z);
+      const double tx = dmul(ab.x, inv_abn), ty = dmul(ab.y, inv_abn), tz = dmul(ab.z, inv_abn);
+      double J[3][6] = {
+          {dmul(-dadd(pzz, pyy), inv_abn), dmul(dmul(ab.y, lp.x), inv_abn), dmul(dmul(ab.z, lp.x), inv_abn), 0.0, tz, -ty},
+          {dmul(dmul(ab.x, lp.y), inv_abn), dmul(-dadd(pzz, pxx), inv_abn), dmul(dmul(ab.z, lp.y), inv_abn), -tz, 0.0, tx},
+          {dmul(dmul(ab.x, lp.z), inv_abn), dmul(dmul(ab.y, lp.z), inv_abn), dmul(-dadd(pyy, pxx), inv_abn), ty, -tx, 0.0}};  // LF:47
       double rho0, sq;
       huber(dadd(dadd(dmul(r[0], r[0]), dmul(r[1], r[1])), dmul(r[2], r[2])), hub, rho0, sq);
       acc[27] += 0.5 * rho0;
       acc[28] += 1.0;
+      if (sq != 1.0) {  // outliers only; x * 1.0 == x
 #pragma unroll
-      for (int ii = 0; ii < 3; ++ii) {
+        for (int ii = 0; ii < 3; ++ii) {
 #pragma unroll
-        for (int jj = 0; jj < 6; ++jj) J[ii][jj] = dmul(J[ii][jj], sq);
-        r[ii] = dmul(r[ii], sq);
-        accumulate_row(acc, J[ii], r[ii]);
+          for (int jj = 0; jj < 6; ++jj) J[ii][jj] = dmul(J[ii][jj], sq);
+          r[ii] = dmul(r[ii], sq);
+        }
       }
+      accumulate_row<3>(acc, J[0], r[0]);
+      accumulate_row<4>(acc, J[1], r[1]);
+      accumulate_row<5>(acc, J[2], r[2]);
     } else {
       const int k = i - ne;
       const double* f = L.surf_pnd + (size_t)k * 7;
@@ -153,18 +169,17 @@ __device__ void evaluate(const LaneDev& L, int ne, int ns, const double* x, doub
       if (!L.fvalid[1][k]) continue;
       const D3 pw = qrot(q, p) + t;                 // LF:83
       double r = dadd(dot3(n, pw), f6);             // LF:84
-      const double jse3[3][6] = {{0, pw.z, -pw.y, 1, 0, 0}, {-pw.z, 0, pw.x, 0, 1, 0}, {pw.y, -pw.x, 0, 0, 0, 1}};
-      double J[6];
-#pragma unroll
-      for (int jj = 0; jj < 6; ++jj) J[jj] = dadd(dadd(dmul(n.x, jse3[0][jj]), dmul(n.y, jse3[1][jj])), dmul(n.z, jse3[2][jj]));  // LF:97
+      double J[6] = {dsub(dmul(n.z, pw.y), dmul(n.y, pw.z)), dsub(dmul(n.x, pw.z), dmul(n.z, pw.x)), dsub(dmul(n.y, pw.x), dmul(n.x, pw.y)), n.x, n.y, n.z};  // LF:97
       double rho0, sq;
       huber(dmul(r, r), hub, rho0, sq);
       acc[27] += 0.5 * rho0;
       acc[29] += 1.0;
+      if (sq != 1.0) {
 #pragma unroll
-      for (int jj = 0; jj < 6; ++jj) J[jj] = dmul(J[jj], sq);
-      r = dmul(r, sq);
-      accumulate_row(acc, J, r);
+        for (int jj = 0; jj < 6; ++jj) J[jj] = dmul(J[jj], sq);
+        r = dmul(r, sq);
+      }
+      accumulate_row<-1>(acc, J, r);
     }
   }
   // Warp reduction of the 30 sums by transposition: in the round with lane distance o every lane keeps one half of its
@@ -219,30 +234,35 @@ __device__ void adopt_linearisation(LmShared& S, bool first) {
   S.cost = S.acc[27];
   if (first)
     for (int j = 0; j < 6; ++j) S.scale[j] = 1.0 / (1.0 + sqrt(S.H[hidx(j, j)]));  // Jacobi scaling, fixed at iteration 0
+}
+
+// Max-norm of the projected gradient x - Plus(x, -g) (gradient tolerance test) for the gradient in S.acc: evaluated by a
+// second thread while thread 0 does the trust-region bookkeeping, adopted only if the step is.
+__device__ double projected_gradient_max(const double* x, const double* g) {
   double ng[6], proj[7];
-  for (int j = 0; j < 6; ++j) ng[j] = -S.g[j];
-  se3_plus(S.x, ng, proj);
+  for (int j = 0; j < 6; ++j) ng[j] = -g[j];
+  se3_plus(x, ng, proj);
   double gm = 0;
-  for (int i = 0; i < 7; ++i) gm = fmax(gm, fabs(S.x[i] - proj[i]));
-  S.grad_max = gm;
+  for (int i = 0; i < 7; ++i) gm = fmax(gm, fabs(x[i] - proj[i]));
+  return gm;
 }
 
 // (S J^T J S + D^2) y = S g by Cholesky; step = -y.  Returns false when the system is not positive definite.
 __device__ bool lm_step(const LmShared& S, double* step) {
   double A[6][6], rhs[6];
+  const double inv_radius = 1.0 / S.radius;
   for (int i = 0; i < 6; ++i) {
     for (int j = i; j < 6; ++j) { A[i][j] = S.H[hidx(i, j)] * S.scale[i] * S.scale[j]; A[j][i] = A[i][j]; }
-    const double lm = sqrt(S.diag[i] / S.radius);  // LevenbergMarquardtStrategy: lm_diagonal = sqrt(diagonal / radius)
-    A[i][i] += lm * lm;
+    A[i][i] += S.diag[i] * inv_radius;  // LevenbergMarquardtStrategy: lm_diagonal = sqrt(diagonal / radius), appended to J, i.e. squared here
     rhs[i] = S.g[i] * S.scale[i];
   }
-  double Lc[6][6], inv[6];  // Cholesky with one reciprocal per column instead of a division per entry
+  double Lc[6][6], inv[6];  // Cholesky with one reciprocal square root per column
   for (int j = 0; j < 6; ++j) {
     double d = A[j][j];
     for (int k = 0; k < j; ++k) d -= Lc[j][k] * Lc[j][k];
     if (!(d > 0)) return false;
-    Lc[j][j] = sqrt(d);
-    inv[j] = 1.0 / Lc[j][j];
+    inv[j] = rsqrt(d);
+    Lc[j][j] = d * inv[j];
     for (int i = j + 1; i < 6; ++i) {
       double sacc = A[i][j];
       for (int k = 0; k < j; ++k) sacc -= Lc[i][k] * Lc[j][k];
@@ -267,7 +287,7 @@ __device__ bool lm_step(const LmShared& S, double* step) {
 
 }  // namespace
 
-__global__ void __cluster_dims__(LM_CLUSTER, 1, 1) __launch_bounds__(LM_THREADS, 2)
+__global__ void __cluster_dims__(LM_CLUSTER, 1, 1) __launch_bounds__(LM_THREADS, LM_THREADS <= 256 ? 2 : 1)
 k_solve(LaneDev* lanes, int lane0, int outer, int finalize, ConfigDev cfg, int max_iters) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
@@ -292,6 +312,45 @@ k_solve(LaneDev* lanes, int lane0, int outer, int finalize, ConfigDev cfg, int m
     }
     if (leader) __syncthreads();
   };
+  // Thread 0 of the leader, between two cluster barriers: close the iteration that just ended
+  // (FinalizeIterationAndCheckIfMinimizerCanContinue) and, unless the solve is over, compute the next trust-region step
+  // and the candidate pose the whole cluster evaluates next (need_eval) -- or shrink the radius after an invalid step.
+  auto plan_step = [&]() {
+    S.need_eval = 0;
+    if (S.step_successful && S.cost < S.minimum_cost) { S.minimum_cost = S.cost; for (int i = 0; i < 7; ++i) S.params[i] = S.x[i]; }
+    if (S.iteration >= max_iters) { S.termination = 0; S.done = 1; return; }
+    if (S.step_successful && S.grad_max <= 1e-10) { S.termination = 3; S.done = 1; return; }
+    if (S.radius <= 1e-32) { S.termination = 5; S.done = 1; return; }
+    ++S.iteration;
+    if (!S.reuse_diagonal)
+      for (int j = 0; j < 6; ++j) S.diag[j] = fmin(fmax(S.H[hidx(j, j)] * S.scale[j] * S.scale[j], 1e-6), 1e32);
+    double step[6];
+    bool valid = lm_step(S, step);
+    S.reuse_diagonal = 1;
+    if (valid) {  // model_cost_change = -step^T (gs + Hs step / 2)
+      double mc = 0;
+      for (int i = 0; i < 6; ++i) {
+        double hs = 0;
+        for (int j = 0; j < 6; ++j) hs += S.H[i <= j ? hidx(i, j) : hidx(j, i)] * S.scale[i] * S.scale[j] * step[j];
+        mc += step[i] * (S.g[i] * S.scale[i] + 0.5 * hs);
+      }
+      S.model_cost_change = -mc;
+      valid = S.model_cost_change > 0.0;
+    }
+    if (!valid) {  // HandleInvalidStep
+      if (++S.num_invalid >= 5) { S.termination = 5; S.done = 1; record(T, S, 0, 0, 0, 0); }
+      else {
+        S.radius = S.radius / S.decrease_factor; S.decrease_factor *= 2.0; S.reuse_diagonal = 1; S.step_successful = 0;
+        record(T, S, 0, 0, 0, 0);
+      }
+    } else {
+      S.num_invalid = 0;
+      double delta[6];
+      for (int j = 0; j < 6; ++j) delta[j] = step[j] * S.scale[j];
+      se3_plus(S.x, delta, S.cand);
+      S.need_eval = 1;
+    }
+  };
   if (run) {
     if (leader && tid == 0) {
       for (int i = 0; i < 7; ++i) { S.x[i] = V.x[i]; S.params[i] = V.x[i]; }
@@ -306,62 +365,30 @@ k_solve(LaneDev* lanes, int lane0, int outer, int finalize, ConfigDev cfg, int m
     evaluate(L, ne, ns, xl, cfg.huber, S, wred, first, stride);
     cluster.sync();
     gather();
-    if (leader && tid == 0) {
-      S.n_edge = (int)S.acc[28]; S.n_surf = (int)S.acc[29];
-      T.n_edge = S.n_edge; T.n_surf = S.n_surf;
-      if (S.n_edge + S.n_surf == 0) {
-        S.done = 1; S.termination = 4;
-      } else {
-        S.x_norm = norm7(S.x);
-        adopt_linearisation(S, true);
-        for (int i = 0; i < 21; ++i) T.H0[i] = S.H[i];
-        for (int i = 0; i < 6; ++i) T.g0[i] = S.g[i];
-        T.cost0 = S.cost;
+    if (leader) {
+      if (tid == 32) S.grad_spec = projected_gradient_max(S.x, S.acc + 21);
+      if (tid == 0) {
+        S.n_edge = (int)S.acc[28]; S.n_surf = (int)S.acc[29];
+        T.n_edge = S.n_edge; T.n_surf = S.n_surf;
+        if (S.n_edge + S.n_surf == 0) {
+          S.done = 1; S.termination = 4;
+        } else {
+          S.x_norm = norm7(S.x);
+          adopt_linearisation(S, true);
+          for (int i = 0; i < 21; ++i) T.H0[i] = S.H[i];
+          for (int i = 0; i < 6; ++i) T.g0[i] = S.g[i];
+          T.cost0 = S.cost;
+        }
+      }
+      __syncthreads();
+      if (tid == 0 && !S.done) {
+        S.grad_max = S.grad_spec;
         record(T, S, 1, 1, 0, 0);
+        plan_step();
       }
     }
     cluster.sync();
     for (;;) {  // done / need_eval / cand are written by the leader's thread 0 between cluster barriers and read right after one
-      if (leader && tid == 0 && !S.done) {
-        S.need_eval = 0;
-        // FinalizeIterationAndCheckIfMinimizerCanContinue
-        if (S.step_successful && S.cost < S.minimum_cost) { S.minimum_cost = S.cost; for (int i = 0; i < 7; ++i) S.params[i] = S.x[i]; }
-        if (S.iteration >= max_iters) { S.termination = 0; S.done = 1; }
-        else if (S.step_successful && S.grad_max <= 1e-10) { S.termination = 3; S.done = 1; }
-        else if (S.radius <= 1e-32) { S.termination = 5; S.done = 1; }
-        else {
-          ++S.iteration;
-          if (!S.reuse_diagonal)
-            for (int j = 0; j < 6; ++j) S.diag[j] = fmin(fmax(S.H[hidx(j, j)] * S.scale[j] * S.scale[j], 1e-6), 1e32);
-          double step[6];
-          bool valid = lm_step(S, step);
-          S.reuse_diagonal = 1;
-          if (valid) {  // model_cost_change = -step^T (gs + Hs step / 2)
-            double mc = 0;
-            for (int i = 0; i < 6; ++i) {
-              double hs = 0;
-              for (int j = 0; j < 6; ++j) hs += S.H[i <= j ? hidx(i, j) : hidx(j, i)] * S.scale[i] * S.scale[j] * step[j];
-              mc += step[i] * (S.g[i] * S.scale[i] + 0.5 * hs);
-            }
-            S.model_cost_change = -mc;
-            valid = S.model_cost_change > 0.0;
-          }
-          if (!valid) {  // HandleInvalidStep
-            if (++S.num_invalid >= 5) { S.termination = 5; S.done = 1; record(T, S, 0, 0, 0, 0); }
-            else {
-              S.radius = S.radius / S.decrease_factor; S.decrease_factor *= 2.0; S.reuse_diagonal = 1; S.step_successful = 0;
-              record(T, S, 0, 0, 0, 0);
-            }
-          } else {
-            S.num_invalid = 0;
-            double delta[6];
-            for (int j = 0; j < 6; ++j) delta[j] = step[j] * S.scale[j];
-            se3_plus(S.x, delta, S.cand);
-            S.need_eval = 1;
-          }
-        }
-      }
-      cluster.sync();
       const int done = lead->done, need = lead->need_eval;
       if (done) break;
       if (need) {
@@ -370,33 +397,45 @@ k_solve(LaneDev* lanes, int lane0, int outer, int finalize, ConfigDev cfg, int m
         evaluate(L, ne, ns, xl, cfg.huber, S, wred, first, stride);
         cluster.sync();
         gather();
-          if (leader && tid == 0) {
-          S.candidate_cost = S.acc[27];
-          double sn = 0;
-          for (int i = 0; i < 7; ++i) sn += (S.x[i] - S.cand[i]) * (S.x[i] - S.cand[i]);
-          sn = sqrt(sn);
-          const double cost_change = S.cost - S.candidate_cost;
-          if (sn <= 1e-8 * (S.x_norm + 1e-8)) { S.termination = 1; S.done = 1; record(T, S, 1, 0, 0, sn); }            // parameter tolerance
-          else if (fabs(cost_change) <= 1e-6 * S.cost) { S.termination = 2; S.done = 1; record(T, S, 1, 0, 0, sn); }    // function tolerance
-          else {
-            const double rel = cost_change / S.model_cost_change;
-            if (rel > 1e-3) {  // HandleSuccessfulStep
-              for (int i = 0; i < 7; ++i) S.x[i] = S.cand[i];
-              S.x_norm = norm7(S.x);
-              adopt_linearisation(S, false);
-              S.step_successful = 1;
-              { const double c = 2.0 * rel - 1.0; S.radius = S.radius / fmax(1.0 / 3.0, 1.0 - c * c * c); }
-              S.radius = fmin(1e16, S.radius);
-              S.decrease_factor = 2.0;
-              S.reuse_diagonal = 0;
-              record(T, S, 1, 1, rel, sn);
-            } else {  // HandleUnsuccessfulStep
-              S.step_successful = 0;
-              S.radius = S.radius / S.decrease_factor; S.decrease_factor *= 2.0; S.reuse_diagonal = 1;
-              record(T, S, 1, 0, rel, sn);
+        if (leader) {
+          if (tid == 32) S.grad_spec = projected_gradient_max(S.cand, S.acc + 21);
+          int accepted = 0;
+          if (tid == 0) {
+            S.candidate_cost = S.acc[27];
+            double sn = 0;
+            for (int i = 0; i < 7; ++i) sn += (S.x[i] - S.cand[i]) * (S.x[i] - S.cand[i]);
+            sn = sqrt(sn);
+            const double cost_change = S.cost - S.candidate_cost;
+            if (sn <= 1e-8 * (S.x_norm + 1e-8)) { S.termination = 1; S.done = 1; record(T, S, 1, 0, 0, sn); }            // parameter tolerance
+            else if (fabs(cost_change) <= 1e-6 * S.cost) { S.termination = 2; S.done = 1; record(T, S, 1, 0, 0, sn); }    // function tolerance
+            else {
+              const double rel = cost_change / S.model_cost_change;
+              if (rel > 1e-3) {  // HandleSuccessfulStep
+                accepted = 1;
+                for (int i = 0; i < 7; ++i) S.x[i] = S.cand[i];
+                S.x_norm = norm7(S.x);
+                adopt_linearisation(S, false);
+                S.step_successful = 1;
+                { const double c = 2.0 * rel - 1.0; S.radius = S.radius / fmax(1.0 / 3.0, 1.0 - c * c * c); }
+                S.radius = fmin(1e16, S.radius);
+                S.decrease_factor = 2.0;
+                S.reuse_diagonal = 0;
+                record(T, S, 1, 1, rel, sn);
+              } else {  // HandleUnsuccessfulStep
+                S.step_successful = 0;
+                S.radius = S.radius / S.decrease_factor; S.decrease_factor *= 2.0; S.reuse_diagonal = 1;
+                record(T, S, 1, 0, rel, sn);
+              }
             }
           }
+          __syncthreads();
+          if (tid == 0 && !S.done) {
+            if (accepted) S.grad_max = S.grad_spec;
+            plan_step();
+          }
         }
+      } else if (leader && tid == 0) {
+        plan_step();  // the step was invalid: retry with the shrunk radius
       }
       cluster.sync();
     }
