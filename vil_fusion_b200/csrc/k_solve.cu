@@ -115,71 +115,152 @@ __device__ __forceinline__ void accumulate_row(double* acc, const double* J, dou
   }
 }
 
-// Robustified cost / gradient / normal matrix of every valid factor at pose x; result in S.acc (all threads sync).
-// Partial sums of this CTA (factor slots first, first + stride, ...) into S.part; ends with a CTA barrier.
+// One line factor (LF:21-52) / one plane factor (LF:79-102) at pose (q, t) into the thread's partial sums.
 //
 // The Jacobians are the reference's products -skew(a-b) * [-skew(lp) | I] / |a-b| (LF:39-47) and n^T * [-skew(pw) | I]
 // (LF:90-97) with the structural zeros of the two skew matrices and of the identity block multiplied out by hand: the
 // terms left are the same roundings in the same order (x * 0 + y == y, (-x) * (-y) == x * y), 24 instead of 126 FP64
-// operations for a line factor and 9 instead of 30 for a plane factor.
-__device__ void evaluate(const LaneDev& L, int ne, int ns, const double* x, double hub, LmShared& S, double (*wred)[NACC], int first, int stride) {
+// operations for a line factor and 9 instead of 30 for a plane factor.  inv_abn = 1 / |a - b| does not depend on the
+// pose (r and J multiply by it where LF:31-33, :47 divide: <= 1 ulp apart).
+__device__ __forceinline__ void edge_factor(double* acc, const Q4& q, const D3& t, const D3& p, const D3& a, const D3& b, double inv_abn, double hub) {
+  const D3 lp = qrot(q, p) + t;                    // LF:26
+  const D3 nu = cross3(lp - a, lp - b);            // LF:28
+  const D3 ab = a - b;
+  double r[3] = {dmul(nu.x, inv_abn), dmul(nu.y, inv_abn), dmul(nu.z, inv_abn)};
+  const double pxx = dmul(ab.x, lp.x), pyy = dmul(ab.y, lp.y), pzz = dmul(ab.z, lp.z);
+  const double tx = dmul(ab.x, inv_abn), ty = dmul(ab.y, inv_abn), tz = dmul(ab.z, inv_abn);
+  double J[3][6] = {
+      {dmul(-dadd(pzz, pyy), inv_abn), dmul(dmul(ab.y, lp.x), inv_abn), dmul(dmul(ab.z, lp.x), inv_abn), 0.0, tz, -ty},
+      {dmul(dmul(ab.x, lp.y), inv_abn), dmul(-dadd(pzz, pxx), inv_abn), dmul(dmul(ab.z, lp.y), inv_abn), -tz, 0.0, tx},
+      {dmul(dmul(ab.x, lp.z), inv_abn), dmul(dmul(ab.y, lp.z), inv_abn), dmul(-dadd(pyy, pxx), inv_abn), ty, -tx, 0.0}};  // LF:47
+  double rho0, sq;
+  huber(dadd(dadd(dmul(r[0], r[0]), dmul(r[1], r[1])), dmul(r[2], r[2])), hub, rho0, sq);
+  acc[27] += 0.5 * rho0;
+  acc[28] += 1.0;
+  if (sq != 1.0) {  // outliers only; x * 1.0 == x
+#pragma unroll
+    for (int ii = 0; ii < 3; ++ii) {
+#pragma unroll
+      for (int jj = 0; jj < 6; ++jj) J[ii][jj] = dmul(J[ii][jj], sq);
+      r[ii] = dmul(r[ii], sq);
+    }
+  }
+  accumulate_row<3>(acc, J[0], r[0]);
+  accumulate_row<4>(acc, J[1], r[1]);
+  accumulate_row<5>(acc, J[2], r[2]);
+}
+__device__ __forceinline__ void surf_factor(double* acc, const Q4& q, const D3& t, const D3& p, const D3& n, double d, double hub) {
+  const D3 pw = qrot(q, p) + t;                 // LF:83
+  double r = dadd(dot3(n, pw), d);              // LF:84
+  double J[6] = {dsub(dmul(n.z, pw.y), dmul(n.y, pw.z)), dsub(dmul(n.x, pw.z), dmul(n.z, pw.x)), dsub(dmul(n.y, pw.x), dmul(n.x, pw.y)), n.x, n.y, n.z};  // LF:97
+  double rho0, sq;
+  huber(dmul(r, r), hub, rho0, sq);
+  acc[27] += 0.5 * rho0;
+  acc[29] += 1.0;
+  if (sq != 1.0) {
+#pragma unroll
+    for (int jj = 0; jj < 6; ++jj) J[jj] = dmul(J[jj], sq);
+    r = dmul(r, sq);
+  }
+  accumulate_row<-1>(acc, J, r);
+}
+
+// The factors do not change between the <= 5 evaluations of one solve, and only about half of the feature slots hold an
+// accepted factor.  Each CTA therefore copies the accepted factors of its slots (slot i belongs to CTA (i / LM_THREADS)
+// % LM_CLUSTER) ONCE into a shared-memory pool -- line records {p, a, b, 1/|a-b|} from the front, plane records {p, n, d}
+// from the back, compacted in slot order by a block-wide scan, so the order of summation is a function of the input only.
+// A solve whose share does not fit the pool (very dense scans) evaluates that CTA from global memory instead.
+constexpr int POOL_DOUBLES = 5400;
+constexpr int EDGE_REC = 10, SURF_REC = 7;
+struct Stage {
+  int n_edge, n_surf, staged;
+};
+
+__device__ void stage_factors(const LaneDev& L, int ne, int ns, int rank, double* pool, int* wsum, Stage& st) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int ce = 0, cs = 0;  // CTA-uniform running counts
+  bool fits = true;
+  for (int base = rank * LM_THREADS; base < ne + ns; base += LM_CLUSTER * LM_THREADS) {
+    const int i = base + tid;
+    const bool is_e = i < ne, is_s = !is_e && i < ne + ns;
+    double rec[9];
+    bool v = false;
+    if (is_e) {
+      const double* f = L.edge_pab + (size_t)i * 9;
+#pragma unroll
+      for (int c = 0; c < 9; ++c) rec[c] = f[c];
+      v = L.fvalid[0][i] != 0;
+    } else if (is_s) {
+      const double* f = L.surf_pnd + (size_t)(i - ne) * 7;
+#pragma unroll
+      for (int c = 0; c < 7; ++c) rec[c] = f[c];
+      v = L.fvalid[1][i - ne] != 0;
+    }
+    const unsigned be = __ballot_sync(0xffffffffu, v && is_e), bs = __ballot_sync(0xffffffffu, v && is_s);
+    if (lane == 0) wsum[warp] = __popc(be) | (__popc(bs) << 16);
+    __syncthreads();
+    int oe = ce, os = cs, te = 0, ts = 0;
+#pragma unroll
+    for (int w = 0; w < LM_THREADS / 32; ++w) {
+      const int x = wsum[w];
+      if (w < warp) { oe += x & 0xffff; os += x >> 16; }
+      te += x & 0xffff; ts += x >> 16;
+    }
+    __syncthreads();  // wsum is rewritten in the next round
+    if (EDGE_REC * (ce + te) + SURF_REC * (cs + ts) > POOL_DOUBLES) { fits = false; break; }
+    const unsigned below = (1u << lane) - 1u;
+    if (v && is_e) {
+      double* o = pool + (size_t)EDGE_REC * (oe + __popc(be & below));
+#pragma unroll
+      for (int c = 0; c < 9; ++c) o[c] = rec[c];
+      o[9] = 1.0 / norm3(d3(rec[3], rec[4], rec[5]) - d3(rec[6], rec[7], rec[8]));
+    } else if (v && is_s) {
+      double* o = pool + POOL_DOUBLES - (size_t)SURF_REC * (os + __popc(bs & below) + 1);
+#pragma unroll
+      for (int c = 0; c < 7; ++c) o[c] = rec[c];
+    }
+    ce += te; cs += ts;
+  }
+  if (tid == 0) { st.n_edge = ce; st.n_surf = cs; st.staged = fits ? 1 : 0; }
+  __syncthreads();
+}
+
+// Robustified cost / gradient / normal matrix of every valid factor at pose x; result in S.acc (all threads sync).
+// Partial sums of this CTA into S.part; ends with a CTA barrier.
+__device__ void evaluate(const LaneDev& L, int ne, int ns, const double* x, double hub, LmShared& S, double (*wred)[NACC], const double* pool, const Stage& st, int first, int stride) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double acc[NACC];
 #pragma unroll
   for (int i = 0; i < NACC; ++i) acc[i] = 0;
   Q4 q; q.x = x[0]; q.y = x[1]; q.z = x[2]; q.w = x[3];
   const D3 t = d3(x[4], x[5], x[6]);
-  for (int i = first; i < ne + ns; i += stride) {
-    if (i < ne) {
-      // the record is read before the validity flag is tested (every slot < ne exists): one L2 round trip, not two
-      const double* f = L.edge_pab + (size_t)i * 9;
-      const D3 p = d3(f[0], f[1], f[2]), a = d3(f[3], f[4], f[5]), b = d3(f[6], f[7], f[8]);
-      if (!L.fvalid[0][i]) continue;
-      const D3 lp = qrot(q, p) + t;                    // LF:26
-      const D3 nu = cross3(lp - a, lp - b);            // LF:28
-      const D3 ab = a - b;
-      const double inv_abn = 1.0 / norm3(ab);  // one division per factor; r and J below multiply by it (LF:31-33, :47 divide: <= 1 ulp apart)
-      double r[3] = {dmul(nu.x, inv_abn), dmul(nu.y, inv_abn), dmul(nu.z, inv_abn)};
-      const double pxx = dmul(ab.x, lp.x), pyy = dmul(ab.y, lp.y), pzz = dmul(ab.z, lp.z);
-      const double tx = dmul(ab.x, inv_abn), ty = dmul(ab.y, inv_abn), tz = dmul(ab.z, inv_abn);
-      double J[3][6] = {
-          {dmul(-dadd(pzz, pyy), inv_abn), dmul(dmul(ab.y, lp.x), inv_abn), dmul(dmul(ab.z, lp.x), inv_abn), 0.0, tz, -ty},
-          {dmul(dmul(ab.x, lp.y), inv_abn), dmul(-dadd(pzz, pxx), inv_abn), dmul(dmul(ab.z, lp.y), inv_abn), -tz, 0.0, tx},
-          {dmul(dmul(ab.x, lp.z), inv_abn), dmul(dmul(ab.y, lp.z), inv_abn), dmul(-dadd(pyy, pxx), inv_abn), ty, -tx, 0.0}};  // LF:47
-      double rho0, sq;
-      huber(dadd(dadd(dmul(r[0], r[0]), dmul(r[1], r[1])), dmul(r[2], r[2])), hub, rho0, sq);
-      acc[27] += 0.5 * rho0;
-      acc[28] += 1.0;
-      if (sq != 1.0) {  // outliers only; x * 1.0 == x
-#pragma unroll
-        for (int ii = 0; ii < 3; ++ii) {
-#pragma unroll
-          for (int jj = 0; jj < 6; ++jj) J[ii][jj] = dmul(J[ii][jj], sq);
-          r[ii] = dmul(r[ii], sq);
-        }
+  if (st.staged) {
+    // line factors to the low threads, plane factors from the high threads down: the two kinds share no warp until the
+    // CTA holds more than LM_THREADS factors, and the tails of both land on different warps
+    for (int j = tid; j < st.n_edge; j += LM_THREADS) {
+      const double* f = pool + (size_t)EDGE_REC * j;
+      edge_factor(acc, q, t, d3(f[0], f[1], f[2]), d3(f[3], f[4], f[5]), d3(f[6], f[7], f[8]), f[9], hub);
+    }
+    for (int j = LM_THREADS - 1 - tid; j < st.n_surf; j += LM_THREADS) {
+      const double* f = pool + POOL_DOUBLES - (size_t)SURF_REC * (j + 1);
+      surf_factor(acc, q, t, d3(f[0], f[1], f[2]), d3(f[3], f[4], f[5]), f[6], hub);
+    }
+  } else {
+    for (int i = first; i < ne + ns; i += stride) {
+      if (i < ne) {
+        // the record is read before the validity flag is tested (every slot < ne exists): one L2 round trip, not two
+        const double* f = L.edge_pab + (size_t)i * 9;
+        const D3 p = d3(f[0], f[1], f[2]), a = d3(f[3], f[4], f[5]), b = d3(f[6], f[7], f[8]);
+        if (!L.fvalid[0][i]) continue;
+        edge_factor(acc, q, t, p, a, b, 1.0 / norm3(a - b), hub);
+      } else {
+        const int k = i - ne;
+        const double* f = L.surf_pnd + (size_t)k * 7;
+        const D3 p = d3(f[0], f[1], f[2]), n = d3(f[3], f[4], f[5]);
+        const double f6 = f[6];
+        if (!L.fvalid[1][k]) continue;
+        surf_factor(acc, q, t, p, n, f6, hub);
       }
-      accumulate_row<3>(acc, J[0], r[0]);
-      accumulate_row<4>(acc, J[1], r[1]);
-      accumulate_row<5>(acc, J[2], r[2]);
-    } else {
-      const int k = i - ne;
-      const double* f = L.surf_pnd + (size_t)k * 7;
-      const D3 p = d3(f[0], f[1], f[2]), n = d3(f[3], f[4], f[5]);
-      const double f6 = f[6];
-      if (!L.fvalid[1][k]) continue;
-      const D3 pw = qrot(q, p) + t;                 // LF:83
-      double r = dadd(dot3(n, pw), f6);             // LF:84
-      double J[6] = {dsub(dmul(n.z, pw.y), dmul(n.y, pw.z)), dsub(dmul(n.x, pw.z), dmul(n.z, pw.x)), dsub(dmul(n.y, pw.x), dmul(n.x, pw.y)), n.x, n.y, n.z};  // LF:97
-      double rho0, sq;
-      huber(dmul(r, r), hub, rho0, sq);
-      acc[27] += 0.5 * rho0;
-      acc[29] += 1.0;
-      if (sq != 1.0) {
-#pragma unroll
-        for (int jj = 0; jj < 6; ++jj) J[jj] = dmul(J[jj], sq);
-        r = dmul(r, sq);
-      }
-      accumulate_row<-1>(acc, J, r);
     }
   }
   // Warp reduction of the 30 sums by transposition: in the round with lane distance o every lane keeps one half of its
@@ -296,6 +377,9 @@ k_solve(LaneDev* lanes, int lane0, int outer, int finalize, ConfigDev cfg, int m
   LaneVars& V = *L.v;
   __shared__ LmShared S;
   __shared__ double wred[LM_THREADS / 32][NACC];
+  __shared__ double pool[POOL_DOUBLES];
+  __shared__ int wsum[LM_THREADS / 32];
+  __shared__ Stage stage;
   LmShared* lead = cluster.map_shared_rank(&S, 0);  // the leader's state, visible to the whole cluster
   const int tid = threadIdx.x;
   const bool leader = rank == 0;
@@ -359,48 +443,40 @@ k_solve(LaneDev* lanes, int lane0, int outer, int finalize, ConfigDev cfg, int m
       S.need_eval = 0;
       T.n_rows = 0;
     }
+    stage_factors(L, ne, ns, rank, pool, wsum, stage);
     double xl[7];
 #pragma unroll
     for (int i = 0; i < 7; ++i) xl[i] = V.x[i];
-    evaluate(L, ne, ns, xl, cfg.huber, S, wred, first, stride);
-    cluster.sync();
-    gather();
-    if (leader) {
-      if (tid == 32) S.grad_spec = projected_gradient_max(S.x, S.acc + 21);
-      if (tid == 0) {
-        S.n_edge = (int)S.acc[28]; S.n_surf = (int)S.acc[29];
-        T.n_edge = S.n_edge; T.n_surf = S.n_surf;
-        if (S.n_edge + S.n_surf == 0) {
-          S.done = 1; S.termination = 4;
-        } else {
-          S.x_norm = norm7(S.x);
-          adopt_linearisation(S, true);
-          for (int i = 0; i < 21; ++i) T.H0[i] = S.H[i];
-          for (int i = 0; i < 6; ++i) T.g0[i] = S.g[i];
-          T.cost0 = S.cost;
-        }
-      }
-      __syncthreads();
-      if (tid == 0 && !S.done) {
-        S.grad_max = S.grad_spec;
-        record(T, S, 1, 1, 0, 0);
-        plan_step();
-      }
-    }
-    cluster.sync();
-    for (;;) {  // done / need_eval / cand are written by the leader's thread 0 between cluster barriers and read right after one
-      const int done = lead->done, need = lead->need_eval;
-      if (done) break;
-      if (need) {
+    // One trip = one evaluation by the whole cluster (trip 0: the start pose, then the candidates) followed by the leader's
+    // serial section; done / cand are written by the leader's thread 0 between cluster barriers and read right after one.
+    for (int trip = 0;; ++trip) {
+      if (trip > 0) {
+        if (lead->done) break;
 #pragma unroll
         for (int i = 0; i < 7; ++i) xl[i] = lead->cand[i];
-        evaluate(L, ne, ns, xl, cfg.huber, S, wred, first, stride);
-        cluster.sync();
-        gather();
-        if (leader) {
-          if (tid == 32) S.grad_spec = projected_gradient_max(S.cand, S.acc + 21);
-          int accepted = 0;
-          if (tid == 0) {
+      }
+      evaluate(L, ne, ns, xl, cfg.huber, S, wred, pool, stage, first, stride);
+      cluster.sync();
+      gather();
+      if (leader) {
+        if (tid == 32) S.grad_spec = projected_gradient_max(trip == 0 ? S.x : S.cand, S.acc + 21);
+        int adopt = 0;
+        if (tid == 0) {
+          if (trip == 0) {
+            S.n_edge = (int)S.acc[28]; S.n_surf = (int)S.acc[29];
+            T.n_edge = S.n_edge; T.n_surf = S.n_surf;
+            if (S.n_edge + S.n_surf == 0) {
+              S.done = 1; S.termination = 4;
+            } else {
+              adopt = 1;
+              S.x_norm = norm7(S.x);
+              adopt_linearisation(S, true);
+              for (int i = 0; i < 21; ++i) T.H0[i] = S.H[i];
+              for (int i = 0; i < 6; ++i) T.g0[i] = S.g[i];
+              T.cost0 = S.cost;
+              record(T, S, 1, 1, 0, 0);
+            }
+          } else {
             S.candidate_cost = S.acc[27];
             double sn = 0;
             for (int i = 0; i < 7; ++i) sn += (S.x[i] - S.cand[i]) * (S.x[i] - S.cand[i]);
@@ -411,7 +487,7 @@ k_solve(LaneDev* lanes, int lane0, int outer, int finalize, ConfigDev cfg, int m
             else {
               const double rel = cost_change / S.model_cost_change;
               if (rel > 1e-3) {  // HandleSuccessfulStep
-                accepted = 1;
+                adopt = 1;
                 for (int i = 0; i < 7; ++i) S.x[i] = S.cand[i];
                 S.x_norm = norm7(S.x);
                 adopt_linearisation(S, false);
@@ -428,14 +504,12 @@ k_solve(LaneDev* lanes, int lane0, int outer, int finalize, ConfigDev cfg, int m
               }
             }
           }
-          __syncthreads();
-          if (tid == 0 && !S.done) {
-            if (accepted) S.grad_max = S.grad_spec;
-            plan_step();
-          }
         }
-      } else if (leader && tid == 0) {
-        plan_step();  // the step was invalid: retry with the shrunk radius
+        __syncthreads();  // grad_spec
+        if (tid == 0 && !S.done) {
+          if (adopt) S.grad_max = S.grad_spec;
+          do plan_step(); while (!S.done && !S.need_eval);  // an invalid step shrinks the radius and is retried right here
+        }
       }
       cluster.sync();
     }
