@@ -16,10 +16,23 @@
 // 1e-2), far inside the pose tolerance (1e-4 rad / 1e-3 m); SURVEY §8a row 9 lists the schedule reproduced.
 #include "vilf_internal.cuh"
 #include <cooperative_groups.h>
+#ifdef VILF_LM_TIMING
+#include <cstdio>
+#endif
 
 namespace vilf {
 
 namespace {
+
+// -DVILF_LM_TIMING: thread 0 of the first sequence's leader CTA stamps clock64() at the phase boundaries and prints the
+// deltas at frame 20 (tools/dev_lmts.py).  Development only.
+#ifdef VILF_LM_TIMING
+__shared__ long long ts_buf[128];
+__shared__ int ts_n;
+#define TS() do { if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && ts_n < 128) ts_buf[ts_n++] = clock64(); } while (0)
+#else
+#define TS() do { } while (0)
+#endif
 
 constexpr int NACC = 30;  // 21 H + 6 g + cost + n_edge + n_surf
 
@@ -27,33 +40,49 @@ struct LmShared {
   double x[7], cand[7], params[7];
   double grad_spec;  // projected-gradient max-norm at the point just evaluated (adopted with the step)
   double H[21], g[6], cost;
-  double acc[NACC];   // cluster-wide sums (leader only)
-  double part[NACC];  // this CTA's partial sums (read by the leader over DSMEM)
+  double acc[NACC];               // cluster-wide sums (leader only)
+  double parts[LM_CLUSTER][NACC];  // leader only: the partial sums every CTA of the cluster stores here over DSMEM
   double scale[6], diag[6];
   double radius, decrease_factor, minimum_cost, x_norm, grad_max, model_cost_change, candidate_cost;
-  int iteration, step_successful, reuse_diagonal, num_invalid, done, need_eval, termination, n_edge, n_surf;
+  int iteration, step_successful, reuse_diagonal, num_invalid, done, need_eval, termination, n_edge, n_surf, n_rows;
 };
 
 __device__ __forceinline__ int hidx(int i, int j) {  // upper triangle, row-major: (i <= j)
   return i * 6 - i * (i - 1) / 2 + (j - i);
 }
 
-// common.h:137-176 se(3) exponential + LocalSE3Parameterization::Plus (EM:34-49)
+// common.h:137-176 se(3) exponential + LocalSE3Parameterization::Plus (EM:34-49).
+// The reference evaluates sin(theta/2)/theta, cos(theta/2), (1-cos theta)/theta^2 and (theta-sin theta)/theta^3 through
+// sqrt, sin, cos and three divisions.  A trust-region step is a rotation of a few milliradians, so for theta < 0.05 the
+// same four functions are summed as power series in theta^2 (through theta^8: truncation < 4e-18), which needs neither
+// theta itself nor a transcendental -- one thread runs this between two cluster barriers, and it was most of that wait.
+// (The series is the more accurate of the two for the last coefficient, which the closed form gets by cancellation.)
 __device__ void se3_plus(const double* x, const double* delta, double* out) {
   const D3 omega = d3(delta[0], delta[1], delta[2]), ups = d3(delta[3], delta[4], delta[5]);
-  const double theta = norm3(omega);
-  const double half = dmul(0.5, theta);
-  double imag, real, sin_half;
-  sincos(half, &sin_half, &real);
-  if (theta < 1e-10) {
-    const double t2 = dmul(theta, theta), t4 = dmul(t2, t2);
+  const double t2 = dot3(omega, omega);  // theta^2
+  double imag, real, ca = 0, cb = 0;
+  const bool tiny = t2 < 1e-20;  // theta < 1e-10 (CM:150, :163)
+  if (tiny) {
+    const double t4 = dmul(t2, t2);
     imag = dadd(dsub(0.5, dmul(0.0208333, t2)), dmul(0.000260417, t4));
+    real = 1.0;  // cos(theta / 2) rounds to 1 below 1e-10
+  } else if (t2 < 2.5e-3) {
+    imag = fma(t2, fma(t2, fma(t2, fma(t2, 1.0 / 185794560.0, -1.0 / 645120.0), 1.0 / 3840.0), -1.0 / 48.0), 0.5);
+    real = fma(t2, fma(t2, fma(t2, fma(t2, 1.0 / 10321920.0, -1.0 / 46080.0), 1.0 / 384.0), -1.0 / 8.0), 1.0);
+    ca = fma(t2, fma(t2, fma(t2, fma(t2, 1.0 / 3628800.0, -1.0 / 40320.0), 1.0 / 720.0), -1.0 / 24.0), 0.5);
+    cb = fma(t2, fma(t2, fma(t2, fma(t2, 1.0 / 39916800.0, -1.0 / 362880.0), 1.0 / 5040.0), -1.0 / 120.0), 1.0 / 6.0);
   } else {
+    const double theta = sqrt(t2);
+    double sin_half, sin_t, cos_t;
+    sincos(dmul(0.5, theta), &sin_half, &real);
+    sincos(theta, &sin_t, &cos_t);
     imag = sin_half / theta;
+    ca = dsub(1, cos_t) / t2;
+    cb = dsub(theta, sin_t) / dmul(t2, theta);  // pow(theta, 3) in CM:170; the product differs by <= 1 ulp
   }
   Q4 dq; dq.x = dmul(imag, omega.x); dq.y = dmul(imag, omega.y); dq.z = dmul(imag, omega.z); dq.w = real;
   double J[3][3];
-  if (theta < 1e-10) {  // J = q.matrix()
+  if (tiny) {  // J = q.matrix()
     const double tx = dmul(2, dq.x), ty = dmul(2, dq.y), tz = dmul(2, dq.z);
     const double twx = dmul(tx, dq.w), twy = dmul(ty, dq.w), twz = dmul(tz, dq.w);
     const double txx = dmul(tx, dq.x), txy = dmul(ty, dq.x), txz = dmul(tz, dq.x);
@@ -61,18 +90,13 @@ __device__ void se3_plus(const double* x, const double* delta, double* out) {
     J[0][0] = dsub(1, dadd(tyy, tzz)); J[0][1] = dsub(txy, twz); J[0][2] = dadd(txz, twy);
     J[1][0] = dadd(txy, twz); J[1][1] = dsub(1, dadd(txx, tzz)); J[1][2] = dsub(tyz, twx);
     J[2][0] = dsub(txz, twy); J[2][1] = dadd(tyz, twx); J[2][2] = dsub(1, dadd(txx, tyy));
-  } else {
+  } else {  // V = I + ca * Omega + cb * Omega^2
     const double Om[3][3] = {{0, -omega.z, omega.y}, {omega.z, 0, -omega.x}, {-omega.y, omega.x, 0}};
     double Om2[3][3];
     for (int i = 0; i < 3; ++i)
       for (int j = 0; j < 3; ++j) Om2[i][j] = dadd(dadd(dmul(Om[i][0], Om[0][j]), dmul(Om[i][1], Om[1][j])), dmul(Om[i][2], Om[2][j]));
-    double sin_t, cos_t;
-    sincos(theta, &sin_t, &cos_t);
-    const double t2 = dmul(theta, theta);
-    const double a = dsub(1, cos_t) / t2;
-    const double b = dsub(theta, sin_t) / dmul(t2, theta);  // pow(theta, 3) in CM:170; the product differs by <= 1 ulp
     for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 3; ++j) J[i][j] = dadd(dadd(i == j ? 1.0 : 0.0, dmul(a, Om[i][j])), dmul(b, Om2[i][j]));
+      for (int j = 0; j < 3; ++j) J[i][j] = dadd(dadd(i == j ? 1.0 : 0.0, dmul(ca, Om[i][j])), dmul(cb, Om2[i][j]));
   }
   const D3 dt = d3(dadd(dadd(dmul(J[0][0], ups.x), dmul(J[0][1], ups.y)), dmul(J[0][2], ups.z)),
                    dadd(dadd(dmul(J[1][0], ups.x), dmul(J[1][1], ups.y)), dmul(J[1][2], ups.z)),
@@ -170,7 +194,7 @@ __device__ __forceinline__ void surf_factor(double* acc, const Q4& q, const D3& 
 // % LM_CLUSTER) ONCE into a shared-memory pool -- line records {p, a, b, 1/|a-b|} from the front, plane records {p, n, d}
 // from the back, compacted in slot order by a block-wide scan, so the order of summation is a function of the input only.
 // A solve whose share does not fit the pool (very dense scans) evaluates that CTA from global memory instead.
-constexpr int POOL_DOUBLES = 5400;
+constexpr int POOL_DOUBLES = 5100;
 constexpr int EDGE_REC = 10, SURF_REC = 7;
 struct Stage {
   int n_edge, n_surf, staged;
@@ -226,8 +250,8 @@ __device__ void stage_factors(const LaneDev& L, int ne, int ns, int rank, double
 }
 
 // Robustified cost / gradient / normal matrix of every valid factor at pose x; result in S.acc (all threads sync).
-// Partial sums of this CTA into S.part; ends with a CTA barrier.
-__device__ void evaluate(const LaneDev& L, int ne, int ns, const double* x, double hub, LmShared& S, double (*wred)[NACC], const double* pool, const Stage& st, int first, int stride) {
+// Partial sums of this CTA into lead_parts (the leader's parts[rank], over DSMEM); the caller's cluster barrier follows.
+__device__ void evaluate(const LaneDev& L, int ne, int ns, const double* x, double hub, double* lead_parts, double (*wred)[NACC], const double* pool, const Stage& st, int first, int stride) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double acc[NACC];
 #pragma unroll
@@ -263,6 +287,7 @@ __device__ void evaluate(const LaneDev& L, int ne, int ns, const double* x, doub
       }
     }
   }
+  TS();
   // Warp reduction of the 30 sums by transposition: in the round with lane distance o every lane keeps one half of its
   // current values and adds the partner's copies of that half, so 16 + 8 + 4 + 2 + 1 = 31 exchanges replace 30 x 5, and
   // lane l ends up with the warp total of sum number rev5(l) (fixed order: deterministic).
@@ -286,12 +311,12 @@ __device__ void evaluate(const LaneDev& L, int ne, int ns, const double* x, doub
     if (idx < NACC) wred[warp][idx] = a32[0];
   }
   __syncthreads();
-  if (tid < NACC) {
+  if (tid < NACC) {  // this CTA's sums go straight into the leader's shared memory; the cluster barrier that follows publishes them
     double v = 0;
     for (int w = 0; w < LM_THREADS / 32; ++w) v += wred[w][tid];
-    S.part[tid] = v;
+    lead_parts[tid] = v;
   }
-  __syncthreads();
+  TS();
 }
 
 __device__ double norm7(const double* v) {
@@ -300,9 +325,9 @@ __device__ double norm7(const double* v) {
   return sqrt(s);
 }
 
-__device__ void record(SolveTraceDev& T, const LmShared& S, int valid, int succ, double rel, double stepn) {
-  if (T.n_rows >= MAX_TRACE_ROWS) return;
-  LmRow& r = T.rows[T.n_rows++];
+__device__ void record(SolveTraceDev& T, LmShared& S, int valid, int succ, double rel, double stepn) {
+  if (S.n_rows >= MAX_TRACE_ROWS) return;  // the row count lives in shared memory: no global round trip per row
+  LmRow& r = T.rows[S.n_rows++];
   r.iteration = S.iteration; r.step_valid = valid; r.step_successful = succ; r.cost = S.cost; r.candidate_cost = S.candidate_cost;
   r.model_cost_change = S.model_cost_change; r.relative_decrease = rel; r.radius = S.radius; r.step_norm = stepn;
   for (int i = 0; i < 7; ++i) r.x[i] = S.x[i];
@@ -383,18 +408,31 @@ k_solve(LaneDev* lanes, int lane0, int outer, int finalize, ConfigDev cfg, int m
   LmShared* lead = cluster.map_shared_rank(&S, 0);  // the leader's state, visible to the whole cluster
   const int tid = threadIdx.x;
   const bool leader = rank == 0;
+#ifdef VILF_LM_TIMING
+  if (tid == 0) ts_n = 0;
+  __syncthreads();
+#endif
   const bool run = V.opt_ran != 0;  // EM:254 decided by the association kernel
   const int ne = V.n_ds[0], ns = V.n_ds[1];
   const int first = rank * LM_THREADS + tid, stride = LM_CLUSTER * LM_THREADS;
   SolveTraceDev& T = L.trace[outer];
-  // leader: gather the 8 partials in rank order
+  // leader: add the 8 partials in rank order
   auto gather = [&]() {
     if (leader && tid < NACC) {
       double v = 0;
-      for (int r = 0; r < LM_CLUSTER; ++r) v += cluster.map_shared_rank(&S, r)->part[tid];
+      for (int r = 0; r < LM_CLUSTER; ++r) v += S.parts[r][tid];
       S.acc[tid] = v;
     }
     if (leader) __syncthreads();
+  };
+  // leader thread 0: hand the outcome of its serial section (finished? / the next candidate pose) to every CTA's own
+  // shared memory, so nobody starts the next trip with a DSMEM round trip
+  auto publish = [&]() {
+    for (int r = 1; r < LM_CLUSTER; ++r) {
+      LmShared* o = cluster.map_shared_rank(&S, r);
+      o->done = S.done;
+      for (int i = 0; i < 7; ++i) o->cand[i] = S.cand[i];
+    }
   };
   // Thread 0 of the leader, between two cluster barriers: close the iteration that just ended
   // (FinalizeIterationAndCheckIfMinimizerCanContinue) and, unless the solve is over, compute the next trust-region step
@@ -441,9 +479,11 @@ k_solve(LaneDev* lanes, int lane0, int outer, int finalize, ConfigDev cfg, int m
       S.radius = 1e4; S.decrease_factor = 2.0; S.minimum_cost = DBL_MAX; S.reuse_diagonal = 0; S.num_invalid = 0;
       S.model_cost_change = 0; S.candidate_cost = 0; S.iteration = 0; S.step_successful = 1; S.done = 0; S.termination = 0;
       S.need_eval = 0;
-      T.n_rows = 0;
+      S.n_rows = 0;
     }
+    TS();
     stage_factors(L, ne, ns, rank, pool, wsum, stage);
+    TS();
     double xl[7];
 #pragma unroll
     for (int i = 0; i < 7; ++i) xl[i] = V.x[i];
@@ -451,13 +491,15 @@ k_solve(LaneDev* lanes, int lane0, int outer, int finalize, ConfigDev cfg, int m
     // serial section; done / cand are written by the leader's thread 0 between cluster barriers and read right after one.
     for (int trip = 0;; ++trip) {
       if (trip > 0) {
-        if (lead->done) break;
+        if (S.done) break;
 #pragma unroll
-        for (int i = 0; i < 7; ++i) xl[i] = lead->cand[i];
+        for (int i = 0; i < 7; ++i) xl[i] = S.cand[i];
       }
-      evaluate(L, ne, ns, xl, cfg.huber, S, wred, pool, stage, first, stride);
+      evaluate(L, ne, ns, xl, cfg.huber, lead->parts[rank], wred, pool, stage, first, stride);
       cluster.sync();
+      TS();
       gather();
+      TS();
       if (leader) {
         if (tid == 32) S.grad_spec = projected_gradient_max(trip == 0 ? S.x : S.cand, S.acc + 21);
         int adopt = 0;
@@ -505,17 +547,22 @@ k_solve(LaneDev* lanes, int lane0, int outer, int finalize, ConfigDev cfg, int m
             }
           }
         }
+        TS();
         __syncthreads();  // grad_spec
         if (tid == 0 && !S.done) {
           if (adopt) S.grad_max = S.grad_spec;
           do plan_step(); while (!S.done && !S.need_eval);  // an invalid step shrinks the radius and is retried right here
         }
+        if (tid == 0) publish();
+        TS();
       }
       cluster.sync();
+      TS();
     }
     if (leader && tid == 0) {
       for (int i = 0; i < 7; ++i) V.x[i] = S.params[i];
       T.termination = S.termination;
+      T.n_rows = S.n_rows;
       T.final_cost = S.cost;
     }
   }
@@ -532,6 +579,13 @@ k_solve(LaneDev* lanes, int lane0, int outer, int finalize, ConfigDev cfg, int m
     o[9] = x[4]; o[10] = x[5]; o[11] = x[6];
     V.frames += 1;
   }
+#ifdef VILF_LM_TIMING
+  if (leader && blockIdx.y == 0 && tid == 0 && V.frames == 20) {
+    printf("LMTS outer %d n %d:", outer, ts_n);
+    for (int i = 1; i < ts_n; ++i) printf(" %d", (int)(ts_buf[i] - ts_buf[i - 1]));
+    printf("\n");
+  }
+#endif
   cluster.sync();  // no CTA may exit while the leader can still read its shared memory
 }
 
