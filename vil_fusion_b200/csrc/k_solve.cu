@@ -344,7 +344,14 @@ __device__ void adopt_linearisation(LmShared& S, bool first) {
 
 // Max-norm of the projected gradient x - Plus(x, -g) (gradient tolerance test) for the gradient in S.acc: evaluated by a
 // second thread while thread 0 does the trust-region bookkeeping, adopted only if the step is.
+// The value is only ever compared with 1e-10, and its quaternion part alone decides almost every time: q - dq * q has
+// 2-norm |1 - dq| = 2 |sin(theta / 4)| (theta = |g_rot|, |q| = 1), so the max-norm is at least |sin(theta / 4)|.  Whenever
+// that exceeds 1e-9 the function returns 1.0 ("not converged") without the full exponential, which with a gradient of
+// tens of radians is the slow path of sin / cos and used to be what the leader's thread 0 waited for.
 __device__ double projected_gradient_max(const double* x, const double* g) {
+  const double t2 = g[0] * g[0] + g[1] * g[1] + g[2] * g[2];
+  if (t2 > 1e-16 && t2 < 36.0) return 1.0;  // theta / 4 in (2.5e-9, 1.5): sin >= 2.5e-9
+  if (t2 >= 36.0 && fabs(sin(0.25 * sqrt(t2))) > 1e-9) return 1.0;
   double ng[6], proj[7];
   for (int j = 0; j < 6; ++j) ng[j] = -g[j];
   se3_plus(x, ng, proj);
@@ -353,41 +360,74 @@ __device__ double projected_gradient_max(const double* x, const double* g) {
   return gm;
 }
 
+// 1 / sqrt(d) from the single-precision estimate and two Newton steps (full double precision for d in float range): this
+// sits six times on the serial chain of the factorisation below.
+__device__ __forceinline__ double rsqrt_newton(double d) {
+  if (!(d > 1e-30 && d < 1e30)) return rsqrt(d);
+  double r = (double)rsqrtf((float)d);
+  const double h = 0.5 * d;
+  r = fma(r, fma(-h * r, r, 0.5), r);
+  r = fma(r, fma(-h * r, r, 0.5), r);
+  return r;
+}
+
 // (S J^T J S + D^2) y = S g by Cholesky; step = -y.  Returns false when the system is not positive definite.
-__device__ bool lm_step(const LmShared& S, double* step) {
-  double A[6][6], rhs[6];
+// model_cost_change = -step^T (S g + S H S step / 2) = (y^T S g + y^T D^2 y) / 2 because y solves the system above.
+// One thread runs this between two cluster barriers: everything is unrolled into registers and fused.
+__device__ bool lm_step(const LmShared& S, double* step, double& model_cost_change) {
+  double A[6][6], rhs[6], d2[6];
   const double inv_radius = 1.0 / S.radius;
+#pragma unroll
   for (int i = 0; i < 6; ++i) {
-    for (int j = i; j < 6; ++j) { A[i][j] = S.H[hidx(i, j)] * S.scale[i] * S.scale[j]; A[j][i] = A[i][j]; }
-    A[i][i] += S.diag[i] * inv_radius;  // LevenbergMarquardtStrategy: lm_diagonal = sqrt(diagonal / radius), appended to J, i.e. squared here
+#pragma unroll
+    for (int j = i; j < 6; ++j) A[j][i] = S.H[hidx(i, j)] * S.scale[i] * S.scale[j];  // lower triangle
+    d2[i] = S.diag[i] * inv_radius;  // LevenbergMarquardtStrategy: lm_diagonal = sqrt(diagonal / radius), appended to J, i.e. squared here
+    A[i][i] += d2[i];
     rhs[i] = S.g[i] * S.scale[i];
   }
-  double Lc[6][6], inv[6];  // Cholesky with one reciprocal square root per column
+  double inv[6];  // Cholesky in place (A becomes L), one reciprocal square root per column
+  bool ok = true;
+#pragma unroll
   for (int j = 0; j < 6; ++j) {
     double d = A[j][j];
-    for (int k = 0; k < j; ++k) d -= Lc[j][k] * Lc[j][k];
-    if (!(d > 0)) return false;
-    inv[j] = rsqrt(d);
-    Lc[j][j] = d * inv[j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) d = fma(-A[j][k], A[j][k], d);
+    ok = ok && d > 0;
+    inv[j] = rsqrt_newton(d);
+    A[j][j] = d * inv[j];
+#pragma unroll
     for (int i = j + 1; i < 6; ++i) {
       double sacc = A[i][j];
-      for (int k = 0; k < j; ++k) sacc -= Lc[i][k] * Lc[j][k];
-      Lc[i][j] = sacc * inv[j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) sacc = fma(-A[i][k], A[j][k], sacc);
+      A[i][j] = sacc * inv[j];
     }
   }
+  if (!ok) return false;
   double z[6], y[6];
+#pragma unroll
   for (int i = 0; i < 6; ++i) {
     double sacc = rhs[i];
-    for (int k = 0; k < i; ++k) sacc -= Lc[i][k] * z[k];
+#pragma unroll
+    for (int k = 0; k < i; ++k) sacc = fma(-A[i][k], z[k], sacc);
     z[i] = sacc * inv[i];
   }
+#pragma unroll
   for (int i = 5; i >= 0; --i) {
     double sacc = z[i];
-    for (int k = i + 1; k < 6; ++k) sacc -= Lc[k][i] * y[k];
+#pragma unroll
+    for (int k = i + 1; k < 6; ++k) sacc = fma(-A[k][i], y[k], sacc);
     y[i] = sacc * inv[i];
   }
   bool finite = true;
-  for (int i = 0; i < 6; ++i) { step[i] = -y[i]; if (!isfinite(step[i])) finite = false; }
+  double m = 0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    step[i] = -y[i];
+    finite = finite && isfinite(y[i]);
+    m = fma(y[i], fma(d2[i], y[i], rhs[i]), m);
+  }
+  model_cost_change = 0.5 * m;
   return finite;
 }
 
@@ -425,14 +465,12 @@ k_solve(LaneDev* lanes, int lane0, int outer, int finalize, ConfigDev cfg, int m
     }
     if (leader) __syncthreads();
   };
-  // leader thread 0: hand the outcome of its serial section (finished? / the next candidate pose) to every CTA's own
+  // leader: hand the outcome of thread 0's serial section (finished? / the next candidate pose) to every CTA's own
   // shared memory, so nobody starts the next trip with a DSMEM round trip
-  auto publish = [&]() {
-    for (int r = 1; r < LM_CLUSTER; ++r) {
-      LmShared* o = cluster.map_shared_rank(&S, r);
-      o->done = S.done;
-      for (int i = 0; i < 7; ++i) o->cand[i] = S.cand[i];
-    }
+  auto publish = [&]() {  // lanes 1 .. LM_CLUSTER-1 of the leader's warp 0, one destination CTA each
+    LmShared* o = cluster.map_shared_rank(&S, tid);
+    o->done = S.done;
+    for (int i = 0; i < 7; ++i) o->cand[i] = S.cand[i];
   };
   // Thread 0 of the leader, between two cluster barriers: close the iteration that just ended
   // (FinalizeIterationAndCheckIfMinimizerCanContinue) and, unless the solve is over, compute the next trust-region step
@@ -444,20 +482,17 @@ k_solve(LaneDev* lanes, int lane0, int outer, int finalize, ConfigDev cfg, int m
     if (S.step_successful && S.grad_max <= 1e-10) { S.termination = 3; S.done = 1; return; }
     if (S.radius <= 1e-32) { S.termination = 5; S.done = 1; return; }
     ++S.iteration;
+    TS();
     if (!S.reuse_diagonal)
       for (int j = 0; j < 6; ++j) S.diag[j] = fmin(fmax(S.H[hidx(j, j)] * S.scale[j] * S.scale[j], 1e-6), 1e32);
-    double step[6];
-    bool valid = lm_step(S, step);
+    double step[6], mcc = 0;
+    TS();
+    bool valid = lm_step(S, step, mcc);
+    TS();
     S.reuse_diagonal = 1;
-    if (valid) {  // model_cost_change = -step^T (gs + Hs step / 2)
-      double mc = 0;
-      for (int i = 0; i < 6; ++i) {
-        double hs = 0;
-        for (int j = 0; j < 6; ++j) hs += S.H[i <= j ? hidx(i, j) : hidx(j, i)] * S.scale[i] * S.scale[j] * step[j];
-        mc += step[i] * (S.g[i] * S.scale[i] + 0.5 * hs);
-      }
-      S.model_cost_change = -mc;
-      valid = S.model_cost_change > 0.0;
+    if (valid) {
+      S.model_cost_change = mcc;
+      valid = mcc > 0.0;
     }
     if (!valid) {  // HandleInvalidStep
       if (++S.num_invalid >= 5) { S.termination = 5; S.done = 1; record(T, S, 0, 0, 0, 0); }
@@ -470,6 +505,7 @@ k_solve(LaneDev* lanes, int lane0, int outer, int finalize, ConfigDev cfg, int m
       double delta[6];
       for (int j = 0; j < 6; ++j) delta[j] = step[j] * S.scale[j];
       se3_plus(S.x, delta, S.cand);
+      TS();
       S.need_eval = 1;
     }
   };
@@ -553,7 +589,10 @@ k_solve(LaneDev* lanes, int lane0, int outer, int finalize, ConfigDev cfg, int m
           if (adopt) S.grad_max = S.grad_spec;
           do plan_step(); while (!S.done && !S.need_eval);  // an invalid step shrinks the radius and is retried right here
         }
-        if (tid == 0) publish();
+        if (tid < 32) {
+          __syncwarp();
+          if (tid >= 1 && tid < LM_CLUSTER) publish();
+        }
         TS();
       }
       cluster.sync();
