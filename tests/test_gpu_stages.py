@@ -320,6 +320,29 @@ def test_solve_random_problems_vs_oracle(g16, orc):
         assert np.abs(po - pg).max() < 1e-9, trial
 
 
+@pytest.mark.parametrize("ke,ks", [(3000, 18000), (0, 5780), (0, 5840), (510, 0), (4000, 1)])
+def test_solve_factor_pool_boundary_and_overflow(g16, orc, ke, ks):
+    """k_solve keeps the accepted factors of each CTA in a shared-memory pool (5100 doubles: 10 per line, 7 per plane
+    factor) and evaluates a CTA whose share does not fit from global memory instead: sizes far beyond the pool, sizes at
+    which only some of the 8 CTAs fit, and one-kind-only problems must all follow the oracle's schedule."""
+    rng = np.random.default_rng(ke * 7 + ks)
+    x = np.zeros(7); x[:3] = rng.normal(0, 0.01, 3); x[3] = np.sqrt(1 - (x[:3] ** 2).sum()); x[4:] = rng.normal(0, 0.2, 3)
+    p = rng.uniform(-30, 30, (ke, 3)); d = rng.normal(size=(ke, 3)); d /= np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-9)
+    c = p + rng.normal(0, 0.05, (ke, 3))
+    pab = np.concatenate([p, c + 0.1 * d, c - 0.1 * d], axis=1)
+    ps = rng.uniform(-30, 30, (ks, 3)); n = rng.normal(size=(ks, 3)); n /= np.maximum(np.linalg.norm(n, axis=1, keepdims=True), 1e-9)
+    pnd = np.concatenate([ps, n, (-(n * ps).sum(1) + rng.normal(0, 0.05, ks))[:, None]], axis=1)
+    H, gv, cost = g16.normal_equations(x, pab, pnd)
+    Ho, go, co = orc.normal_eq(0.1, x, pab, pnd)
+    assert np.abs(H - Ho).max() <= 1e-11 * np.abs(Ho).max() and np.abs(gv - go).max() <= 1e-11 * max(1.0, np.abs(go).max())
+    assert abs(cost - co) <= 1e-12 * co
+    po, tro, termo = orc.solve(0.1, 4, x, pab, pnd)
+    pg, trg, termg = g16.solve(x, pab, pnd, 4)
+    assert termo == termg and tro.shape == trg.shape
+    assert np.array_equal(tro[:, :3], trg[:, :3])
+    assert np.abs(po - pg).max() < 1e-9
+
+
 @pytest.mark.parametrize("leaf,spacing", [(0.2, 0.2), (0.1, 0.12), (0.4, 0.4)])
 def test_knn5_dense_maps_fine_cells_early_exit(cabi, orc, leaf, spacing):
     """Maps filtered at a fine leaf get search cells finer than the gate radius and a shell-by-shell walk with early exit
