@@ -362,7 +362,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         ach = (ab / dur_s / 1e9) if ab else None
         traffic = None
         try:  # DRAM bytes of the same kernel from the committed ncu --set full capture, scaled to this launch's sequence count
-            tt = json.load(open(os.path.join(ROOT, "profiles", "r1j_traffic.json")))["kernels"]
+            tt = json.load(open(os.path.join(ROOT, "profiles", "r1k_traffic.json")))["kernels"]
             ent = tt.get(dk.replace("k_sector_select", "k_sector_warp<16>"))
             if ent:
                 per = ent["dram_bytes_per_launch"]
@@ -374,7 +374,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         roof = dict(bound="hbm", kernel=f"{dp}/{dk}", achieved=ach, peak=peak, unit="GB/s", frac=(ach / peak) if ach else None, traffic=traffic,
                     peak_source="MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                     share_of_step=dms / tot, launches_timed=dn, avg_launch_us=dur_s * 1e6, algorithmic_bytes_per_launch=ab,
-                    note="event-to-event interval (includes the launch gap); per-frame working set is L2-resident, so this path is latency-, not HBM-bound (DESIGN.md §6); traffic = dram bytes of this kernel in profiles/r1j_traffic.json scaled to the launch's sequence count")
+                    note="event-to-event interval (includes the launch gap); per-frame working set is L2-resident, so this path is latency-, not HBM-bound (DESIGN.md §6); traffic = dram bytes of this kernel in profiles/r1k_traffic.json scaled to the launch's sequence count")
 
     # ---- the two stages the north star names, at a size where HBM matters (BASELINE configs[2]: ~1e6 map points) ----
     large = None

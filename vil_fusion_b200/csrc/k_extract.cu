@@ -502,27 +502,37 @@ __device__ __forceinline__ uint32_t curv_prefix(double c) { return __float_as_ui
 
 // sorted[0..m): elements ordered by (23-bit prefix, index).  Order every run of equal prefixes by (fp64 value, index).
 // Returns false when a run is too long for the transposition passes (the caller then falls back to an exact rank sort).
+// Ties are a handful of isolated pairs per sector: each lane remembers which of its positions p = lane + 32 k start a tied
+// pair (p, p + 1) -- swapping two elements of one run does not change which pairs are tied -- and the odd-even
+// transposition rounds visit only those, stopping after an odd and an even round in a row without a swap.
 __device__ __forceinline__ bool fix_tie_runs(const double* val, uint16_t* sorted, int m, int lane) {
   constexpr int MAX_RUN = 8;
-  // pair (p, p+1) is "tied" when both elements share the prefix
-  bool any = false, too_long = false;
-  for (int p = lane; p + 1 < m; p += 32) {
+  unsigned tied = 0;  // bit k: positions lane + 32 k and lane + 32 k + 1 share the prefix
+  bool too_long = false;
+  for (int p = lane, k = 0; p + 1 < m; p += 32, ++k) {
     const uint32_t a = curv_prefix(val[sorted[p]]), b = curv_prefix(val[sorted[p + 1]]);
     if (a == b) {
-      any = true;
+      tied |= 1u << k;
       if (p + MAX_RUN < m && curv_prefix(val[sorted[p + MAX_RUN]]) == a) too_long = true;
     }
   }
   if (__any_sync(0xffffffffu, too_long)) return false;
-  if (!__any_sync(0xffffffffu, any)) return true;
-  for (int round = 0; round < MAX_RUN; ++round) {  // odd-even transposition sorts runs of up to MAX_RUN elements in MAX_RUN rounds
-    const int par = round & 1;
-    for (int p = 2 * lane + par; p + 1 < m; p += 64) {
+  if (!__any_sync(0xffffffffu, tied != 0)) return true;
+  bool prev_swapped = true;
+  for (int round = 0; round < MAX_RUN; ++round) {  // runs of up to MAX_RUN elements are sorted after MAX_RUN rounds at the latest
+    bool swapped = false;
+    unsigned todo = ((lane ^ round) & 1) == 0 ? tied : 0u;  // the parity of p is the parity of the lane
+    while (todo) {
+      const int p = lane + 32 * (__ffs(todo) - 1);
+      todo &= todo - 1;
       const int ea = sorted[p], eb = sorted[p + 1];
       const double va = val[ea], vb = val[eb];
-      if (curv_prefix(va) == curv_prefix(vb) && ((va > vb) | ((va == vb) & (ea > eb)))) { sorted[p] = (uint16_t)eb; sorted[p + 1] = (uint16_t)ea; }
+      if ((va > vb) | ((va == vb) & (ea > eb))) { sorted[p] = (uint16_t)eb; sorted[p + 1] = (uint16_t)ea; swapped = true; }
     }
     __syncwarp();
+    swapped = __any_sync(0xffffffffu, swapped);
+    if (!swapped && !prev_swapped) break;
+    prev_swapped = swapped;
   }
   return true;
 }
