@@ -441,7 +441,11 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
     if roof:
         out["roofline"] = roof
         out["kernels_ms"] = kern_table[:12]
-        out["stage_ms"] = stage
+        n_frames = max(1, max((r[2] for r in kern_table if r[0].endswith("k_frame_reset")), default=1))
+        per_stage = {}
+        for name, ms_k, _n in kern_table:  # event-to-event kernel intervals of one stream group, summed per stage, per frame
+            per_stage[name.split("/")[0]] = per_stage.get(name.split("/")[0], 0.0) + ms_k / n_frames
+        out["stage_ms"] = per_stage
     return out
 
 
