@@ -358,6 +358,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CT, 2) k_voxel_clus
 }
 
 void launch_voxel_cluster(const Launch& L, const VoxJob* jobs_dev, int njobs, bool bbox_done, const ConfigDev&) {
+#if VILF_VOX_CLUSTER > 8
+  cudaFuncSetAttribute(k_voxel_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);  // A/B builds only
+#endif
   dim3 g(CL, njobs);
   k_voxel_cluster<<<g, CT, 0, L.st>>>(jobs_dev, bbox_done ? 1 : 0);
   L.tick(K_VOX_CLUSTER);
@@ -372,6 +375,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CT, 2) k_grid_clust
 }
 
 void launch_grid_cluster(const Launch& L, const GridJob* jobs_dev, int njobs, const ConfigDev&) {
+#if VILF_VOX_CLUSTER > 8
+  cudaFuncSetAttribute(k_grid_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);  // A/B builds only
+#endif
   dim3 g(CL, njobs);
   k_grid_cluster<<<g, CT, 0, L.st>>>(jobs_dev);
   L.tick(K_GRID_CLUSTER);
