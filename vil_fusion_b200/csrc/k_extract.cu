@@ -3,9 +3,11 @@
 //   k_frame_reset        per-frame scratch reset + constant-velocity pose prediction (EM:238-243)
 //   k_ring_partition     getLaserCloud (FE:54-110): range gate + vertical-angle -> ring id, and the stable partition of
 //                        the scan by ring (arrival order kept inside a ring, FE:108), one cluster per sequence
-//   k_sector_select      featureEdge_Surf + featureExtractionFromSector (FE:112-220): one CTA per
-//                        (ring, sector): 11-tap fp32 curvature, rank-sort in shared memory, warp-serial
-//                        greedy edge pick with +-5 neighbour suppression, surf = everything not picked
+//   k_sector_warp<EPL>   featureEdge_Surf + featureExtractionFromSector (FE:112-220): one WARP per (ring, sector):
+//                        11-tap fp32 curvature, register bitonic sort of 32-bit (curvature prefix, index) keys with
+//                        exact tie repair, warp-serial greedy edge pick with +-5 neighbour suppression, surf =
+//                        everything not picked
+//   k_sector_select      the same per CTA with a shared-memory sort: fallback for sectors longer than 512 elements
 //   k_compact_features   concatenates the per-sector lists in (ring, sector) order = the reference's
 //                        push_back order of cloud_Edge / cloud_Surf
 #include "k_sort.cuh"
