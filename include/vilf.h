@@ -128,7 +128,10 @@ int vilf_get_pose(vilf_handle* h, double pose_out[7], double* rt12_or_null);
 /* Overwrite parameter_opti (EM:383; q_w_c / t_w_c alias it) and, when update_odom != 0, globalOdom as EM:291-293 does. */
 int vilf_set_pose(vilf_handle* h, const double pose[7], int update_odom);
 /* The constant-velocity prediction that opens optimation_processing (EM:238-243): globalOdom <- globalOdom *
- * (globalOdom_last^-1 * globalOdom), globalOdom_last <- old globalOdom, parameter_opti <- predicted pose. */
+ * (globalOdom_last^-1 * globalOdom), globalOdom_last <- old globalOdom, parameter_opti <- predicted pose.
+ * ONLY for the step-by-step path (vilf_predict, vilf_factors, vilf_solve, vilf_create_submap): vilf_update,
+ * vilf_update_points and vilf_process_scan apply the same prediction themselves, so calling vilf_predict before one of
+ * them predicts twice. */
 int vilf_predict(vilf_handle* h, double pose_out[7]);
 /* EstimationMapping::createSubMap (EM:298-352) on explicit voxel-filtered scan features at the current parameter_opti:
  * transform + append to both local maps, crop box +-crop_half about the pose, voxel filter, rebuild the search grids. */

@@ -19,8 +19,8 @@
 //
 // ceres::Problem / ceres::LossFunction do not exist any more (the solver is a device kernel); the two factor methods
 // keep their name, their order of effects (transform with the current pose, 5-NN in the current local map, fit,
-// gate, append a factor) and their diagnostics ("not enough edge feature." below 20 / "not enough surf feature."
-// below 50, EM:168-171, :227-230).  optimation_processing() does all of it on the device in one submission.
+// gate, append a factor) and their diagnostics ("not enough edge feature." / "no enough surf feature.", both below 20
+// factors, EM:168-171, :227-230).  optimation_processing() does all of it on the device in one submission.
 //
 // F-LOAM names (BASELINE.json north_star) are provided as aliases on OdomEstimationClass at the end of this file.
 #pragma once
@@ -110,7 +110,7 @@ class EstimationMapping {
     }
     for (int r = 0; r < nrows; ++r) {
       if (rows[8 * r + 0] < 20) std::cout << "not enough edge feature." << std::endl;  // EM:168-171
-      if (rows[8 * r + 1] < 50) std::cout << "not enough surf feature." << std::endl;  // EM:227-230
+      if (rows[8 * r + 1] < 20) std::cout << "no enough surf feature." << std::endl;  // EM:227-230
     }
     prev_map_[0] = c[4];
     prev_map_[1] = c[5];
@@ -130,6 +130,8 @@ class EstimationMapping {
     append_cloud(*out, surf_.data(), (std::size_t)n_out);
   }
   // EM:238-243: constant-velocity prediction (globalOdom, globalOdom_last, parameter_opti).
+  // Step-by-step path only: optimation_processing() predicts by itself (EM:238-243), so predictPose() followed by
+  // optimation_processing() would apply the constant-velocity step twice.
   void predictPose() {
     double pose[7];
     sess_->check(vilf_predict(sess_->handle(), pose), "predictPose");
@@ -176,7 +178,7 @@ class EstimationMapping {
         ++added;
       }
     }
-    if (added < 50) std::cout << "not enough surf feature." << std::endl;
+    if (added < 20) std::cout << "no enough surf feature." << std::endl;  // EM:227-230
     return added;
   }
   // EM:275-283: ceres::Solve(DENSE_QR, max_num_iterations = 4) on the factors added since ProblemReset(); updates
@@ -250,13 +252,7 @@ class EstimationMapping {
     if (!trust_resident_ || sess_->resident_tag() == 0) return false;
     const Session::Resident& r = sess_->resident;
     if (r.tag != sess_->resident_tag() || e->points.size() != r.n_edge || s->points.size() != r.n_surf) return false;
-    return same(e, r.first_edge, r.last_edge) && same(s, r.first_surf, r.last_surf);
-  }
-  static bool same(const CloudPtr& c, const float first[4], const float last[4]) {
-    if (c->points.empty()) return true;
-    const PointType &a = c->points.front(), &b = c->points.back();
-    return a.x == first[0] && a.y == first[1] && a.z == first[2] && a.intensity == first[3] && b.x == last[0] && b.y == last[1] && b.z == last[2] &&
-           b.intensity == last[3];
+    return Session::content_hash(*e) == r.hash_edge && Session::content_hash(*s) == r.hash_surf;
   }
   void refreshPose() {
     double rt[12], st[31];

@@ -59,9 +59,8 @@ class featureExtraction {
       r.tag = sess_->new_tag();
       r.n_edge = static_cast<std::size_t>(ne);
       r.n_surf = static_cast<std::size_t>(ns);
-      std::memset(&r.first_edge[0], 0, 16); std::memset(&r.first_surf[0], 0, 16); std::memset(&r.last_edge[0], 0, 16); std::memset(&r.last_surf[0], 0, 16);
-      if (ne) { std::memcpy(r.first_edge, edge_.data(), 16); std::memcpy(r.last_edge, edge_.data() + 4 * (ne - 1), 16); }
-      if (ns) { std::memcpy(r.first_surf, surf_.data(), 16); std::memcpy(r.last_surf, surf_.data() + 4 * (ns - 1), 16); }
+      r.hash_edge = Session::content_hash(*cloud_Edge);
+      r.hash_surf = Session::content_hash(*cloud_Surf);
     } else {
       sess_->invalidate_resident();
     }

@@ -12,6 +12,7 @@
 #pragma once
 
 #include <cstdint>
+#include <cstring>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -51,13 +52,25 @@ class Session {
   }
 
   // Which host clouds correspond to the features currently resident on the device: extractFeature records the sizes
-  // and a content tag of what it appended; optimation_processing / localMapInited use the resident copy when the
-  // clouds they are given still match.
+  // and a hash of EVERY point it appended; optimation_processing / localMapInited use the resident copy only when the
+  // clouds they are given still hash to the same value (a caller who edits any point in between gets an upload).
   struct Resident {
     std::uint64_t tag;
     std::size_t n_edge, n_surf;
-    float first_edge[4], first_surf[4], last_edge[4], last_surf[4];
+    std::uint64_t hash_edge, hash_surf;
   };
+  // 64-bit FNV-1a over the x, y, z, intensity bit patterns of a cloud (works for pcl::PointXYZI's padded layout too).
+  template <class CloudT>
+  static std::uint64_t content_hash(const CloudT& c) {
+    std::uint64_t h = 1469598103934665603ull;
+    for (std::size_t i = 0; i < c.points.size(); ++i) {
+      const float v[4] = {c.points[i].x, c.points[i].y, c.points[i].z, c.points[i].intensity};
+      std::uint32_t w[4];
+      std::memcpy(w, v, 16);
+      for (int k = 0; k < 4; ++k) { h ^= w[k]; h *= 1099511628211ull; }
+    }
+    return h;
+  }
   Resident resident = Resident();
   std::uint64_t new_tag() { return resident_tag_ = next_tag_++; }
   std::uint64_t resident_tag() const { return resident_tag_; }

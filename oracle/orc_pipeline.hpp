@@ -46,6 +46,11 @@ struct Smooth { double value; size_t ind; };
 
 // FE:54-110.  Returns ring id or -1 (dropped).  `ring` is used when cfg.n_scan == 0.
 inline int ring_of(const Config& c, const P4& p, int explicit_ring) {
+  // Non-finite returns: FE:56-57 only fills an index vector, so they stay in the cloud; for N_SCANS 16/32/64 the x86 build
+  // drops them anyway (comparisons with NaN are false, int(NaN) == INT_MIN fails FE:78 / :86 / :98; +-inf fails the range or
+  // the scanID test).  The explicit-ring and "wrong scan number" modes would push NaN points into a ring and hand NaN to
+  // std::sort's comparator (undefined behaviour); oracle and CUDA path both drop them in every mode instead.
+  if (!(std::isfinite(p.x) && std::isfinite(p.y) && std::isfinite(p.z))) return -1;
   float dxy = std::sqrt(p.x * p.x + p.y * p.y);  // CM:59-62 (float sqrt)
   double distance = dxy;
   if (distance < c.lidar_min || distance > c.lidar_max) return -1;  // FE:70

@@ -55,3 +55,14 @@ def pose_err(a, b):
     chord = min(np.linalg.norm(qa - qb), np.linalg.norm(qa + qb))  # = 2 sin(angle / 4); stable near zero
     ang = 4.0 * np.arcsin(min(1.0, chord / 2.0))
     return float(ang), float(np.linalg.norm(np.asarray(a[4:], float) - np.asarray(b[4:], float)))
+
+
+def check_knn(gi, gd, oi, od, gate=1.0):
+    inside = od < gate
+    assert np.array_equal(gd[inside], od[inside])
+    neq = inside & (gi != oi)
+    if neq.any():  # only documented distance ties (T2) may pick a different index
+        rows = np.nonzero(neq.any(axis=1))[0]
+        for r in rows:
+            for k in np.nonzero(neq[r])[0]:
+                assert (od[r] == od[r, k]).sum() >= 2 or gd[r, k] == od[r, k], (r, k)

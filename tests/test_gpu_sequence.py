@@ -3,7 +3,7 @@ sequences, every sensor layout, the lock-step batch, the asynchronous API, state
 import numpy as np
 import pytest
 
-from conftest import pose_err
+from conftest import check_knn, pose_err
 
 pytestmark = pytest.mark.gpu
 
@@ -300,4 +300,54 @@ def test_config5_128_beams_fine_voxels(cabi, orc, synth):
     assert np.array_equal(o.solves()[:, :4], g.solves()[:, :4])  # same factor counts, terminations and iteration counts
     c = g.counts()
     assert c["status"] == 0 and c["n_map_edge"] > 5000
+    g.close()
+
+
+def test_config3_dense_hdl64_million_point_maps(cabi, orc, synth):
+    """BASELINE.json configs[2]: a dense-world HDL-64E sequence whose live local maps (EM:327-350 crop + voxel filter, EM:256-257
+    rebuild of the search structure) hold ~1e6 points; the large-map path (maps beyond one cluster's 2^19 points) is the one that
+    runs.  Free-running against the oracle on every frame; then the three large-map stages on the oracle's own ~1e6 map points."""
+    D = synth.DENSE
+    frames = 300
+    seq = synth.Sequence(D["sensor"], frames, seed=7, density=D["density"], speed=D["speed"])
+    o = orc.Odometry(orc.config(edge_leaf=D["edge_leaf"], surf_leaf=D["surf_leaf"]))
+    g = cabi.Odometry(cabi.default_config(edge_leaf=D["edge_leaf"], surf_leaf=D["surf_leaf"], max_scan_points=116000, max_map_points=D["max_map_points"],
+                                          max_ring_points=1864))
+    worst = [0.0, 0.0]
+    for i in range(frames):
+        x = np.ascontiguousarray(seq[i][0])
+        po, _, _ = o.process_scan(x)
+        pg = g.process_scan(x)
+        e = pose_err(po, pg)
+        worst = [max(worst[0], e[0]), max(worst[1], e[1])]
+        assert e[0] <= TOL_ROT and e[1] <= TOL_TRANS, (i, e)
+        if i % 50 == 49:  # maps along the way, not only at the end
+            maps_close(orc, cabi, o, g)
+            assert np.array_equal(o.solves()[:, :4], g.solves()[:, :4]), i
+    maps_close(orc, cabi, o, g)
+    assert np.array_equal(o.solves()[:, :4], g.solves()[:, :4])
+    c = g.counts()
+    assert c["status"] == 0 and c["frames"] == frames - 1
+    assert c["n_map_edge"] + c["n_map_surf"] >= 1_000_000, c
+    assert max(c["n_map_edge"], c["n_map_surf"]) > (1 << 19), c
+    # ---- stage level, on the ~1e6 real map points (all of them, and all queries) ----
+    me, ms = o.cloud(orc.MAP_EDGE), o.cloud(orc.MAP_SURF)
+    big = np.ascontiguousarray(np.concatenate([me, ms]))
+    assert big.shape[0] >= 1_000_000
+    for leaf in (0.2, 0.4):
+        vo, _ = orc.voxel_grid(big, leaf)
+        vg, guard = g.voxel_downsample(big, leaf)
+        assert guard == 0 and np.array_equal(vg, vo), leaf
+    ctr = [float(v) for v in g.pose()[0][4:]]
+    half = 60.0
+    co, _ = orc.voxel_grid(orc.crop_box(big, [ctr[a] - half for a in range(3)], [ctr[a] + half for a in range(3)]), 0.2)
+    cg = g.crop_voxel_downsample(big, ctr, half, 0.2)
+    assert np.array_equal(cg, co)
+    rng = np.random.default_rng(3)
+    q = ms[rng.integers(0, ms.shape[0], 200_000)].copy()
+    q[:, :3] += rng.normal(0, 0.05, (q.shape[0], 3)).astype(np.float32)
+    io, do = orc.knn(ms, q, 5)
+    ig, dg = g.knn5(ms, q)
+    assert (do[:, 4] < np.float32(1.0)).mean() > 0.9
+    check_knn(ig, dg, io, do)  # exact wherever the reference uses the result (EM:129 / :189 gate); indices equal up to distance ties
     g.close()

@@ -3,6 +3,8 @@ Bit-exact for indices / fp32 geometry; fp64 fits bit-exact (same operation order
 import numpy as np
 import pytest
 
+from conftest import check_knn
+
 pytestmark = pytest.mark.gpu
 
 
@@ -115,6 +117,41 @@ def test_wrong_scan_number_goes_to_ring0(cabi, orc, golden):
     g.close()
 
 
+def test_extract_drops_non_finite_returns(cabi, orc, synth, g64, hdl64_frames):
+    """Organized clouds of real drivers carry NaN / Inf rows.  FE:56-57 leaves them in the cloud; the x86 reference drops them
+    at the scanID range test (int(NaN) == INT_MIN).  The device must drop them too: same edge / surf indices as the oracle,
+    which must equal the extraction of the scan with those rows deleted (indices remapped)."""
+    x = hdl64_frames[1][0].copy()
+    rng = np.random.default_rng(9)
+    bad = np.sort(rng.choice(x.shape[0], 700, replace=False))
+    x[bad[0::4], 0] = np.nan
+    x[bad[1::4], 2] = np.nan
+    x[bad[2::4], 1] = np.inf
+    x[bad[3::4], 2] = -np.inf
+    cfg = orc.config()
+    oe, oes, os_, oss = orc.extract(cfg, x)
+    g64.feature_extract(x)
+    e, es = g64.features(0)
+    s, ss = g64.features(1)
+    assert np.array_equal(es, oes) and np.array_equal(ss, oss)
+    assert np.array_equal(e, oe) and np.array_equal(s, os_)
+    assert np.isfinite(e).all() and np.isfinite(s).all() and len(es) > 1000
+    keep = np.setdiff1d(np.arange(x.shape[0]), bad)
+    ce, ces, cs, css = orc.extract(cfg, x[keep])
+    assert np.array_equal(keep[ces], oes) and np.array_equal(keep[css], oss)
+    # explicit ring ids: non-finite returns are dropped in that mode as well
+    seq = synth.Sequence("beams128", 1, seed=4)
+    y, ring = seq[0]
+    y = y.copy()
+    y[5::97, 1] = np.nan
+    g = cabi.Odometry(cabi.default_config(n_scan=0, n_rings=128, max_scan_points=270000, max_map_points=1 << 16))
+    _, oes, _, oss = orc.extract(orc.config(n_scan=0, n_rings=128), y, ring)
+    g.feature_extract(y, ring)
+    assert np.array_equal(g.features(0)[1], oes) and np.array_equal(g.features(1)[1], oss)
+    assert np.isfinite(g.features(1)[0]).all()
+    g.close()
+
+
 # ---------------- voxel grid / crop box ----------------
 def test_voxel_goldens(g16, golden):
     for leaf in (0.4, 0.8):
@@ -170,17 +207,6 @@ def test_voxel_edge_cases_and_properties(g64, orc):
 
 
 # ---------------- 5-NN ----------------
-def check_knn(gi, gd, oi, od, gate=1.0):
-    inside = od < gate
-    assert np.array_equal(gd[inside], od[inside])
-    neq = inside & (gi != oi)
-    if neq.any():  # only documented distance ties (T2) may pick a different index
-        rows = np.nonzero(neq.any(axis=1))[0]
-        for r in rows:
-            for k in np.nonzero(neq[r])[0]:
-                assert (od[r] == od[r, k]).sum() >= 2 or gd[r, k] == od[r, k], (r, k)
-
-
 def test_knn_golden_and_reference_kdtree(g16, golden):
     gi, gd = g16.knn5(golden["knn_map"], golden["knn_q"])
     check_knn(gi, gd, golden["ref_knn_idx"], golden["ref_knn_d2"])

@@ -109,6 +109,22 @@ def numpy_extract(xyzi, n_scan=16, lidar_min=3.0, lidar_max=90.0, thr=0.1):
     return np.asarray(edge, np.int32), np.asarray(surf, np.int32)
 
 
+def test_extract_drops_non_finite_returns(orc, golden):
+    """FE:56-57 leaves NaN rows in the cloud; the x86 reference drops them at the scanID range test (int(NaN) == INT_MIN).
+    Extraction of a scan with NaN / Inf rows == extraction of the scan with those rows deleted, indices remapped."""
+    cfg = orc.config(n_scan=16, n_rings=16)
+    x = golden["scan0"].copy()
+    bad = np.arange(7, x.shape[0], 53)
+    x[bad[0::3], 0] = np.nan
+    x[bad[1::3], 2] = np.nan
+    x[bad[2::3], 2] = np.inf
+    e, es, s, ss = orc.extract(cfg, x)
+    keep = np.setdiff1d(np.arange(x.shape[0]), bad)
+    ce, ces, cs, css = orc.extract(cfg, x[keep])
+    assert np.array_equal(keep[ces], es) and np.array_equal(keep[css], ss)
+    assert np.isfinite(e).all() and np.isfinite(s).all()
+
+
 def test_extract_vs_independent_numpy(orc, golden):
     cfg = orc.config(n_scan=16, n_rings=16)
     _, es, _, ss = orc.extract(cfg, golden["scan1"])

@@ -119,6 +119,10 @@ struct KeyGenRing {
   __device__ uint32_t key(int job, int i) const {
     const LaneDev& L = lanes[lane0 + job];
     const float4 p = L.scan[sel][i];
+    // Non-finite returns (organized clouds of real drivers carry NaN rows): removeNaNFromPointCloud at FE:56-57 only fills an
+    // index vector, the points stay in cloud_in; the x86 reference then drops them because every comparison with NaN is false
+    // and int(NaN) == INT_MIN fails the scanID range test (FE:78, :86, :98).  (int)NaN is 0 on the device, so drop them here.
+    if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) return 255u;
     const float dxy = __fsqrt_rn(fadd(fmul(p.x, p.x), fmul(p.y, p.y)));  // DistanceXY, CM:59-62 (fp32)
     const double distance = (double)dxy;
     if (distance < cfg.lidar_min || distance > cfg.lidar_max) return 255u;  // FE:70
@@ -352,7 +356,7 @@ __global__ void __launch_bounds__(256) k_sector_select(LaneDev* lanes, int lane0
     fz = fadd(fadd(fadd(fadd(fadd(fz, p[1].z), p[2].z), p[3].z), p[4].z), p[5].z);
     const double dx = fx, dy = fy, dz = fz;
     const double c = dadd(dadd(dmul(dx, dx), dmul(dy, dy)), dmul(dz, dz));
-    val[e] = (unsigned long long)__double_as_longlong(c == 0.0 ? 0.0 : c);  // -0.0 cannot occur (sum of squares); NaN-free input
+    val[e] = (unsigned long long)__double_as_longlong(c == 0.0 ? 0.0 : c);  // -0.0 cannot occur (sum of squares); non-finite returns never reach a ring (KeyGenRing::key)
   }
   // std::sort ascending by curvature (FE:115); equal curvatures ordered by index (tie class T1 made canonical): a bitonic
   // network over the element INDICES (keys stay in place), NP = power of two >= m, padding entries sort to the end.
@@ -611,7 +615,7 @@ __global__ void __launch_bounds__(32 * SEC_WPC) k_sector_warp(LaneDev* lanes, in
     fz = fadd(fadd(fadd(fadd(fadd(fz, p[1].z), p[2].z), p[3].z), p[4].z), p[5].z);
     const double dx = fx, dy = fy, dz = fz;
     const double c = dadd(dadd(dmul(dx, dx), dmul(dy, dy)), dmul(dz, dz));
-    val[e] = c == 0.0 ? 0.0 : c;  // (+0.0; the input is NaN-free, FE:56-57)
+    val[e] = c == 0.0 ? 0.0 : c;  // (+0.0; non-finite returns never reach a ring, KeyGenRing::key)
   }
   __syncwarp();
   // std::sort ascending by curvature (FE:115); equal curvatures ordered by index (tie class T1 made canonical).

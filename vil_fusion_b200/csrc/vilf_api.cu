@@ -428,11 +428,20 @@ int enqueue_frame(Ctx* C, int lane0, int nl, bool first, bool with_extract, int 
       cudaGraph_t graph = nullptr;
       CK(cudaStreamBeginCapture(C->st, cudaStreamCaptureModeThreadLocal));
       issue_frame(C, lane0, nl, first, with_extract, sel, cur, nullptr);
-      CK(cudaStreamEndCapture(C->st, &graph));
-      CK(cudaGraphInstantiate(&G.exec, graph, 0));
-      CK(cudaGraphDestroy(graph));
-      G.launches = (int)(C->launches - before);
+      // a failure between Begin and End must not leave the stream in capture mode or an empty entry in the table
+      cudaError_t ce = cudaStreamEndCapture(C->st, &graph);
+      if (ce == cudaSuccess) ce = cudaGraphInstantiate(&G.exec, graph, 0);
+      if (graph) cudaGraphDestroy(graph);
+      const int captured = (int)(C->launches - before);
       C->launches = before;
+      if (ce != cudaSuccess) {
+        G.exec = nullptr;
+        C->graphs.erase(std::make_tuple(lane0, nl, sel, cur));
+        cudaGetLastError();
+        snprintf(C->err, sizeof(C->err), "CUDA graph capture of the frame failed: %s", cudaGetErrorString(ce));
+        return VILF_ERR_CUDA;
+      }
+      G.launches = captured;
     }
     CK(cudaGraphLaunch(G.exec, C->st));
     C->launches += G.launches;
