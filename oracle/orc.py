@@ -32,7 +32,7 @@ class Config(C.Structure):
         ("lidar_min", C.c_double), ("lidar_max", C.c_double), ("edge_threshold", C.c_double),
         ("edge_leaf", C.c_double), ("surf_leaf", C.c_double), ("crop_half", C.c_double),
         ("knn_gate", C.c_double), ("huber", C.c_double),
-        ("outer_iters", C.c_int), ("lm_max_iters", C.c_int), ("voxel_order", C.c_int), ("_pad", C.c_int),
+        ("outer_iters", C.c_int), ("lm_max_iters", C.c_int), ("voxel_order", C.c_int), ("knn_ties", C.c_int),
     ]
 
 
@@ -124,9 +124,10 @@ def _knn(fn, mp, q, k):
     return idx, d2
 
 
-def knn(mp, q, k: int = 5):
-    """Oracle kd-tree (restated FLANN single index): exact k-NN, ascending squared fp32 distances."""
-    return _knn(lib().orc_knn, mp, q, k)
+def knn(mp, q, k: int = 5, canonical: bool = False):
+    """Oracle kd-tree (restated FLANN single index): exact k-NN, ascending squared fp32 distances.  canonical=True resolves
+    equal distances (tie class T2) by ascending map index — the CUDA path's rule — instead of FLANN's visiting order."""
+    return _knn(lib().orc_knn_canonical if canonical else lib().orc_knn, mp, q, k)
 
 
 def ref_knn(mp, q, k: int = 5):

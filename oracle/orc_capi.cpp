@@ -10,14 +10,14 @@ extern "C" {
 struct orc_config {
   int n_scan, n_rings;
   double lidar_min, lidar_max, edge_threshold, edge_leaf, surf_leaf, crop_half, knn_gate, huber;
-  int outer_iters, lm_max_iters, voxel_order, _pad;
+  int outer_iters, lm_max_iters, voxel_order, knn_ties;
 };
 
 static Config to_cfg(const orc_config* c) {
   Config k;
   k.n_scan = c->n_scan; k.n_rings = c->n_rings; k.lidar_min = c->lidar_min; k.lidar_max = c->lidar_max;
   k.edge_threshold = c->edge_threshold; k.edge_leaf = c->edge_leaf; k.surf_leaf = c->surf_leaf; k.crop_half = c->crop_half;
-  k.knn_gate = c->knn_gate; k.huber = c->huber; k.outer_iters = c->outer_iters; k.lm_max_iters = c->lm_max_iters; k.voxel_order = c->voxel_order;
+  k.knn_gate = c->knn_gate; k.huber = c->huber; k.outer_iters = c->outer_iters; k.lm_max_iters = c->lm_max_iters; k.voxel_order = c->voxel_order; k.knn_ties = c->knn_ties;
   return k;
 }
 static Cloud to_cloud(const float* p, int n) {
@@ -30,7 +30,7 @@ void orc_default_config(orc_config* c) {
   Config k;
   c->n_scan = k.n_scan; c->n_rings = k.n_rings; c->lidar_min = k.lidar_min; c->lidar_max = k.lidar_max; c->edge_threshold = k.edge_threshold;
   c->edge_leaf = k.edge_leaf; c->surf_leaf = k.surf_leaf; c->crop_half = k.crop_half; c->knn_gate = k.knn_gate; c->huber = k.huber;
-  c->outer_iters = k.outer_iters; c->lm_max_iters = k.lm_max_iters; c->voxel_order = k.voxel_order; c->_pad = 0;
+  c->outer_iters = k.outer_iters; c->lm_max_iters = k.lm_max_iters; c->voxel_order = k.voxel_order; c->knn_ties = k.knn_ties;
 }
 
 // Stage 1.  Output buffers hold up to n points; *_src = index of the point in the input scan.
@@ -68,6 +68,15 @@ void orc_knn(const float* map, int m, const float* q, int nq, int k, int* idx, f
   for (int i = 0; i < nq; ++i) t.knn(q + 4 * (size_t)i, k, idx + (size_t)k * i, d2 + (size_t)k * i);
 }
 
+// the same with tie class T2 resolved canonically: ascending (d^2, map index) instead of FLANN's first-visited-wins
+void orc_knn_canonical(const float* map, int m, const float* q, int nq, int k, int* idx, float* d2) {
+  Cloud c = to_cloud(map, m);
+  KdTree t;
+  t.set_canonical_ties(true);
+  t.build(&c);
+  for (int i = 0; i < nq; ++i) t.knn(q + 4 * (size_t)i, k, idx + (size_t)k * i, d2 + (size_t)k * i);
+}
+
 // Data association at `pose` (EM:117-232).  edge_ab: 6 doubles per edge point (a, b); surf_nd: 4 per surf point (n, d).
 void orc_factors(const orc_config* c, const double* pose, const float* edge, int ne, const float* surf, int ns, const float* map_e, int me,
                  const float* map_s, int ms, uint8_t* edge_valid, double* edge_ab, int* edge_nn, float* edge_d2, uint8_t* surf_valid,
@@ -75,6 +84,8 @@ void orc_factors(const orc_config* c, const double* pose, const float* edge, int
   Config k = to_cfg(c);
   Cloud E = to_cloud(edge, ne), S = to_cloud(surf, ns), ME = to_cloud(map_e, me), MS = to_cloud(map_s, ms);
   KdTree te, ts;
+  te.set_canonical_ties(k.knn_ties == 1);
+  ts.set_canonical_ties(k.knn_ties == 1);
   te.build(&ME);
   ts.build(&MS);
   Quat q{pose[0], pose[1], pose[2], pose[3]};

@@ -37,6 +37,8 @@ struct Config {
   int outer_iters = 2;          // EM:260
   int lm_max_iters = 4;         // EM:277
   int voxel_order = 0;          // 0: within-voxel order = input order (stable); 1: std::sort like PCL (unstable)
+  int knn_ties = 0;             // tie class T2 (equal fp32 squared distances): 0 = FLANN / nanoflann order (first visited wins,
+                                // the reference's behaviour); 1 = canonical (d^2, map index) order, the CUDA path's rule
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -227,6 +229,7 @@ class KdTree {
   struct Node { int child1, child2; int left, right; int divfeat; float divlow, divhigh; };
   struct Interval { float low, high; };
 
+  void set_canonical_ties(bool on) { canonical_ = on; }
   void build(const Cloud* cloud, int leaf_max = 15) {
     pts_ = cloud;
     leaf_max_ = leaf_max;
@@ -335,10 +338,10 @@ class KdTree {
     }
     lim2 = left;
   }
-  static void add_point(float dist, int index, int k, int* idx, float* d2, int& count) {
+  void add_point(float dist, int index, int k, int* idx, float* d2, int& count) const {
     int i;
     for (i = count; i > 0; --i) {
-      if (d2[i - 1] > dist) { if (i < k) { d2[i] = d2[i - 1]; idx[i] = idx[i - 1]; } }
+      if (d2[i - 1] > dist || (canonical_ && d2[i - 1] == dist && idx[i - 1] > index)) { if (i < k) { d2[i] = d2[i - 1]; idx[i] = idx[i - 1]; } }
       else break;
     }
     if (i < k) { d2[i] = dist; idx[i] = index; }
@@ -355,7 +358,9 @@ class KdTree {
         { float d = q[0] - p.x; dist += d * d; }
         { float d = q[1] - p.y; dist += d * d; }
         { float d = q[2] - p.z; dist += d * d; }
-        if (dist < worst) add_point(dist, index, k, idx, d2, count);
+        // canonical ties: an equal distance with a lower index displaces the current k-th (the subtree pruning test below
+        // already visits every branch whose lower bound EQUALS the k-th distance, so no tied candidate is missed)
+        if (dist < worst || (canonical_ && count == k && dist == d2[k - 1] && index < idx[k - 1])) add_point(dist, index, k, idx, d2, count);
       }
       return;
     }
@@ -374,6 +379,7 @@ class KdTree {
   }
 
   const Cloud* pts_ = nullptr;
+  bool canonical_ = false;
   int leaf_max_ = 15;
   int root_ = -1;
   std::vector<int> vind_;
@@ -759,6 +765,8 @@ class Odometry {
     timing.ds += t1 - t0;
     traces.clear();
     if (map_edge.size() > 10 && map_surf.size() > 50) {  // EM:254
+      tree_edge.set_canonical_ties(cfg.knn_ties == 1);
+      tree_surf.set_canonical_ties(cfg.knn_ties == 1);
       tree_edge.build(&map_edge);
       tree_surf.build(&map_surf);
       double t2 = now_s();

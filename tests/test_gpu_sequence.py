@@ -306,11 +306,19 @@ def test_config5_128_beams_fine_voxels(cabi, orc, synth):
 def test_config3_dense_hdl64_million_point_maps(cabi, orc, synth):
     """BASELINE.json configs[2]: a dense-world HDL-64E sequence whose live local maps (EM:327-350 crop + voxel filter, EM:256-257
     rebuild of the search structure) hold ~1e6 points; the large-map path (maps beyond one cluster's 2^19 points) is the one that
-    runs.  Free-running against the oracle on every frame; then the three large-map stages on the oracle's own ~1e6 map points."""
+    runs.  Free-running against the oracle on every frame; then the three large-map stages on the oracle's own ~1e6 map points.
+
+    Tie class T2 at this scale: 4.4e4 queries per outer iteration meet an exact fp32 distance tie at the 5th / 6th neighbour
+    about every 50 frames (first at frame 46 of this sequence: indices 197469 vs 203676, d^2 = 0.015903158 both).  FLANN keeps
+    the first visited, the CUDA path the lower map index; the poses then split by ~2e-8 m and, a few frames later, single
+    points fall on the other side of a 0.1 m voxel face.  So the strict comparison (every frame, maps to 1e-5 m, identical
+    solver summaries) runs against the oracle with the CANONICAL tie rule (oracle Config.knn_ties = 1, checked against brute
+    force in tests/test_oracle.py); against the FLANN-order oracle the poses are held to the north-star tolerance."""
     D = synth.DENSE
-    frames = 300
+    frames, flann_frames = 300, 100
     seq = synth.Sequence(D["sensor"], frames, seed=7, density=D["density"], speed=D["speed"])
-    o = orc.Odometry(orc.config(edge_leaf=D["edge_leaf"], surf_leaf=D["surf_leaf"]))
+    o = orc.Odometry(orc.config(edge_leaf=D["edge_leaf"], surf_leaf=D["surf_leaf"], knn_ties=1))
+    of = orc.Odometry(orc.config(edge_leaf=D["edge_leaf"], surf_leaf=D["surf_leaf"]))
     g = cabi.Odometry(cabi.default_config(edge_leaf=D["edge_leaf"], surf_leaf=D["surf_leaf"], max_scan_points=116000, max_map_points=D["max_map_points"],
                                           max_ring_points=1864))
     worst = [0.0, 0.0]
@@ -321,9 +329,14 @@ def test_config3_dense_hdl64_million_point_maps(cabi, orc, synth):
         e = pose_err(po, pg)
         worst = [max(worst[0], e[0]), max(worst[1], e[1])]
         assert e[0] <= TOL_ROT and e[1] <= TOL_TRANS, (i, e)
+        if i < flann_frames:
+            pf, _, _ = of.process_scan(x)
+            ef = pose_err(pf, pg)
+            assert ef[0] <= TOL_ROT and ef[1] <= TOL_TRANS, (i, ef)
         if i % 50 == 49:  # maps along the way, not only at the end
             maps_close(orc, cabi, o, g)
             assert np.array_equal(o.solves()[:, :4], g.solves()[:, :4]), i
+    assert worst[0] < 1e-9 and worst[1] < 1e-9, worst  # with one tie rule the two free-running trajectories do not separate
     maps_close(orc, cabi, o, g)
     assert np.array_equal(o.solves()[:, :4], g.solves()[:, :4])
     c = g.counts()
@@ -346,8 +359,11 @@ def test_config3_dense_hdl64_million_point_maps(cabi, orc, synth):
     rng = np.random.default_rng(3)
     q = ms[rng.integers(0, ms.shape[0], 200_000)].copy()
     q[:, :3] += rng.normal(0, 0.05, (q.shape[0], 3)).astype(np.float32)
-    io, do = orc.knn(ms, q, 5)
+    io, do = orc.knn(ms, q, 5, canonical=True)
     ig, dg = g.knn5(ms, q)
-    assert (do[:, 4] < np.float32(1.0)).mean() > 0.9
-    check_knn(ig, dg, io, do)  # exact wherever the reference uses the result (EM:129 / :189 gate); indices equal up to distance ties
+    inside = do < np.float32(1.0)  # exact wherever the reference uses the result (EM:129 / :189 gate)
+    assert inside[:, 4].mean() > 0.9
+    assert np.array_equal(dg[inside], do[inside]) and np.array_equal(ig[inside], io[inside])
+    i2, d2 = orc.knn(ms, q, 5)  # FLANN visiting order: same distances, indices equal up to exact ties
+    check_knn(ig, dg, i2, d2)
     g.close()

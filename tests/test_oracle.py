@@ -41,6 +41,23 @@ def test_kdtree_is_exact_vs_bruteforce_and_scipy(orc):
     assert (np.sort(si, 1) == np.sort(idx, 1)).mean() > 0.999  # fp64 vs fp32 distance ties aside
 
 
+def test_kdtree_canonical_tie_rule_vs_bruteforce(orc):
+    """Config.knn_ties = 1 / orc.knn(canonical=True): equal fp32 distances (tie class T2) ordered by map index — the rule of
+    the CUDA path — instead of FLANN's first-visited-wins.  Same distances as the FLANN-order search, indices == brute force
+    sorted by (d^2, index) on a lattice full of exact ties."""
+    rng = np.random.default_rng(0)
+    mp = np.zeros((20000, 4), np.float32); mp[:, :3] = np.round(rng.uniform(-8, 8, (20000, 3)) * 4) / 4
+    q = np.zeros((1500, 4), np.float32); q[:, :3] = np.round(rng.uniform(-8, 8, (1500, 3)) * 2) / 2
+    i0, d0 = orc.knn(mp, q)
+    i1, d1 = orc.knn(mp, q, canonical=True)
+    assert np.array_equal(d0, d1) and (i0 != i1).any()
+    for r in range(0, 1500, 5):
+        d = q[r, :3][None] - mp[:, :3]
+        bf = ((d[:, 0] * d[:, 0]) + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+        o = np.lexsort((np.arange(len(bf)), bf))[:5]
+        assert np.array_equal(o, i1[r]) and np.array_equal(bf[o], d1[r])
+
+
 def test_extract_goldens(orc, golden):
     cfg = orc.config(n_scan=16, n_rings=16)
     e, es, s, ss = orc.extract(cfg, golden["scan0"])
