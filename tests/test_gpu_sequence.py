@@ -315,7 +315,7 @@ def test_config3_dense_hdl64_million_point_maps(cabi, orc, synth):
     solver summaries) runs against the oracle with the CANONICAL tie rule (oracle Config.knn_ties = 1, checked against brute
     force in tests/test_oracle.py); against the FLANN-order oracle the poses are held to the north-star tolerance."""
     D = synth.DENSE
-    frames, flann_frames = 300, 100
+    frames, flann_frames = 360, 100
     seq = synth.Sequence(D["sensor"], frames, seed=7, density=D["density"], speed=D["speed"])
     o = orc.Odometry(orc.config(edge_leaf=D["edge_leaf"], surf_leaf=D["surf_leaf"], knn_ties=1))
     of = orc.Odometry(orc.config(edge_leaf=D["edge_leaf"], surf_leaf=D["surf_leaf"]))

@@ -40,6 +40,9 @@ constexpr int MAX_OUTER = 4;
 constexpr int ST_SECTOR_TOO_LONG = 1;
 constexpr int ST_MAP_CAPACITY = 2;
 constexpr int ST_SCAN_CAPACITY = 4;
+constexpr int ST_KEY_RANGE = 8;     // cell-ordered map: the cloud spans more than 2^32 (cell, voxel) keys
+constexpr int ST_PCL_GUARD = 16;    // cell-ordered map: PCL's int32 guard would skip the voxel filter (legacy path handles it)
+constexpr int ST_ORPHANS = 32;      // more than ORPHAN_CAP centroids crossed a voxel face in one update
 
 struct ConfigDev {
   int n_scan, n_rings, rings_total;
@@ -52,6 +55,7 @@ struct ConfigDev {
   int outer_iters, lm_max_iters;
   int cap_scan, cap_map;
   int flags_no_cluster;  // VILF_FLAG_NO_CLUSTER: grid-wide multi-launch kernels everywhere
+  CellGeom cg[2];        // cell-ordered edge / surf map geometry
 };
 
 // One iteration row of the trust-region trace (same columns as the oracle's LmIter).
@@ -143,6 +147,66 @@ struct GridJob {
   int rings;          // 2^k: cells of Chebyshev distance <= rings around the query cell cover the gate radius
 };
 
+// ---- cell-ordered local map (k_cellmap.cu) ----
+// A local map is stored sorted by (search cell, voxel inside the cell): cells are cubes of 2^shift voxels of the map's own
+// voxel filter, so ONE order serves both pcl::VoxelGrid (a voxel is a run of equal keys; the per-frame update is a merge of
+// the sorted map with the few thousand sorted new points) and the 5-NN search (a cell is a contiguous range; an open-addressing
+// table maps cell -> [start, end)).
+constexpr int MERGE_TILE = 2048;     // merged elements per CTA tile of the map update
+constexpr int MERGE_THREADS = 512;
+constexpr int ORPHAN_CAP = 256;      // centroids that rounded across a voxel face, re-inserted with the next frame's points
+constexpr int VOX_BIAS = 1 << 20;    // voxel coordinates are biased into 21 unsigned bits per axis
+struct CellGeom {
+  float inv_leaf;  // PCL's inverse_leaf_size_ = 1.0f / leaf
+  float leaf;
+  int shift;       // log2(voxels per cell edge)
+  int shells;      // cells of Chebyshev distance <= shells around the query cell cover the gate radius
+};
+struct MergeVars {
+  int n_in;        // orphans + voxel-filtered scan features = size of the new-point sort job
+  int n_orph_in;   // orphans at the head of newpts (the registered cloud starts behind them)
+  int n_live;      // new points inside the crop box
+  int n_old, n_tot, n_tiles;
+  int vb[6];       // voxel-coordinate bounding box of the live new points
+  int bits;        // significant bits of their relative sort keys
+  int fb[6];       // ordered-int fp32 bounding box of every live point (PCL's "leaf size too small" guard)
+  int n_live_all;
+  int n_orph;      // orphans waiting for the next update
+  int hmask;       // cell table size - 1 of the map being written
+  int pad_[3];
+};
+struct TileAgg {   // per merge tile, written by the counting pass
+  int count;             // voxels (map points) the tile emits
+  int last_run_start;    // tile-relative index of the first point of the last cell run
+  unsigned long long first_cell, last_cell;
+};
+struct MergeJob {
+  const float4* old_pts; float4* out_pts;
+  int* n_map;                 // in: points of the old map, out: points of the new one
+  const float4* src; const int* n_src; const double* pose;   // voxel-filtered scan features to append at `pose` (EM:308-324); pose null: src is in the map frame
+  const double* crop_center; double crop_half;  // EM:327-336; crop_center null: no crop box
+  float4* newpts; float4* nsorted; unsigned long long* nkey;
+  SortJob sort;               // new points: (relative key, index) pairs
+  MergeVars* mv;
+  uint32_t* part;             // [max_tiles + 1] old elements before every tile boundary (merge path)
+  TileAgg* agg;               // [max_tiles]
+  uint2* table; int hcap;     // cell -> [start, end) of the map being written
+  int* meta;                  // [0] cell table mask, [1] has_orig (0 after an update)
+  float4* orphans;
+  CellGeom g;
+  int cap_out, cap_new, max_tiles;
+  int* status;
+};
+struct CellBuildJob {         // arbitrary cloud (PCL order = input order) -> cell-ordered map + original indices + cell table
+  const float4* src; const int* n;
+  float4* dst; uint32_t* orig;
+  uint2* table; int hcap;
+  int* meta;                  // [0] mask, [1] has_orig = 1, [2..7] voxel bbox, [8] bits
+  SortJob sort;
+  CellGeom g;
+  int* status;
+};
+
 // Per-lane device pointers.
 struct LaneDev {
   LaneVars* v;
@@ -164,6 +228,8 @@ struct LaneDev {
   double* edge_pab;    // [cap][9]
   double* surf_pnd;    // [cap][7]
   int* nn_idx[2]; float* nn_d2[2];  // [cap][5] (test hooks)
+  // cell-ordered maps: search table, PCL index of every point (valid while meta[1] != 0), meta
+  uint2* ctab[2]; uint32_t* corig[2]; int* cmeta[2];
 };
 
 // ---- ordered-int float mapping for atomicMin/atomicMax ----
@@ -245,7 +311,8 @@ __device__ __forceinline__ float4 associate(const double* x, float4 p) {
 enum KernelId {
   K_RESET = 0, K_RING_KEYHIST, K_SORT_HIST, K_SORT_SCATTER, K_SECTOR, K_COMPACT, K_VOX_BBOX, K_VOX_KEYHIST, K_VOX_HEADS, K_VOX_CENTROID,
   K_MAP_APPEND, K_MAP_INIT, K_GRID_ZERO, K_GRID_COUNT, K_GRID_SCAN_PARTIAL, K_GRID_SCAN_FINAL, K_GRID_SCATTER, K_KNN_FIT, K_KNN_ONLY,
-  K_SOLVE, K_FIT, K_VOX_CLUSTER, K_GRID_CLUSTER, K_DEPTH_CLOUD, K_DEPTH_QUERY, K_RING_PARTITION, K_COUNT
+  K_SOLVE, K_FIT, K_VOX_CLUSTER, K_GRID_CLUSTER, K_DEPTH_CLOUD, K_DEPTH_QUERY, K_RING_PARTITION,
+  K_NEW_XFORM, K_NEW_KEYHIST, K_MERGE_PART, K_MERGE_COUNT, K_MERGE_EMIT, K_CELL_BUILD, K_KNN_CELL, K_COUNT
 };
 constexpr int PROF_PHASES = 5;      // 0 extract, 1 scan downsample, 2 association + solve, 3 map update, 4 grid build
 constexpr int PROF_TAGS = PROF_PHASES * 32;
@@ -289,6 +356,15 @@ void launch_grid_build(const Launch& L, const GridJob* jobs_dev, int njobs, cons
 void launch_knn_fit(const Launch& L, LaneDev* lanes, const GridJob* grid_jobs, int lane0, int nlanes, int cur, const ConfigDev& cfg,
                     const double* pose_override);
 void launch_knn_only(const Launch& L, const GridJob* job_dev, const float4* q, const int* nq_dev, int* idx, float* d2, const ConfigDev& cfg);
+// k_cellmap.cu
+cudaError_t init_cellmap_kernels();
+void launch_cell_update(const Launch& L, const MergeJob* jobs_dev, const SortJob* sort_jobs_dev, int njobs, int max_tiles);
+void launch_cell_build(const Launch& L, const CellBuildJob* jobs_dev, const SortJob* sort_jobs_dev, int njobs);
+void launch_knn_cell_fit(const Launch& L, LaneDev* lanes, int lane0, int nlanes, int cur, const ConfigDev& cfg, const double* pose_override);
+void launch_knn_cell_only(const Launch& L, const float4* pts, const int* n_dev, const uint2* table, const int* meta, const uint32_t* orig, CellGeom g,
+                          const float4* q, const int* nq_dev, int* idx, float* d2, const ConfigDev& cfg);
+void launch_cell_unpermute(const Launch& L, const float4* pts, const uint32_t* orig, const int* n_dev, float4* out, int cap);
+void launch_fit(const Launch& L, LaneDev* lanes, int lane0, int nlanes, int cur, const ConfigDev& cfg);
 // k_depth.cu
 void launch_depth(const Launch& L, const float4* in, const int* n_dev, int from_scan, const double* T_dev, float4* sph, int* oidx, int* count,
                   const float* feats_dev, int m, float thr, float* depth_dev, int* nn_dev);
