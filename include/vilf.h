@@ -63,6 +63,8 @@ typedef struct vilf_config {
 /* Implementation-selection flags (results are bit-identical either way; used by the parity tests and for profiling). */
 #define VILF_FLAG_NO_CLUSTER 1 /* never take the one-cluster-per-cloud kernels; always the grid-wide multi-launch path */
 #define VILF_FLAG_NO_GRAPH 2   /* launch every kernel of a frame individually instead of replaying the captured CUDA graph */
+#define VILF_FLAG_LEGACY_MAP 4 /* round-1 map path: radix-sorted voxel filter of the whole map + hashed search grid rebuilt every frame,
+                                 instead of the cell-ordered map (merge update + cell table) */
 
 int vilf_default_config(vilf_config* cfg);
 
@@ -203,7 +205,12 @@ const char* vilf_profile_kernel_name(int kernel);
  * runs `iters` times between CUDA events on the handle's stream, after one warm-up run).
  * stage 0: spatial-hash build over `map` + 5-NN of the nq queries -> ms_out[0] = build, ms_out[1] = query (per run); the grid
  *          cell is the one a map voxel-filtered at `leaf` gets (leaf <= 0: the handle's default), ms_out[2] = shells, ms_out[3] = cell.
- * stage 1: crop box (+-100 m about the origin) + voxel filter at `leaf` of `map` -> ms_out[0] per run, ms_out[2] = voxels out. */
+ * stage 1: crop box (+-100 m about the origin) + voxel filter at `leaf` of the UNSORTED cloud `map` (radix path) -> ms_out[0] per run,
+ *          ms_out[2] = voxels out.
+ * stage 2: the per-frame map maintenance (createSubMap, EM:298-352): `map` is voxel-filtered at `leaf` once (untimed; ms_out[1] = that
+ *          time, ms_out[2] = points of the filtered map), then every run appends the nq points `q`, applies the crop box and the
+ *          voxel filter and rebuilds the search structure -> ms_out[0] per run, ms_out[3] = points out.  Cell-ordered maps do this
+ *          as one merge update; with VILF_FLAG_LEGACY_MAP it is the radix filter over the concatenation (search grid not included). */
 int vilf_bench_stage(vilf_handle* h, int stage, const float* map, int m, const float* q, int nq, float leaf, int iters, double ms_out[4]);
 /* Number of kernels this library has launched on the handle's context since creation. */
 int vilf_launch_count(vilf_handle* h, int64_t* launches);

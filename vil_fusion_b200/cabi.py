@@ -82,6 +82,7 @@ def _p(a, t):
 
 FLAG_NO_CLUSTER = 1
 FLAG_NO_GRAPH = 2
+FLAG_LEGACY_MAP = 4
 MAP_EDGE, MAP_SURF, DS_EDGE, DS_SURF, REGISTERED, NO_REGISTERED = range(6)
 
 

@@ -562,6 +562,9 @@ void launch_knn_fit(const Launch& L, LaneDev* lanes, const GridJob* grid_jobs, i
   dim3 g(KNN_G * 4, nlanes);
   k_knn_assoc<<<g, KNN_THREADS, 0, L.st>>>(lanes, grid_jobs, lane0, cfg, pose_override);
   L.tick(K_KNN_FIT);
+  launch_fit(L, lanes, lane0, nlanes, cur, cfg);
+}
+void launch_fit(const Launch& L, LaneDev* lanes, int lane0, int nlanes, int cur, const ConfigDev& cfg) {
   dim3 g2(FIT_G, nlanes);
   k_fit<<<g2, 128, 0, L.st>>>(lanes, lane0, cur, cfg);
   L.tick(K_FIT);

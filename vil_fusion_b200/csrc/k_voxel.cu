@@ -58,7 +58,7 @@ __device__ __forceinline__ void vox_warp_range(int n, int cta, int warp, int& be
 __global__ void __launch_bounds__(256) k_vox_heads(const VoxJob* __restrict__ jobs) {
   const VoxJob& J = jobs[blockIdx.y];
   const int n = J.vv->n_valid;
-  const int guard = J.vv->guard;
+  const int guard = J.vv->guard | J.emit_all;
   const uint32_t* key = J.sort.key[sort_passes(J.vv->bits, J.sort.npass) & 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int beg, end;
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256) k_vox_heads(const VoxJob* __restrict__ jo
 __global__ void __launch_bounds__(256) k_vox_centroid(const VoxJob* __restrict__ jobs) {
   const VoxJob& J = jobs[blockIdx.y];
   const int n = J.vv->n_valid;
-  const int guard = J.vv->guard;
+  const int guard = J.vv->guard | J.emit_all;
   const int res = sort_passes(J.vv->bits, J.sort.npass) & 1;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   __shared__ int red[8];
@@ -196,6 +196,10 @@ void launch_map_append(const Launch& L, LaneDev* lanes, int lane0, int nlanes, i
   dim3 g(148, nlanes);
   k_map_append<<<g, 256, 0, L.st>>>(lanes, lane0, cur, cfg);
   L.tick(K_MAP_APPEND);
+}
+void launch_map_init_commit(const Launch& L, LaneDev* lanes, int lane0, int nlanes, const ConfigDev& cfg) {
+  k_map_init_commit<<<1, nlanes, 0, L.st>>>(lanes, lane0, cfg);
+  L.tick(K_MAP_INIT);
 }
 void launch_map_init(const Launch& L, LaneDev* lanes, int lane0, int nlanes, int cur, const ConfigDev& cfg) {
   dim3 g(148, nlanes);

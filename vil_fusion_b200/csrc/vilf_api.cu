@@ -56,6 +56,19 @@ struct Ctx {
   std::map<std::tuple<int, int, int, int>, FrameGraph> graphs;
   bool use_graphs = true;
   bool cluster_scan = false, cluster_map = false;  // one-cluster-per-cloud path (k_cluster.cu) for scan / map clouds
+  // cell-ordered maps (k_cellmap.cu): merge update + cell table; off with VILF_FLAG_LEGACY_MAP
+  bool cellmap = true;
+  int max_tiles = 0;
+  MergeJob* merge_dev[2] = {nullptr, nullptr}; SortJob* merge_sort_dev = nullptr;      // [cur][nlanes*2]
+  CellBuildJob* build_dev[2] = {nullptr, nullptr}; SortJob* build_sort_dev = nullptr;  // [cur][nlanes*2]: first-frame map from the raw features
+  std::vector<MergeJob> merge_host[2];
+  std::vector<CellBuildJob> build_host[2];
+  MergeVars* mv_dev = nullptr;  // [nlanes*2 + 2]
+  // aux cell map (explicit maps: vilf_knn5, vilf_bench_stage, state import staging)
+  float4* aux_cm_pts[2] = {nullptr, nullptr}; uint2* aux_ctab = nullptr; uint32_t* aux_corig = nullptr; int* aux_cmeta = nullptr;
+  CellBuildJob* aux_build_dev = nullptr; SortJob* aux_build_sort_dev = nullptr; CellBuildJob aux_build_host;
+  MergeJob* aux_merge_dev = nullptr; SortJob* aux_merge_sort_dev = nullptr; MergeJob aux_merge_host; int aux_max_tiles = 0;
+  int aux_hcap = 0;
   int cap_aux = 0;
   float4* aux_in = nullptr; float4* aux_out = nullptr;
   int* aux_n = nullptr;      // [4] n_in, n_out, nq, spare
@@ -156,6 +169,35 @@ void grid_geometry(const Ctx* C, double leaf, GridJob& G) {
   G.rings = rings;
 }
 
+// Search cells of a cell-ordered map: cubes of 2^shift voxels of the map's own voxel filter.  Start from the smallest power of
+// two whose cube edge covers the gate radius (one shell of 27 cells suffices); dense maps (>= 8 voxels per cell edge) get finer
+// cells and more shells with early exit, like grid_geometry above.
+CellGeom cell_geometry(const Ctx* C, double leaf) {
+  CellGeom g;
+  g.leaf = (float)leaf;
+  g.inv_leaf = 1.0f / (float)leaf;  // inverse_leaf_size_ = Array4f::Ones() / leaf_size_.array()
+  const double reach = std::sqrt(C->ucfg.knn_gate) * 1.001;
+  int shift = 0;
+  while ((double)(1 << shift) * (double)g.leaf < reach && shift < 12) ++shift;
+  int shells = 1;
+  while (shells < 4 && (1 << shift) >= 8) { --shift; shells *= 2; }
+  g.shift = shift; g.shells = shells;
+  return g;
+}
+
+int alloc_merge(Ctx* C, MergeJob& M, int cap_new, int cap_map_total) {
+  memset(&M, 0, sizeof(M));
+  M.cap_new = cap_new;
+  M.max_tiles = (cap_map_total + cap_new + MERGE_TILE - 1) / MERGE_TILE + 1;
+  CK(dalloc(C, &M.newpts, (size_t)cap_new));
+  CK(dalloc(C, &M.nsorted, (size_t)cap_new));
+  CK(dalloc(C, &M.nkey, (size_t)cap_new));
+  CK(dalloc(C, &M.part, (size_t)M.max_tiles + 2));
+  CK(dalloc(C, &M.agg, (size_t)M.max_tiles + 1));
+  CK(dalloc(C, &M.orphans, (size_t)ORPHAN_CAP));
+  return VILF_OK;
+}
+
 int alloc_grid(Ctx* C, GridJob& G, const float4* pts, const int* n, int cap, double leaf) {
   G.pts = pts; G.n = n;
   grid_geometry(C, leaf, G);
@@ -223,6 +265,16 @@ int build_ctx(Ctx* C) {
   c.flags_no_cluster = (u.flags & VILF_FLAG_NO_CLUSTER) ? 1 : 0;
   C->cluster_scan = allow_cluster && capS <= CLUSTER_MAX_POINTS;
   C->cluster_map = allow_cluster && capM <= CLUSTER_MAX_POINTS;
+  C->cellmap = !(u.flags & VILF_FLAG_LEGACY_MAP);
+  c.cg[0] = cell_geometry(C, u.edge_leaf);
+  c.cg[1] = cell_geometry(C, u.surf_leaf);
+  CK(init_cellmap_kernels());
+  const int capN = capS + ORPHAN_CAP;  // new points of one update
+  int hcapM = 1024;
+  while (hcapM < 2 * (capM + capN)) hcapM <<= 1;
+  CK(dalloc(C, &C->mv_dev, (size_t)NL * 2 + 2));
+  for (int b = 0; b < 2; ++b) { C->merge_host[b].resize(NL * 2); C->build_host[b].resize(NL * 2); }
+  std::vector<SortJob> merge_sort(NL * 2), build_sort(NL * 2);
   C->lanes_host.resize(NL);
   std::vector<SortJob> ring_jobs[2] = {std::vector<SortJob>(NL), std::vector<SortJob>(NL)};
   std::vector<VoxJob> vox_scan(NL * 2), vox_map[2] = {std::vector<VoxJob>(NL * 2), std::vector<VoxJob>(NL * 2)};
@@ -295,14 +347,48 @@ int build_ctx(Ctx* C) {
       }
       vox_map_sort[l * 2 + w] = srt;
     }
-    for (int w = 0; w < 2; ++w) {
-      GridJob G0;
-      rc = alloc_grid(C, G0, L.map[w][0], &L.v->n_map[w], capM, w ? u.surf_leaf : u.edge_leaf);
-      if (rc) return rc;
-      grid[0][l * 2 + w] = G0;
-      GridJob G1 = G0;  // the two buffers are never indexed at the same time: share the grid storage
-      G1.pts = L.map[w][1];
-      grid[1][l * 2 + w] = G1;
+    if (!C->cellmap) {
+      for (int w = 0; w < 2; ++w) {
+        GridJob G0;
+        rc = alloc_grid(C, G0, L.map[w][0], &L.v->n_map[w], capM, w ? u.surf_leaf : u.edge_leaf);
+        if (rc) return rc;
+        grid[0][l * 2 + w] = G0;
+        GridJob G1 = G0;  // the two buffers are never indexed at the same time: share the grid storage
+        G1.pts = L.map[w][1];
+        grid[1][l * 2 + w] = G1;
+      }
+    } else {
+      for (int w = 0; w < 2; ++w) {
+        CK(dalloc(C, &L.ctab[w], (size_t)hcapM));
+        CK(dalloc(C, &L.corig[w], (size_t)capM));
+        CK(dalloc(C, &L.cmeta[w], 16));
+        MergeJob M;
+        rc = alloc_merge(C, M, capN, capM);
+        if (rc) return rc;
+        M.n_map = &L.v->n_map[w];
+        M.src = L.ds[w]; M.n_src = &L.v->n_ds[w]; M.pose = L.v->x;
+        M.crop_center = &L.v->x[4]; M.crop_half = c.crop_half;
+        M.mv = C->mv_dev + l * 2 + w;
+        M.table = L.ctab[w]; M.hcap = hcapM; M.meta = L.cmeta[w];
+        M.g = c.cg[w]; M.cap_out = c.cap_map; M.status = &L.v->status;
+        rc = alloc_sort(C, M.sort, &M.mv->n_in, &M.mv->bits, 0, 4, capN, false);
+        if (rc) return rc;
+        merge_sort[l * 2 + w] = M.sort;
+        C->max_tiles = M.max_tiles;
+        for (int b = 0; b < 2; ++b) {
+          MergeJob Mb = M;
+          Mb.old_pts = L.map[w][b]; Mb.out_pts = L.map[w][b ^ 1];
+          C->merge_host[b][l * 2 + w] = Mb;
+          CellBuildJob B;
+          memset(&B, 0, sizeof(B));
+          B.src = L.feat[w]; B.n = w ? &L.v->n_surf : &L.v->n_edge;
+          B.dst = L.map[w][b]; B.orig = L.corig[w]; B.table = L.ctab[w]; B.hcap = hcapM; B.meta = L.cmeta[w];
+          B.sort = vox_map_sort[l * 2 + w]; B.sort.n = B.n; B.sort.bits = B.meta + 8;
+          B.g = c.cg[w]; B.status = &L.v->status;
+          C->build_host[b][l * 2 + w] = B;
+        }
+        build_sort[l * 2 + w] = C->build_host[0][l * 2 + w].sort;
+      }
     }
     LaneVars& V = vars0[l];
     memset(&V, 0, sizeof(V));
@@ -327,11 +413,23 @@ int build_ctx(Ctx* C) {
     CK(cudaMemcpy(C->vox_map_sort_dev[b], vox_map_sort.data(), sizeof(SortJob) * NL * 2, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(C->grid_dev[b], grid[b].data(), sizeof(GridJob) * NL * 2, cudaMemcpyHostToDevice));
   }
+  if (C->cellmap) {
+    for (int b = 0; b < 2; ++b) {
+      CK(dalloc(C, &C->merge_dev[b], (size_t)NL * 2));
+      CK(cudaMemcpy(C->merge_dev[b], C->merge_host[b].data(), sizeof(MergeJob) * NL * 2, cudaMemcpyHostToDevice));
+      CK(dalloc(C, &C->build_dev[b], (size_t)NL * 2));
+      CK(cudaMemcpy(C->build_dev[b], C->build_host[b].data(), sizeof(CellBuildJob) * NL * 2, cudaMemcpyHostToDevice));
+    }
+    CK(dalloc(C, &C->merge_sort_dev, (size_t)NL * 2));
+    CK(cudaMemcpy(C->merge_sort_dev, merge_sort.data(), sizeof(SortJob) * NL * 2, cudaMemcpyHostToDevice));
+    CK(dalloc(C, &C->build_sort_dev, (size_t)NL * 2));
+    CK(cudaMemcpy(C->build_sort_dev, build_sort.data(), sizeof(SortJob) * NL * 2, cudaMemcpyHostToDevice));
+  }
   // aux
   C->cap_aux = capM;
   CK(dalloc(C, &C->aux_in, (size_t)capM));
   CK(dalloc(C, &C->aux_out, (size_t)capM));
-  CK(dalloc(C, &C->aux_n, 8));
+  CK(dalloc(C, &C->aux_n, 16));
   CK(dalloc(C, &C->aux_pose, 8));
   CK(dalloc(C, &C->aux_idx, (size_t)capM * 5));
   CK(dalloc(C, &C->aux_d2, (size_t)capM * 5));
@@ -352,6 +450,33 @@ int build_ctx(Ctx* C) {
     C->aux_grid_host = G;
     if (rc) return rc;
     CK(cudaMemcpy(C->aux_grid_dev, &G, sizeof(GridJob), cudaMemcpyHostToDevice));
+  }
+  if (C->cellmap) {
+    int hc = 1024;
+    while (hc < 4 * capM) hc <<= 1;
+    C->aux_hcap = hc;
+    for (int b = 0; b < 2; ++b) CK(dalloc(C, &C->aux_cm_pts[b], (size_t)capM));
+    CK(dalloc(C, &C->aux_ctab, (size_t)hc));
+    CK(dalloc(C, &C->aux_corig, (size_t)capM));
+    CK(dalloc(C, &C->aux_cmeta, 16));
+    CK(dalloc(C, &C->aux_build_dev, 1));
+    CK(dalloc(C, &C->aux_build_sort_dev, 1));
+    CK(dalloc(C, &C->aux_merge_dev, 1));
+    CK(dalloc(C, &C->aux_merge_sort_dev, 1));
+    CellBuildJob& B = C->aux_build_host;
+    memset(&B, 0, sizeof(B));
+    B.src = C->aux_in; B.n = C->aux_n; B.dst = C->aux_cm_pts[0]; B.orig = C->aux_corig; B.table = C->aux_ctab; B.hcap = hc; B.meta = C->aux_cmeta;
+    B.sort = C->aux_vox_host.sort; B.sort.n = B.n; B.sort.bits = B.meta + 8;
+    B.g = c.cg[u.edge_leaf < u.surf_leaf ? 0 : 1]; B.status = C->aux_n + 3;
+    MergeJob& M = C->aux_merge_host;
+    int rc = alloc_merge(C, M, capM, capM);
+    if (rc) return rc;
+    C->aux_max_tiles = M.max_tiles;
+    M.old_pts = C->aux_cm_pts[0]; M.out_pts = C->aux_cm_pts[1]; M.n_map = C->aux_n + 5;
+    M.src = C->aux_out; M.n_src = C->aux_n + 2; M.pose = nullptr; M.crop_center = nullptr; M.crop_half = 0;
+    M.mv = C->mv_dev + NL * 2;
+    M.table = C->aux_ctab; M.hcap = hc; M.meta = C->aux_cmeta; M.g = B.g; M.cap_out = capM; M.status = C->aux_n + 3;
+    M.sort = C->aux_vox_host.sort; M.sort.n = &M.mv->n_in; M.sort.bits = &M.mv->bits;
   }
   CK(dalloc(C, &C->depth_feat, (size_t)DEPTH_MAX_FEATURES * 3));
   CK(dalloc(C, &C->depth_out, (size_t)DEPTH_MAX_FEATURES));
@@ -385,13 +510,18 @@ int status_to_rc(Ctx* C, int status) {
   if (status & ST_SECTOR_TOO_LONG) return fail(C, VILF_ERR_UNSUPPORTED, "a ring has more returns than the sector kernel supports (6*2048+10)");
   if (status & ST_MAP_CAPACITY) return fail(C, VILF_ERR_CAPACITY, "local map exceeds max_map_points");
   if (status & ST_SCAN_CAPACITY) return fail(C, VILF_ERR_CAPACITY, "scan exceeds max_scan_points");
+  if (status & ST_KEY_RANGE) return fail(C, VILF_ERR_UNSUPPORTED, "cloud spans more than 2^32 (cell, voxel) keys at this leaf size; use VILF_FLAG_LEGACY_MAP");
+  if (status & ST_PCL_GUARD) return fail(C, VILF_ERR_UNSUPPORTED, "leaf size too small for the cropped map (PCL's int32 guard would skip the voxel filter); use VILF_FLAG_LEGACY_MAP");
+  if (status & ST_ORPHANS) return fail(C, VILF_ERR_CAPACITY, "more than 256 voxel centroids crossed a voxel face in one map update");
   return VILF_OK;
 }
 
 // createSubMap (EM:298-352) for lanes [lane0, lane0+nl): append the voxel-filtered scan features at the current pose,
 // crop + voxel-filter both maps into the other buffer, rebuild the search grids, flip the buffers.
 void issue_submap(Ctx* C, const Launch& L, int lane0, int nl, int cur, ProfSink* sink) {
-  if (C->cluster_map) {
+  if (C->cellmap) {
+    launch_cell_update(L, C->merge_dev[cur] + lane0 * 2, C->merge_sort_dev + lane0 * 2, nl * 2, C->max_tiles);
+  } else if (C->cluster_map) {
     launch_voxel_cluster(L, C->vox_map_dev[cur] + lane0 * 2, nl * 2, false, C->cfg);
   } else {
     launch_map_append(L, C->lanes_dev, lane0, nl, cur, C->cfg);
@@ -468,7 +598,12 @@ void issue_frame(Ctx* C, int lane0, int nl, bool first, bool with_extract, int s
   phase(0);
   launch_frame_reset(L, C->lanes_dev, lane0, nl, C->vv_dev, VV_PER_LANE, first ? 0 : 1);
   if (with_extract) launch_extract(L, C->lanes_dev, C->ring_jobs_dev[sel], lane0, nl, sel, cfg);
-  if (first) {
+  if (first && C->cellmap) {
+    phase(4);
+    launch_cell_build(L, C->build_dev[cur] + lane0 * 2, C->build_sort_dev + lane0 * 2, nl * 2);
+    phase(3);
+    launch_map_init_commit(L, C->lanes_dev, lane0, nl, cfg);
+  } else if (first) {
     phase(3);
     launch_map_init(L, C->lanes_dev, lane0, nl, cur, cfg);
     phase(4);
@@ -479,7 +614,8 @@ void issue_frame(Ctx* C, int lane0, int nl, bool first, bool with_extract, int s
     else launch_voxel(L, C->vox_scan_dev + lane0 * 2, nl * 2, C->vox_scan_sort_dev + lane0 * 2, with_extract);
     phase(2);
     for (int it = 0; it < cfg.outer_iters; ++it) {
-      launch_knn_fit(L, C->lanes_dev, C->grid_dev[cur], lane0, nl, cur, cfg, nullptr);
+      if (C->cellmap) launch_knn_cell_fit(L, C->lanes_dev, lane0, nl, cur, cfg, nullptr);
+      else launch_knn_fit(L, C->lanes_dev, C->grid_dev[cur], lane0, nl, cur, cfg, nullptr);
       launch_solve(L, C->lanes_dev, lane0, nl, it, it == cfg.outer_iters - 1 ? 1 : 0, cfg, cfg.lm_max_iters);
     }
     phase(3);
@@ -564,6 +700,68 @@ int wait_common(Ctx* C, int lane0, int nl, int64_t ticket, double* poses) {
     status |= S.vars_pin[i].status;
   }
   return status_to_rc(C, status);
+}
+
+int host_sort_passes(int bits) { int p = (bits + SORT_RADIX_BITS - 1) / SORT_RADIX_BITS; return p < 1 ? 1 : (p > 4 ? 4 : p); }
+
+// Cell-ordered map `w` of a lane -> the reference's map order (ascending PCL voxel index, or the input order of a map that was
+// never filtered) in aux_out on the device; optionally the PCL index of every stored point.  Off the per-frame path
+// (vilf_get_cloud, vilf_factors).
+int map_to_pcl(Ctx* C, int lane, int w, int* n_out, std::vector<int32_t>* rank) {
+  LaneDev& L = C->lanes_host[lane];
+  const int cur = C->cur[lane];
+  LaneVars V;
+  int rc = read_vars(C, lane, &V);
+  if (rc) return rc;
+  const int n = V.n_map[w];
+  *n_out = n;
+  if (n > C->cap_aux) return fail(C, VILF_ERR_CAPACITY, "map exceeds the staging capacity");
+  if (rank) rank->assign((size_t)(n > 0 ? n : 1), -1);
+  if (n == 0) return VILF_OK;
+  int meta[2];
+  CK(cudaMemcpy(meta, L.cmeta[w], sizeof(meta), cudaMemcpyDeviceToHost));
+  if (meta[1]) {  // never filtered since it was loaded: the original positions are stored
+    launch_cell_unpermute(mk(C), L.map[w][cur], L.corig[w], &L.v->n_map[w], C->aux_out, C->cap_aux);
+    CK(cudaGetLastError());
+    if (rank) CK(cudaMemcpyAsync(rank->data(), L.corig[w], (size_t)n * 4, cudaMemcpyDeviceToHost, C->st));
+    CK(cudaStreamSynchronize(C->st));
+    return VILF_OK;
+  }
+  // a filtered map: PCL's output order is ascending voxel index -> stable sort by PCL's own index, every point emitted
+  VoxJob J = C->aux_vox_host;
+  J.in = L.map[w][cur]; J.n_in = &L.v->n_map[w];
+  J.leaf = w ? C->cfg.surf_leaf : C->cfg.edge_leaf;
+  J.crop = 0; J.passthrough = 0; J.emit_all = 1; J.sort.n = J.n_in;
+  CK(cudaMemcpyAsync(C->aux_vox_dev, &J, sizeof(J), cudaMemcpyHostToDevice, C->st));
+  CK(cudaMemcpyAsync(C->aux_sort_dev, &J.sort, sizeof(SortJob), cudaMemcpyHostToDevice, C->st));
+  VoxVars vv;
+  memset(&vv, 0, sizeof(vv));
+  vv.bbox[0] = vv.bbox[1] = vv.bbox[2] = INT_MAX;
+  vv.bbox[3] = vv.bbox[4] = vv.bbox[5] = INT_MIN;
+  CK(cudaMemcpyAsync(J.vv, &vv, sizeof(vv), cudaMemcpyHostToDevice, C->st));
+  CK(cudaStreamSynchronize(C->st));
+  launch_voxel(mk(C), C->aux_vox_dev, 1, C->aux_sort_dev, false);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(&vv, J.vv, sizeof(vv), cudaMemcpyDeviceToHost, C->st));
+  CK(cudaMemcpyAsync(C->aux_sort_dev, &C->aux_vox_host.sort, sizeof(SortJob), cudaMemcpyHostToDevice, C->st));
+  CK(cudaStreamSynchronize(C->st));
+  if (vv.guard) return fail(C, VILF_ERR_UNSUPPORTED, "PCL's int32 voxel-index guard fires on this map; its order is undefined");
+  if (rank) {
+    std::vector<uint32_t> val((size_t)n);
+    CK(cudaMemcpy(val.data(), J.sort.val[host_sort_passes(vv.bits) & 1], (size_t)n * 4, cudaMemcpyDeviceToHost));
+    for (int r = 0; r < n; ++r) (*rank)[val[r]] = r;
+  }
+  return VILF_OK;
+}
+
+// Arbitrary cloud already staged in aux_in / aux_n[0] -> cell-ordered map described by B.
+int run_cell_build(Ctx* C, const CellBuildJob& B) {
+  CK(cudaMemcpyAsync(C->aux_build_dev, &B, sizeof(B), cudaMemcpyHostToDevice, C->st));
+  CK(cudaMemcpyAsync(C->aux_build_sort_dev, &B.sort, sizeof(SortJob), cudaMemcpyHostToDevice, C->st));
+  CK(cudaStreamSynchronize(C->st));  // B lives on the caller's stack
+  launch_cell_build(mk(C), C->aux_build_dev, C->aux_build_sort_dev, 1);
+  CK(cudaGetLastError());
+  return VILF_OK;
 }
 
 int upload_features(Ctx* C, int lane, const float* edge, int ne, const float* surf, int ns) {
@@ -871,8 +1069,13 @@ int vilf_get_features(vilf_handle* h, int which, float* pts, int32_t* src, int c
 
 static int map_init_impl(Ctx* C, int lane) {
   const Launch L = mk(C);
-  launch_map_init(L, C->lanes_dev, lane, 1, C->cur[lane], C->cfg);
-  build_grids(C, L, C->grid_dev[C->cur[lane]] + lane * 2, 2, C->cluster_map);
+  if (C->cellmap) {
+    launch_cell_build(L, C->build_dev[C->cur[lane]] + lane * 2, C->build_sort_dev + lane * 2, 2);
+    launch_map_init_commit(L, C->lanes_dev, lane, 1, C->cfg);
+  } else {
+    launch_map_init(L, C->lanes_dev, lane, 1, C->cur[lane], C->cfg);
+    build_grids(C, L, C->grid_dev[C->cur[lane]] + lane * 2, 2, C->cluster_map);
+  }
   CK(cudaGetLastError());
   C->have_map[lane] = 1; C->last_init[lane] = 1;
   return finish_sync(C, lane, nullptr);
@@ -988,7 +1191,15 @@ int vilf_get_cloud(vilf_handle* h, int which, float* out, int cap, int* n) {
   const int cur = C->cur[h->lane];
   const float4* part[2] = {nullptr, nullptr};
   int cnt[2] = {0, 0};
-  if (which <= 1) { part[0] = L.map[which][cur]; cnt[0] = V.n_map[which]; }
+  if (which <= 1 && C->cellmap) {  // stored in cell order: hand it out in the reference's order
+    rc = map_to_pcl(C, h->lane, which, &cnt[0], nullptr);
+    if (rc) return rc;
+    part[0] = C->aux_out;
+  } else if (which == 4 && C->cellmap && !C->last_init[h->lane]) {  // EM:315, :323: the transformed features, behind the orphans
+    MergeVars mv[2];
+    CK(cudaMemcpy(mv, C->mv_dev + h->lane * 2, sizeof(mv), cudaMemcpyDeviceToHost));
+    for (int w = 0; w < 2; ++w) { part[w] = C->merge_host[0][h->lane * 2 + w].newpts + mv[w].n_orph_in; cnt[w] = mv[w].n_in - mv[w].n_orph_in; }
+  } else if (which <= 1) { part[0] = L.map[which][cur]; cnt[0] = V.n_map[which]; }
   else if (which <= 3) { part[0] = L.ds[which - 2]; cnt[0] = V.n_ds[which - 2]; }
   else if (C->last_init[h->lane]) {  // EM:110-114
     part[0] = L.feat[0]; cnt[0] = V.n_edge; part[1] = L.feat[1]; cnt[1] = V.n_surf;
@@ -1032,8 +1243,19 @@ int vilf_knn5(vilf_handle* h, const float* map, int m, const float* q, int nq, i
   CK(cudaMemcpyAsync(C->aux_n, hdr, sizeof(hdr), cudaMemcpyHostToDevice, C->st));
   CK(cudaStreamSynchronize(C->st));
   const Launch L = mk(C);
-  build_grids(C, L, C->aux_grid_dev, 1, !(C->ucfg.flags & VILF_FLAG_NO_CLUSTER) && m <= CLUSTER_MAX_POINTS);
-  launch_knn_only(L, C->aux_grid_dev, C->aux_out, C->aux_n + 2, C->aux_idx, C->aux_d2, C->cfg);
+  if (C->cellmap) {
+    int rc = run_cell_build(C, C->aux_build_host);
+    if (rc) return rc;
+    launch_knn_cell_only(L, C->aux_cm_pts[0], C->aux_n, C->aux_ctab, C->aux_cmeta, C->aux_corig, C->aux_build_host.g, C->aux_out, C->aux_n + 2, C->aux_idx,
+                         C->aux_d2, C->cfg);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(hdr, C->aux_n, sizeof(hdr), cudaMemcpyDeviceToHost, C->st));
+    CK(cudaStreamSynchronize(C->st));
+    if (hdr[3]) return status_to_rc(C, hdr[3]);
+  } else {
+    build_grids(C, L, C->aux_grid_dev, 1, !(C->ucfg.flags & VILF_FLAG_NO_CLUSTER) && m <= CLUSTER_MAX_POINTS);
+    launch_knn_only(L, C->aux_grid_dev, C->aux_out, C->aux_n + 2, C->aux_idx, C->aux_d2, C->cfg);
+  }
   CK(cudaGetLastError());
   if (nq) {
     CK(cudaMemcpyAsync(idx, C->aux_idx, (size_t)nq * 5 * 4, cudaMemcpyDeviceToHost, C->st));
@@ -1046,18 +1268,39 @@ int vilf_knn5(vilf_handle* h, const float* map, int m, const float* q, int nq, i
 int vilf_bench_stage(vilf_handle* h, int stage, const float* map, int m, const float* q, int nq, float leaf, int iters, double ms_out[4]) {
   HCHECK(h);
   CK(cudaSetDevice(C->device));
-  if (!map || m < 1 || iters < 1 || !ms_out || (stage != 0 && stage != 1) || (stage == 0 && (!q || nq < 1)) || (stage == 1 && !(leaf > 0)))
+  if (!map || m < 1 || iters < 1 || !ms_out || stage < 0 || stage > 2 || (stage != 1 && (!q || nq < 1)) || (stage >= 1 && !(leaf > 0)))
     return fail(C, VILF_ERR_INVALID, "bad arguments");
-  if (m > C->cap_aux || nq > C->cap_aux) return fail(C, VILF_ERR_CAPACITY, "map or query set exceeds capacity");
+  if (m > C->cap_aux || nq > C->cap_aux || (stage == 2 && m + nq > C->cap_aux)) return fail(C, VILF_ERR_CAPACITY, "map or query set exceeds capacity");
   const bool small = !(C->ucfg.flags & VILF_FLAG_NO_CLUSTER) && m <= CLUSTER_MAX_POINTS;
   cudaEvent_t ev[3];
   for (int i = 0; i < 3; ++i) CK(cudaEventCreate(&ev[i]));
   CK(cudaMemcpyAsync(C->aux_in, map, (size_t)m * 16, cudaMemcpyHostToDevice, C->st));
-  int hdr[4] = {m, 0, nq, 0};
+  int hdr[8] = {m, 0, nq, 0, 0, 0, 0, 0};
   CK(cudaMemcpyAsync(C->aux_n, hdr, sizeof(hdr), cudaMemcpyHostToDevice, C->st));
   double acc[2] = {0, 0};
   const Launch L = mk(C);
-  if (stage == 0) {
+  if (stage == 0 && C->cellmap) {
+    CellBuildJob B = C->aux_build_host;
+    if (leaf > 0) B.g = cell_geometry(C, (double)leaf);  // search cells sized for a map filtered at `leaf`
+    CK(cudaMemcpyAsync(C->aux_build_dev, &B, sizeof(B), cudaMemcpyHostToDevice, C->st));
+    CK(cudaMemcpyAsync(C->aux_build_sort_dev, &B.sort, sizeof(SortJob), cudaMemcpyHostToDevice, C->st));
+    CK(cudaMemcpyAsync(C->aux_out, q, (size_t)nq * 16, cudaMemcpyHostToDevice, C->st));
+    CK(cudaStreamSynchronize(C->st));
+    for (int it = -1; it < iters; ++it) {  // iteration -1 warms up
+      CK(cudaEventRecord(ev[0], C->st));
+      launch_cell_build(L, C->aux_build_dev, C->aux_build_sort_dev, 1);
+      CK(cudaEventRecord(ev[1], C->st));
+      launch_knn_cell_only(L, C->aux_cm_pts[0], C->aux_n, C->aux_ctab, C->aux_cmeta, C->aux_corig, B.g, C->aux_out, C->aux_n + 2, C->aux_idx, C->aux_d2, C->cfg);
+      CK(cudaEventRecord(ev[2], C->st));
+      CK(cudaStreamSynchronize(C->st));
+      CK(cudaGetLastError());
+      float a = 0, b = 0;
+      CK(cudaEventElapsedTime(&a, ev[0], ev[1]));
+      CK(cudaEventElapsedTime(&b, ev[1], ev[2]));
+      if (it >= 0) { acc[0] += a; acc[1] += b; }
+    }
+    ms_out[0] = acc[0] / iters; ms_out[1] = acc[1] / iters; ms_out[2] = (double)B.g.shells; ms_out[3] = (double)B.g.leaf * (double)(1 << B.g.shift);
+  } else if (stage == 0) {
     GridJob Gb = C->aux_grid_host;
     if (leaf > 0) grid_geometry(C, (double)leaf, Gb);  // search-grid cell sized for a map filtered at `leaf`
     CK(cudaMemcpyAsync(C->aux_grid_dev, &Gb, sizeof(Gb), cudaMemcpyHostToDevice, C->st));
@@ -1078,7 +1321,9 @@ int vilf_bench_stage(vilf_handle* h, int stage, const float* map, int m, const f
     }
     ms_out[0] = acc[0] / iters; ms_out[1] = acc[1] / iters; ms_out[2] = (double)Gb.rings; ms_out[3] = 1.0 / (double)Gb.inv_cell;
     CK(cudaMemcpy(C->aux_grid_dev, &C->aux_grid_host, sizeof(GridJob), cudaMemcpyHostToDevice));
-  } else {
+  } else if (stage == 1 || !C->cellmap) {
+    // stage 1: crop box + voxel filter of an UNSORTED cloud (radix path).  Legacy stage 2: the per-frame map maintenance of the
+    // radix path = the same filter over [voxel-filtered map ..., nq appended points].
     VoxJob J = C->aux_vox_host;
     J.leaf = leaf; J.crop = 2; J.passthrough = 0;
     for (int a = 0; a < 3; ++a) { J.crop_lo[a] = -100.0f; J.crop_hi[a] = 100.0f; }  // EM:327-336 about the origin
@@ -1087,14 +1332,29 @@ int vilf_bench_stage(vilf_handle* h, int stage, const float* map, int m, const f
     memset(&vv, 0, sizeof(vv));
     vv.bbox[0] = vv.bbox[1] = vv.bbox[2] = INT_MAX;
     vv.bbox[3] = vv.bbox[4] = vv.bbox[5] = INT_MIN;
-    int n_out = 0;
+    int n_out = 0, n_before = m;
+    if (stage == 2) {  // filter once (untimed), then time the filter of [filtered map, new points]
+      CK(cudaMemcpyAsync(J.vv, &vv, sizeof(vv), cudaMemcpyHostToDevice, C->st));
+      if (small) launch_voxel_cluster(L, C->aux_vox_dev, 1, false, C->cfg);
+      else launch_voxel(L, C->aux_vox_dev, 1, C->aux_sort_dev, false);
+      CK(cudaMemcpyAsync(hdr, C->aux_n, sizeof(hdr), cudaMemcpyDeviceToHost, C->st));
+      CK(cudaStreamSynchronize(C->st));
+      CK(cudaGetLastError());
+      n_before = hdr[1];
+      CK(cudaMemcpyAsync(C->aux_in, C->aux_out, (size_t)n_before * 16, cudaMemcpyDeviceToDevice, C->st));
+      CK(cudaMemcpyAsync(C->aux_in + n_before, q, (size_t)nq * 16, cudaMemcpyHostToDevice, C->st));
+      hdr[0] = n_before + nq; hdr[1] = 0;
+      CK(cudaMemcpyAsync(C->aux_n, hdr, 16, cudaMemcpyHostToDevice, C->st));
+      CK(cudaStreamSynchronize(C->st));
+    }
+    const bool small2 = !(C->ucfg.flags & VILF_FLAG_NO_CLUSTER) && hdr[0] <= CLUSTER_MAX_POINTS;
     for (int it = -1; it < iters; ++it) {
       CK(cudaMemcpyAsync(J.vv, &vv, sizeof(vv), cudaMemcpyHostToDevice, C->st));
       CK(cudaEventRecord(ev[0], C->st));
-      if (small) launch_voxel_cluster(L, C->aux_vox_dev, 1, false, C->cfg);
+      if (small2) launch_voxel_cluster(L, C->aux_vox_dev, 1, false, C->cfg);
       else launch_voxel(L, C->aux_vox_dev, 1, C->aux_sort_dev, false);
       CK(cudaEventRecord(ev[1], C->st));
-      CK(cudaMemcpyAsync(hdr, C->aux_n, sizeof(hdr), cudaMemcpyDeviceToHost, C->st));
+      CK(cudaMemcpyAsync(hdr, C->aux_n, 16, cudaMemcpyDeviceToHost, C->st));
       CK(cudaStreamSynchronize(C->st));
       CK(cudaGetLastError());
       float a = 0;
@@ -1102,7 +1362,54 @@ int vilf_bench_stage(vilf_handle* h, int stage, const float* map, int m, const f
       if (it >= 0) acc[0] += a;
       n_out = hdr[1];
     }
-    ms_out[0] = acc[0] / iters; ms_out[1] = 0; ms_out[2] = (double)n_out; ms_out[3] = 0;
+    ms_out[0] = acc[0] / iters; ms_out[1] = 0; ms_out[2] = stage == 2 ? (double)n_before : (double)n_out; ms_out[3] = (double)n_out;
+  } else {
+    // stage 2, cell-ordered map: what createSubMap costs per frame — a voxel-filtered map in cell order (built untimed from the
+    // cloud by one update of an empty map) merged with nq new points: crop box + voxel filter + cell table in one update.
+    MergeJob A = C->aux_merge_host;
+    A.g = cell_geometry(C, (double)leaf);
+    A.old_pts = C->aux_cm_pts[1]; A.out_pts = C->aux_cm_pts[0]; A.n_map = C->aux_n + 5;
+    A.src = C->aux_in; A.n_src = C->aux_n;
+    A.crop_center = C->aux_pose; A.crop_half = 100.0;  // EM:327-336 about the origin
+    double ctr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    CK(cudaMemcpyAsync(C->aux_pose, ctr, sizeof(ctr), cudaMemcpyHostToDevice, C->st));
+    MergeVars mz;
+    memset(&mz, 0, sizeof(mz));
+    CK(cudaMemcpyAsync(A.mv, &mz, sizeof(mz), cudaMemcpyHostToDevice, C->st));
+    CK(cudaMemcpyAsync(C->aux_merge_dev, &A, sizeof(A), cudaMemcpyHostToDevice, C->st));
+    CK(cudaMemcpyAsync(C->aux_merge_sort_dev, &A.sort, sizeof(SortJob), cudaMemcpyHostToDevice, C->st));
+    CK(cudaMemcpyAsync(C->aux_out, q, (size_t)nq * 16, cudaMemcpyHostToDevice, C->st));
+    CK(cudaStreamSynchronize(C->st));
+    CK(cudaEventRecord(ev[0], C->st));
+    launch_cell_update(L, C->aux_merge_dev, C->aux_merge_sort_dev, 1, C->aux_max_tiles);
+    CK(cudaEventRecord(ev[1], C->st));
+    CK(cudaMemcpyAsync(hdr, C->aux_n, sizeof(hdr), cudaMemcpyDeviceToHost, C->st));
+    CK(cudaStreamSynchronize(C->st));
+    CK(cudaGetLastError());
+    float prep = 0;
+    CK(cudaEventElapsedTime(&prep, ev[0], ev[1]));
+    const int n_before = hdr[5];
+    if (hdr[3]) { for (int i = 0; i < 3; ++i) cudaEventDestroy(ev[i]); return status_to_rc(C, hdr[3]); }
+    MergeJob Bj = A;
+    Bj.old_pts = C->aux_cm_pts[0]; Bj.out_pts = C->aux_cm_pts[1]; Bj.n_map = C->aux_n + 6;
+    Bj.src = C->aux_out; Bj.n_src = C->aux_n + 2;
+    CK(cudaMemcpyAsync(C->aux_merge_dev, &Bj, sizeof(Bj), cudaMemcpyHostToDevice, C->st));
+    CK(cudaStreamSynchronize(C->st));
+    int n_out = 0;
+    for (int it = -1; it < iters; ++it) {
+      CK(cudaMemcpyAsync(C->aux_n + 6, C->aux_n + 5, sizeof(int), cudaMemcpyDeviceToDevice, C->st));
+      CK(cudaEventRecord(ev[0], C->st));
+      launch_cell_update(L, C->aux_merge_dev, C->aux_merge_sort_dev, 1, C->aux_max_tiles);
+      CK(cudaEventRecord(ev[1], C->st));
+      CK(cudaMemcpyAsync(hdr, C->aux_n, sizeof(hdr), cudaMemcpyDeviceToHost, C->st));
+      CK(cudaStreamSynchronize(C->st));
+      CK(cudaGetLastError());
+      float a = 0;
+      CK(cudaEventElapsedTime(&a, ev[0], ev[1]));
+      if (it >= 0) acc[0] += a;
+      n_out = hdr[6];
+    }
+    ms_out[0] = acc[0] / iters; ms_out[1] = (double)prep; ms_out[2] = (double)n_before; ms_out[3] = (double)n_out;
   }
   for (int i = 0; i < 3; ++i) cudaEventDestroy(ev[i]);
   return VILF_OK;
@@ -1172,7 +1479,8 @@ int vilf_factors(vilf_handle* h, const double pose[7], const float* edge, int n_
   }
   CK(cudaMemsetAsync(L.edge_pab, 0, (size_t)(n_edge > 0 ? n_edge : 1) * 72, C->st));
   CK(cudaMemsetAsync(L.surf_pnd, 0, (size_t)(n_surf > 0 ? n_surf : 1) * 56, C->st));
-  launch_knn_fit(mk(C), C->lanes_dev, C->grid_dev[C->cur[lane]], lane, 1, C->cur[lane], C->cfg, C->aux_pose);
+  if (C->cellmap) launch_knn_cell_fit(mk(C), C->lanes_dev, lane, 1, C->cur[lane], C->cfg, C->aux_pose);
+  else launch_knn_fit(mk(C), C->lanes_dev, C->grid_dev[C->cur[lane]], lane, 1, C->cur[lane], C->cfg, C->aux_pose);
   CK(cudaGetLastError());
   std::vector<double> pab((size_t)(n_edge > 0 ? n_edge : 1) * 9), pnd((size_t)(n_surf > 0 ? n_surf : 1) * 7);
   if (n_edge) {
@@ -1189,6 +1497,19 @@ int vilf_factors(vilf_handle* h, const double pose[7], const float* edge, int n_
   }
   CK(cudaMemcpyAsync(C->vars_dev + lane, &V, sizeof(V), cudaMemcpyHostToDevice, C->st));  // restore counts
   CK(cudaStreamSynchronize(C->st));
+  if (C->cellmap) {  // neighbour indices refer to the cell-ordered storage: report them in the reference's map order
+    for (int w = 0; w < 2; ++w) {
+      int32_t* nn = w ? surf_nn : edge_nn;
+      const int n = w ? n_surf : n_edge;
+      if (!nn || !n) continue;
+      std::vector<int32_t> rank;
+      int nm = 0;
+      rc = map_to_pcl(C, lane, w, &nm, &rank);
+      if (rc) return rc;
+      for (size_t i = 0; i < (size_t)n * 5; ++i)
+        if (nn[i] >= 0 && nn[i] < nm) nn[i] = rank[nn[i]];
+    }
+  }
   if (edge_ab) for (int i = 0; i < n_edge; ++i) memcpy(edge_ab + (size_t)i * 6, pab.data() + (size_t)i * 9 + 3, 6 * sizeof(double));
   if (surf_nd) for (int i = 0; i < n_surf; ++i) memcpy(surf_nd + (size_t)i * 4, pnd.data() + (size_t)i * 7 + 3, 4 * sizeof(double));
   return VILF_OK;
@@ -1271,9 +1592,30 @@ int vilf_state_import(vilf_handle* h, const double s[31], const float* map_edge,
   V.n_map[0] = n_edge; V.n_map[1] = n_surf; V.status = 0;
   const int cur = C->cur[lane];
   CK(cudaMemcpyAsync(C->vars_dev + lane, &V, sizeof(V), cudaMemcpyHostToDevice, C->st));
-  if (n_edge) CK(cudaMemcpyAsync(L.map[0][cur], map_edge, (size_t)n_edge * 16, cudaMemcpyHostToDevice, C->st));
-  if (n_surf) CK(cudaMemcpyAsync(L.map[1][cur], map_surf, (size_t)n_surf * 16, cudaMemcpyHostToDevice, C->st));
-  build_grids(C, mk(C), C->grid_dev[cur] + lane * 2, 2, C->cluster_map);
+  if (C->cellmap) {
+    for (int w = 0; w < 2; ++w) {
+      const int n = w ? n_surf : n_edge;
+      const float* src = w ? map_surf : map_edge;
+      if (n > C->cap_aux) return fail(C, VILF_ERR_CAPACITY, "map exceeds capacity");
+      if (n) CK(cudaMemcpyAsync(C->aux_in, src, (size_t)n * 16, cudaMemcpyHostToDevice, C->st));
+      int hdr[4] = {n, 0, 0, 0};
+      CK(cudaMemcpyAsync(C->aux_n, hdr, sizeof(hdr), cudaMemcpyHostToDevice, C->st));
+      CellBuildJob B = C->build_host[cur][lane * 2 + w];
+      B.src = C->aux_in; B.n = C->aux_n; B.sort.n = C->aux_n; B.status = C->aux_n + 3;
+      rc = run_cell_build(C, B);
+      if (rc) return rc;
+      CK(cudaMemcpyAsync(hdr, C->aux_n, sizeof(hdr), cudaMemcpyDeviceToHost, C->st));
+      CK(cudaStreamSynchronize(C->st));
+      if (hdr[3]) return status_to_rc(C, hdr[3]);
+    }
+    MergeVars mz[2];
+    memset(mz, 0, sizeof(mz));
+    CK(cudaMemcpyAsync(C->mv_dev + lane * 2, mz, sizeof(mz), cudaMemcpyHostToDevice, C->st));  // no orphans carried over
+  } else {
+    if (n_edge) CK(cudaMemcpyAsync(L.map[0][cur], map_edge, (size_t)n_edge * 16, cudaMemcpyHostToDevice, C->st));
+    if (n_surf) CK(cudaMemcpyAsync(L.map[1][cur], map_surf, (size_t)n_surf * 16, cudaMemcpyHostToDevice, C->st));
+    build_grids(C, mk(C), C->grid_dev[cur] + lane * 2, 2, C->cluster_map);
+  }
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(C->st));
   C->have_map[lane] = 1;
@@ -1317,7 +1659,8 @@ const char* vilf_profile_kernel_name(int kernel) {
   static const char* names[K_COUNT] = {"k_frame_reset", "k_sort_keyhist<KeyGenRing>", "k_sort_hist", "k_sort_scatter", "k_sector_select", "k_compact_features",
                                        "k_vox_bbox", "k_sort_keyhist<KeyGenVoxel>", "k_vox_heads", "k_vox_centroid", "k_map_append", "k_map_init",
                                        "k_grid_zero", "k_grid_count", "k_grid_scan_partial", "k_grid_scan_final", "k_grid_scatter", "k_knn_assoc",
-                                       "k_knn_only", "k_solve", "k_fit", "k_voxel_cluster", "k_grid_cluster", "k_depth_cloud", "k_depth_query", "k_ring_partition"};
+                                       "k_knn_only", "k_solve", "k_fit", "k_voxel_cluster", "k_grid_cluster", "k_depth_cloud", "k_depth_query", "k_ring_partition",
+                                       "k_new_xform", "k_sort_keyhist<KeyGenNew>", "k_merge_partition", "k_merge<count>", "k_merge<emit>", "k_cell_build", "k_knn_cell_assoc"};
   return (kernel >= 0 && kernel < K_COUNT) ? names[kernel] : "";
 }
 int vilf_launch_count(vilf_handle* h, int64_t* launches) {

@@ -44,6 +44,14 @@ constexpr int ST_KEY_RANGE = 8;     // cell-ordered map: the cloud spans more th
 constexpr int ST_PCL_GUARD = 16;    // cell-ordered map: PCL's int32 guard would skip the voxel filter (legacy path handles it)
 constexpr int ST_ORPHANS = 32;      // more than ORPHAN_CAP centroids crossed a voxel face in one update
 
+// geometry of a cell-ordered map (k_cellmap.cu)
+struct CellGeom {
+  float inv_leaf;  // PCL's inverse_leaf_size_ = 1.0f / leaf
+  float leaf;
+  int shift;       // log2(voxels per cell edge)
+  int shells;      // cells of Chebyshev distance <= shells around the query cell cover the gate radius
+};
+
 struct ConfigDev {
   int n_scan, n_rings, rings_total;
   double lidar_min, lidar_max, edge_threshold, knn_gate, huber, crop_half;
@@ -115,6 +123,7 @@ struct VoxJob {
   int crop;                 // 0 none; 1 box = crop_center +- crop_half (EM:327-336); 2 explicit fp32 bounds
   float crop_lo[3], crop_hi[3];
   int passthrough;          // 1: no voxel filter, output = (cropped) input in order
+  int emit_all;             // 1: sort by voxel index but emit EVERY point (cell-ordered map -> PCL order, grid-wide path only)
   const double* crop_center;  // 3 doubles on the device (pose translation)
   double crop_half;
   float4* out;
@@ -156,12 +165,6 @@ constexpr int MERGE_TILE = 2048;     // merged elements per CTA tile of the map 
 constexpr int MERGE_THREADS = 512;
 constexpr int ORPHAN_CAP = 256;      // centroids that rounded across a voxel face, re-inserted with the next frame's points
 constexpr int VOX_BIAS = 1 << 20;    // voxel coordinates are biased into 21 unsigned bits per axis
-struct CellGeom {
-  float inv_leaf;  // PCL's inverse_leaf_size_ = 1.0f / leaf
-  float leaf;
-  int shift;       // log2(voxels per cell edge)
-  int shells;      // cells of Chebyshev distance <= shells around the query cell cover the gate radius
-};
 struct MergeVars {
   int n_in;        // orphans + voxel-filtered scan features = size of the new-point sort job
   int n_orph_in;   // orphans at the head of newpts (the registered cloud starts behind them)
@@ -347,6 +350,7 @@ void launch_extract(const Launch& L, LaneDev* lanes, const SortJob* ring_jobs, i
 void launch_voxel(const Launch& L, const VoxJob* jobs_dev, int njobs, const SortJob* sort_jobs_dev, bool bbox_done);
 void launch_map_append(const Launch& L, LaneDev* lanes, int lane0, int nlanes, int cur, const ConfigDev& cfg);
 void launch_map_init(const Launch& L, LaneDev* lanes, int lane0, int nlanes, int cur, const ConfigDev& cfg);
+void launch_map_init_commit(const Launch& L, LaneDev* lanes, int lane0, int nlanes, const ConfigDev& cfg);
 // k_cluster.cu
 constexpr int CLUSTER_MAX_POINTS = 1 << 19;  // clouds up to this size take the one-cluster-per-cloud path
 void launch_voxel_cluster(const Launch& L, const VoxJob* jobs_dev, int njobs, bool bbox_done, const ConfigDev& cfg);
