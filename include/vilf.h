@@ -63,8 +63,15 @@ typedef struct vilf_config {
 /* Implementation-selection flags (results are bit-identical either way; used by the parity tests and for profiling). */
 #define VILF_FLAG_NO_CLUSTER 1 /* never take the one-cluster-per-cloud kernels; always the grid-wide multi-launch path */
 #define VILF_FLAG_NO_GRAPH 2   /* launch every kernel of a frame individually instead of replaying the captured CUDA graph */
-#define VILF_FLAG_LEGACY_MAP 4 /* round-1 map path: radix-sorted voxel filter of the whole map + hashed search grid rebuilt every frame,
-                                 instead of the cell-ordered map (merge update + cell table) */
+/* Map storage.  Two implementations of the local maps give identical results:
+ *  - cell-ordered maps (k_cellmap.cu): the map stays sorted by (search cell, voxel); createSubMap is a merge of the sorted
+ *    map with the frame's few thousand new points, the search table comes out of the same pass, the 5-NN search runs one
+ *    warp per query.  Cost grows with the new points, not with the map: the path for large maps.
+ *  - radix-sorted maps (k_cluster.cu / k_voxel.cu + k_knn.cu): the whole map is voxel-filtered by a radix sort every frame
+ *    and a hashed grid is rebuilt; one 8-CTA cluster per cloud.  Faster while a map fits one cluster (<= 2^19 points).
+ * Default: cell-ordered when max_map_points + max_scan_points > 2^19, radix-sorted otherwise; the flags force one. */
+#define VILF_FLAG_LEGACY_MAP 4 /* force the radix-sorted maps */
+#define VILF_FLAG_CELL_MAP 8   /* force the cell-ordered maps */
 
 int vilf_default_config(vilf_config* cfg);
 
@@ -196,8 +203,8 @@ int vilf_state_import(vilf_handle* h, const double state31[31], const float* map
  * Profiling adds event records between stages; enable only for roofline runs. */
 int vilf_profile_enable(vilf_handle* h, int on);
 int vilf_profile_read(vilf_handle* h, double ms_out[7], int64_t* frames, int reset);
-/* Per-kernel view of the same events: tag = phase * 32 + kernel, phase 0 extract, 1 scan downsample,
- * 2 association + solve, 3 map update, 4 grid build; n_tags must be 160.  An interval runs from the end of the
+/* Per-kernel view of the same events: tag = phase * 64 + kernel, phase 0 extract, 1 scan downsample,
+ * 2 association + solve, 3 map update, 4 grid build; n_tags must be 320.  An interval runs from the end of the
  * previous kernel to the end of this one, i.e. it includes the launch gap. */
 int vilf_profile_read_kernels(vilf_handle* h, double* ms_out, int64_t* launches_out, int n_tags, int reset);
 const char* vilf_profile_kernel_name(int kernel);

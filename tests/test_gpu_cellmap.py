@@ -1,7 +1,8 @@
-"""The cell-ordered map path (k_cellmap.cu: merge update + cell table + warp-per-query 5-NN, the default) against the round-1
-path (VILF_FLAG_LEGACY_MAP: radix-sorted voxel filter of the whole map + hashed grid rebuilt every frame), bit for bit.
-The legacy path is itself held to the oracle by the other test files; every other GPU test runs the cell-ordered path against
-the oracle directly."""
+"""The cell-ordered map path (k_cellmap.cu: merge update + cell table + warp-per-query 5-NN; the default for maps beyond one
+cluster's 2^19 points, forced here with VILF_FLAG_CELL_MAP) against the radix-sorted path (VILF_FLAG_LEGACY_MAP: voxel filter
+of the whole map + hashed grid rebuilt every frame), bit for bit, and against the oracle.  The dense configs[2] sequence
+(tests/test_gpu_sequence.py) runs the cell-ordered path by default; test_cell_map_long_sequences_vs_oracle below holds it to the
+oracle on the standard sequences as well."""
 import numpy as np
 import pytest
 
@@ -13,7 +14,7 @@ ALL_CLOUDS = (0, 1, 2, 3, 4, 5)
 
 
 def pair(cabi, **kw):
-    return cabi.Odometry(cabi.default_config(**kw)), cabi.Odometry(cabi.default_config(flags=cabi.FLAG_LEGACY_MAP, **kw))
+    return cabi.Odometry(cabi.default_config(flags=cabi.FLAG_CELL_MAP, **kw)), cabi.Odometry(cabi.default_config(flags=cabi.FLAG_LEGACY_MAP, **kw))
 
 
 @pytest.mark.parametrize("sensor,kw,frames", [
@@ -76,7 +77,7 @@ def test_map_update_edge_cases(cabi, orc):
     """createSubMap through the merge: nothing new, everything new, everything cropped away, many points per voxel on both
     sides, points exactly on voxel faces; maps compared with the oracle's crop box + voxel filter of the concatenation."""
     rng = np.random.default_rng(4)
-    g = cabi.Odometry(cabi.default_config(max_scan_points=60000, max_map_points=1 << 17))
+    g = cabi.Odometry(cabi.default_config(max_scan_points=60000, max_map_points=1 << 17, flags=cabi.FLAG_CELL_MAP))
 
     def cloud(n, lo, hi, snap=None):
         c = np.zeros((n, 4), np.float32)
@@ -131,11 +132,33 @@ def test_pcl_guard_is_reported(cabi):
     """A leaf so small that PCL's int32 voxel-index guard would skip the filter is refused loudly by the cell-ordered path
     (the legacy path reproduces PCL's pass-through)."""
     rng = np.random.default_rng(1)
-    g = cabi.Odometry(cabi.default_config(edge_leaf=0.01, surf_leaf=0.01, max_scan_points=4096, max_map_points=1 << 14))
+    g = cabi.Odometry(cabi.default_config(edge_leaf=0.01, surf_leaf=0.01, max_scan_points=4096, max_map_points=1 << 14, flags=cabi.FLAG_CELL_MAP))
     c = np.zeros((3000, 4), np.float32); c[:, :3] = rng.uniform(-90, 90, (3000, 3))
     with pytest.raises(cabi.VilfError) as e:
         g.map_init(c[:500], c)
         g.set_pose([0, 0, 0, 1, 0, 0, 0])
         g.create_submap(c[:100], c[:1000])
     assert e.value.code == 4
+    g.close()
+
+
+@pytest.mark.parametrize("sensor,n_scan,cap,frames", [("hdl64", 64, 116000, 300), ("vlp32", 32, 58000, 300)])
+def test_cell_map_long_sequences_vs_oracle(cabi, orc, synth, sensor, n_scan, cap, frames):
+    """Free-running against the CPU oracle with the cell-ordered maps forced on a standard-size sequence: every frame inside the
+    north-star tolerance, final maps within 1e-5 m, identical solver summaries."""
+    from conftest import pose_err
+    seq = synth.Sequence(sensor, frames, seed=23)
+    o = orc.Odometry(orc.config(n_scan=n_scan, n_rings=n_scan))
+    g = cabi.Odometry(cabi.default_config(n_scan=n_scan, n_rings=n_scan, max_scan_points=cap, max_map_points=1 << 18, max_ring_points=1864, flags=cabi.FLAG_CELL_MAP))
+    for i in range(frames):
+        x = np.ascontiguousarray(seq[i][0])
+        po, _, _ = o.process_scan(x)
+        pg = g.process_scan(x)
+        e = pose_err(po, pg)
+        assert e[0] <= 1e-4 and e[1] <= 1e-3, (i, e)
+    for which in (0, 1):
+        mo, mg = o.cloud(which), g.cloud(which)
+        assert mo.shape == mg.shape and np.abs(mo - mg).max() <= 1e-5
+    assert np.array_equal(o.solves()[:, :4], g.solves()[:, :4])
+    assert g.counts()["status"] == 0
     g.close()

@@ -83,6 +83,7 @@ def _p(a, t):
 FLAG_NO_CLUSTER = 1
 FLAG_NO_GRAPH = 2
 FLAG_LEGACY_MAP = 4
+FLAG_CELL_MAP = 8
 MAP_EDGE, MAP_SURF, DS_EDGE, DS_SURF, REGISTERED, NO_REGISTERED = range(6)
 
 
@@ -277,13 +278,13 @@ class Odometry:
 
     def profile_kernels(self, reset: bool = True):
         """{(phase, kernel name): (ms, launches)} accumulated since the last reset."""
-        ms = np.zeros(160); cnt = np.zeros(160, np.int64)
-        self._ck(lib().vilf_profile_read_kernels(self._h, _p(ms, C.c_double), _p(cnt, C.c_int64), 160, int(reset)))
+        ms = np.zeros(320); cnt = np.zeros(320, np.int64)
+        self._ck(lib().vilf_profile_read_kernels(self._h, _p(ms, C.c_double), _p(cnt, C.c_int64), 320, int(reset)))
         lib().vilf_profile_kernel_name.restype = C.c_char_p
         phases = ["extract", "scan_ds", "assoc_solve", "map_update", "grid_build"]
         out = {}
         for tag in np.nonzero(cnt)[0]:
-            out[(phases[tag // 32], lib().vilf_profile_kernel_name(int(tag % 32)).decode())] = (float(ms[tag]), int(cnt[tag]))
+            out[(phases[tag // 64], lib().vilf_profile_kernel_name(int(tag % 64)).decode())] = (float(ms[tag]), int(cnt[tag]))
         return out
 
     def launch_count(self) -> int:

@@ -7,10 +7,10 @@
 //
 // Update (k_new_xform .. k_merge<EMIT>).  The previous map is already in key order and voxel-filtered; a frame adds a few
 // thousand points.  So instead of re-sorting ~1e6 points (the radix path: 3-4 passes of 16 B per point plus a gather) only the
-// new points are sorted, and the map update is a MERGE: merge-path tiles of 2048 elements, each staged in shared memory once,
+// new points are sorted, and the map update is a MERGE: merge-path tiles of 1024 elements, each staged in shared memory once,
 // crop box applied on the fly, every voxel run summed sequentially in fp32 in PCL's order (old points first, then the new
-// ones, in input order), output = the other map buffer.  A counting pass sizes the tiles' outputs (no atomics, no look-back
-// spinning); the emitting pass writes points and the cell table.  Algorithmic bytes: 16 B read per old point + 16 B written
+// ones, in input order), output = the other map buffer.  A counting pass sizes the tiles' outputs, a one-CTA scan turns the
+// counts into offsets (no atomics, no look-back spinning), the emitting pass writes points and the cell table.  Algorithmic bytes: 16 B read per old point + 16 B written
 // per kept voxel; the second read of the old map comes from L2.
 //
 // Search (k_knn_cell*).  One WARP per query: lane l probes neighbour cell l of the 27 (open addressing, verified by the cell of
@@ -24,6 +24,7 @@
 // (vilf_get_cloud, vilf_factors) converts to PCL order on demand.
 #include "k_sort.cuh"
 #include "k_voxel.cuh"
+#include "k_cluster_sort.cuh"
 
 namespace vilf {
 
@@ -169,6 +170,7 @@ struct KeyGenCell {
 
 __global__ void __launch_bounds__(256) k_cb_gather(const CellBuildJob* __restrict__ jobs) {
   const CellBuildJob& J = jobs[blockIdx.y];
+  if (*J.status & ST_KEY_RANGE) return;  // keys are meaningless: the call fails with VILF_ERR_UNSUPPORTED
   const int n = *J.n;
   const int bits = J.meta[8];
   const int res = sort_passes(bits, J.sort.npass) & 1;
@@ -193,6 +195,7 @@ __global__ void __launch_bounds__(256) k_cb_gather(const CellBuildJob* __restric
 }
 __global__ void __launch_bounds__(256) k_cb_ends(const CellBuildJob* __restrict__ jobs) {
   const CellBuildJob& J = jobs[blockIdx.y];
+  if (*J.status & ST_KEY_RANGE) return;
   const int n = *J.n;
   const int bits = J.meta[8];
   const uint32_t* __restrict__ key = J.sort.key[sort_passes(bits, J.sort.npass) & 1];
@@ -203,9 +206,10 @@ __global__ void __launch_bounds__(256) k_cb_ends(const CellBuildJob* __restrict_
     if (i == n - 1 || (key[i + 1] >> s3) != c) {  // last point of a cell: find the slot its first point claimed
       const unsigned long long ck = key64_pt(J.dst[i], J.g) >> s3;
       uint32_t h = cell_slot(ck) & mask;
-      for (;;) {
+      for (uint32_t probes = 0; probes <= mask; ++probes) {  // (always found: k_cb_gather inserted the cell)
         const uint32_t st = J.table[h].x;
-        if (st != SLOT_EMPTY && (key64_pt(J.dst[st], J.g) >> s3) == ck) { J.table[h].y = (uint32_t)i + 1u; break; }
+        if (st == SLOT_EMPTY) break;
+        if ((key64_pt(J.dst[st], J.g) >> s3) == ck) { J.table[h].y = (uint32_t)i + 1u; break; }
         h = (h + 1) & mask;
       }
     }
@@ -333,22 +337,128 @@ struct KeyGenNew {
   }
 };
 
+// The same three steps (transform + crop + voxel bounding box, keys, stable radix sort) plus the sorted copy, for up to
+// CLUSTER_MAX_POINTS new points, in ONE kernel on one 8-CTA cluster per map: the grid-wide version above costs seven dependent
+// launches for a few thousand points.  Phases are separated by cluster barriers, histograms and partial boxes travel over
+// distributed shared memory (k_cluster_sort.cuh).
+struct NewShared {
+  VoxShared V;
+  int vb[8];  // this CTA's voxel bounding box (min xyz, max xyz) and live count
+};
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CT, 2) k_new_cluster(const MergeJob* __restrict__ jobs) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const MergeJob& J = jobs[blockIdx.y];
+  MergeVars& V = *J.mv;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ NewShared S;
+  const int n_orph = min(V.n_orph, ORPHAN_CAP);
+  const int n_src_all = *J.n_src;
+  const int n_src = min(n_src_all, J.cap_new - n_orph);
+  const int n = n_orph + n_src;
+  int cchunk = (n + CL - 1) / CL;
+  cchunk = (cchunk + CT - 1) / CT * CT;
+  const int wchunk = cchunk / CW;  // multiple of 32
+  const int cbeg = min(n, rank * cchunk), cend = min(n, cbeg + cchunk);
+  const int wbeg = min(cend, cbeg + warp * wchunk), wend = min(cend, wbeg + wchunk);
+  float lo[3], hi[3];
+  merge_crop(J, lo, hi);
+  const CellGeom g = J.g;
+  // ---- phase 0: append (EM:308-324) + crop test + voxel bounding box ----
+  {
+    double x[7];
+    if (J.pose) {
+#pragma unroll
+      for (int i = 0; i < 7; ++i) x[i] = J.pose[i];
+    }
+    int mn[3] = {INT_MAX, INT_MAX, INT_MAX}, mx[3] = {INT_MIN, INT_MIN, INT_MIN};
+    int live = 0;
+    for (int i = cbeg + tid; i < cend; i += CT) {
+      float4 p;
+      if (i < n_orph) p = J.orphans[i];
+      else { p = J.src[i - n_orph]; if (J.pose) p = associate(x, p); }
+      J.newpts[i] = p;
+      if (outside(p, lo, hi)) continue;
+      ++live;
+      int v[3];
+      voxel_of(p, g.inv_leaf, v[0], v[1], v[2]);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { const int b = (int)vbias(v[a]); mn[a] = min(mn[a], b); mx[a] = max(mx[a], b); }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { mn[a] = __reduce_min_sync(0xffffffffu, mn[a]); mx[a] = __reduce_max_sync(0xffffffffu, mx[a]); }
+    live = __reduce_add_sync(0xffffffffu, live);
+    int* sm = reinterpret_cast<int*>(&S.V.wcnt[0][0]);  // scratch, free until the first pass
+    if (lane == 0) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { sm[warp * 7 + a] = mn[a]; sm[warp * 7 + 3 + a] = mx[a]; }
+      sm[warp * 7 + 6] = live;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int tl = 0;
+      for (int w = 0; w < CW; ++w) {
+        for (int a = 0; a < 3; ++a) { mn[a] = min(mn[a], sm[w * 7 + a]); mx[a] = max(mx[a], sm[w * 7 + 3 + a]); }
+        tl += sm[w * 7 + 6];
+      }
+      for (int a = 0; a < 3; ++a) { S.vb[a] = mn[a]; S.vb[3 + a] = mx[a]; }
+      S.vb[6] = tl;
+    }
+    cluster.sync();  // partial boxes and the transformed points are visible to the whole cluster
+  }
+  int vlo[3] = {INT_MAX, INT_MAX, INT_MAX}, vhi[3] = {INT_MIN, INT_MIN, INT_MIN};
+  int n_live = 0;
+  for (int c = 0; c < CL; ++c) {
+    const int* rb = cluster.map_shared_rank(&S, c)->vb;
+    for (int a = 0; a < 3; ++a) { vlo[a] = min(vlo[a], rb[a]); vhi[a] = max(vhi[a], rb[3 + a]); }
+    n_live += rb[6];
+  }
+  RelKey rk;
+  rk.setup(vlo, vhi, g.shift, n_live > 0);
+  if (rank == 0 && tid == 0) {
+    V.n_in = n; V.n_orph_in = n_orph; V.n_live = n_live; V.bits = rk.bits;
+    V.n_live_all = 0;
+    V.fb[0] = V.fb[1] = V.fb[2] = INT_MAX; V.fb[3] = V.fb[4] = V.fb[5] = INT_MIN;
+    if (n_orph + n_src_all > J.cap_new) atomicOr(J.status, ST_SCAN_CAPACITY);
+    if (!rk.ok) atomicOr(J.status, ST_KEY_RANGE);
+  }
+  __syncthreads();  // the scratch in S.V.wcnt is reused by the sort
+  // ---- phase 1: keys + stable radix sort (cropped-out points carry the sentinel and end up behind the live ones) ----
+  const float4* __restrict__ np = J.newpts;
+  cluster_radix_sort(cluster, S.V, J.sort, wbeg, wend, rk.bits, [&](int i) {
+    const float4 p = __ldcg(np + i);
+    if (outside(p, lo, hi)) return rk.sentinel();
+    int vx, vy, vz;
+    voxel_of(p, g.inv_leaf, vx, vy, vz);
+    return rk.key(vx, vy, vz);
+  });
+  // ---- phase 2: sorted copy of the live points and their 63-bit keys ----
+  const uint2* __restrict__ pr = J.sort.pair[sort_passes(rk.bits, J.sort.npass) & 1];
+  for (int j = rank * CT + tid; j < n_live; j += CL * CT) {
+    const float4 p = __ldcg(np + __ldcg(pr + j).y);
+    J.nsorted[j] = p;
+    J.nkey[j] = key64_pt(p, g);
+  }
+  cluster.sync();  // no CTA may exit while a peer can still read its shared memory
+}
+
 // ------------------------------------------------------------------------------------------------
 // map update, step 2: merge-path partition + sorted copy of the new points
 // ------------------------------------------------------------------------------------------------
 // Tile t owns merged positions [t * MERGE_TILE, (t + 1) * MERGE_TILE); part[t] = old-map elements before that diagonal
 // (ties: old elements first — PCL sums a voxel in cloud order, and the old map precedes the appended points, EM:313-323).
 // One warp per diagonal: 32-ary search, so ~3 rounds of two dependent loads instead of ~15.
-__global__ void __launch_bounds__(256) k_merge_partition(const MergeJob* __restrict__ jobs) {
+__global__ void __launch_bounds__(256) k_merge_partition(const MergeJob* __restrict__ jobs, int gather) {
   const MergeJob& J = jobs[blockIdx.y];
   MergeVars& V = *J.mv;
-  const int n_old = *J.n_map, n_new = V.n_live;
+  const bool bad = (*J.status & ST_KEY_RANGE) != 0;  // the new points could not be keyed: the call fails, nothing is merged
+  const int n_old = bad ? 0 : *J.n_map, n_new = bad ? 0 : V.n_live;
   const int n_tot = n_old + n_new;
   const int n_tiles = (n_tot + MERGE_TILE - 1) / MERGE_TILE;
   const int res = sort_passes(V.bits, J.sort.npass) & 1;
   const uint32_t* __restrict__ val = J.sort.val[res];
-  // sorted copy of the live new points and their keys (coalesced loads in the merge)
-  for (int j = blockIdx.x * 256 + threadIdx.x; j < n_new; j += gridDim.x * 256) {
+  // sorted copy of the live new points and their keys (coalesced loads in the merge), unless k_new_cluster made it
+  for (int j = blockIdx.x * 256 + threadIdx.x; gather && j < n_new; j += gridDim.x * 256) {
     const float4 p = J.newpts[val[j]];
     J.nsorted[j] = p;
     J.nkey[j] = key64_pt(p, J.g);
@@ -366,7 +476,9 @@ __global__ void __launch_bounds__(256) k_merge_partition(const MergeJob* __restr
       bool more = false;
       if (a < hi) {
         const unsigned long long ko = key64_pt(J.old_pts[a], J.g);
-        const unsigned long long kn = key64_pt(J.newpts[val[d - a - 1]], J.g);
+        // (the cluster sort leaves interleaved pairs and has already written nkey; the grid-wide sort leaves split arrays and
+        // nkey is being written by this very kernel)
+        const unsigned long long kn = gather ? key64_pt(J.newpts[val[d - a - 1]], J.g) : J.nkey[d - a - 1];
         more = ko <= kn;
       }
       const unsigned m = __ballot_sync(0xffffffffu, more);   // a prefix of the lanes
@@ -387,17 +499,17 @@ __global__ void __launch_bounds__(256) k_merge_partition(const MergeJob* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
-// map update, step 3: the merge (counting pass, emitting pass)
+// map update, step 3: the merge (counting pass, tile scan, emitting pass)
 // ------------------------------------------------------------------------------------------------
+constexpr int MPER = MERGE_TILE / MERGE_THREADS;  // merged positions per thread (consecutive)
+constexpr int MWARPS = MERGE_THREADS / 32;
 struct MergeShared {
   float4 pts[MERGE_TILE];                 // old part [0, a), new part [a, a + b); later the tile's output points
   unsigned long long keys[MERGE_TILE];    // their keys; later the output points' cell keys
   unsigned short order[MERGE_TILE];       // merged position -> staged index; later the list of cell heads
   unsigned char live[MERGE_TILE];
-  uint32_t scan[MERGE_THREADS / 32];
-  int carry_start; unsigned long long carry_cell; int have_prev;
-  int base;
-  float bb[MERGE_THREADS / 32][7];
+  uint32_t scan[MWARPS];
+  float bb[MWARPS][7];
 };
 
 __device__ __forceinline__ uint32_t merge_block_scan(uint32_t v, uint32_t* buf, uint32_t* total) {
@@ -409,13 +521,13 @@ __device__ __forceinline__ uint32_t merge_block_scan(uint32_t v, uint32_t* buf, 
   __syncthreads();
   uint32_t woff = 0, tot = 0;
 #pragma unroll
-  for (int w = 0; w < MERGE_THREADS / 32; ++w) { const uint32_t c = buf[w]; if (w < warp) woff += c; tot += c; }
+  for (int w = 0; w < MWARPS; ++w) { const uint32_t c = buf[w]; if (w < warp) woff += c; tot += c; }
   *total = tot;
   return woff + inc - v;
 }
 
 template <bool EMIT>
-__global__ void __launch_bounds__(MERGE_THREADS, 2) k_merge(const MergeJob* __restrict__ jobs) {
+__global__ void __launch_bounds__(MERGE_THREADS, 4) k_merge(const MergeJob* __restrict__ jobs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   MergeShared& S = *reinterpret_cast<MergeShared*>(smem_raw);
   const MergeJob& J = jobs[blockIdx.y];
@@ -436,11 +548,23 @@ __global__ void __launch_bounds__(MERGE_THREADS, 2) k_merge(const MergeJob* __re
   const CellGeom g = J.g;
   const int s3 = 3 * g.shift;
   const int a0 = (int)J.part[t], a1 = (int)J.part[t + 1];
+  TileOut TO;
+  if (EMIT) TO = J.tout[t];
   const int d0 = t * MERGE_TILE, d1 = min(d0 + MERGE_TILE, n_tot);
   const int b0 = d0 - a0, b1 = d1 - a1;
   const int na = a1 - a0, nb = b1 - b0, nt = na + nb;
   float lo[3], hi[3];
   merge_crop(J, lo, hi);
+  // key of the merged element in front of the tile (run continuation) — ~0 when there is none; loads issued ahead of the staging
+  unsigned long long prev_key = ~0ull;
+  {
+    float4 po = make_float4(0.f, 0.f, 0.f, 0.f);
+    unsigned long long kn = 0;
+    if (a0 > 0) po = J.old_pts[a0 - 1];
+    if (b0 > 0) kn = J.nkey[b0 - 1];
+    if (a0 > 0) prev_key = key64_pt(po, g);
+    if (b0 > 0) prev_key = (prev_key == ~0ull || kn > prev_key) ? kn : prev_key;
+  }
 
   if (!EMIT) {  // the counting pass also clears the cell table of the map being written
     const int H = V.hmask + 1;
@@ -452,114 +576,123 @@ __global__ void __launch_bounds__(MERGE_THREADS, 2) k_merge(const MergeJob* __re
   // ---- stage the tile: old part, new part; bounding box of the live points (PCL guard) ----
   float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   int nlive = 0;
-  for (int i = tid; i < nt; i += MERGE_THREADS) {
-    float4 p;
-    unsigned long long k;
-    bool lv;
-    if (i < na) {
-      p = J.old_pts[a0 + i];
-      k = key64_pt(p, g);
-      lv = !outside(p, lo, hi);
-    } else {
-      p = J.nsorted[b0 + i - na];
-      k = J.nkey[b0 + i - na];
-      lv = true;
+  {
+    float4 pb[MPER];
+    unsigned long long kb[MPER];
+#pragma unroll
+    for (int it = 0; it < MPER; ++it) {  // all loads of the tile in flight before the first key is computed
+      const int i = it * MERGE_THREADS + tid;
+      kb[it] = 0;
+      if (i < na) pb[it] = J.old_pts[a0 + i];
+      else if (i < nt) { pb[it] = J.nsorted[b0 + i - na]; kb[it] = J.nkey[b0 + i - na]; }
     }
-    S.pts[i] = p; S.keys[i] = k; S.live[i] = lv ? 1 : 0;
-    if (!EMIT && lv) {
-      ++nlive;
-      mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
-      mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
-      mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
+#pragma unroll
+    for (int it = 0; it < MPER; ++it) {
+      const int i = it * MERGE_THREADS + tid;
+      if (i >= nt) continue;
+      const float4 p = pb[it];
+      bool lv = true;
+      unsigned long long k = kb[it];
+      if (i < na) { k = key64_pt(p, g); lv = !outside(p, lo, hi); }
+      S.pts[i] = p; S.keys[i] = k; S.live[i] = lv ? 1 : 0;
+      if (!EMIT && lv) {
+        ++nlive;
+        mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
+        mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
+        mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
+      }
     }
   }
-  // key of the merged element in front of the tile (run continuation) — ~0 when there is none
-  unsigned long long prev_key = ~0ull;
-  if (a0 > 0) prev_key = key64_pt(J.old_pts[a0 - 1], g);
-  if (b0 > 0) { const unsigned long long kn = J.nkey[b0 - 1]; prev_key = (prev_key == ~0ull || kn > prev_key) ? kn : prev_key; }
   __syncthreads();
 
   // ---- merged order: old i -> i + #(new < key), new j -> j + #(old <= key) ----
-  for (int i = tid; i < nt; i += MERGE_THREADS) {
-    const unsigned long long k = S.keys[i];
-    int r;
-    if (i < na) {
-      int l = 0, h = nb;  // lower_bound in the new part
-      while (l < h) { const int m = (l + h) >> 1; if (S.keys[na + m] < k) l = m + 1; else h = m; }
-      r = i + l;
-    } else {
-      int l = 0, h = na;  // upper_bound in the old part
-      while (l < h) { const int m = (l + h) >> 1; if (S.keys[m] <= k) l = m + 1; else h = m; }
-      r = (i - na) + l;
+  if (nb == 0) {
+    for (int i = tid; i < nt; i += MERGE_THREADS) S.order[i] = (unsigned short)i;
+  } else {
+    for (int i = tid; i < nt; i += MERGE_THREADS) {
+      const unsigned long long k = S.keys[i];
+      int r;
+      if (i < na) {
+        int l = 0, h = nb;  // lower_bound in the new part
+        while (l < h) { const int m = (l + h) >> 1; if (S.keys[na + m] < k) l = m + 1; else h = m; }
+        r = i + l;
+      } else {
+        int l = 0, h = na;  // upper_bound in the old part
+        while (l < h) { const int m = (l + h) >> 1; if (S.keys[m] <= k) l = m + 1; else h = m; }
+        r = (i - na) + l;
+      }
+      S.order[r] = (unsigned short)i;
     }
-    S.order[r] = (unsigned short)i;
   }
   __syncthreads();
 
   // ---- every run head sums its voxel: PCL's `centroid += point` in cloud order, fp32, then `/= count` ----
-  constexpr int PER = MERGE_TILE / MERGE_THREADS;
-  float4 outp[PER];
-  unsigned long long outk[PER];
-  bool has[PER];
+  // thread `tid` owns the consecutive merged positions [tid * MPER, tid * MPER + MPER)
+  float4 outp[MPER];
+  unsigned long long outk[MPER];
+  uint32_t hasm = 0;
+  {
+    const int r0 = tid * MPER;
+    unsigned long long pk = r0 == 0 ? prev_key : (r0 - 1 < nt ? S.keys[S.order[r0 - 1]] : 0ull);
 #pragma unroll
-  for (int it = 0; it < PER; ++it) {
-    const int r = it * MERGE_THREADS + tid;
-    has[it] = false;
-    outk[it] = 0;
-    outp[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r >= nt) continue;
-    const unsigned long long k = S.keys[S.order[r]];
-    const unsigned long long pk = r > 0 ? S.keys[S.order[r - 1]] : prev_key;
-    if (k == pk) continue;  // continues a run: its head (in this or an earlier tile) sums it
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    int cnt = 0;
-    int rr = r;
-    for (; rr < nt; ++rr) {
-      const int li = S.order[rr];
-      if (S.keys[li] != k) break;
-      if (S.live[li]) {
-        const float4 q = S.pts[li];
-        acc.x = fadd(acc.x, q.x); acc.y = fadd(acc.y, q.y); acc.z = fadd(acc.z, q.z); acc.w = fadd(acc.w, q.w);
-        ++cnt;
+    for (int it = 0; it < MPER; ++it) {
+      const int r = r0 + it;
+      outk[it] = 0;
+      outp[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r >= nt) continue;
+      const unsigned long long k = S.keys[S.order[r]];
+      const bool head = k != pk;  // otherwise it continues a run: its head (in this or an earlier tile) sums it
+      pk = k;
+      if (!head) continue;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      int cnt = 0;
+      int rr = r;
+      for (; rr < nt; ++rr) {
+        const int li = S.order[rr];
+        if (S.keys[li] != k) break;
+        if (S.live[li]) {
+          const float4 q = S.pts[li];
+          acc.x = fadd(acc.x, q.x); acc.y = fadd(acc.y, q.y); acc.z = fadd(acc.z, q.z); acc.w = fadd(acc.w, q.w);
+          ++cnt;
+        }
       }
+      if (rr == nt && d1 < n_tot) {  // the run may go on behind the tile: the rest of its old points first, then its new ones
+        for (int a = a1; a < n_old; ++a) {
+          const float4 q = J.old_pts[a];
+          if (key64_pt(q, g) != k) break;
+          if (!outside(q, lo, hi)) { acc.x = fadd(acc.x, q.x); acc.y = fadd(acc.y, q.y); acc.z = fadd(acc.z, q.z); acc.w = fadd(acc.w, q.w); ++cnt; }
+        }
+        for (int b = b1; b < n_new; ++b) {
+          if (J.nkey[b] != k) break;
+          const float4 q = J.nsorted[b];
+          acc.x = fadd(acc.x, q.x); acc.y = fadd(acc.y, q.y); acc.z = fadd(acc.z, q.z); acc.w = fadd(acc.w, q.w); ++cnt;
+        }
+      }
+      if (cnt == 0) continue;  // every point of the voxel left the crop box
+      const float4 c = centroid_of(acc, cnt);
+      if (cnt > 1 && key64_pt(c, g) != k) {
+        // fp32 rounding put the centroid across a face of its voxel: stored here it would break the map's order.  PCL would
+        // count it into the neighbouring voxel at the next update; it is set aside and re-inserted with the next new points.
+        if (EMIT) {
+          const int o = atomicAdd(&V.n_orph, 1);
+          if (o < ORPHAN_CAP) J.orphans[o] = c; else atomicOr(J.status, ST_ORPHANS);
+        }
+        continue;
+      }
+      hasm |= 1u << it; outp[it] = c; outk[it] = k >> s3;
     }
-    if (rr == nt && d1 < n_tot) {  // the run may go on behind the tile: the rest of its old points first, then its new ones
-      for (int a = a1; a < n_old; ++a) {
-        const float4 q = J.old_pts[a];
-        if (key64_pt(q, g) != k) break;
-        if (!outside(q, lo, hi)) { acc.x = fadd(acc.x, q.x); acc.y = fadd(acc.y, q.y); acc.z = fadd(acc.z, q.z); acc.w = fadd(acc.w, q.w); ++cnt; }
-      }
-      for (int b = b1; b < n_new; ++b) {
-        if (J.nkey[b] != k) break;
-        const float4 q = J.nsorted[b];
-        acc.x = fadd(acc.x, q.x); acc.y = fadd(acc.y, q.y); acc.z = fadd(acc.z, q.z); acc.w = fadd(acc.w, q.w); ++cnt;
-      }
-    }
-    if (cnt == 0) continue;  // every point of the voxel left the crop box
-    const float4 c = centroid_of(acc, cnt);
-    if (cnt > 1 && key64_pt(c, g) != k) {
-      // fp32 rounding put the centroid across a face of its voxel: stored here it would break the map's order.  PCL would
-      // count it into the neighbouring voxel at the next update; it is set aside and re-inserted with the next new points.
-      if (EMIT) {
-        const int o = atomicAdd(&V.n_orph, 1);
-        if (o < ORPHAN_CAP) J.orphans[o] = c; else atomicOr(J.status, ST_ORPHANS);
-      }
-      continue;
-    }
-    has[it] = true; outp[it] = c; outk[it] = k >> s3;
   }
   __syncthreads();  // all reads of the staged tile are done: its storage now takes the compacted outputs
 
   // ---- compact the outputs in merged order ----
-  uint32_t run = 0;
+  uint32_t tot_out;
+  {
+    uint32_t o = merge_block_scan((uint32_t)__popc(hasm), S.scan, &tot_out);
 #pragma unroll
-  for (int it = 0; it < PER; ++it) {
-    uint32_t tot;
-    const uint32_t ex = merge_block_scan(has[it] ? 1u : 0u, S.scan, &tot);
-    if (has[it]) { S.pts[run + ex] = outp[it]; S.keys[run + ex] = outk[it]; }
-    run += tot;
+    for (int it = 0; it < MPER; ++it)
+      if (hasm & (1u << it)) { S.pts[o] = outp[it]; S.keys[o] = outk[it]; ++o; }
   }
-  const int count = (int)run;
+  const int count = (int)tot_out;
   __syncthreads();
 
   if (!EMIT) {
@@ -580,7 +713,7 @@ __global__ void __launch_bounds__(MERGE_THREADS, 2) k_merge(const MergeJob* __re
     __syncthreads();
     if (tid == 0) {
       int tl = 0;
-      for (int w = 0; w < MERGE_THREADS / 32; ++w) {
+      for (int w = 0; w < MWARPS; ++w) {
         for (int a = 0; a < 3; ++a) { mn[a] = fminf(mn[a], S.bb[w][a]); mx[a] = fmaxf(mx[a], S.bb[w][3 + a]); }
         tl += __float_as_int(S.bb[w][6]);
       }
@@ -601,57 +734,27 @@ __global__ void __launch_bounds__(MERGE_THREADS, 2) k_merge(const MergeJob* __re
     return;
   }
 
-  // ---- emitting pass: where do this tile's outputs go, and which cell run is open in front of it? ----
-  {
-    uint32_t part = 0;
-    for (int i = tid; i < t; i += MERGE_THREADS) part += (uint32_t)J.agg[i].count;
-    uint32_t tot;
-    merge_block_scan(part, S.scan, &tot);
-    if (tid == 0) {
-      S.base = (int)tot;
-      // walk back to the start of the cell run that holds the last output in front of this tile
-      int have = 0, start = 0;
-      unsigned long long cell = 0;
-      int b = (int)tot;  // outputs before tile tt + 1
-      for (int tt = t - 1; tt >= 0; --tt) {
-        const TileAgg A = J.agg[tt];
-        if (A.count == 0) continue;
-        b -= A.count;  // outputs before tile tt
-        if (!have) { have = 1; cell = A.last_cell; }
-        if (A.last_run_start > 0 || A.first_cell != cell) { start = b + A.last_run_start; break; }
-        // the whole tile is one run of `cell` (or its tail starts at 0): it may have begun earlier
-        start = b;
-        bool cont = false;
-        for (int t2 = tt - 1; t2 >= 0; --t2) {
-          const TileAgg B = J.agg[t2];
-          if (B.count == 0) continue;
-          cont = B.last_cell == cell;
-          break;
-        }
-        if (!cont) break;
-      }
-      S.have_prev = have; S.carry_start = start; S.carry_cell = cell;
-    }
-    __syncthreads();
-  }
-  const int base = S.base;
+  // ---- emitting pass: points, then the cell table (head c closes the cell in front of it) ----
+  const int base = TO.base;
   const uint32_t hmask = (uint32_t)V.hmask;
   for (int o = tid; o < count; o += MERGE_THREADS)
     if (base + o < J.cap_out) J.out_pts[base + o] = S.pts[o];
-  // cell heads of this tile, compacted in order; head c closes the cell in front of it
-  uint32_t nheads = 0;
+  // cell heads of this tile, compacted in order: thread `tid` looks at outputs [tid * MPER, tid * MPER + MPER)
+  uint32_t nheads;
   {
-    uint32_t runh = 0;
-    for (int ob = 0; ob < count; ob += MERGE_THREADS) {
-      const int o = ob + tid;
-      bool head = false;
-      if (o < count) head = o > 0 ? (S.keys[o] != S.keys[o - 1]) : (!S.have_prev || S.keys[0] != S.carry_cell);
-      uint32_t tot;
-      const uint32_t ex = merge_block_scan(head ? 1u : 0u, S.scan, &tot);
-      if (head) S.order[runh + ex] = (unsigned short)o;
-      runh += tot;
+    const int o0 = tid * MPER;
+    uint32_t hm = 0;
+#pragma unroll
+    for (int it = 0; it < MPER; ++it) {
+      const int o = o0 + it;
+      if (o >= count) continue;
+      const bool head = o > 0 ? (S.keys[o] != S.keys[o - 1]) : (!TO.have_prev || S.keys[0] != TO.carry_cell);
+      if (head) hm |= 1u << it;
     }
-    nheads = runh;
+    uint32_t c = merge_block_scan((uint32_t)__popc(hm), S.scan, &nheads);
+#pragma unroll
+    for (int it = 0; it < MPER; ++it)
+      if (hm & (1u << it)) S.order[c++] = (unsigned short)(o0 + it);
     __syncthreads();
   }
   for (int c = tid; c < (int)nheads; c += MERGE_THREADS) {
@@ -659,20 +762,82 @@ __global__ void __launch_bounds__(MERGE_THREADS, 2) k_merge(const MergeJob* __re
     if (c > 0) {
       const int po = S.order[c - 1];
       table_insert(J.table, hmask, S.keys[po], (uint32_t)(base + po), (uint32_t)(base + o));
-    } else if (S.have_prev) {
-      table_insert(J.table, hmask, S.carry_cell, (uint32_t)S.carry_start, (uint32_t)(base + o));
+    } else if (TO.have_prev) {
+      table_insert(J.table, hmask, TO.carry_cell, (uint32_t)TO.carry_start, (uint32_t)(base + o));
     }
   }
-  if (t == n_tiles - 1 && tid == 0) {  // the last tile closes the last cell and publishes the result
+  if (t == n_tiles - 1 && tid == 0) {  // the last tile closes the last cell
     const int total = base + count;
     if (nheads > 0) { const int po = S.order[nheads - 1]; table_insert(J.table, hmask, S.keys[po], (uint32_t)(base + po), (uint32_t)total); }
-    else if (S.have_prev) table_insert(J.table, hmask, S.carry_cell, (uint32_t)S.carry_start, (uint32_t)total);
+    else if (TO.have_prev) table_insert(J.table, hmask, TO.carry_cell, (uint32_t)TO.carry_start, (uint32_t)total);
+  }
+}
+
+// Between the two passes, one CTA per map: where every tile's outputs go (exclusive prefix of the counts) and which cell run is
+// open in front of it (cell key + index of that run's first point; a run may span several tiles).  Also publishes the size of the
+// new map and evaluates PCL's "leaf size is too small" guard on the bounding box the counting pass reduced.
+constexpr int MSCAN_THREADS = 1024;
+__global__ void __launch_bounds__(MSCAN_THREADS) k_merge_scan(const MergeJob* __restrict__ jobs) {
+  const MergeJob& J = jobs[blockIdx.x];
+  MergeVars& V = *J.mv;
+  const int n_tiles = min(V.n_tiles, J.max_tiles);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int* s_base = reinterpret_cast<int*>(smem_raw);            // [n_tiles + 1]
+  int* s_prev = s_base + (J.max_tiles + 2);                   // last non-empty tile in front of tile t, or -1
+  __shared__ int wsum[32], wmax[32];
+  __shared__ int run_sum, run_max;
+  if (tid == 0) { run_sum = 0; run_max = -1; }
+  __syncthreads();
+  for (int b = 0; b < n_tiles; b += MSCAN_THREADS) {
+    const int t = b + tid;
+    const int c = t < n_tiles ? J.agg[t].count : 0;
+    int inc = c, mxi = c > 0 ? t : -1;
+    for (int off = 1; off < 32; off <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, inc, off), m = __shfl_up_sync(0xffffffffu, mxi, off);
+      if (lane >= off) { inc += u; mxi = max(mxi, m); }
+    }
+    if (lane == 31) { wsum[warp] = inc; wmax[warp] = mxi; }
+    __syncthreads();
+    int woff = 0, wm = -1;
+    for (int w = 0; w < warp; ++w) { woff += wsum[w]; wm = max(wm, wmax[w]); }
+    const int incl = run_sum + woff + inc;          // inclusive prefix of the counts
+    const int last = max(run_max, max(wm, mxi));    // last non-empty tile <= t
+    const int pl = __shfl_up_sync(0xffffffffu, last, 1);  // exclusive "last non-empty": the inclusive value of the previous tile
+    if (t < n_tiles) {
+      s_base[t] = incl - c;
+      s_prev[t] = lane > 0 ? pl : max(run_max, wm);
+    }
+    __syncthreads();
+    if (tid == MSCAN_THREADS - 1) { run_sum = incl; run_max = last; }
+    __syncthreads();
+  }
+  const int total = run_sum;
+  for (int t = tid; t < n_tiles; t += MSCAN_THREADS) {
+    TileOut O;
+    O.base = s_base[t]; O.have_prev = 0; O.carry_start = 0; O.carry_cell = 0;
+    int p = s_prev[t];
+    if (p >= 0) {
+      O.have_prev = 1;
+      O.carry_cell = J.agg[p].last_cell;
+      for (;;) {  // walk back to the tile in which the run of carry_cell starts
+        const TileAgg A = J.agg[p];
+        if (A.last_run_start > 0) { O.carry_start = s_base[p] + A.last_run_start; break; }
+        O.carry_start = s_base[p];  // the whole tile is one run of this cell: it may have begun earlier
+        const int pp = s_prev[p];
+        if (pp < 0 || J.agg[pp].last_cell != O.carry_cell) break;
+        p = pp;
+      }
+    }
+    J.tout[t] = O;
+  }
+  if (tid == 0) {
     if (total > J.cap_out) atomicOr(J.status, ST_MAP_CAPACITY);
     *J.n_map = min(total, J.cap_out);
-    J.meta[0] = (int)hmask; J.meta[1] = 0;
+    J.meta[0] = V.hmask; J.meta[1] = 0;
     // PCL's "leaf size is too small" guard (voxel_grid.hpp): the reference would hand the cloud through unfiltered
     if (V.n_live_all > 0) {
-      const float inv = g.inv_leaf;
+      const float inv = J.g.inv_leaf;
       long long prod = 1;
       for (int a = 0; a < 3; ++a) prod *= (long long)(fmul(fsub(ord2f(V.fb[3 + a]), ord2f(V.fb[a])), inv)) + 1;
       if (prod > (long long)INT_MAX) atomicOr(J.status, ST_PCL_GUARD);
@@ -686,23 +851,31 @@ cudaError_t init_cellmap_kernels() {
   return cudaFuncSetAttribute(k_merge<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MergeShared));
 }
 
-void launch_cell_update(const Launch& L, const MergeJob* jobs_dev, const SortJob* sort_jobs_dev, int njobs, int max_tiles) {
-  k_merge_reset<<<(njobs + 127) / 128, 128, 0, L.st>>>(jobs_dev, njobs);
-  L.tick(K_NEW_XFORM);
+void launch_cell_update(const Launch& L, const MergeJob* jobs_dev, const SortJob* sort_jobs_dev, int njobs, int max_tiles, bool cluster_new) {
   dim3 g(74, njobs);
-  k_new_xform<<<g, 256, 0, L.st>>>(jobs_dev);
-  L.tick(K_NEW_XFORM);
-  KeyGenNew gen;
-  gen.jobs = jobs_dev;
-  dim3 gs(SORT_G, njobs);
-  k_sort_keyhist<KeyGenNew><<<gs, SORT_THREADS, 0, L.st>>>(sort_jobs_dev, gen);
-  L.tick(K_NEW_KEYHIST);
-  for (int pass = 0; pass < 4; ++pass) launch_sort_scatter(L, sort_jobs_dev, njobs, pass);
-  k_merge_partition<<<g, 256, 0, L.st>>>(jobs_dev);
+  if (cluster_new) {
+    dim3 gc(CL, njobs);
+    k_new_cluster<<<gc, CT, 0, L.st>>>(jobs_dev);
+    L.tick(K_NEW_XFORM);
+  } else {
+    k_merge_reset<<<(njobs + 127) / 128, 128, 0, L.st>>>(jobs_dev, njobs);
+    L.tick(K_NEW_XFORM);
+    k_new_xform<<<g, 256, 0, L.st>>>(jobs_dev);
+    L.tick(K_NEW_XFORM);
+    KeyGenNew gen;
+    gen.jobs = jobs_dev;
+    dim3 gs(SORT_G, njobs);
+    k_sort_keyhist<KeyGenNew><<<gs, SORT_THREADS, 0, L.st>>>(sort_jobs_dev, gen);
+    L.tick(K_NEW_KEYHIST);
+    for (int pass = 0; pass < 4; ++pass) launch_sort_scatter(L, sort_jobs_dev, njobs, pass);
+  }
+  k_merge_partition<<<g, 256, 0, L.st>>>(jobs_dev, cluster_new ? 0 : 1);
   L.tick(K_MERGE_PART);
   dim3 gm(max_tiles, njobs);
   k_merge<false><<<gm, MERGE_THREADS, sizeof(MergeShared), L.st>>>(jobs_dev);
   L.tick(K_MERGE_COUNT);
+  k_merge_scan<<<njobs, MSCAN_THREADS, (size_t)(2 * max_tiles + 8) * sizeof(int), L.st>>>(jobs_dev);
+  L.tick(K_MERGE_PART);
   k_merge<true><<<gm, MERGE_THREADS, sizeof(MergeShared), L.st>>>(jobs_dev);
   L.tick(K_MERGE_EMIT);
 }
@@ -716,10 +889,13 @@ struct CellMapView {
   const uint32_t* orig;  // PCL index of every point, or null when the PCL order is the voxel order (any map after an update)
   uint32_t hmask;
   CellGeom g;
+  int n;
 };
 
 // Is map point a before map point b in the reference's map order?  Only consulted on exact fp32 distance ties (tie class T2).
-__device__ __noinline__ bool pcl_before(const CellMapView& M, int a, int b) {
+// (Inlined on purpose: as a __noinline__ callee taking the view by reference it made k_knn_cell_assoc fault — the view is then
+// selected at run time between two local structs and the generic pointer to it was wrong in the callee.)
+__device__ __forceinline__ bool pcl_before(const CellMapView& M, int a, int b) {
   if (b == INT_MAX) return true;
   if (a == INT_MAX) return false;
   if (M.orig) return M.orig[a] < M.orig[b];
@@ -731,36 +907,71 @@ __device__ __noinline__ bool pcl_before(const CellMapView& M, int a, int b) {
   if (ax != bx) return ax < bx;
   return a < b;
 }
-__device__ __forceinline__ bool closer_cell(const CellMapView& M, float d, int id, float bd, int bid) {
-  if (d < bd) return true;
-  if (d > bd) return false;
-  return pcl_before(M, id, bid);
+// The warp's candidate pool lives in shared memory: POOL_CAP (distance, index) pairs.  Top five of pool[0, npool), nearest first,
+// replicated in every lane: lane l looks after entries l and l + 32; five rounds of redux.sync min on the distance bits
+// (non-negative floats order like their bit patterns), exact ties resolved by the reference's map order.
+constexpr int POOL_CAP = 64;
+__device__ __forceinline__ void pool_top5(const CellMapView& M, const uint2* pool, int npool, float (&rd)[5], int (&ri)[5]) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+  uint2 e0 = make_uint2(0xFFFFFFFFu, (uint32_t)INT_MAX), e1 = e0;
+  if (lane < npool) e0 = pool[lane];
+  if (lane + 32 < npool) e1 = pool[lane + 32];
+  // keep the lane's better entry in e0
+  if (e1.x < e0.x || (e1.x == e0.x && e1.x != 0xFFFFFFFFu && pcl_before(M, (int)e1.y, (int)e0.y))) { const uint2 t = e0; e0 = e1; e1 = t; }
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const uint32_t mnk = __reduce_min_sync(FULL, e0.x);
+    if (mnk == 0xFFFFFFFFu) { rd[k] = FLT_MAX; ri[k] = INT_MAX; continue; }  // uniform: the pool is exhausted
+    unsigned who = __ballot_sync(FULL, e0.x == mnk);
+    int w = __ffs(who) - 1;
+    int wi = __shfl_sync(FULL, (int)e0.y, w);
+    who &= who - 1;
+    while (who) {  // equal distances (tie class T2): the reference's map order decides
+      const int w2 = __ffs(who) - 1;
+      const int i2 = __shfl_sync(FULL, (int)e0.y, w2);
+      if (pcl_before(M, i2, wi)) { w = w2; wi = i2; }
+      who &= who - 1;
+    }
+    rd[k] = __uint_as_float(mnk); ri[k] = wi;
+    if (lane == w) { e0 = e1; e1 = make_uint2(0xFFFFFFFFu, (uint32_t)INT_MAX); }
+  }
+}
+// After a reduction the pool is its own top five.
+__device__ __forceinline__ int pool_reseed(uint2* pool, const float (&rd)[5], const int (&ri)[5]) {
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+  if (lane < 5) {
+    const float d = lane == 0 ? rd[0] : lane == 1 ? rd[1] : lane == 2 ? rd[2] : lane == 3 ? rd[3] : rd[4];
+    const int i = lane == 0 ? ri[0] : lane == 1 ? ri[1] : lane == 2 ? ri[2] : lane == 3 ? ri[3] : ri[4];
+    pool[lane] = make_uint2(__float_as_uint(d), (uint32_t)i);
+  }
+  __syncwarp();
+  return (ri[0] != INT_MAX) + (ri[1] != INT_MAX) + (ri[2] != INT_MAX) + (ri[3] != INT_MAX) + (ri[4] != INT_MAX);
 }
 
 // Called by a whole warp with one query; returns (replicated in every lane) the five nearest map points inside the gate in
-// ascending (d^2, PCL index) order; FLT_MAX / INT_MAX where fewer than five lie inside the gate.
-__device__ __forceinline__ void warp_knn5(const CellMapView& M, float gate_f, float qx, float qy, float qz, float (&bd)[5], int (&bi)[5]) {
+// ascending (d^2, PCL index) order; FLT_MAX / INT_MAX where fewer than five lie inside the gate.  `pool` = POOL_CAP entries of
+// shared memory owned by this warp.
+//
+// Candidates are read 32 at a time (coalesced runs: a cell is a contiguous range, the cells of an x-row follow each other).  The few
+// that fall inside the gate are appended to the pool (ballot + popc rank, one shared-memory store each); the pool is reduced to its
+// best five only when it would overflow, between shells (early exit) and at the end, and every reduction tightens the gate to
+// the fifth distance known so far.
+__device__ __forceinline__ void warp_knn5(const CellMapView& M, float gate_f, float qx, float qy, float qz, uint2* pool, float (&bd)[5], int (&bi)[5]) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
   const int s = M.g.shift;
   const float inv = M.g.inv_leaf;
-#pragma unroll
-  for (int k = 0; k < 5; ++k) { bd[k] = FLT_MAX; bi[k] = INT_MAX; }
   int vx, vy, vz;
   voxel_of(make_float4(qx, qy, qz, 0.f), inv, vx, vy, vz);
   const int qcx = (int)(vbias(vx) >> s), qcy = (int)(vbias(vy) >> s), qcz = (int)(vbias(vz) >> s);
   const int ncmax = (1 << (21 - s)) - 1;
-  // distance from the query to the nearest face of its own cell, in cells (for the early exit between shells)
-  float fmin_cells = 0.f;
-  {
-    const float k = (float)(1 << s);
-    const float ux = fmul(qx, inv) - (float)(((qcx << s) - VOX_BIAS)), uy = fmul(qy, inv) - (float)(((qcy << s) - VOX_BIAS)),
-                uz = fmul(qz, inv) - (float)(((qcz << s) - VOX_BIAS));
-    const float f = fminf(fminf(fminf(ux, k - ux), fminf(uy, k - uy)), fminf(uz, k - uz));
-    fmin_cells = fmaxf(0.f, f / k - 1e-4f);
-  }
-  const double cell = (double)M.g.leaf * (double)(1 << s) * (1.0 - 1e-5);  // a lower bound of the cell edge (inverse_leaf is rounded)
   const int shells = M.g.shells;
+  int npool = 0;
+  float gate_dyn = gate_f;  // once five neighbours are known nothing farther than the fifth can matter (ties are kept: <=)
   for (int r = 1; r <= shells; ++r) {
     const int side = 2 * r + 1, ncell = side * side * side;
     for (int cb = 0; cb < ncell; cb += 32) {
@@ -782,14 +993,14 @@ __device__ __forceinline__ void warp_knn5(const CellMapView& M, float gate_f, fl
         }
       }
       const uint32_t cnt = e0 - s0;
+      if (!__any_sync(FULL, cnt != 0u)) continue;  // a batch of empty cells (outer shells of a sparse neighbourhood)
       uint32_t inc = cnt;
 #pragma unroll
       for (int off = 1; off < 32; off <<= 1) { const uint32_t u = __shfl_up_sync(FULL, inc, off); if (lane >= off) inc += u; }
       const uint32_t total = __shfl_sync(FULL, inc, 31);
       for (uint32_t c0 = 0; c0 < total; c0 += 32) {
         const uint32_t c = c0 + lane;
-        // owner = first lane whose inclusive count exceeds c
-        int l = 0, h = 31;
+        int l = 0, h = 31;  // owner = first lane whose inclusive count exceeds c
 #pragma unroll
         for (int it = 0; it < 5; ++it) {
           const int m = (l + h) >> 1;
@@ -804,42 +1015,41 @@ __device__ __forceinline__ void warp_knn5(const CellMapView& M, float gate_f, fl
           const float4 p = __ldg(M.pts + idx);
           const float ddx = fsub(qx, p.x), ddy = fsub(qy, p.y), ddz = fsub(qz, p.z);
           cd = fadd(fadd(fmul(ddx, ddx), fmul(ddy, ddy)), fmul(ddz, ddz));  // FLANN L2_Simple<float>
-          cand = cd < gate_f;  // neighbours at or beyond the gate can never be used (EM:129 / :189)
+          cand = cd < gate_f && cd <= gate_dyn;  // neighbours at or beyond the gate can never be used (EM:129 / :189)
         }
-        for (;;) {  // move the best remaining candidates of this batch into the list, nearest first (at most five rounds)
-          const bool better = cand && closer_cell(M, cd, idx, bd[4], bi[4]);
-          if (!__any_sync(FULL, better)) break;
-          const uint32_t key = better ? __float_as_uint(cd) : 0xFFFFFFFFu;
-          const uint32_t mnk = __reduce_min_sync(FULL, key);
-          unsigned who = __ballot_sync(FULL, better && key == mnk);
-          int w = __ffs(who) - 1;
-          int wi = __shfl_sync(FULL, idx, w);
-          who &= who - 1;
-          while (who) {  // equal distances inside one batch: the reference's map order decides
-            const int w2 = __ffs(who) - 1;
-            const int i2 = __shfl_sync(FULL, idx, w2);
-            if (pcl_before(M, i2, wi)) { w = w2; wi = i2; }
-            who &= who - 1;
-          }
-          const float wd = __uint_as_float(mnk);
-          // insert (wd, wi): it is closer than the current fifth
-          bd[4] = wd; bi[4] = wi;
-#pragma unroll
-          for (int k = 4; k > 0; --k) {
-            const bool sw = closer_cell(M, bd[k], bi[k], bd[k - 1], bi[k - 1]);
-            const float dk = sw ? bd[k - 1] : bd[k], dk1 = sw ? bd[k] : bd[k - 1];
-            const int ik = sw ? bi[k - 1] : bi[k], ik1 = sw ? bi[k] : bi[k - 1];
-            bd[k] = dk; bd[k - 1] = dk1; bi[k] = ik; bi[k - 1] = ik1;
-          }
-          if (lane == w) cand = false;
+        const unsigned m = __ballot_sync(FULL, cand);
+        if (m == 0u) continue;
+        const int cm = __popc(m);
+        if (npool + cm > POOL_CAP) {  // reduce the pool to its best five (npool <= 32 + 5 afterwards)
+          float rd[5]; int ri[5];
+          pool_top5(M, pool, npool, rd, ri);
+          npool = pool_reseed(pool, rd, ri);
+          gate_dyn = rd[4];  // FLT_MAX while fewer than five are known
         }
+        if (cand) pool[npool + __popc(m & lt)] = make_uint2(__float_as_uint(cd), (uint32_t)idx);
+        npool += cm;
       }
     }
-    if (r < shells) {  // after shell r every unseen point is farther than (r + f) cells
+    if (r < shells) {  // after shell r every unseen point is farther than (r + f) cells: is the fifth best already closer?
+      float rd[5]; int ri[5];
+      pool_top5(M, pool, npool, rd, ri);
+      const float k = (float)(1 << s);
+      const float ux = fmul(qx, inv) - (float)(((qcx << s) - VOX_BIAS)), uy = fmul(qy, inv) - (float)(((qcy << s) - VOX_BIAS)),
+                  uz = fmul(qz, inv) - (float)(((qcz << s) - VOX_BIAS));
+      const float f = fminf(fminf(fminf(ux, k - ux), fminf(uy, k - uy)), fminf(uz, k - uz));  // voxels to the nearest face of the query's cell
+      const float fmin_cells = fmaxf(0.f, f / k - 1e-4f);
+      const double cell = (double)M.g.leaf * (double)(1 << s) * (1.0 - 1e-5);  // a lower bound of the cell edge (inverse_leaf is rounded)
       const double reach = ((double)r + (double)fmin_cells) * cell;
-      if ((double)bd[4] < reach * reach * (1.0 - 1e-5)) break;
+      if ((double)rd[4] < reach * reach * (1.0 - 1e-5)) {
+#pragma unroll
+        for (int q = 0; q < 5; ++q) { bd[q] = rd[q]; bi[q] = ri[q]; }
+        return;
+      }
+      npool = pool_reseed(pool, rd, ri);
+      gate_dyn = rd[4];
     }
   }
+  pool_top5(M, pool, npool, bd, bi);
 }
 
 constexpr int KC_THREADS = 256;
@@ -851,37 +1061,50 @@ __global__ void __launch_bounds__(KC_THREADS) k_knn_cell_assoc(LaneDev* lanes, i
   const int me = V.n_map[0], ms = V.n_map[1];
   if (!(me > 10 && ms > 50)) return;  // EM:254
   const int ne = V.n_ds[0], ns = V.n_ds[1];
+  const int nq = ne + ns;
+  if (blockIdx.x == 0 && threadIdx.x == 0) V.opt_ran = 1;
+  if ((int)blockIdx.x * 32 >= nq) return;  // the grid is sized for a full scan; most CTAs have nothing to do
   double x[7];
 #pragma unroll
   for (int i = 0; i < 7; ++i) x[i] = pose_override ? pose_override[i] : V.x[i];
-  if (blockIdx.x == 0 && threadIdx.x == 0) V.opt_ran = 1;
   const int lane = threadIdx.x & 31;
   const int wpb = KC_THREADS / 32;
-  const int nq = ne + ns;
-  CellMapView M[2];
+  CellMapView Me, Ms;
+  Me.pts = L.map[0][cur]; Me.table = L.ctab[0]; Me.hmask = (uint32_t)L.cmeta[0][0]; Me.orig = L.cmeta[0][1] ? L.corig[0] : nullptr; Me.g = cfg.cg[0]; Me.n = me;
+  Ms.pts = L.map[1][cur]; Ms.table = L.ctab[1]; Ms.hmask = (uint32_t)L.cmeta[1][0]; Ms.orig = L.cmeta[1][1] ? L.corig[1] : nullptr; Ms.g = cfg.cg[1]; Ms.n = ms;
+  // A CTA takes 32 consecutive queries: warp 0 runs the fp64 transform (EM:355-363) with one query per lane (the FP64 pipe is
+  // narrow: 32 lanes repeating the same transform cost as much as 32 different ones), then every warp searches four of them.
+  __shared__ float4 sq[32];
+  __shared__ uint2 spool[KC_THREADS / 32][POOL_CAP];
+  for (int qb = blockIdx.x * 32; qb < nq; qb += gridDim.x * 32) {
+    __syncthreads();  // sq of the previous round is no longer read
+    if (threadIdx.x < 32) {
+      const int myq = qb + lane;
+      if (myq < nq) sq[lane] = associate(x, myq < ne ? L.ds[0][myq] : L.ds[1][myq - ne]);
+    }
+    __syncthreads();
+    const int nb = min(32, nq - qb);
+    for (int j = threadIdx.x >> 5; j < nb; j += wpb) {
+      const int q = qb + j;
+      const float4 pw = sq[j];
+      const int w = q >= ne ? 1 : 0;
+      const int k = w ? q - ne : q;
+      float rd[5];
+      int ri[5];
+      const CellMapView M = w ? Ms : Me;
+      warp_knn5(M, cfg.knn_gate_f, pw.x, pw.y, pw.z, spool[threadIdx.x >> 5], rd, ri);
 #pragma unroll
-  for (int w = 0; w < 2; ++w) {
-    M[w].pts = L.map[w][cur]; M[w].table = L.ctab[w]; M[w].hmask = (uint32_t)L.cmeta[w][0];
-    M[w].orig = L.cmeta[w][1] ? L.corig[w] : nullptr; M[w].g = cfg.cg[w];
-  }
-  for (int q = blockIdx.x * wpb + (threadIdx.x >> 5); q < nq; q += gridDim.x * wpb) {
-    const int w = q >= ne ? 1 : 0;
-    const int k = w ? q - ne : q;
-    const float4 pw = associate(x, L.ds[w][k]);  // EM:355-363
-    float rd[5];
-    int ri[5];
-    warp_knn5(w ? M[1] : M[0], cfg.knn_gate_f, pw.x, pw.y, pw.z, rd, ri);
-#pragma unroll
-    for (int j = 0; j < 5; ++j)
-      if (lane == j) {
-        L.nn_idx[w][k * 5 + j] = ri[j] == INT_MAX ? -1 : ri[j];
-        L.nn_d2[w][k * 5 + j] = rd[j];
-      }
+      for (int t = 0; t < 5; ++t)
+        if (lane == t) {
+          L.nn_idx[w][k * 5 + t] = ri[t] == INT_MAX ? -1 : ri[t];
+          L.nn_d2[w][k * 5 + t] = rd[t];
+        }
+    }
   }
 }
 
 void launch_knn_cell_fit(const Launch& L, LaneDev* lanes, int lane0, int nlanes, int cur, const ConfigDev& cfg, const double* pose_override) {
-  dim3 g(KNN_G * 2, nlanes);
+  dim3 g(KNN_G * 8, nlanes);
   k_knn_cell_assoc<<<g, KC_THREADS, 0, L.st>>>(lanes, lane0, cur, cfg, pose_override);
   L.tick(K_KNN_CELL);
   launch_fit(L, lanes, lane0, nlanes, cur, cfg);
@@ -895,8 +1118,9 @@ __global__ void __launch_bounds__(KC_THREADS) k_knn_cell_only(const float4* __re
   const int lane = threadIdx.x & 31;
   const int wpb = KC_THREADS / 32;
   CellMapView M;
-  M.pts = pts; M.table = table; M.hmask = (uint32_t)meta[0]; M.orig = meta[1] ? orig : nullptr; M.g = g;
+  M.pts = pts; M.table = table; M.hmask = (uint32_t)meta[0]; M.orig = meta[1] ? orig : nullptr; M.g = g; M.n = *n_dev;
   const bool empty = *n_dev == 0;
+  __shared__ uint2 spool[KC_THREADS / 32][POOL_CAP];
   for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < nq; i += gridDim.x * wpb) {
     const float4 p = q[i];
     float rd[5];
@@ -905,7 +1129,7 @@ __global__ void __launch_bounds__(KC_THREADS) k_knn_cell_only(const float4* __re
 #pragma unroll
       for (int j = 0; j < 5; ++j) { rd[j] = FLT_MAX; ri[j] = INT_MAX; }
     } else {
-      warp_knn5(M, gate_f, p.x, p.y, p.z, rd, ri);
+      warp_knn5(M, gate_f, p.x, p.y, p.z, spool[threadIdx.x >> 5], rd, ri);
     }
 #pragma unroll
     for (int j = 0; j < 5; ++j)

@@ -4,6 +4,7 @@
 #include "../../include/vilf.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cmath>
 #include <new>
@@ -12,6 +13,15 @@
 #include <vector>
 
 using namespace vilf;
+
+namespace vilf {
+int g_debug_sync = 0;
+void debug_sync_check(cudaStream_t st, int kid) {
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) fprintf(stderr, "[vilf] kernel id %d (%s) failed: %s\n", kid, vilf_profile_kernel_name(kid), cudaGetErrorString(e));
+}
+}  // namespace vilf
 
 namespace {
 
@@ -23,7 +33,7 @@ constexpr int MAX_MARKS = PROF_MAX_EVENTS;
 
 struct Slot {
   cudaEvent_t done = nullptr;
-  cudaEvent_t stage[MAX_MARKS] = {};  // profiling: event k closes an interval attributed to stage_tag[k] (phase*32 + kernel)
+  cudaEvent_t stage[MAX_MARKS] = {};  // profiling: event k closes an interval attributed to stage_tag[k] (phase*64 + kernel)
   int stage_tag[MAX_MARKS] = {};
   ProfSink sink;
   LaneVars* vars_pin = nullptr;  // [nlanes]
@@ -169,19 +179,20 @@ void grid_geometry(const Ctx* C, double leaf, GridJob& G) {
   G.rings = rings;
 }
 
-// Search cells of a cell-ordered map: cubes of 2^shift voxels of the map's own voxel filter.  Start from the smallest power of
-// two whose cube edge covers the gate radius (one shell of 27 cells suffices); dense maps (>= 8 voxels per cell edge) get finer
-// cells and more shells with early exit, like grid_geometry above.
+// Search cells of a cell-ordered map: cubes of 2^shift voxels of the map's own voxel filter.  Two voxels per cell edge and as
+// many shells as the gate radius needs: on a voxel-filtered surface the first shell (a box of six voxels) already holds ~36
+// candidates and the fifth neighbour (~1.3 leaf sizes away) lies inside the distance the shell guarantees, so the walk stops
+// after it; coarser cells only multiply the candidates (ncu: the search is instruction-issue bound, ~25 instructions per
+// candidate batch and ~60 per batch of 32 probed cells).  Leaves at or above the gate radius need one voxel per cell.
 CellGeom cell_geometry(const Ctx* C, double leaf) {
   CellGeom g;
   g.leaf = (float)leaf;
   g.inv_leaf = 1.0f / (float)leaf;  // inverse_leaf_size_ = Array4f::Ones() / leaf_size_.array()
   const double reach = std::sqrt(C->ucfg.knn_gate) * 1.001;
-  int shift = 0;
-  while ((double)(1 << shift) * (double)g.leaf < reach && shift < 12) ++shift;
-  int shells = 1;
-  while (shells < 4 && (1 << shift) >= 8) { --shift; shells *= 2; }
-  g.shift = shift; g.shells = shells;
+  int shift = (double)g.leaf >= reach ? 0 : 1;
+  int shells = (int)std::ceil(reach / ((double)(1 << shift) * (double)g.leaf));
+  while (shells > 6 && shift < 12) { ++shift; shells = (int)std::ceil(reach / ((double)(1 << shift) * (double)g.leaf)); }
+  g.shift = shift; g.shells = shells < 1 ? 1 : shells;
   return g;
 }
 
@@ -194,6 +205,7 @@ int alloc_merge(Ctx* C, MergeJob& M, int cap_new, int cap_map_total) {
   CK(dalloc(C, &M.nkey, (size_t)cap_new));
   CK(dalloc(C, &M.part, (size_t)M.max_tiles + 2));
   CK(dalloc(C, &M.agg, (size_t)M.max_tiles + 1));
+  CK(dalloc(C, &M.tout, (size_t)M.max_tiles + 1));
   CK(dalloc(C, &M.orphans, (size_t)ORPHAN_CAP));
   return VILF_OK;
 }
@@ -261,11 +273,12 @@ int build_ctx(Ctx* C) {
   CK(dalloc(C, &C->lanes_dev, (size_t)NL));
   for (int b = 0; b < 2; ++b) CK(dalloc(C, &C->grid_dev[b], (size_t)NL * 2));
   const bool allow_cluster = !(u.flags & VILF_FLAG_NO_CLUSTER);
-  C->use_graphs = !(u.flags & VILF_FLAG_NO_GRAPH);
+  g_debug_sync = getenv("VILF_DEBUG_SYNC") != nullptr;
+  C->use_graphs = !(u.flags & VILF_FLAG_NO_GRAPH) && !g_debug_sync;
   c.flags_no_cluster = (u.flags & VILF_FLAG_NO_CLUSTER) ? 1 : 0;
   C->cluster_scan = allow_cluster && capS <= CLUSTER_MAX_POINTS;
   C->cluster_map = allow_cluster && capM <= CLUSTER_MAX_POINTS;
-  C->cellmap = !(u.flags & VILF_FLAG_LEGACY_MAP);
+  C->cellmap = (u.flags & VILF_FLAG_CELL_MAP) ? true : (u.flags & VILF_FLAG_LEGACY_MAP) ? false : capM > CLUSTER_MAX_POINTS;
   c.cg[0] = cell_geometry(C, u.edge_leaf);
   c.cg[1] = cell_geometry(C, u.surf_leaf);
   CK(init_cellmap_kernels());
@@ -520,7 +533,8 @@ int status_to_rc(Ctx* C, int status) {
 // crop + voxel-filter both maps into the other buffer, rebuild the search grids, flip the buffers.
 void issue_submap(Ctx* C, const Launch& L, int lane0, int nl, int cur, ProfSink* sink) {
   if (C->cellmap) {
-    launch_cell_update(L, C->merge_dev[cur] + lane0 * 2, C->merge_sort_dev + lane0 * 2, nl * 2, C->max_tiles);
+    launch_cell_update(L, C->merge_dev[cur] + lane0 * 2, C->merge_sort_dev + lane0 * 2, nl * 2, C->max_tiles,
+                       !C->cfg.flags_no_cluster && C->cfg.cap_scan + ORPHAN_CAP <= CLUSTER_MAX_POINTS);
   } else if (C->cluster_map) {
     launch_voxel_cluster(L, C->vox_map_dev[cur] + lane0 * 2, nl * 2, false, C->cfg);
   } else {
@@ -1381,7 +1395,7 @@ int vilf_bench_stage(vilf_handle* h, int stage, const float* map, int m, const f
     CK(cudaMemcpyAsync(C->aux_out, q, (size_t)nq * 16, cudaMemcpyHostToDevice, C->st));
     CK(cudaStreamSynchronize(C->st));
     CK(cudaEventRecord(ev[0], C->st));
-    launch_cell_update(L, C->aux_merge_dev, C->aux_merge_sort_dev, 1, C->aux_max_tiles);
+    launch_cell_update(L, C->aux_merge_dev, C->aux_merge_sort_dev, 1, C->aux_max_tiles, false);
     CK(cudaEventRecord(ev[1], C->st));
     CK(cudaMemcpyAsync(hdr, C->aux_n, sizeof(hdr), cudaMemcpyDeviceToHost, C->st));
     CK(cudaStreamSynchronize(C->st));
@@ -1399,7 +1413,8 @@ int vilf_bench_stage(vilf_handle* h, int stage, const float* map, int m, const f
     for (int it = -1; it < iters; ++it) {
       CK(cudaMemcpyAsync(C->aux_n + 6, C->aux_n + 5, sizeof(int), cudaMemcpyDeviceToDevice, C->st));
       CK(cudaEventRecord(ev[0], C->st));
-      launch_cell_update(L, C->aux_merge_dev, C->aux_merge_sort_dev, 1, C->aux_max_tiles);
+      launch_cell_update(L, C->aux_merge_dev, C->aux_merge_sort_dev, 1, C->aux_max_tiles,
+                         !C->cfg.flags_no_cluster && nq + ORPHAN_CAP <= CLUSTER_MAX_POINTS);  // like the per-frame path: one cluster sorts the new points
       CK(cudaEventRecord(ev[1], C->st));
       CK(cudaMemcpyAsync(hdr, C->aux_n, sizeof(hdr), cudaMemcpyDeviceToHost, C->st));
       CK(cudaStreamSynchronize(C->st));
@@ -1637,7 +1652,7 @@ int vilf_profile_read(vilf_handle* h, double ms_out[7], int64_t* frames, int res
   if (ms_out) {
     for (int i = 0; i < N_STAGE; ++i) ms_out[i] = 0;
     for (int tag = 0; tag < PROF_TAGS; ++tag) {
-      const int ph = tag / 32, k = tag % 32;
+      const int ph = tag / PROF_KSLOTS, k = tag % PROF_KSLOTS;
       int stage = ph == 0 ? 0 : ph == 1 ? 1 : ph == 4 ? 2 : ph == 3 ? 5 : (k == K_SOLVE ? 4 : 3);
       ms_out[stage] += C->kernel_ms[tag];
     }

@@ -161,8 +161,8 @@ struct GridJob {
 // voxel filter, so ONE order serves both pcl::VoxelGrid (a voxel is a run of equal keys; the per-frame update is a merge of
 // the sorted map with the few thousand sorted new points) and the 5-NN search (a cell is a contiguous range; an open-addressing
 // table maps cell -> [start, end)).
-constexpr int MERGE_TILE = 2048;     // merged elements per CTA tile of the map update
-constexpr int MERGE_THREADS = 512;
+constexpr int MERGE_TILE = 1024;     // merged elements per CTA tile of the map update
+constexpr int MERGE_THREADS = 256;
 constexpr int ORPHAN_CAP = 256;      // centroids that rounded across a voxel face, re-inserted with the next frame's points
 constexpr int VOX_BIAS = 1 << 20;    // voxel coordinates are biased into 21 unsigned bits per axis
 struct MergeVars {
@@ -183,6 +183,13 @@ struct TileAgg {   // per merge tile, written by the counting pass
   int last_run_start;    // tile-relative index of the first point of the last cell run
   unsigned long long first_cell, last_cell;
 };
+struct TileOut {   // per merge tile, written by the scan between the two passes
+  int base;              // outputs in front of the tile
+  int have_prev;         // is there any output in front of it?
+  int carry_start;       // index of the first point of the cell run that is open in front of the tile
+  int pad_;
+  unsigned long long carry_cell;
+};
 struct MergeJob {
   const float4* old_pts; float4* out_pts;
   int* n_map;                 // in: points of the old map, out: points of the new one
@@ -193,6 +200,7 @@ struct MergeJob {
   MergeVars* mv;
   uint32_t* part;             // [max_tiles + 1] old elements before every tile boundary (merge path)
   TileAgg* agg;               // [max_tiles]
+  TileOut* tout;              // [max_tiles]
   uint2* table; int hcap;     // cell -> [start, end) of the map being written
   int* meta;                  // [0] cell table mask, [1] has_orig (0 after an update)
   float4* orphans;
@@ -318,7 +326,8 @@ enum KernelId {
   K_NEW_XFORM, K_NEW_KEYHIST, K_MERGE_PART, K_MERGE_COUNT, K_MERGE_EMIT, K_CELL_BUILD, K_KNN_CELL, K_COUNT
 };
 constexpr int PROF_PHASES = 5;      // 0 extract, 1 scan downsample, 2 association + solve, 3 map update, 4 grid build
-constexpr int PROF_TAGS = PROF_PHASES * 32;
+constexpr int PROF_KSLOTS = 64;     // kernel ids per phase in a profile tag
+constexpr int PROF_TAGS = PROF_PHASES * PROF_KSLOTS;
 constexpr int PROF_MAX_EVENTS = 96;
 
 // Optional per-kernel timing: one CUDA event after every launch, tagged (phase, kernel).
@@ -327,15 +336,18 @@ struct ProfSink {
   int* tag;
   int n, cap, phase;
 };
+extern int g_debug_sync;  // VILF_DEBUG_SYNC=1: synchronise after every kernel and name the one that faults (forces VILF_FLAG_NO_GRAPH)
+void debug_sync_check(cudaStream_t st, int kid);
 struct Launch {
   cudaStream_t st;
   int64_t* counter;  // kernels launched
   ProfSink* prof;    // null unless profiling
   void tick(int kid) const {
     ++*counter;
+    if (g_debug_sync) debug_sync_check(st, kid);
     if (prof && prof->n < prof->cap) {
       cudaEventRecord(prof->ev[prof->n], st);
-      prof->tag[prof->n++] = kid + 32 * prof->phase;
+      prof->tag[prof->n++] = kid + PROF_KSLOTS * prof->phase;
     }
   }
 };
@@ -362,7 +374,7 @@ void launch_knn_fit(const Launch& L, LaneDev* lanes, const GridJob* grid_jobs, i
 void launch_knn_only(const Launch& L, const GridJob* job_dev, const float4* q, const int* nq_dev, int* idx, float* d2, const ConfigDev& cfg);
 // k_cellmap.cu
 cudaError_t init_cellmap_kernels();
-void launch_cell_update(const Launch& L, const MergeJob* jobs_dev, const SortJob* sort_jobs_dev, int njobs, int max_tiles);
+void launch_cell_update(const Launch& L, const MergeJob* jobs_dev, const SortJob* sort_jobs_dev, int njobs, int max_tiles, bool cluster_new);
 void launch_cell_build(const Launch& L, const CellBuildJob* jobs_dev, const SortJob* sort_jobs_dev, int njobs);
 void launch_knn_cell_fit(const Launch& L, LaneDev* lanes, int lane0, int nlanes, int cur, const ConfigDev& cfg, const double* pose_override);
 void launch_knn_cell_only(const Launch& L, const float4* pts, const int* n_dev, const uint2* table, const int* meta, const uint32_t* orig, CellGeom g,

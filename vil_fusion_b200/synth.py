@@ -211,13 +211,14 @@ class Sequence:
     """Lazy seeded sequence of scans: seq[i] -> (xyzi, ring); deterministic per (seed, i)."""
 
     def __init__(self, sensor: str = "hdl64", n_frames: int = 100, seed: int = 0,
-                 density: float = 1.0, noise: float = 0.01, speed: float = 1.0, order: int = 0):
+                 density: float = 1.0, noise: float = 0.01, speed: float = 1.0, order: int = 0, world_length: float | None = None):
         self.sensor = SENSORS[sensor]()
         self.n_frames = n_frames
         self.seed = seed
         self.noise = noise
         self.order = order
-        self.world = make_world(seed, length=max(400.0, n_frames * speed + 300.0), density=density)
+        # the world generator draws side by side, so its objects depend on the length: pin it to compare runs of different lengths
+        self.world = make_world(seed, length=world_length if world_length else max(400.0, n_frames * speed + 300.0), density=density)
         self.R, self.t = trajectory(n_frames, seed, speed)
 
     def __len__(self) -> int:
