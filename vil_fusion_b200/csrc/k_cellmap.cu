@@ -973,15 +973,27 @@ __device__ __forceinline__ void warp_knn5(const CellMapView& M, float gate_f, fl
   int npool = 0;
   float gate_dyn = gate_f;  // once five neighbours are known nothing farther than the fifth can matter (ties are kept: <=)
   for (int r = 1; r <= shells; ++r) {
-    const int side = 2 * r + 1, ncell = side * side * side;
+    // cells of Chebyshev distance exactly r (r = 1: the whole 27-cell cube): the two z faces, then the square rings of the layers between
+    const int side = 2 * r + 1, face = side * side, ring = 8 * r;
+    const int ncell = r == 1 ? 27 : 2 * face + (side - 2) * ring;
     for (int cb = 0; cb < ncell; cb += 32) {
       const int t = cb + lane;
       uint32_t s0 = 0, e0 = 0;
       if (t < ncell) {
-        const int dx = t % side - r, dy = (t / side) % side - r, dz = t / (side * side) - r;
+        int dx, dy, dz;
+        if (r == 1) {
+          dx = t % 3 - 1; dy = (t / 3) % 3 - 1; dz = t / 9 - 1;
+        } else if (t < 2 * face) {
+          const int u = t < face ? t : t - face;
+          dx = u % side - r; dy = u / side - r; dz = t < face ? -r : r;
+        } else {
+          const int u = t - 2 * face, v = u % ring, sd = v / (2 * r), off = v % (2 * r);
+          dz = u / ring - r + 1;
+          dx = sd == 0 ? -r + off : sd == 1 ? r : sd == 2 ? r - off : -r;
+          dy = sd == 0 ? -r : sd == 1 ? -r + off : sd == 2 ? r : r - off;
+        }
         const int cx = qcx + dx, cy = qcy + dy, cz = qcz + dz;
-        const bool shell = r == 1 || max(max(abs(dx), abs(dy)), abs(dz)) == r;  // the interior was visited in the previous round
-        if (shell && cx >= 0 && cy >= 0 && cz >= 0 && cx <= ncmax && cy <= ncmax && cz <= ncmax) {
+        if (cx >= 0 && cy >= 0 && cz >= 0 && cx <= ncmax && cy <= ncmax && cz <= ncmax) {
           const unsigned long long ck = cellkey_cells((uint32_t)cx, (uint32_t)cy, (uint32_t)cz, s);
           uint32_t h = cell_slot(ck) & M.hmask;
           for (;;) {

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
+#include <algorithm>
 #include <new>
 #include <map>
 #include <tuple>
@@ -179,17 +180,26 @@ void grid_geometry(const Ctx* C, double leaf, GridJob& G) {
   G.rings = rings;
 }
 
-// Search cells of a cell-ordered map: cubes of 2^shift voxels of the map's own voxel filter.  Two voxels per cell edge and as
-// many shells as the gate radius needs: on a voxel-filtered surface the first shell (a box of six voxels) already holds ~36
-// candidates and the fifth neighbour (~1.3 leaf sizes away) lies inside the distance the shell guarantees, so the walk stops
-// after it; coarser cells only multiply the candidates (ncu: the search is instruction-issue bound, ~25 instructions per
-// candidate batch and ~60 per batch of 32 probed cells).  Leaves at or above the gate radius need one voxel per cell.
+// Search cells of a cell-ordered map: cubes of 2^shift voxels of the map's own voxel filter, walked shell by shell with early
+// exit.  Cell edge = the smallest power-of-two multiple of the leaf that is >= max(2 leaves, 0.4 x gate radius):
+//  - on a dense voxel-filtered surface the first shell (a box of three cells) then holds a few dozen candidates and the fifth
+//    neighbour (~1.3 leaves away) lies inside the distance that shell guarantees, so the walk stops after it;
+//  - in the sparse far field of a lidar map (point spacing set by the beams, not by the leaf) cells much finer than the gate make
+//    every query walk many shells of empty cells.  Measured on the configs[2] sequence (leaf 0.1 m, ~1e6 map points, 3.7e4 queries
+//    per sequence and iteration, 4 sequences): 229 us per search launch with 0.2 m cells, 95 us with 0.4 m, 180 us with 0.8 m
+//    (the hashed 0.25 m grid of the radix path: 247 us).
+// Leaves at or above the gate radius use one voxel per cell.
 CellGeom cell_geometry(const Ctx* C, double leaf) {
   CellGeom g;
   g.leaf = (float)leaf;
   g.inv_leaf = 1.0f / (float)leaf;  // inverse_leaf_size_ = Array4f::Ones() / leaf_size_.array()
   const double reach = std::sqrt(C->ucfg.knn_gate) * 1.001;
-  int shift = (double)g.leaf >= reach ? 0 : 1;
+  int shift = 0;
+  if ((double)g.leaf < reach) {
+    const double target = std::max(2.0 * (double)g.leaf, 0.4 * reach);
+    while ((double)(1 << shift) * (double)g.leaf < target * (1.0 - 1e-6) && shift < 12) ++shift;
+  }
+  if (const char* e = getenv("VILF_CELL_SHIFT")) shift = atoi(e);  // experiments only
   int shells = (int)std::ceil(reach / ((double)(1 << shift) * (double)g.leaf));
   while (shells > 6 && shift < 12) { ++shift; shells = (int)std::ceil(reach / ((double)(1 << shift) * (double)g.leaf)); }
   g.shift = shift; g.shells = shells < 1 ? 1 : shells;
