@@ -161,6 +161,50 @@ int vilf_get_cloud(vilf_handle* h, int which, float* out, int cap, int* n);
 int vilf_feature_depth(vilf_handle* h, const float* cloud_cam, int n, const double T_lidar_cam[16], const float* feats, int m, int num_bins,
                        float* depth_out, int32_t* nn_out, int* n_cloud);
 
+/* ---- next to the path: ScanContext place recognition ----
+ * SCManager of src/global_fusion/include/Scancontext/Scancontext.h (SC below) on the GPU: the polar max-height descriptor
+ * (makeScancontext SC:42-83), ring key / sector key (SC:86-115), the column-shift cosine distance (fastAlignUsingVkey,
+ * distDirectSC, distanceBtnScanContext SC:119-193) and the loop-candidate search (makeAndSaveScancontextAndKeys,
+ * detectLoopClosureID SC:196-299).  The ring-key kd-tree of the reference is an exact k-NN; here it is an exact exhaustive
+ * search with the same metric and summation order, snapshot semantics included (the "tree" is rebuilt every
+ * tree_making_period-th detection from all keys but the num_exclude_recent newest, SC:227-238).  Descriptors are
+ * double[num_ring][num_sector], ROW-major (Eigen::MatrixXd is column-major: transpose when handing one to Eigen).
+ * pcl::IterativeClosestPoint (poseGraphOptimization.cpp:376-444) is not part of this interface. */
+typedef struct vilf_sc vilf_sc;
+typedef struct vilf_sc_params {
+  double lidar_height;        /* SC:313 LIDAR_HEIGHT (2.0) */
+  int32_t num_ring;           /* SC:315 PC_NUM_RING (20) */
+  int32_t num_sector;         /* SC:316 PC_NUM_SECTOR (60) */
+  double max_radius;          /* SC:318 PC_MAX_RADIUS (80.0; setMaximumRadius SC:305) */
+  int32_t num_exclude_recent; /* SC:323 (30) */
+  int32_t num_candidates;     /* SC:324 NUM_CANDIDATES_FROM_TREE (3; at most 4 here) */
+  double search_ratio;        /* SC:327 (0.1) */
+  double dist_thres;          /* SC:329 SC_DIST_THRES (0.2; setSCdistThres SC:300) */
+  int32_t tree_making_period; /* SC:332 (30) */
+  int32_t max_keyframes;      /* capacity: key frames kept on the device */
+  int32_t max_points;         /* capacity: points of one host cloud */
+  int32_t pad_;
+} vilf_sc_params;
+int vilf_sc_default_params(vilf_sc_params* p);
+int vilf_sc_create(const vilf_sc_params* p, int device, vilf_sc** out);
+int vilf_sc_destroy(vilf_sc* sc);
+const char* vilf_sc_last_error(vilf_sc* sc);
+/* SCManager::makeAndSaveScancontextAndKeys (SC:196-208) of a host cloud [n][4]. */
+int vilf_sc_make_and_save(vilf_sc* sc, const float* xyzi, int n);
+/* The same for the cloud the odometry handle would hand out as getMapCloud(MapCloud) (EM:371-375; what the node publishes on
+ * /GlobalMap and global_fusion turns into a key frame) — taken where it lies in device memory, no copy through the host. */
+int vilf_sc_make_and_save_resident(vilf_sc* sc, vilf_handle* h);
+/* SCManager::detectLoopClosureID (SC:210-299): loop_id = matched key frame or -1, yaw_diff_rad = deg2rad(shift * 360 / num_sector);
+ * min_dist / nn_idx = the values the reference prints (10000000 / 0 when the early return of SC:220-224 is taken). */
+int vilf_sc_detect_loop_closure(vilf_sc* sc, int* loop_id, float* yaw_diff_rad, double* min_dist, int* nn_idx);
+/* polarcontexts_[index], polarcontext_invkeys_[index], polarcontext_vkeys_[index]; negative index counts from the back. */
+int vilf_sc_get(vilf_sc* sc, int index, double* desc, double* ringkey, double* sectorkey);
+int vilf_sc_size(vilf_sc* sc, int* n);
+/* SCManager::distanceBtnScanContext (SC:163-193) of two explicit descriptors / of two stored key frames. */
+int vilf_sc_distance(vilf_sc* sc, const double* sc1, const double* sc2, double* dist, int* shift);
+int vilf_sc_distance_between(vilf_sc* sc, int i, int j, double* dist, int* shift);
+int vilf_sc_launch_count(vilf_sc* sc, int64_t* launches);
+
 /* ---- stage-level entry points (unit parity against the oracle; they clobber per-frame scratch only) ---- */
 /* pcl::VoxelGrid<PointXYZI>::filter (EM:248-251, :347-350). Returns n_out; *guard = 1 when PCL's
  * "leaf size too small" int32 guard fired and the output is the input. */

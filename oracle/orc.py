@@ -14,15 +14,16 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "_build", "liborc.so")
 _REF = os.path.join(_HERE, "_ref", "libref_nanoflann.so")
+_REF_SC = os.path.join(_HERE, "_ref", "libref_sckeys.so")
 
 
 def build(force: bool = False) -> None:
     """Compile the oracle (and oracle/_ref when /root/reference is present)."""
     if force or not os.path.exists(_LIB) or any(
-        os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB) for f in ("orc_capi.cpp", "orc_pipeline.hpp", "orc_math.hpp", "orc_depth.hpp")
+        os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB) for f in ("orc_capi.cpp", "orc_pipeline.hpp", "orc_math.hpp", "orc_depth.hpp", "orc_scancontext.hpp")
     ):
         subprocess.run(["make", "-C", _HERE, "_build/liborc.so"], check=True, capture_output=True)
-    if os.path.isdir("/root/reference") and (force or not os.path.exists(_REF)):
+    if os.path.isdir("/root/reference") and (force or not os.path.exists(_REF) or not os.path.exists(_REF_SC)):
         subprocess.run(["make", "-C", _HERE, "ref"], check=True, capture_output=True)
 
 
@@ -302,3 +303,85 @@ class Odometry:
         t = np.zeros(7)
         lib().orc_odom_get_timing(self._h, _p(t, C.c_double))
         return dict(extract=t[0], scan_ds=t[1], kd_build=t[2], assoc=t[3], solve=t[4], map_update=t[5], frames=int(t[6]))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# ScanContext (src/global_fusion/include/Scancontext/Scancontext.h)
+# ---------------------------------------------------------------------------------------------------------
+class SCParams(C.Structure):
+    _fields_ = [("lidar_height", C.c_double), ("num_ring", C.c_int), ("num_sector", C.c_int), ("max_radius", C.c_double),
+                ("num_exclude_recent", C.c_int), ("num_candidates", C.c_int), ("search_ratio", C.c_double), ("dist_thres", C.c_double),
+                ("tree_making_period", C.c_int), ("pad_", C.c_int)]
+
+
+def sc_params(**kw) -> SCParams:
+    p = SCParams()
+    lib().orc_sc_default_params(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
+def sc_make(pts, params: SCParams | None = None):
+    """makeScancontext + ring key + sector key -> (desc [ring, sector], ringkey [ring], sectorkey [sector])."""
+    p = params or sc_params()
+    pts = _f32(pts)
+    d = np.zeros((p.num_ring, p.num_sector)); rk = np.zeros(p.num_ring); sk = np.zeros(p.num_sector)
+    lib().orc_sc_make(C.byref(p), _p(pts, C.c_float), pts.shape[0], _p(d, C.c_double), _p(rk, C.c_double), _p(sk, C.c_double))
+    return d, rk, sk
+
+
+def sc_distance(sc1, sc2, params: SCParams | None = None):
+    """distanceBtnScanContext -> (distance, column shift)."""
+    p = params or sc_params()
+    a = _f64(sc1); b = _f64(sc2)
+    dist = C.c_double(); sh = C.c_int()
+    lib().orc_sc_distance(C.byref(p), _p(a, C.c_double), _p(b, C.c_double), C.byref(dist), C.byref(sh))
+    return dist.value, sh.value
+
+
+def sc_key_dist(a, b):
+    a = _f32(a); b = _f32(b)
+    lib().orc_sc_key_dist.restype = C.c_float
+    return float(lib().orc_sc_key_dist(_p(a, C.c_float), _p(b, C.c_float), a.shape[0]))
+
+
+class SCManager:
+    def __init__(self, params: SCParams | None = None):
+        self.p = params or sc_params()
+        lib().orc_sc_create.restype = C.c_void_p
+        self._h = C.c_void_p(lib().orc_sc_create(C.byref(self.p)))
+
+    def add(self, pts):
+        pts = _f32(pts)
+        lib().orc_sc_add(self._h, _p(pts, C.c_float), pts.shape[0])
+
+    def detect(self):
+        """detectLoopClosureID -> (loop id or -1, yaw difference [rad], nearest distance, nearest index)."""
+        lid = C.c_int(); yaw = C.c_float(); md = C.c_double(); nn = C.c_int()
+        lib().orc_sc_detect(self._h, C.byref(lid), C.byref(yaw), C.byref(md), C.byref(nn))
+        return lid.value, yaw.value, md.value, nn.value
+
+    def close(self):
+        if self._h:
+            lib().orc_sc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def ref_sc_key_knn(keys, query, k: int = 3):
+    """The reference's own ring-key kd-tree (oracle/_ref/libref_sckeys.so): (indices [k], squared distances [k])."""
+    if not os.path.exists(_REF_SC):
+        raise RuntimeError("oracle/_ref/libref_sckeys.so not built")
+    r = C.CDLL(_REF_SC)
+    keys = _f32(keys); query = _f32(query)
+    idx = np.zeros(k, np.int64); d2 = np.zeros(k, np.float32)
+    r.ref_sc_key_knn(_p(keys, C.c_float), keys.shape[0], keys.shape[1], _p(query, C.c_float), k, _p(idx, C.c_longlong), _p(d2, C.c_float))
+    return idx, d2

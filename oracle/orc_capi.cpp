@@ -2,6 +2,7 @@
 // bench.py's CPU-baseline legs only).  NOT product code; PARITY UNPINNED, see orc_pipeline.hpp.
 #include "orc_pipeline.hpp"
 #include "orc_depth.hpp"
+#include "orc_scancontext.hpp"
 
 using namespace orc;
 
@@ -286,5 +287,39 @@ void orc_node_outputs(const double* rt12, double* last7, double* rel7, double* p
   last7[0] = q.x; last7[1] = q.y; last7[2] = q.z; last7[3] = q.w; last7[4] = t.x; last7[5] = t.y; last7[6] = t.z;
 }
 
+
+// ---- ScanContext (Scancontext.h) ----
+struct orc_sc_params { double lidar_height; int num_ring, num_sector; double max_radius; int num_exclude_recent, num_candidates; double search_ratio, dist_thres; int tree_making_period, pad_; };
+static SCParams to_sc(const orc_sc_params* p) {
+  SCParams P;
+  if (p) { P.lidar_height = p->lidar_height; P.num_ring = p->num_ring; P.num_sector = p->num_sector; P.max_radius = p->max_radius;
+           P.num_exclude_recent = p->num_exclude_recent; P.num_candidates = p->num_candidates; P.search_ratio = p->search_ratio;
+           P.dist_thres = p->dist_thres; P.tree_making_period = p->tree_making_period; }
+  return P;
+}
+void orc_sc_default_params(orc_sc_params* p) {
+  SCParams P;
+  p->lidar_height = P.lidar_height; p->num_ring = P.num_ring; p->num_sector = P.num_sector; p->max_radius = P.max_radius;
+  p->num_exclude_recent = P.num_exclude_recent; p->num_candidates = P.num_candidates; p->search_ratio = P.search_ratio;
+  p->dist_thres = P.dist_thres; p->tree_making_period = P.tree_making_period; p->pad_ = 0;
+}
+void orc_sc_make(const orc_sc_params* p, const float* pts, int n, double* desc, double* ringkey, double* sectorkey) {
+  SCParams P = to_sc(p);
+  sc_make(P, pts, n, desc);
+  if (ringkey) sc_ringkey(P, desc, ringkey);
+  if (sectorkey) sc_sectorkey(P, desc, sectorkey);
+}
+void orc_sc_distance(const orc_sc_params* p, const double* sc1, const double* sc2, double* dist, int* shift) {
+  auto r = sc_distance(to_sc(p), sc1, sc2);
+  *dist = r.first; *shift = r.second;
+}
+void* orc_sc_create(const orc_sc_params* p) { SCManager* m = new SCManager(); m->P = to_sc(p); return m; }
+void orc_sc_destroy(void* h) { delete (SCManager*)h; }
+void orc_sc_add(void* h, const float* pts, int n) { ((SCManager*)h)->add(pts, n); }
+void orc_sc_detect(void* h, int* loop_id, float* yaw, double* min_dist, int* nn_idx) {
+  auto r = ((SCManager*)h)->detect(min_dist, nn_idx);
+  *loop_id = r.first; *yaw = r.second;
+}
+float orc_sc_key_dist(const float* a, const float* b, int dim) { return sc_key_dist(a, b, dim); }
 
 }  // extern "C"

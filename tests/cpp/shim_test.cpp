@@ -17,6 +17,7 @@
 #include "vilf/EstimationMapping.hpp"
 #include "vilf/featureDepth.hpp"
 #include "vilf/nodeOutputs.hpp"
+#include "vilf/Scancontext.hpp"
 
 using vilf::Cloud;
 using vilf::CloudPtr;
@@ -184,6 +185,21 @@ int main(int argc, char** argv) {
       vilf::PointType pi = scans[0]->points[0], po;
       odomEstimation.pointAssociateToMap(&pi, &po);
       if (!(std::isfinite(po.x) && std::isfinite(po.y) && std::isfinite(po.z))) return 1;
+    }
+    {  // D: the loop detector of global_fusion (poseGraphOptimization.cpp:553, :585-600) on the same scans, as key frames
+      vilf::SCManager scManager;
+      scManager.NUM_EXCLUDE_RECENT = 2; scManager.TREE_MAKING_PERIOD_ = 1;
+      scManager.setSCdistThres(0.3); scManager.setMaximumRadius(80.0);
+      for (size_t i = 0; i < scans.size(); ++i) scManager.makeAndSaveScancontextAndKeys(*scans[i]);
+      scManager.makeAndSaveScancontextAndKeys(*scans[0]);  // revisit of key frame 0
+      std::pair<int, float> r = scManager.detectLoopClosureID();
+      std::pair<double, int> d = scManager.distanceBtnScanContext((int)scans.size(), 0);
+      if (r.first != 0 || r.second != 0.0f || d.first != 0.0 || d.second != 0 || scManager.size() != (int)scans.size() + 1) {
+        std::fprintf(stderr, "SCManager mirror: expected loop 0 at distance 0, got id %d yaw %g dist %g shift %d\n", r.first, r.second, d.first, d.second);
+        return 1;
+      }
+      std::vector<double> a = scManager.getScancontext(0), b = scManager.getScancontext(-1);
+      if (a != b || scManager.distanceBtnScanContext(a, b).first != 0.0) { std::fprintf(stderr, "SCManager mirror: revisit descriptor differs\n"); return 1; }
     }
     double dab = 0, dac = 0;
     for (size_t i = 0; i < pa.size(); ++i) {

@@ -43,8 +43,13 @@ def test_mirror_keeps_the_reference_method_surface():
                  "class OdomEstimationClass", "void initMapWithPoints(", "void updatePointsToMap(", "int addEdgeCostFactor(", "int addSurfCostFactor(",
                  "void addPointsToMap(", "void pointAssociateToMap(", "void downSamplingToMap(", "void getMap("):
         assert name in em, name
+    sc = open(os.path.join(INC, "Scancontext.hpp")).read()
+    for name in ("class SCManager", "void makeAndSaveScancontextAndKeys(", "std::pair<int, float> detectLoopClosureID(", "void setSCdistThres(", "void setMaximumRadius(",
+                 "distanceBtnScanContext(", "double LIDAR_HEIGHT", "int PC_NUM_RING", "int PC_NUM_SECTOR", "double PC_MAX_RADIUS", "int NUM_EXCLUDE_RECENT",
+                 "int NUM_CANDIDATES_FROM_TREE", "double SEARCH_RATIO", "double SC_DIST_THRES", "int TREE_MAKING_PERIOD_"):
+        assert name in sc, name
     # the mirror goes through the C ABI only: no CUDA, torch or oracle in the headers
-    for txt in (fe, em, open(os.path.join(INC, "session.hpp")).read(), open(os.path.join(INC, "cloud.hpp")).read()):
+    for txt in (fe, em, sc, open(os.path.join(INC, "session.hpp")).read(), open(os.path.join(INC, "cloud.hpp")).read()):
         assert not re.search(r"cuda_runtime|torch|oracle", txt)
 
 

@@ -41,6 +41,8 @@ SYMBOLS = [
     "vilf_get_pose", "vilf_set_pose", "vilf_predict", "vilf_create_submap", "vilf_get_cloud", "vilf_voxel_downsample", "vilf_crop_voxel_downsample", "vilf_crop_box", "vilf_knn5",
     "vilf_factors", "vilf_normal_equations", "vilf_solve", "vilf_get_solves", "vilf_state_export", "vilf_state_import",
     "vilf_profile_enable", "vilf_profile_read", "vilf_profile_read_kernels", "vilf_profile_kernel_name", "vilf_launch_count", "vilf_get_stream", "vilf_get_counts", "vilf_debug_voxel_phases", "vilf_bench_stage", "vilf_feature_depth",
+    "vilf_sc_default_params", "vilf_sc_create", "vilf_sc_destroy", "vilf_sc_last_error", "vilf_sc_make_and_save", "vilf_sc_make_and_save_resident",
+    "vilf_sc_detect_loop_closure", "vilf_sc_get", "vilf_sc_size", "vilf_sc_distance", "vilf_sc_distance_between", "vilf_sc_launch_count",
 ]
 
 _lib = None
@@ -436,3 +438,90 @@ def node_outputs(rt12, last):
     if rc:
         raise VilfError(rc, "vilf_node_outputs")
     return rel, path, last
+
+
+# ---------------------------------------------------------------------------------------------------------
+# ScanContext place recognition (include/vilf.h: vilf_sc_*; SCManager of src/global_fusion/include/Scancontext/Scancontext.h)
+# ---------------------------------------------------------------------------------------------------------
+class SCParams(C.Structure):
+    _fields_ = [("lidar_height", C.c_double), ("num_ring", C.c_int32), ("num_sector", C.c_int32), ("max_radius", C.c_double),
+                ("num_exclude_recent", C.c_int32), ("num_candidates", C.c_int32), ("search_ratio", C.c_double), ("dist_thres", C.c_double),
+                ("tree_making_period", C.c_int32), ("max_keyframes", C.c_int32), ("max_points", C.c_int32), ("pad_", C.c_int32)]
+
+
+def sc_params(**kw) -> SCParams:
+    p = SCParams()
+    lib().vilf_sc_default_params(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
+class SCManager:
+    """SCManager of the reference on the GPU: add() = makeAndSaveScancontextAndKeys, detect() = detectLoopClosureID."""
+
+    def __init__(self, params: SCParams | None = None, device: int = 0):
+        self.p = params if params is not None else sc_params()
+        h = C.c_void_p()
+        rc = lib().vilf_sc_create(C.byref(self.p), device, C.byref(h))
+        if rc:
+            raise VilfError(rc, "vilf_sc_create failed (is a CUDA device visible?)")
+        self._h = h
+        lib().vilf_sc_last_error.restype = C.c_char_p
+        lib().vilf_sc_last_error.argtypes = [C.c_void_p]
+
+    def _ck(self, rc):
+        if rc:
+            raise VilfError(rc, lib().vilf_sc_last_error(self._h).decode())
+
+    def close(self):
+        if self._h:
+            lib().vilf_sc_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add(self, xyzi):
+        xyzi = _f32(xyzi)
+        self._ck(lib().vilf_sc_make_and_save(self._h, _p(xyzi, C.c_float), xyzi.shape[0]))
+
+    def add_resident(self, odom: "Odometry"):
+        self._ck(lib().vilf_sc_make_and_save_resident(self._h, odom._h))
+
+    def detect(self):
+        """-> (loop id or -1, yaw difference [rad], nearest distance, nearest index)"""
+        lid = C.c_int(); yaw = C.c_float(); md = C.c_double(); nn = C.c_int()
+        self._ck(lib().vilf_sc_detect_loop_closure(self._h, C.byref(lid), C.byref(yaw), C.byref(md), C.byref(nn)))
+        return lid.value, yaw.value, md.value, nn.value
+
+    def get(self, index: int = -1):
+        d = np.zeros((self.p.num_ring, self.p.num_sector)); rk = np.zeros(self.p.num_ring); sk = np.zeros(self.p.num_sector)
+        self._ck(lib().vilf_sc_get(self._h, index, _p(d, C.c_double), _p(rk, C.c_double), _p(sk, C.c_double)))
+        return d, rk, sk
+
+    def __len__(self):
+        n = C.c_int()
+        self._ck(lib().vilf_sc_size(self._h, C.byref(n)))
+        return n.value
+
+    def distance(self, sc1, sc2):
+        a = _f64(sc1); b = _f64(sc2)
+        dist = C.c_double(); sh = C.c_int()
+        self._ck(lib().vilf_sc_distance(self._h, _p(a, C.c_double), _p(b, C.c_double), C.byref(dist), C.byref(sh)))
+        return dist.value, sh.value
+
+    def distance_between(self, i: int, j: int):
+        dist = C.c_double(); sh = C.c_int()
+        self._ck(lib().vilf_sc_distance_between(self._h, i, j, C.byref(dist), C.byref(sh)))
+        return dist.value, sh.value
+
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        self._ck(lib().vilf_sc_launch_count(self._h, C.byref(n)))
+        return n.value

@@ -1685,7 +1685,7 @@ const char* vilf_profile_kernel_name(int kernel) {
                                        "k_vox_bbox", "k_sort_keyhist<KeyGenVoxel>", "k_vox_heads", "k_vox_centroid", "k_map_append", "k_map_init",
                                        "k_grid_zero", "k_grid_count", "k_grid_scan_partial", "k_grid_scan_final", "k_grid_scatter", "k_knn_assoc",
                                        "k_knn_only", "k_solve", "k_fit", "k_voxel_cluster", "k_grid_cluster", "k_depth_cloud", "k_depth_query", "k_ring_partition",
-                                       "k_new_xform", "k_sort_keyhist<KeyGenNew>", "k_merge_partition", "k_merge<count>", "k_merge<emit>", "k_cell_build", "k_knn_cell_assoc"};
+                                       "k_new_xform", "k_sort_keyhist<KeyGenNew>", "k_merge_partition", "k_merge<count>", "k_merge<emit>", "k_cell_build", "k_knn_cell_assoc", "k_sc"};
   return (kernel >= 0 && kernel < K_COUNT) ? names[kernel] : "";
 }
 int vilf_launch_count(vilf_handle* h, int64_t* launches) {
@@ -1723,3 +1723,20 @@ int vilf_get_counts(vilf_handle* h, int32_t out8[8]) {
 }
 
 }  // extern "C"
+
+namespace vilf {
+// cloudNoRegistered as vilf_get_cloud(h, 5) hands it out (EM:110-114 after localMapInited, EM:304-305 otherwise), in place.
+int resident_scan_features(vilf_handle* h, const float4* p[2], const int* n[2], cudaStream_t* st, int* device) {
+  if (!h || !h->ctx) return VILF_ERR_INVALID;
+  Ctx* C = h->ctx;
+  const int lane = h->lane;
+  if (!C->have_map[lane]) return VILF_ERR_STATE;
+  LaneDev& L = C->lanes_host[lane];
+  LaneVars* V = C->vars_dev + lane;
+  if (C->last_init[lane]) { p[0] = L.feat[0]; n[0] = &V->n_edge; p[1] = L.feat[1]; n[1] = &V->n_surf; }
+  else { p[0] = L.ds[0]; n[0] = &V->n_ds[0]; p[1] = L.ds[1]; n[1] = &V->n_ds[1]; }
+  *st = C->st;
+  *device = C->device;
+  return VILF_OK;
+}
+}  // namespace vilf

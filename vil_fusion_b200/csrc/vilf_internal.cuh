@@ -9,6 +9,8 @@
 #include <limits.h>
 #include <math.h>
 
+struct vilf_handle;
+
 namespace vilf {
 
 constexpr int MAX_RINGS = 128;       // ring ids are 8-bit sort keys; 255 = dropped point
@@ -323,7 +325,7 @@ enum KernelId {
   K_RESET = 0, K_RING_KEYHIST, K_SORT_HIST, K_SORT_SCATTER, K_SECTOR, K_COMPACT, K_VOX_BBOX, K_VOX_KEYHIST, K_VOX_HEADS, K_VOX_CENTROID,
   K_MAP_APPEND, K_MAP_INIT, K_GRID_ZERO, K_GRID_COUNT, K_GRID_SCAN_PARTIAL, K_GRID_SCAN_FINAL, K_GRID_SCATTER, K_KNN_FIT, K_KNN_ONLY,
   K_SOLVE, K_FIT, K_VOX_CLUSTER, K_GRID_CLUSTER, K_DEPTH_CLOUD, K_DEPTH_QUERY, K_RING_PARTITION,
-  K_NEW_XFORM, K_NEW_KEYHIST, K_MERGE_PART, K_MERGE_COUNT, K_MERGE_EMIT, K_CELL_BUILD, K_KNN_CELL, K_COUNT
+  K_NEW_XFORM, K_NEW_KEYHIST, K_MERGE_PART, K_MERGE_COUNT, K_MERGE_EMIT, K_CELL_BUILD, K_KNN_CELL, K_SC, K_COUNT
 };
 constexpr int PROF_PHASES = 5;      // 0 extract, 1 scan downsample, 2 association + solve, 3 map update, 4 grid build
 constexpr int PROF_KSLOTS = 64;     // kernel ids per phase in a profile tag
@@ -384,6 +386,20 @@ void launch_fit(const Launch& L, LaneDev* lanes, int lane0, int nlanes, int cur,
 // k_depth.cu
 void launch_depth(const Launch& L, const float4* in, const int* n_dev, int from_scan, const double* T_dev, float4* sph, int* oidx, int* count,
                   const float* feats_dev, int m, float thr, float* depth_dev, int* nn_dev);
+// k_scancontext.cu (place recognition next to the path: SCManager, Scancontext.h:42-299)
+struct ScParams {
+  double lidar_height, max_radius, search_ratio, dist_thres;
+  int num_ring, num_sector, num_exclude_recent, num_candidates, tree_making_period;
+};
+cudaError_t init_sc_kernels();
+// vilf_api.cu: the cloud getMapCloud(MapCloud) hands to the node (EM:371-375 = /GlobalMap) where it lies on the device, as two segments;
+// `st` = the stream the odometry writes them on
+int resident_scan_features(vilf_handle* h, const float4* p[2], const int* n[2], cudaStream_t* st, int* device);
+void launch_sc_make(const Launch& L, const float4* p0, const int* n0_dev, const float4* p1, const int* n1_dev, const ScParams& P, int* bins, double* desc,
+                    double* ringkey, double* sectorkey, float* invkey);
+void launch_sc_distance(const Launch& L, const double* sc1, const double* sc2, const ScParams& P, double* out);
+void launch_sc_detect(const Launch& L, const float* keys, int n_snapshot, const float* cur_key, const double* descs, int cur_index, const ScParams& P, float* dist,
+                      double* res);
 // k_solve.cu
 void launch_solve(const Launch& L, LaneDev* lanes, int lane0, int nlanes, int outer, int finalize, const ConfigDev& cfg, int max_iters);
 
