@@ -40,11 +40,11 @@ WORKLOADS = {
     "hdl64": dict(sensor="hdl64", n_scan=64, n_rings=64, desc="synthetic HDL-64E 64x1800 sequence(s), leaf 0.4/0.8 (configs[3] per-GPU unit)"),
     "vlp32": dict(sensor="vlp32", n_scan=32, n_rings=32, desc="synthetic 32x1800 sequence(s), leaf 0.4/0.8 (configs[1])"),
     "beams128": dict(sensor="beams128", n_scan=0, n_rings=128, desc="synthetic 128x2048 sequence(s), explicit ring ids (configs[4] shape)"),
-    # BASELINE.json configs[2]: dense world, 0.1 m voxels, ~1e6 points in the +-100 m crop once the maps have filled (vil_fusion_b200/synth.py DENSE)
+    # BASELINE.json configs[2]: dense world, 0.09 m voxels, ~1e6 points in the +-100 m crop once the maps have filled (vil_fusion_b200/synth.py DENSE)
     "hdl64_dense": dict(sensor="hdl64", n_scan=64, n_rings=64, seq_kw=dict(density=synth.DENSE["density"], speed=synth.DENSE["speed"], world_length=700.0),
                         cfg_kw=dict(edge_leaf=synth.DENSE["edge_leaf"], surf_leaf=synth.DENSE["surf_leaf"]), map_cap=synth.DENSE["max_map_points"], seqs=4,
                         preroll=320, cpu_frames=20,
-                        desc="synthetic HDL-64E 64x1800 sequence(s) in a 3x denser world at 0.4 m/frame, leaf 0.1/0.1: ~1e6 live map points per sequence (configs[2])"),
+                        desc="synthetic HDL-64E 64x1800 sequence(s) in a 3x denser world at 0.4 m/frame, leaf 0.09/0.09: >= 1e6 live map points per sequence (configs[2])"),
 }
 
 

@@ -58,6 +58,13 @@ typedef struct vilf_config {
   int32_t max_map_points;  /* capacity: points per local map (edge and surf each) */
   int32_t max_ring_points; /* capacity: returns per ring (sizes the selection kernel's shared memory); 0 = 12298, the kernel's limit */
   int32_t flags;           /* VILF_FLAG_* bits; 0 by default */
+  /* The ring-field / range-image extractor (class featureExtract, FX = include/featureExtract.hpp) replaces the ring-angle
+   * extractor as stage 1 when VILF_FLAG_RANGE_IMAGE is set.  It needs n_scan == 0 (ring ids come with every scan, FX:341),
+   * n_rings = its N_SCAN (FX:86); lidar_min / lidar_max are its lidarMinRange / lidarMaxRange (FX:88-89, defaults 3 / 200). */
+  int32_t horizon_scan;      /* FX:85  Horizon_SCAN (1800), at most 6138 */
+  int32_t downsample_rate;   /* FX:87  downsampleRate (1): only rings with ring % rate == 0 are used */
+  double ri_edge_threshold;  /* FX:90  edgeThreshold (1.0), on the squared range curvature */
+  double ri_surf_threshold;  /* FX:91  surfThreshold (0.1) */
 } vilf_config;
 
 /* Implementation-selection flags (results are bit-identical either way; used by the parity tests and for profiling). */
@@ -72,6 +79,7 @@ typedef struct vilf_config {
  * Default: cell-ordered when max_map_points + max_scan_points > 2^19, radix-sorted otherwise; the flags force one. */
 #define VILF_FLAG_LEGACY_MAP 4 /* force the radix-sorted maps */
 #define VILF_FLAG_CELL_MAP 8   /* force the cell-ordered maps */
+#define VILF_FLAG_RANGE_IMAGE 16 /* stage 1 = featureExtract::extractFeature (FX:96-115) instead of featureExtraction::extractFeature */
 
 int vilf_default_config(vilf_config* cfg);
 

@@ -67,6 +67,12 @@ class EstimationMapping {
     fe.shareSession(sess_);
     applyConfig();
   }
+  // the same for any stage-1 class with shareSession(const SessionPtr&) (vilf::featureExtract, the ring-field extractor)
+  template <class Stage1>
+  void shareSessionWith(Stage1& fe) {
+    fe.shareSession(sess_);
+    applyConfig();
+  }
   const SessionPtr& session() const { return sess_; }
   void setTrustResident(bool on) { trust_resident_ = on; }  // false: always upload the clouds that are passed in
 

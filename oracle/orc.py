@@ -20,7 +20,7 @@ _REF_SC = os.path.join(_HERE, "_ref", "libref_sckeys.so")
 def build(force: bool = False) -> None:
     """Compile the oracle (and oracle/_ref when /root/reference is present)."""
     if force or not os.path.exists(_LIB) or any(
-        os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB) for f in ("orc_capi.cpp", "orc_pipeline.hpp", "orc_math.hpp", "orc_depth.hpp", "orc_scancontext.hpp")
+        os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB) for f in ("orc_capi.cpp", "orc_pipeline.hpp", "orc_math.hpp", "orc_depth.hpp", "orc_scancontext.hpp", "orc_rangeimage.hpp")
     ):
         subprocess.run(["make", "-C", _HERE, "_build/liborc.so"], check=True, capture_output=True)
     if os.path.isdir("/root/reference") and (force or not os.path.exists(_REF) or not os.path.exists(_REF_SC)):
@@ -34,6 +34,7 @@ class Config(C.Structure):
         ("edge_leaf", C.c_double), ("surf_leaf", C.c_double), ("crop_half", C.c_double),
         ("knn_gate", C.c_double), ("huber", C.c_double),
         ("outer_iters", C.c_int), ("lm_max_iters", C.c_int), ("voxel_order", C.c_int), ("knn_ties", C.c_int),
+        ("eig_alg", C.c_int), ("plane_alg", C.c_int), ("centroid_div", C.c_int), ("lm_solver", C.c_int),  # sensitivity alternates (orc_pipeline.hpp: Config)
     ]
 
 
@@ -222,15 +223,17 @@ def surf_eval(pose, pnd):
     return r, J
 
 
-def eig3(Cm):
+def eig3(Cm, alt: bool = False):
+    """EM:150.  alt: Eigen 3.3.7's tridiagonal QR iteration instead of cyclic Jacobi (sensitivity alternate)."""
     Cm = _f64(Cm); w = np.zeros(3); V = np.zeros((3, 3))
-    lib().orc_eig3(_p(Cm, C.c_double), _p(w, C.c_double), _p(V, C.c_double))
+    (lib().orc_eig3_alt if alt else lib().orc_eig3)(_p(Cm, C.c_double), _p(w, C.c_double), _p(V, C.c_double))
     return w, V
 
 
-def lstsq5x3(A, b):
+def lstsq5x3(A, b, alt: bool = False):
+    """EM:198.  alt: Householder QR without column pivoting instead of the column-pivoted one (sensitivity alternate)."""
     A = _f64(A); b = _f64(b); n = np.zeros(3)
-    lib().orc_lstsq5x3(_p(A, C.c_double), _p(b, C.c_double), _p(n, C.c_double))
+    (lib().orc_lstsq5x3_alt if alt else lib().orc_lstsq5x3)(_p(A, C.c_double), _p(b, C.c_double), _p(n, C.c_double))
     return n
 
 
@@ -385,3 +388,41 @@ def ref_sc_key_knn(keys, query, k: int = 3):
     idx = np.zeros(k, np.int64); d2 = np.zeros(k, np.float32)
     r.ref_sc_key_knn(_p(keys, C.c_float), keys.shape[0], keys.shape[1], _p(query, C.c_float), k, _p(idx, C.c_longlong), _p(d2, C.c_float))
     return idx, d2
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Ring-field / range-image feature extractor (src/visual_inertial_lidar/feature_tracker/include/featureExtract.hpp)
+# ---------------------------------------------------------------------------------------------------------
+class RIParams(C.Structure):
+    _fields_ = [("n_scan", C.c_int), ("horizon_scan", C.c_int), ("downsample_rate", C.c_int), ("pad_", C.c_int),
+                ("lidar_min", C.c_double), ("lidar_max", C.c_double), ("edge_threshold", C.c_double), ("surf_threshold", C.c_double)]
+
+
+def ri_params(**kw) -> RIParams:
+    p = RIParams()
+    lib().orc_ri_default_params(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
+def ri_extract(params: RIParams, xyzi, ring, debug: bool = False):
+    """featureExtract::extractFeature -> (edge [ne,4], edge_src [ne], surf [ns,4], surf_src [ns]) (+ dict of the intermediate arrays)."""
+    xyzi = _f32(xyzi)
+    ring = np.ascontiguousarray(ring, dtype=np.uint16)
+    n = xyzi.shape[0]
+    m = max(n, 1)
+    edge = np.empty((m, 4), np.float32); surf = np.empty((m, 4), np.float32); es = np.empty(m, np.int32); ss = np.empty(m, np.int32)
+    ne = C.c_int(); ns = C.c_int(); nsem = C.c_int()
+    dsrc = np.zeros(m, np.int32); dcol = np.zeros(m, np.int32); drng = np.zeros(m, np.float32); dcurv = np.zeros(m, np.float32); dpick = np.zeros(m, np.int32)
+    rse = np.zeros((params.n_scan, 2), np.int32)
+    lib().orc_ri_extract(C.byref(params), _p(xyzi, C.c_float), _p(ring, C.c_uint16), n, _p(edge, C.c_float), _p(es, C.c_int), C.byref(ne),
+                         _p(surf, C.c_float), _p(ss, C.c_int), C.byref(ns), _p(dsrc, C.c_int), _p(dcol, C.c_int), _p(drng, C.c_float), _p(dcurv, C.c_float),
+                         _p(dpick, C.c_int), C.byref(nsem), _p(rse, C.c_int))
+    out = (edge[:ne.value].copy(), es[:ne.value].copy(), surf[:ns.value].copy(), ss[:ns.value].copy())
+    if debug:
+        k = nsem.value
+        return out + (dict(src=dsrc[:k].copy(), col=dcol[:k].copy(), range=drng[:k].copy(), curvature=dcurv[:k].copy(), picked=dpick[:k].copy(), ring_start_end=rse),)
+    return out

@@ -3,6 +3,7 @@
 #include "orc_pipeline.hpp"
 #include "orc_depth.hpp"
 #include "orc_scancontext.hpp"
+#include "orc_rangeimage.hpp"
 
 using namespace orc;
 
@@ -12,6 +13,7 @@ struct orc_config {
   int n_scan, n_rings;
   double lidar_min, lidar_max, edge_threshold, edge_leaf, surf_leaf, crop_half, knn_gate, huber;
   int outer_iters, lm_max_iters, voxel_order, knn_ties;
+  int eig_alg, plane_alg, centroid_div, lm_solver;
 };
 
 static Config to_cfg(const orc_config* c) {
@@ -19,6 +21,7 @@ static Config to_cfg(const orc_config* c) {
   k.n_scan = c->n_scan; k.n_rings = c->n_rings; k.lidar_min = c->lidar_min; k.lidar_max = c->lidar_max;
   k.edge_threshold = c->edge_threshold; k.edge_leaf = c->edge_leaf; k.surf_leaf = c->surf_leaf; k.crop_half = c->crop_half;
   k.knn_gate = c->knn_gate; k.huber = c->huber; k.outer_iters = c->outer_iters; k.lm_max_iters = c->lm_max_iters; k.voxel_order = c->voxel_order; k.knn_ties = c->knn_ties;
+  k.eig_alg = c->eig_alg; k.plane_alg = c->plane_alg; k.centroid_div = c->centroid_div; k.lm_solver = c->lm_solver;
   return k;
 }
 static Cloud to_cloud(const float* p, int n) {
@@ -32,6 +35,7 @@ void orc_default_config(orc_config* c) {
   c->n_scan = k.n_scan; c->n_rings = k.n_rings; c->lidar_min = k.lidar_min; c->lidar_max = k.lidar_max; c->edge_threshold = k.edge_threshold;
   c->edge_leaf = k.edge_leaf; c->surf_leaf = k.surf_leaf; c->crop_half = k.crop_half; c->knn_gate = k.knn_gate; c->huber = k.huber;
   c->outer_iters = k.outer_iters; c->lm_max_iters = k.lm_max_iters; c->voxel_order = k.voxel_order; c->knn_ties = k.knn_ties;
+  c->eig_alg = k.eig_alg; c->plane_alg = k.plane_alg; c->centroid_div = k.centroid_div; c->lm_solver = k.lm_solver;
 }
 
 // Stage 1.  Output buffers hold up to n points; *_src = index of the point in the input scan.
@@ -176,6 +180,19 @@ void orc_eig3(const double* C9, double* w3, double* V9) {
   eig3_sym(C, w3, V);
   std::memcpy(V9, V.m, sizeof(V.m));
 }
+// the sensitivity alternates (orc_math.hpp): Eigen 3.3.7's tridiagonal QR iteration, unpivoted Householder plane fit
+void orc_eig3_alt(const double* C9, double* w3, double* V9) {
+  M3 C, V;
+  std::memcpy(C.m, C9, sizeof(C.m));
+  eig3_sym_eigen(C, w3, V);
+  std::memcpy(V9, V.m, sizeof(V.m));
+}
+void orc_lstsq5x3_alt(const double* A15, const double* b5, double* n3) {
+  double A[5][3];
+  std::memcpy(A, A15, sizeof(A));
+  V3 n = lstsq5x3_colpiv(A, b5, false);
+  n3[0] = n.x; n3[1] = n.y; n3[2] = n.z;
+}
 void orc_lstsq5x3(const double* A15, const double* b5, double* n3) {
   double A[5][3];
   std::memcpy(A, A15, sizeof(A));
@@ -287,6 +304,38 @@ void orc_node_outputs(const double* rt12, double* last7, double* rel7, double* p
   last7[0] = q.x; last7[1] = q.y; last7[2] = q.z; last7[3] = q.w; last7[4] = t.x; last7[5] = t.y; last7[6] = t.z;
 }
 
+
+// ---- ring-field / range-image extractor (featureExtract.hpp) ----
+struct orc_ri_params { int n_scan, horizon_scan, downsample_rate, pad_; double lidar_min, lidar_max, edge_threshold, surf_threshold; };
+void orc_ri_default_params(orc_ri_params* p) {
+  RIParams P;
+  p->n_scan = P.n_scan; p->horizon_scan = P.horizon_scan; p->downsample_rate = P.downsample_rate; p->pad_ = 0;
+  p->lidar_min = P.lidar_min; p->lidar_max = P.lidar_max; p->edge_threshold = P.edge_threshold; p->surf_threshold = P.surf_threshold;
+}
+// edge / surf: [n][4] capacity n each; dbg_* optional, capacity n each (semantic-cloud order), ring_se optional [2 * n_scan]
+void orc_ri_extract(const orc_ri_params* p, const float* xyzi, const uint16_t* ring, int n, float* edge, int* edge_src, int* n_edge, float* surf, int* surf_src,
+                    int* n_surf, int* dbg_src, int* dbg_col, float* dbg_range, float* dbg_curv, int* dbg_picked, int* n_sem, int* ring_se) {
+  RIParams P;
+  P.n_scan = p->n_scan; P.horizon_scan = p->horizon_scan; P.downsample_rate = p->downsample_rate; P.lidar_min = p->lidar_min; P.lidar_max = p->lidar_max;
+  P.edge_threshold = p->edge_threshold; P.surf_threshold = p->surf_threshold;
+  Cloud e, s;
+  std::vector<int> es, ss;
+  RIDebug D;
+  ri_extract(P, (const P4*)xyzi, ring, n, e, es, s, ss, &D);
+  *n_edge = (int)e.size(); *n_surf = (int)s.size();
+  if (!e.empty()) { std::memcpy(edge, e.data(), e.size() * sizeof(P4)); std::memcpy(edge_src, es.data(), es.size() * sizeof(int)); }
+  if (!s.empty()) { std::memcpy(surf, s.data(), s.size() * sizeof(P4)); std::memcpy(surf_src, ss.data(), ss.size() * sizeof(int)); }
+  const size_t m = D.src.size();
+  if (n_sem) *n_sem = (int)m;
+  if (m) {
+    if (dbg_src) std::memcpy(dbg_src, D.src.data(), m * sizeof(int));
+    if (dbg_col) std::memcpy(dbg_col, D.col.data(), m * sizeof(int));
+    if (dbg_range) std::memcpy(dbg_range, D.range.data(), m * sizeof(float));
+    if (dbg_curv) std::memcpy(dbg_curv, D.curvature.data(), m * sizeof(float));
+    if (dbg_picked) std::memcpy(dbg_picked, D.picked.data(), m * sizeof(int));
+  }
+  if (ring_se) for (int i = 0; i < P.n_scan; ++i) { ring_se[2 * i] = D.start[i]; ring_se[2 * i + 1] = D.end[i]; }
+}
 
 // ---- ScanContext (Scancontext.h) ----
 struct orc_sc_params { double lidar_height; int num_ring, num_sector; double max_radius; int num_exclude_recent, num_candidates; double search_ratio, dist_thres; int tree_making_period, pad_; };

@@ -7,6 +7,7 @@
 // that the hot path relies on.  Each function cites the call site it serves.
 #pragma once
 #include <cmath>
+#include <limits>
 #include <cstring>
 #include <algorithm>
 
@@ -190,10 +191,107 @@ inline void eig3_sym(const M3& C, double w[3], M3& V) {
   V = Vs;
 }
 
+// ALTERNATE of eig3_sym for the sensitivity study (tools/sensitivity.py; Config.eig_alg = 1): the algorithm Eigen 3.3.7's
+// SelfAdjointEigenSolver<Matrix3d>::compute() actually runs (Eigen/src/Eigenvalues/SelfAdjointEigenSolver.h, Tridiagonalization.h,
+// Jacobi.h — NOT under /root/reference; restated from the published source): scale by the largest |coefficient| of the lower
+// triangle, the closed-form 3x3 Householder tridiagonalisation (tridiagonalization_inplace_selector<MatrixType, 3, false>),
+// implicit symmetric QR steps with Wilkinson shift (tridiagonal_qr_step) until every sub-diagonal entry is negligible against its
+// diagonal neighbours (2 * eps), at most 30 * n iterations, eigenvalues sorted ascending by selection, scaled back.
+inline void eig3_sym_eigen(const M3& C, double w[3], M3& V) {
+  double m[3][3];  // lower triangle of C
+  double scale = 0;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j <= i; ++j) { m[i][j] = C.m[i][j]; scale = std::max(scale, std::fabs(C.m[i][j])); }
+  if (scale == 0) scale = 1;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j <= i; ++j) m[i][j] /= scale;
+  double diag[3], sub[2];
+  double Q[3][3];
+  {
+    const double tol = std::numeric_limits<double>::min();
+    diag[0] = m[0][0];
+    const double v1norm2 = m[2][0] * m[2][0];
+    if (v1norm2 <= tol) {
+      diag[1] = m[1][1]; diag[2] = m[2][2]; sub[0] = m[1][0]; sub[1] = m[2][1];
+      for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Q[i][j] = i == j ? 1.0 : 0.0;
+    } else {
+      const double beta = std::sqrt(m[1][0] * m[1][0] + v1norm2);
+      const double invBeta = 1.0 / beta;
+      const double m01 = m[1][0] * invBeta, m02 = m[2][0] * invBeta;
+      const double q = 2.0 * m01 * m[2][1] + m02 * (m[2][2] - m[1][1]);
+      diag[1] = m[1][1] + m02 * q;
+      diag[2] = m[2][2] - m02 * q;
+      sub[0] = beta;
+      sub[1] = m[2][1] - m01 * q;
+      const double Qi[3][3] = {{1, 0, 0}, {0, m01, m02}, {0, m02, -m01}};
+      std::memcpy(Q, Qi, sizeof(Q));
+    }
+  }
+  const int n = 3;
+  int end = n - 1, start = 0, iter = 0;
+  const double considerAsZero = std::numeric_limits<double>::min();
+  const double precision = 2.0 * std::numeric_limits<double>::epsilon();
+  while (end > 0) {
+    for (int i = start; i < end; ++i)
+      if (std::fabs(sub[i]) <= (std::fabs(diag[i]) + std::fabs(diag[i + 1])) * precision || std::fabs(sub[i]) <= considerAsZero) sub[i] = 0;
+    while (end > 0 && sub[end - 1] == 0.0) end--;
+    if (end <= 0) break;
+    iter++;
+    if (iter > 30 * n) break;
+    start = end - 1;
+    while (start > 0 && sub[start - 1] != 0.0) start--;
+    // tridiagonal_qr_step
+    const double td = (diag[end - 1] - diag[end]) * 0.5;
+    const double e = sub[end - 1];
+    double mu = diag[end];
+    if (td == 0.0) mu -= std::fabs(e);
+    else {
+      const double e2 = e * e;
+      double h;  // numext::hypot
+      {
+        const double ax = std::fabs(td), ay = std::fabs(e);
+        double p, qp;
+        if (ax > ay) { p = ax; qp = ay / p; } else { p = ay; qp = ax / p; }
+        h = p == 0.0 ? 0.0 : p * std::sqrt(1.0 + qp * qp);
+      }
+      if (e2 == 0.0) mu -= (e / (td + (td > 0.0 ? 1.0 : -1.0))) * (e / h);
+      else mu -= e2 / (td + (td > 0.0 ? h : -h));
+    }
+    double x = diag[start] - mu;
+    double z = sub[start];
+    for (int k = start; k < end; ++k) {
+      double c, s;  // JacobiRotation::makeGivens(x, z)
+      if (z == 0.0) { c = x < 0.0 ? -1.0 : 1.0; s = 0.0; }
+      else if (x == 0.0) { c = 0.0; s = z < 0.0 ? 1.0 : -1.0; }
+      else if (std::fabs(x) > std::fabs(z)) { const double t = z / x; double u = std::sqrt(1.0 + t * t); if (x < 0.0) u = -u; c = 1.0 / u; s = -t * c; }
+      else { const double t = x / z; double u = std::sqrt(1.0 + t * t); if (z < 0.0) u = -u; s = -1.0 / u; c = -t * s; }
+      const double sdk = s * diag[k] + c * sub[k];
+      const double dkp1 = s * sub[k] + c * diag[k + 1];
+      diag[k] = c * (c * diag[k] - s * sub[k]) - s * (c * sub[k] - s * diag[k + 1]);
+      diag[k + 1] = s * sdk + c * dkp1;
+      sub[k] = c * sdk - s * dkp1;
+      if (k > start) sub[k - 1] = c * sub[k - 1] - s * z;
+      x = sub[k];
+      if (k < end - 1) { z = -s * sub[k + 1]; sub[k + 1] = c * sub[k + 1]; }
+      for (int i = 0; i < 3; ++i) {  // Q = Q * G: applyOnTheRight(k, k + 1, rot)
+        const double xi = Q[i][k], yi = Q[i][k + 1];
+        Q[i][k] = c * xi - s * yi;
+        Q[i][k + 1] = s * xi + c * yi;
+      }
+    }
+  }
+  for (int i = 0; i < n - 1; ++i) {  // selection sort, ascending
+    int k = i;
+    for (int j = i + 1; j < n; ++j) if (diag[j] < diag[k]) k = j;
+    if (k > i) { std::swap(diag[i], diag[k]); for (int r = 0; r < 3; ++r) std::swap(Q[r][i], Q[r][k]); }
+  }
+  for (int i = 0; i < 3; ++i) { w[i] = diag[i] * scale; for (int j = 0; j < 3; ++j) V.m[i][j] = Q[i][j]; }
+}
+
 // 5x3 least squares  min ||A n - b||  standing in for Eigen's colPivHouseholderQr().solve()
 // (EstimationMapping.hpp:198): Householder QR with column pivoting on the largest remaining
 // column norm (recomputed, not down-dated), then back substitution and un-pivoting.
-inline V3 lstsq5x3_colpiv(const double Ain[5][3], const double bin[5]) {
+inline V3 lstsq5x3_colpiv(const double Ain[5][3], const double bin[5], bool pivot = true) {
   double A[5][3], b[5];
   std::memcpy(A, Ain, sizeof(A));
   std::memcpy(b, bin, sizeof(b));
@@ -215,6 +313,7 @@ inline V3 lstsq5x3_colpiv(const double Ain[5][3], const double bin[5]) {
       double s = 0;
       for (int i = k; i < 5; ++i) s += A[i][j] * A[i][j];
       if (s > bn) { bn = s; best = j; }
+      if (!pivot) break;  // sensitivity alternate: Eigen's plain HouseholderQR (no column exchange)
     }
     if (npiv == 3 && bn < thr * (5 - k)) { npiv = k; break; }
     if (best != k) {

@@ -37,6 +37,11 @@ struct Config {
   int outer_iters = 2;          // EM:260
   int lm_max_iters = 4;         // EM:277
   int voxel_order = 0;          // 0: within-voxel order = input order (stable); 1: std::sort like PCL (unstable)
+  // Alternates of the third-party restatements, for the sensitivity envelope only (tools/sensitivity.py); all 0 = the oracle proper.
+  int eig_alg = 0;              // EM:150: 0 cyclic Jacobi, 1 Eigen 3.3.7's tridiagonal QR iteration (orc_math.hpp: eig3_sym_eigen)
+  int plane_alg = 0;            // EM:198: 0 column-pivoted Householder QR, 1 Householder QR without column pivoting (Eigen's HouseholderQR)
+  int centroid_div = 0;         // voxel centroid: 0 `sum / count` (Eigen >= 3.3 operator/=), 1 `sum * (1 / count)` (Eigen 3.2 operator/=)
+  int lm_solver = 0;            // EM:283: 0 Householder QR of [J; D] (Ceres DENSE_QR), 1 normal equations + Cholesky (what the CUDA path does)
   int knn_ties = 0;             // tie class T2 (equal fp32 squared distances): 0 = FLANN / nanoflann order (first visited wins,
                                 // the reference's behaviour); 1 = canonical (d^2, map index) order, the CUDA path's rule
 };
@@ -187,7 +192,7 @@ inline bool voxel_grid(const Cloud& in, float leaf, int order_mode, Cloud& out, 
     int i2 = (int)(std::floor(in[i].z * inv) - (float)min_b[2]);
     keys.push_back({(unsigned)(i0 * mul[0] + i1 * mul[1] + i2 * mul[2]), (unsigned)i});
   }
-  if (order_mode == 1)  // what PCL does: std::sort on idx only; within-voxel order unspecified (tie class T3)
+  if (order_mode & 1)  // what PCL does: std::sort on idx only; within-voxel order unspecified (tie class T3)
     std::sort(keys.begin(), keys.end(), [](const VoxKey& a, const VoxKey& b) { return a.idx < b.idx; });
   else  // canonical: input order inside a voxel
     std::stable_sort(keys.begin(), keys.end(), [](const VoxKey& a, const VoxKey& b) { return a.idx < b.idx; });
@@ -201,7 +206,8 @@ inline bool voxel_grid(const Cloud& in, float leaf, int order_mode, Cloud& out, 
       c[0] += p.x; c[1] += p.y; c[2] += p.z; c[3] += p.i;
     }
     const float cnt = (float)(i - index);
-    out.push_back({c[0] / cnt, c[1] / cnt, c[2] / cnt, c[3] / cnt});
+    if (order_mode & 2) { const float rc = 1.0f / cnt; out.push_back({c[0] * rc, c[1] * rc, c[2] * rc, c[3] * rc}); }  // sensitivity alternate
+    else out.push_back({c[0] / cnt, c[1] / cnt, c[2] / cnt, c[3] / cnt});
     if (first_pt) first_pt->push_back((int)keys[index].pt);
     index = i;
   }
@@ -421,7 +427,7 @@ inline void edge_factors(const Config& c, Quat q, V3 t, const Cloud& edge, const
           for (int cc = 0; cc < 3; ++cc) cov.m[r][cc] = cov.m[r][cc] + v[r] * v[cc];
       }
       double w3[3]; M3 V;
-      eig3_sym(cov, w3, V);
+      if (c.eig_alg == 1) eig3_sym_eigen(cov, w3, V); else eig3_sym(cov, w3, V);
       V3 dir{V.m[0][2], V.m[1][2], V.m[2][2]};  // EM:151
       if (w3[2] > 3 * w3[1]) {                    // EM:153
         EdgeFactor f;
@@ -448,7 +454,7 @@ inline void surf_factors(const Config& c, Quat q, V3 t, const Cloud& surf, const
     if (d2[4] < c.knn_gate) {
       double A[5][3], b[5];
       for (int j = 0; j < 5; ++j) { A[j][0] = map[idx[j]].x; A[j][1] = map[idx[j]].y; A[j][2] = map[idx[j]].z; b[j] = -1.0; }
-      V3 n = lstsq5x3_colpiv(A, b);  // EM:198
+      V3 n = lstsq5x3_colpiv(A, b, c.plane_alg != 1);  // EM:198
       double nn = norm(n);
       double d = 1.0 / nn;           // EM:199
       n = {n.x / nn, n.y / nn, n.z / nn};  // EM:200 normalize(): v /= norm
@@ -609,10 +615,32 @@ inline void dense_qr_solve(double* A, int m, int ld, double* rhs, double x[6]) {
   }
 }
 
+// Sensitivity alternate of the line above (Config.lm_solver = 1): the same minimiser from (J^T J + D^2) y = J^T r by Cholesky.
+inline void normal_cholesky_solve(const double* J, int m, int ld, const double* r, const double D[6], double x[6]) {
+  double H[6][6], g[6];
+  for (int i = 0; i < 6; ++i) {
+    double s = 0;
+    for (int k = 0; k < m; ++k) s += J[(size_t)i * ld + k] * r[k];
+    g[i] = s;
+    for (int j = i; j < 6; ++j) { double t = 0; for (int k = 0; k < m; ++k) t += J[(size_t)i * ld + k] * J[(size_t)j * ld + k]; H[i][j] = H[j][i] = t; }
+    H[i][i] += D[i] * D[i];
+  }
+  double L[6][6] = {};
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j <= i; ++j) {
+      double s = H[i][j];
+      for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
+      L[i][j] = i == j ? std::sqrt(s) : s / L[j][j];
+    }
+  double y[6];
+  for (int i = 0; i < 6; ++i) { double s = g[i]; for (int k = 0; k < i; ++k) s -= L[i][k] * y[k]; y[i] = s / L[i][i]; }
+  for (int i = 5; i >= 0; --i) { double s = y[i]; for (int k = i + 1; k < 6; ++k) s -= L[k][i] * x[k]; x[i] = s / L[i][i]; }
+}
+
 inline double norm7(const double* v) { double s = 0; for (int i = 0; i < 7; ++i) s += v[i] * v[i]; return std::sqrt(s); }
 
 // TrustRegionMinimizer::Minimize (ceres 2.0 internal/ceres/trust_region_minimizer.cc) on this problem.
-inline void ceres_solve(const Problem& prob, double params[7], int max_iters, SolveTrace* trace) {
+inline void ceres_solve(const Problem& prob, double params[7], int max_iters, SolveTrace* trace, int lm_solver = 0) {
   const int m = prob.rows();
   if (trace) { trace->n_edge = (int)prob.edges->size(); trace->n_surf = (int)prob.surfs->size(); trace->iters.clear(); }
   if (m == 0) { if (trace) trace->termination = 4; return; }
@@ -678,7 +706,8 @@ inline void ceres_solve(const Problem& prob, double params[7], int max_iters, So
     for (int j = 0; j < 6; ++j) { for (int i = 0; i < 6; ++i) Jwork[(size_t)j * ld + m + i] = 0; Jwork[(size_t)j * ld + m + j] = lm_diag[j]; }
     for (int r = 0; r < m; ++r) rhs[r] = res[r];
     for (int i = 0; i < 6; ++i) rhs[m + i] = 0;
-    dense_qr_solve(Jwork.data(), ld, ld, rhs.data(), step);
+    if (lm_solver == 1) normal_cholesky_solve(Jm.data(), m, ld, res.data(), lm_diag, step);  // sensitivity alternate
+    else dense_qr_solve(Jwork.data(), ld, ld, rhs.data(), step);
     reuse_diagonal = true;
     bool finite = true;
     for (int j = 0; j < 6; ++j) { step[j] = -step[j]; if (!std::isfinite(step[j])) finite = false; }
@@ -759,8 +788,8 @@ class Odometry {
     Quat q = mat2q(odom.R);  // EM:242
     x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w;
     x[4] = odom.t.x; x[5] = odom.t.y; x[6] = odom.t.z;
-    voxel_grid(edge_in, (float)cfg.edge_leaf, cfg.voxel_order, ds_edge);  // EM:248-251
-    voxel_grid(surf_in, (float)cfg.surf_leaf, cfg.voxel_order, ds_surf);
+    voxel_grid(edge_in, (float)cfg.edge_leaf, vox_mode(), ds_edge);  // EM:248-251
+    voxel_grid(surf_in, (float)cfg.surf_leaf, vox_mode(), ds_surf);
     double t1 = now_s();
     timing.ds += t1 - t0;
     traces.clear();
@@ -783,7 +812,7 @@ class Odometry {
         timing.assoc += tb - ta;
         Problem prob{&ef, &sf, cfg.huber};
         SolveTrace tr;
-        ceres_solve(prob, x, cfg.lm_max_iters, &tr);
+        ceres_solve(prob, x, cfg.lm_max_iters, &tr, cfg.lm_solver);
         traces.push_back(tr);
         timing.solve += now_s() - tb;
       }
@@ -812,10 +841,11 @@ class Odometry {
     Cloud ce, cs;
     crop_box(map_edge, mn, mx, ce);
     crop_box(map_surf, mn, mx, cs);
-    voxel_grid(ce, (float)cfg.edge_leaf, cfg.voxel_order, map_edge);
-    voxel_grid(cs, (float)cfg.surf_leaf, cfg.voxel_order, map_surf);
+    voxel_grid(ce, (float)cfg.edge_leaf, vox_mode(), map_edge);
+    voxel_grid(cs, (float)cfg.surf_leaf, vox_mode(), map_surf);
   }
 
+  int vox_mode() const { return (cfg.voxel_order & 1) | (cfg.centroid_div ? 2 : 0); }
   Config cfg;
   double x[7] = {0, 0, 0, 1, 0, 0, 0};  // EM:383 parameter_opti
   Iso odom, odom_last;

@@ -18,6 +18,7 @@
 #include "vilf/featureDepth.hpp"
 #include "vilf/nodeOutputs.hpp"
 #include "vilf/Scancontext.hpp"
+#include "vilf/featureExtract.hpp"
 
 using vilf::Cloud;
 using vilf::CloudPtr;
@@ -200,6 +201,33 @@ int main(int argc, char** argv) {
       }
       std::vector<double> a = scManager.getScancontext(0), b = scManager.getScancontext(-1);
       if (a != b || scManager.distanceBtnScanContext(a, b).first != 0.0) { std::fprintf(stderr, "SCManager mirror: revisit descriptor differs\n"); return 1; }
+    }
+    if (argc > 4) {  // E (shim_test ... rings): the ring-field extractor class (featureExtract.hpp) in front of the same estimator
+      const int n_rings = std::atoi(argv[4]);
+      vilf::ParamMap nh2;
+      nh2.set("N_SCAN", n_rings); nh2.set("Horizon_SCAN", 1800); nh2.set("lidarMaxRange", 90.0);
+      nh2.set("/EdgeLeafSize", 0.4); nh2.set("/SurfLeafSize", 0.8);
+      featureExtract extractor;
+      EstimationMapping Estimator;
+      extractor.initParam(nh2);
+      Estimator.initParameter(nh2);
+      Estimator.shareSessionWith(extractor);
+      for (size_t i = 0; i < scans.size(); ++i) {
+        std::vector<vilf::PointXYZIRT> pts(scans[i]->points.size());
+        for (size_t k = 0; k < pts.size(); ++k) {
+          const vilf::PointType& p = scans[i]->points[k];
+          const double el = std::atan2((double)p.z, std::sqrt((double)p.x * p.x + (double)p.y * p.y)) * 180.0 / M_PI;
+          int ring = (int)std::floor((el + 92.0 / 3.0) * 3.0 / 4.0);  // the synthetic 32-beam layout (FE:85)
+          pts[k].x = p.x; pts[k].y = p.y; pts[k].z = p.z; pts[k].intensity = p.intensity;
+          pts[k].ring = (std::uint16_t)(ring < 0 ? 0 : ring >= n_rings ? n_rings - 1 : ring);
+        }
+        CloudPtr e = vilf::make_cloud(), s = vilf::make_cloud();
+        extractor.extractFeatureFromPoints(pts, e, s);
+        if (e->points.empty() || s->points.empty()) { std::fprintf(stderr, "featureExtract mirror: no features at frame %zu\n", i); return 1; }
+        if (i == 0) Estimator.localMapInited(e, s); else Estimator.optimation_processing(e, s);
+      }
+      if (!(std::fabs(Estimator.parameter_opti[4]) > 0.5)) { std::fprintf(stderr, "featureExtract mirror: the estimator did not move (x = %g)\n", Estimator.parameter_opti[4]); return 1; }
+      std::printf("featureExtract + EstimationMapping: x = %.3f after %zu frames\n", Estimator.parameter_opti[4], scans.size());
     }
     double dab = 0, dac = 0;
     for (size_t i = 0; i < pa.size(); ++i) {

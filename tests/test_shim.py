@@ -48,8 +48,12 @@ def test_mirror_keeps_the_reference_method_surface():
                  "distanceBtnScanContext(", "double LIDAR_HEIGHT", "int PC_NUM_RING", "int PC_NUM_SECTOR", "double PC_MAX_RADIUS", "int NUM_EXCLUDE_RECENT",
                  "int NUM_CANDIDATES_FROM_TREE", "double SEARCH_RATIO", "double SC_DIST_THRES", "int TREE_MAKING_PERIOD_"):
         assert name in sc, name
+    fx = open(os.path.join(INC, "featureExtract.hpp")).read()
+    for name in ("class featureExtract", "void initParam(", "bool extractFeature(", '"Horizon_SCAN"', '"N_SCAN"', '"downsampleRate"', '"lidarMinRange"', '"lidarMaxRange"',
+                 '"edgeThreshold"', '"surfThreshold"', '"SurfLeafSize"', "struct VelodynePointXYZIRT"):
+        assert name in fx, name
     # the mirror goes through the C ABI only: no CUDA, torch or oracle in the headers
-    for txt in (fe, em, sc, open(os.path.join(INC, "session.hpp")).read(), open(os.path.join(INC, "cloud.hpp")).read()):
+    for txt in (fe, em, sc, fx, open(os.path.join(INC, "session.hpp")).read(), open(os.path.join(INC, "cloud.hpp")).read()):
         assert not re.search(r"cuda_runtime|torch|oracle", txt)
 
 
@@ -72,8 +76,9 @@ def test_mirror_matches_oracle_in_node_order(tmp_path, synth, orc):
     seq = synth.Sequence("vlp32", frames, seed=4)
     scans = [seq[i][0] for i in range(frames)]
     write_scans(tmp_path / "scans.bin", scans)
-    r = subprocess.run([exe, str(tmp_path / "scans.bin"), "32", str(tmp_path / "poses.bin")], capture_output=True, text=True)
+    r = subprocess.run([exe, str(tmp_path / "scans.bin"), "32", str(tmp_path / "poses.bin"), "32"], capture_output=True, text=True)
     assert r.returncode == 0, (r.stdout, r.stderr)
+    assert "featureExtract + EstimationMapping" in r.stdout  # the ring-field extractor class in front of the same estimator
     poses = np.fromfile(tmp_path / "poses.bin", dtype=np.float64).reshape(frames, 7)
     o = orc.Odometry(orc.config(n_scan=32, n_rings=32))
     for i in range(frames):

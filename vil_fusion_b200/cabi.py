@@ -30,6 +30,7 @@ class Config(C.Structure):
         ("knn_gate", C.c_double), ("huber", C.c_double),
         ("outer_iters", C.c_int32), ("lm_max_iters", C.c_int32),
         ("max_scan_points", C.c_int32), ("max_map_points", C.c_int32), ("max_ring_points", C.c_int32), ("flags", C.c_int32),
+        ("horizon_scan", C.c_int32), ("downsample_rate", C.c_int32), ("ri_edge_threshold", C.c_double), ("ri_surf_threshold", C.c_double),
     ]
 
 
@@ -86,6 +87,7 @@ FLAG_NO_CLUSTER = 1
 FLAG_NO_GRAPH = 2
 FLAG_LEGACY_MAP = 4
 FLAG_CELL_MAP = 8
+FLAG_RANGE_IMAGE = 16
 MAP_EDGE, MAP_SURF, DS_EDGE, DS_SURF, REGISTERED, NO_REGISTERED = range(6)
 
 

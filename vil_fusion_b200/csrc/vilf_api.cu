@@ -1,6 +1,7 @@
 // C ABI of libvilf_cuda.so (include/vilf.h): device context, per-sequence state, the per-frame launch
 // sequence and the stage-level entry points.  No CPU fallback: every entry point needs a CUDA device.
 #include "vilf_internal.cuh"
+#include <nvtx3/nvToolsExt.h>
 #include "../../include/vilf.h"
 
 #include <cstdio>
@@ -258,11 +259,14 @@ int build_ctx(Ctx* C) {
     while (c.sector_np < c.max_sector) c.sector_np <<= 1;
   }
   c.cap_scan = u.max_scan_points; c.cap_map = u.max_map_points;
+  c.range_image = (u.flags & VILF_FLAG_RANGE_IMAGE) ? 1 : 0;
+  c.horizon = u.horizon_scan; c.ri_down = u.downsample_rate > 0 ? u.downsample_rate : 1; c.ri_edge_thr = u.ri_edge_threshold; c.ri_surf_thr = u.ri_surf_threshold;
   const int NL = C->nlanes;
   const int capS = c.cap_scan, capM = c.cap_map + c.cap_scan;
 
   CK(cudaSetDevice(C->device));
   CK(init_extract_kernels());
+  CK(init_rangeimage_kernels());
   CK(cudaStreamCreateWithFlags(&C->st, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&C->copy_st, cudaStreamNonBlocking));
   for (int i = 0; i < 2; ++i) {
@@ -320,6 +324,12 @@ int build_ctx(Ctx* C) {
     CK(dalloc(C, &L.sec_cnt, (size_t)MAX_RINGS * SECTORS));
     CK(dalloc(C, &L.sec_edge, (size_t)MAX_RINGS * SECTORS * EDGES_PER_SECTOR));
     CK(dalloc(C, &L.sec_edge_src, (size_t)MAX_RINGS * SECTORS * EDGES_PER_SECTOR));
+    if (c.range_image) {
+      CK(dalloc(C, &L.ri_owner, (size_t)c.n_rings * c.horizon));
+      CK(dalloc(C, &L.ri_info, (size_t)(MAX_RINGS + 1) * 4));
+      CK(dalloc(C, &L.ri_src, (size_t)capS)); CK(dalloc(C, &L.ri_col, (size_t)capS)); CK(dalloc(C, &L.ri_range, (size_t)capS)); CK(dalloc(C, &L.ri_curv, (size_t)capS));
+      CK(dalloc(C, &L.ri_picked, (size_t)capS)); CK(dalloc(C, &L.ri_label, (size_t)capS));
+    }
     CK(dalloc(C, &L.sec_surf, (size_t)capS));
     CK(dalloc(C, &L.sec_surf_src, (size_t)capS));
     for (int w = 0; w < 2; ++w) {
@@ -560,6 +570,12 @@ void enqueue_submap(Ctx* C, const Launch& L, int lane0, int nl, ProfSink* sink) 
   for (int l = lane0; l < lane0 + nl; ++l) C->cur[l] = cur ^ 1;
 }
 
+// Stage 1: featureExtraction::extractFeature (FE:223-232) or, with VILF_FLAG_RANGE_IMAGE, featureExtract::extractFeature (FX:96-115).
+void stage1(Ctx* C, const Launch& L, int lane0, int nl, int sel) {
+  if (C->cfg.range_image) launch_extract_range_image(L, C->lanes_dev, lane0, nl, sel, C->cfg);
+  else launch_extract(L, C->lanes_dev, C->ring_jobs_dev[sel], lane0, nl, sel, C->cfg);
+}
+
 // The per-frame launch sequence for lanes [lane0, lane0+nl), which all share `cur`, `first` and the scan slot.
 // with_extract = 0: features were uploaded by the caller (vilf_update_points / vilf_map_init_points).
 void issue_frame(Ctx* C, int lane0, int nl, bool first, bool with_extract, int sel, int cur, ProfSink* sink);
@@ -597,7 +613,10 @@ int enqueue_frame(Ctx* C, int lane0, int nl, bool first, bool with_extract, int 
       }
       G.launches = captured;
     }
-    CK(cudaGraphLaunch(G.exec, C->st));
+    nvtxRangePushA("vilf:frame(graph)");
+    const cudaError_t ge = cudaGraphLaunch(G.exec, C->st);
+    nvtxRangePop();
+    CK(ge);
     C->launches += G.launches;
   } else {
     issue_frame(C, lane0, nl, first, with_extract, sel, cur, sink);
@@ -617,11 +636,16 @@ int enqueue_frame(Ctx* C, int lane0, int nl, bool first, bool with_extract, int 
 // The launch sequence of one frame (no host-side state changes: it is also what a graph capture records).
 void issue_frame(Ctx* C, int lane0, int nl, bool first, bool with_extract, int sel, int cur, ProfSink* sink) {
   const Launch L = mk(C, sink);
-  auto phase = [&](int p) { if (sink) sink->phase = p; };
+  // NVTX range per stage (SURVEY.md §5 tracing row): visible in Nsight Systems around the launches (or, for a graph-replayed frame,
+  // around its one-time capture; the replay itself is the range "vilf:frame(graph)" in enqueue_frame)
+  static const char* const kStage[5] = {"vilf:extract", "vilf:scan_downsample", "vilf:associate+solve", "vilf:map_update", "vilf:search_build"};
+  bool open = false;
+  auto phase = [&](int p) { if (sink) sink->phase = p; if (open) nvtxRangePop(); nvtxRangePushA(kStage[p]); open = true; };
+  struct Closer { bool& o; ~Closer() { if (o) nvtxRangePop(); } } closer{open};
   const ConfigDev& cfg = C->cfg;
   phase(0);
   launch_frame_reset(L, C->lanes_dev, lane0, nl, C->vv_dev, VV_PER_LANE, first ? 0 : 1);
-  if (with_extract) launch_extract(L, C->lanes_dev, C->ring_jobs_dev[sel], lane0, nl, sel, cfg);
+  if (with_extract) stage1(C, L, lane0, nl, sel);
   if (first && C->cellmap) {
     phase(4);
     launch_cell_build(L, C->build_dev[cur] + lane0 * 2, C->build_sort_dev + lane0 * 2, nl * 2);
@@ -680,8 +704,10 @@ int submit_common(Ctx* C, int lane0, int nl, const float* const* xyzi, const int
     if (n[i] > 0) CK(cudaMemcpyAsync(L.scan[sel], xyzi[i], (size_t)n[i] * 16, kind, C->copy_st));
     if (ring && ring[i] && n[i] > 0) CK(cudaMemcpyAsync(L.ring_in[sel], ring[i], (size_t)n[i] * 2, kind, C->copy_st));
     S.vars_pin[i].n_scan[sel] = n[i];
-    CK(cudaMemcpyAsync(&L.v->n_scan[sel], &S.vars_pin[i].n_scan[sel], sizeof(int), cudaMemcpyHostToDevice, C->copy_st));
   }
+  // the point counts of all lanes in ONE strided copy (a 4-byte column of the pinned LaneVars array -> the same column on the device)
+  CK(cudaMemcpy2DAsync(&C->vars_dev[lane0].n_scan[sel], sizeof(LaneVars), &S.vars_pin[0].n_scan[sel], sizeof(LaneVars), sizeof(int), (size_t)nl,
+                       cudaMemcpyHostToDevice, C->copy_st));
   CK(cudaEventRecord(C->h2d_done[sel], C->copy_st));
   CK(cudaStreamWaitEvent(C->st, C->h2d_done[sel], 0));
   S.profiled = C->profile;
@@ -888,6 +914,7 @@ int vilf_default_config(vilf_config* c) {
   c->edge_leaf = 0.4; c->surf_leaf = 0.8; c->crop_half = 100.0; c->knn_gate = 1.0; c->huber = 0.1;
   c->outer_iters = 2; c->lm_max_iters = 4;
   c->max_scan_points = 300000; c->max_map_points = 1 << 20; c->max_ring_points = 0; c->flags = 0;
+  c->horizon_scan = 1800; c->downsample_rate = 1; c->ri_edge_threshold = 1.0; c->ri_surf_threshold = 0.1;  // featureExtract.hpp:85-91
   return VILF_OK;
 }
 
@@ -896,6 +923,7 @@ int vilf_create_batch(const vilf_config* cfg, int device, int count, vilf_handle
   if (cfg->n_scan < 0 || (cfg->n_scan == 0 && (cfg->n_rings < 1 || cfg->n_rings > MAX_RINGS))) return VILF_ERR_INVALID;
   if (cfg->outer_iters < 1 || cfg->outer_iters > MAX_OUTER || cfg->lm_max_iters < 0) return VILF_ERR_INVALID;
   if (cfg->max_scan_points < 1024 || cfg->max_map_points < 1024 || !(cfg->edge_leaf > 0) || !(cfg->surf_leaf > 0) || !(cfg->knn_gate > 0)) return VILF_ERR_INVALID;
+  if ((cfg->flags & VILF_FLAG_RANGE_IMAGE) && (cfg->n_scan != 0 || cfg->horizon_scan < 64 || cfg->horizon_scan > 6138 || cfg->downsample_rate < 1)) return VILF_ERR_INVALID;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return VILF_ERR_CUDA;
   Ctx* C = new (std::nothrow) Ctx();
@@ -1063,7 +1091,7 @@ int vilf_feature_extract(vilf_handle* h, const float* xyzi, int n, const uint16_
   CK(cudaMemcpyAsync(&L.v->n_scan[0], &n, sizeof(int), cudaMemcpyHostToDevice, C->st));
   CK(cudaMemsetAsync(&L.v->status, 0, sizeof(int), C->st));
   CK(cudaStreamSynchronize(C->st));
-  launch_extract(mk(C), C->lanes_dev, C->ring_jobs_dev[0], h->lane, 1, 0, C->cfg);
+  stage1(C, mk(C), h->lane, 1, 0);
   CK(cudaGetLastError());
   LaneVars V;
   int rc = read_vars(C, h->lane, &V);
@@ -1685,7 +1713,7 @@ const char* vilf_profile_kernel_name(int kernel) {
                                        "k_vox_bbox", "k_sort_keyhist<KeyGenVoxel>", "k_vox_heads", "k_vox_centroid", "k_map_append", "k_map_init",
                                        "k_grid_zero", "k_grid_count", "k_grid_scan_partial", "k_grid_scan_final", "k_grid_scatter", "k_knn_assoc",
                                        "k_knn_only", "k_solve", "k_fit", "k_voxel_cluster", "k_grid_cluster", "k_depth_cloud", "k_depth_query", "k_ring_partition",
-                                       "k_new_xform", "k_sort_keyhist<KeyGenNew>", "k_merge_partition", "k_merge<count>", "k_merge<emit>", "k_cell_build", "k_knn_cell_assoc", "k_sc"};
+                                       "k_new_xform", "k_sort_keyhist<KeyGenNew>", "k_merge_partition", "k_merge<count>", "k_merge<emit>", "k_cell_build", "k_knn_cell_assoc", "k_sc", "k_ri_*", "k_ri_select"};
   return (kernel >= 0 && kernel < K_COUNT) ? names[kernel] : "";
 }
 int vilf_launch_count(vilf_handle* h, int64_t* launches) {

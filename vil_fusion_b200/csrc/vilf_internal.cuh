@@ -66,6 +66,9 @@ struct ConfigDev {
   int cap_scan, cap_map;
   int flags_no_cluster;  // VILF_FLAG_NO_CLUSTER: grid-wide multi-launch kernels everywhere
   CellGeom cg[2];        // cell-ordered edge / surf map geometry
+  // ring-field / range-image extractor (k_rangeimage.cu), stage 1 when range_image != 0
+  int range_image, horizon, ri_down;
+  double ri_edge_thr, ri_surf_thr;
 };
 
 // One iteration row of the trust-region trace (same columns as the oracle's LmIter).
@@ -243,6 +246,9 @@ struct LaneDev {
   int* nn_idx[2]; float* nn_d2[2];  // [cap][5] (test hooks)
   // cell-ordered maps: search table, PCL index of every point (valid while meta[1] != 0), meta
   uint2* ctab[2]; uint32_t* corig[2]; int* cmeta[2];
+  // range-image extractor: image cell -> first input point, per-ring counters, then per image point (row-major): input index,
+  // column, range, curvature, marks, labels
+  int* ri_owner; int* ri_info; int* ri_src; int* ri_col; float* ri_range; float* ri_curv; uint8_t* ri_picked; uint8_t* ri_label;
 };
 
 // ---- ordered-int float mapping for atomicMin/atomicMax ----
@@ -325,7 +331,7 @@ enum KernelId {
   K_RESET = 0, K_RING_KEYHIST, K_SORT_HIST, K_SORT_SCATTER, K_SECTOR, K_COMPACT, K_VOX_BBOX, K_VOX_KEYHIST, K_VOX_HEADS, K_VOX_CENTROID,
   K_MAP_APPEND, K_MAP_INIT, K_GRID_ZERO, K_GRID_COUNT, K_GRID_SCAN_PARTIAL, K_GRID_SCAN_FINAL, K_GRID_SCATTER, K_KNN_FIT, K_KNN_ONLY,
   K_SOLVE, K_FIT, K_VOX_CLUSTER, K_GRID_CLUSTER, K_DEPTH_CLOUD, K_DEPTH_QUERY, K_RING_PARTITION,
-  K_NEW_XFORM, K_NEW_KEYHIST, K_MERGE_PART, K_MERGE_COUNT, K_MERGE_EMIT, K_CELL_BUILD, K_KNN_CELL, K_SC, K_COUNT
+  K_NEW_XFORM, K_NEW_KEYHIST, K_MERGE_PART, K_MERGE_COUNT, K_MERGE_EMIT, K_CELL_BUILD, K_KNN_CELL, K_SC, K_RANGE_IMAGE, K_RI_SELECT, K_COUNT
 };
 constexpr int PROF_PHASES = 5;      // 0 extract, 1 scan downsample, 2 association + solve, 3 map update, 4 grid build
 constexpr int PROF_KSLOTS = 64;     // kernel ids per phase in a profile tag
@@ -360,6 +366,9 @@ void launch_sort_scatter(const Launch& L, const SortJob* jobs_dev, int njobs, in
 cudaError_t init_extract_kernels();  // per-device function attributes; call once per context
 void launch_frame_reset(const Launch& L, LaneDev* lanes, int lane0, int nlanes, VoxVars* vv, int vv_per_lane, int predict);
 void launch_extract(const Launch& L, LaneDev* lanes, const SortJob* ring_jobs, int lane0, int nlanes, int sel, const ConfigDev& cfg);
+// k_rangeimage.cu
+cudaError_t init_rangeimage_kernels();
+void launch_extract_range_image(const Launch& L, LaneDev* lanes, int lane0, int nlanes, int sel, const ConfigDev& cfg);
 // k_voxel.cu
 void launch_voxel(const Launch& L, const VoxJob* jobs_dev, int njobs, const SortJob* sort_jobs_dev, bool bbox_done);
 void launch_map_append(const Launch& L, LaneDev* lanes, int lane0, int nlanes, int cur, const ConfigDev& cfg);

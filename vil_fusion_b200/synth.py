@@ -80,10 +80,11 @@ def beams128() -> Sensor:
 SENSORS = {"hdl64": hdl64, "vlp32": vlp32, "beams128": beams128, "vlp16": vlp16}
 
 # BASELINE.json configs[2] ("HDL-64E sequence with 100 m local-map crop, ~1M map points, kNN stress"): a world three times as
-# cluttered as the default corridor, driven at 0.4 m per frame, mapped at 0.1 m voxels.  Measured with the CPU oracle: the
-# +-100 m crop then holds ~0.28 M edge + ~0.69 M surf points after 260 frames and passes 1e6 around frame 310-340; the surf map
-# alone exceeds 2^19 points from frame ~160 on.
-DENSE = dict(sensor="hdl64", density=3.0, speed=0.4, edge_leaf=0.1, surf_leaf=0.1, max_map_points=1 << 21)
+# cluttered as the default corridor, driven at 0.4 m per frame, mapped at 0.09 m voxels.  Measured with the CPU restatement (seed 7):
+# the +-100 m crop holds 1.05 M points (0.27 M edge + 0.78 M surf) at frame 200 and 1.14-1.19 M from frame 260 on (the crop box is
+# full after 250 frames = 100 m; after that the size follows the scenery); the surf map alone exceeds 2^19 points from frame ~140 on.
+# (At 0.1 m voxels the same world oscillates between 0.88 M and 1.16 M; a denser world does not help, the facades already form a wall.)
+DENSE = dict(sensor="hdl64", density=3.0, speed=0.4, edge_leaf=0.09, surf_leaf=0.09, max_map_points=1 << 21)
 
 
 @dataclass
