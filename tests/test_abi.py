@@ -32,9 +32,21 @@ def test_default_config_is_the_reference_yaml(cabi):
     assert (c.outer_iters, c.lm_max_iters) == (2, 4)
 
 
-def test_config_struct_layout_matches_header(cabi):
-    # 2 x int32, 8 x double, 6 x int32 -> 8 + 64 + 24
-    assert C.sizeof(cabi.Config) == 96
+def test_config_struct_layout_matches_header(cabi, tmp_path):
+    """The ctypes mirrors of vilf_config / vilf_sc_params have the size and field offsets the C compiler gives include/vilf.h."""
+    import subprocess
+    src = tmp_path / "layout.c"
+    fields_cfg = [f[0] for f in cabi.Config._fields_]
+    fields_sc = [f[0] for f in cabi.SCParams._fields_]
+    body = "".join(f'printf("%zu ", offsetof(vilf_config, {f}));' for f in fields_cfg) + 'printf("%zu\\n", sizeof(vilf_config));'
+    body += "".join(f'printf("%zu ", offsetof(vilf_sc_params, {f}));' for f in fields_sc) + 'printf("%zu\\n", sizeof(vilf_sc_params));'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "vilf.h"\nint main(void) {' + body + "return 0; }\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
+    assert [int(v) for v in out[0].split()] == [getattr(cabi.Config, f).offset for f in fields_cfg] + [C.sizeof(cabi.Config)]
+    assert [int(v) for v in out[1].split()] == [getattr(cabi.SCParams, f).offset for f in fields_sc] + [C.sizeof(cabi.SCParams)]
+    assert C.sizeof(cabi.Config) == 120  # 2 x int32, 8 x double, 6 x int32, 2 x int32, 2 x double
 
 
 def test_invalid_arguments_are_rejected_without_touching_cuda(cabi):

@@ -23,6 +23,7 @@
 // distance ties are resolved by PCL rank (recomputed from the two points on the rare tie), and the API boundary
 // (vilf_get_cloud, vilf_factors) converts to PCL order on demand.
 #include "k_sort.cuh"
+#include <cstdlib>
 #include "k_voxel.cuh"
 #include "k_cluster_sort.cuh"
 
@@ -1064,7 +1065,216 @@ __device__ __forceinline__ void warp_knn5(const CellMapView& M, float gate_f, fl
   pool_top5(M, pool, npool, bd, bi);
 }
 
+// ------------------------------------------------------------------------------------------------
+// 5-NN: EIGHT lanes per query (the default; VILF_KNN_WARP=1 selects the warp-per-query search above for A/B runs)
+// ------------------------------------------------------------------------------------------------
+// The warp-per-query search costs ~1.3 k (sparse maps) to ~4 k (1e6-point maps) warp instructions per query and is issue bound
+// (profiles/r2_*): per 32 candidates it pays a 5-step owner search, three shuffles, a ballot and the pool bookkeeping, and the 27
+// table probes run on lanes that mostly find empty cells.  Here a query belongs to a group of eight lanes (four queries per warp),
+// as in the hashed-grid search of k_knn.cu: lane sl probes cells sl, sl + 8, ... of a shell and walks ITS cells' contiguous ranges
+// alone, keeping a private top five in registers (a candidate costs ~12 instructions: load, distance, compare); the eight lists
+// are merged at the end by five rounds of an 8-lane arg-min.  Early exit between shells as before (the smallest private fifth
+// distance bounds the group's fifth from above).  Same exact (d^2, PCL order) result, bit for bit.
+struct Top5C {
+  float d[5];
+  int id[5];
+};
+__device__ __forceinline__ bool closer_cell(const CellMapView& M, float d, int id, float bd, int bid) {
+  if (d < bd) return true;
+  if (d > bd || d == FLT_MAX) return false;
+  return pcl_before(M, id, bid);  // exact fp32 tie (class T2): the reference's map order decides
+}
+__device__ __forceinline__ void top5c_insert(const CellMapView& M, Top5C& t, float cd, int ci) {  // precondition: closer than t[4]
+  t.d[4] = cd; t.id[4] = ci;
+#pragma unroll
+  for (int k = 4; k > 0; --k) {
+    const bool sw = closer_cell(M, t.d[k], t.id[k], t.d[k - 1], t.id[k - 1]);
+    const float dk = sw ? t.d[k - 1] : t.d[k], dk1 = sw ? t.d[k] : t.d[k - 1];
+    const int ik = sw ? t.id[k - 1] : t.id[k], ik1 = sw ? t.id[k] : t.id[k - 1];
+    t.d[k] = dk; t.d[k - 1] = dk1; t.id[k] = ik; t.id[k - 1] = ik1;
+  }
+}
+__device__ __forceinline__ void cell_consider(const CellMapView& M, Top5C& best, float gate_f, float qx, float qy, float qz, const float4 c, int ci) {
+  const float ddx = fsub(qx, c.x), ddy = fsub(qy, c.y), ddz = fsub(qz, c.z);
+  const float cd = fadd(fadd(fmul(ddx, ddx), fmul(ddy, ddy)), fmul(ddz, ddz));  // FLANN L2_Simple<float>
+  if (cd < gate_f && cd <= best.d[4]) {
+    if (closer_cell(M, cd, ci, best.d[4], best.id[4])) top5c_insert(M, best, cd, ci);
+  }
+}
+// [start, end) of cell (cx, cy, cz), or an empty range
+__device__ __forceinline__ void cell_lookup(const CellMapView& M, int cx, int cy, int cz, int ncmax, uint32_t& s0, uint32_t& e0) {
+  s0 = 0; e0 = 0;
+  if (cx < 0 || cy < 0 || cz < 0 || cx > ncmax || cy > ncmax || cz > ncmax) return;
+  const int s = M.g.shift;
+  const unsigned long long ck = cellkey_cells((uint32_t)cx, (uint32_t)cy, (uint32_t)cz, s);
+  uint32_t h = cell_slot(ck) & M.hmask;
+  for (;;) {
+    const uint2 e = __ldg(M.table + h);
+    if (e.x == SLOT_EMPTY) return;
+    if ((key64_pt(__ldg(M.pts + e.x), M.g) >> (3 * s)) == ck) { s0 = e.x; e0 = e.y; return; }
+    h = (h + 1) & M.hmask;
+  }
+}
+__device__ __forceinline__ void shell_cell(int r, int t, int& dx, int& dy, int& dz) {  // cell t of the shell of Chebyshev radius r >= 2
+  const int side = 2 * r + 1, face = side * side, ring = 8 * r;
+  if (t < 2 * face) {
+    const int u = t < face ? t : t - face;
+    dx = u % side - r; dy = u / side - r; dz = t < face ? -r : r;
+  } else {
+    const int u = t - 2 * face, v = u % ring, sd = v / (2 * r), off = v % (2 * r);
+    dz = u / ring - r + 1;
+    dx = sd == 0 ? -r + off : sd == 1 ? r : sd == 2 ? r - off : -r;
+    dy = sd == 0 ? -r : sd == 1 ? -r + off : sd == 2 ? r : r - off;
+  }
+}
+
+constexpr int KG = 8;  // lanes per query
+// Called by all 32 lanes; the lanes of a group (lane >> 3) pass the same query and the same map.  Result replicated in the group.
+__device__ __forceinline__ void group_knn5_cell(const CellMapView& M, float gate_f, float qx, float qy, float qz, bool active, float (&rd)[5], int (&ri)[5]) {
+  const unsigned FULL = 0xffffffffu;
+  const int sl = threadIdx.x & (KG - 1);
+  Top5C best;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) { best.d[k] = FLT_MAX; best.id[k] = INT_MAX; }
+  const int s = M.g.shift;
+  const int ncmax = (1 << (21 - s)) - 1;
+  int qcx = 0, qcy = 0, qcz = 0;
+  if (active) {
+    int vx, vy, vz;
+    voxel_of(make_float4(qx, qy, qz, 0.f), M.g.inv_leaf, vx, vy, vz);
+    qcx = (int)(vbias(vx) >> s); qcy = (int)(vbias(vy) >> s); qcz = (int)(vbias(vz) >> s);
+    // shell 1 = the 27-cell cube: lane sl owns cells sl, sl + 8, sl + 16, sl + 24; the four probes are independent
+    uint32_t s0[4], e0[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = sl + KG * j;
+      s0[j] = 0; e0[j] = 0;
+      if (c < 27) cell_lookup(M, qcx + c % 3 - 1, qcy + (c / 3) % 3 - 1, qcz + c / 9 - 1, ncmax, s0[j], e0[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      for (uint32_t p = s0[j]; p < e0[j]; ++p) cell_consider(M, best, gate_f, qx, qy, qz, __ldg(M.pts + p), (int)p);
+  }
+  const int shells = M.g.shells;
+  const int rmax = __reduce_max_sync(FULL, active ? shells : 1);
+  if (rmax > 1) {
+    float fmin_cells = 0.f;
+    if (active) {
+      const float k = (float)(1 << s), inv = M.g.inv_leaf;
+      const float ux = fmul(qx, inv) - (float)(((qcx << s) - VOX_BIAS)), uy = fmul(qy, inv) - (float)(((qcy << s) - VOX_BIAS)),
+                  uz = fmul(qz, inv) - (float)(((qcz << s) - VOX_BIAS));
+      const float f = fminf(fminf(fminf(ux, k - ux), fminf(uy, k - uy)), fminf(uz, k - uz));  // voxels to the nearest face of the query's cell
+      fmin_cells = fmaxf(0.f, f / k - 1e-4f);
+    }
+    const double cell = (double)M.g.leaf * (double)(1 << s) * (1.0 - 1e-5);  // a lower bound of the cell edge (inverse_leaf is rounded)
+    for (int r = 1; r < rmax; ++r) {  // shells 1..r are done; is shell r + 1 needed?
+      float ub = best.d[4];           // a lane's own fifth distance bounds the group's from above
+#pragma unroll
+      for (int off = 1; off < KG; off <<= 1) ub = fminf(ub, __shfl_xor_sync(FULL, ub, off));
+      const double reach = ((double)r + (double)fmin_cells) * cell;
+      const bool done = !active || r >= shells || (double)ub < reach * reach * (1.0 - 1e-5);
+      if (__all_sync(FULL, done)) break;
+      if (!done) {
+        const int R = r + 1, side = 2 * R + 1;
+        const int ncell = 2 * side * side + (side - 2) * 8 * R;
+        for (int t = sl; t < ncell; t += KG) {
+          int dx, dy, dz;
+          shell_cell(R, t, dx, dy, dz);
+          uint32_t a, b;
+          cell_lookup(M, qcx + dx, qcy + dy, qcz + dz, ncmax, a, b);
+          for (uint32_t p = a; p < b; ++p) cell_consider(M, best, gate_f, qx, qy, qz, __ldg(M.pts + p), (int)p);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int round = 0; round < 5; ++round) {  // merge the eight private lists: group arg-min, the owner pops
+    float wd = best.d[0];
+    int wi = best.id[0];
+#pragma unroll
+    for (int off = 1; off < KG; off <<= 1) {
+      const float od = __shfl_xor_sync(FULL, wd, off);
+      const int oi = __shfl_xor_sync(FULL, wi, off);
+      const bool take = active && oi != INT_MAX && (wi == INT_MAX || closer_cell(M, od, oi, wd, wi));
+      wd = take ? od : wd;
+      wi = take ? oi : wi;
+    }
+    rd[round] = wd; ri[round] = wi;
+    const bool pop = (best.id[0] == wi) & (wi != INT_MAX);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { best.d[k] = pop ? best.d[k + 1] : best.d[k]; best.id[k] = pop ? best.id[k + 1] : best.id[k]; }
+    best.d[4] = pop ? FLT_MAX : best.d[4];
+    best.id[4] = pop ? INT_MAX : best.id[4];
+  }
+}
+
 constexpr int KC_THREADS = 256;
+
+__global__ void __launch_bounds__(KC_THREADS) k_knn_cell8_assoc(LaneDev* lanes, int lane0, int cur, ConfigDev cfg, const double* pose_override) {
+  const int ln = lane0 + blockIdx.y;
+  const LaneDev& L = lanes[ln];
+  LaneVars& V = *L.v;
+  const int me = V.n_map[0], ms = V.n_map[1];
+  if (!(me > 10 && ms > 50)) return;  // EM:254
+  const int ne = V.n_ds[0], ns = V.n_ds[1];
+  const int nq = ne + ns;
+  if (blockIdx.x == 0 && threadIdx.x == 0) V.opt_ran = 1;
+  if ((int)blockIdx.x * 32 >= nq) return;
+  double x[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) x[i] = pose_override ? pose_override[i] : V.x[i];
+  CellMapView Me, Ms;
+  Me.pts = L.map[0][cur]; Me.table = L.ctab[0]; Me.hmask = (uint32_t)L.cmeta[0][0]; Me.orig = L.cmeta[0][1] ? L.corig[0] : nullptr; Me.g = cfg.cg[0]; Me.n = me;
+  Ms.pts = L.map[1][cur]; Ms.table = L.ctab[1]; Ms.hmask = (uint32_t)L.cmeta[1][0]; Ms.orig = L.cmeta[1][1] ? L.corig[1] : nullptr; Ms.g = cfg.cg[1]; Ms.n = ms;
+  // A CTA takes 32 consecutive queries per round: warp 0 runs the fp64 transform (EM:355-363) with one query per lane, then each of
+  // the 32 eight-lane groups searches one of them.
+  __shared__ float4 sq[32];
+  const int grp = threadIdx.x >> 3, sl = threadIdx.x & 7;
+  for (int qb = blockIdx.x * 32; qb < nq; qb += gridDim.x * 32) {
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const int myq = qb + (int)threadIdx.x;
+      if (myq < nq) sq[threadIdx.x] = associate(x, myq < ne ? L.ds[0][myq] : L.ds[1][myq - ne]);
+    }
+    __syncthreads();
+    const int q = qb + grp;
+    const bool active = q < nq;
+    const float4 pw = active ? sq[grp] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int w = (active && q >= ne) ? 1 : 0;
+    const int k = w ? q - ne : q;
+    float rd[5];
+    int ri[5];
+    // a warp holds four groups; at the edge / surf boundary they may use different maps: run the search once per map in use
+    const unsigned want1 = __ballot_sync(0xffffffffu, active && w == 1), want0 = __ballot_sync(0xffffffffu, active && w == 0);
+#pragma unroll
+    for (int t = 0; t < 5; ++t) { rd[t] = FLT_MAX; ri[t] = INT_MAX; }
+    if (want0) {
+      float d0[5]; int i0[5];
+      group_knn5_cell(Me, cfg.knn_gate_f, pw.x, pw.y, pw.z, active && w == 0, d0, i0);
+      if (active && w == 0) {
+#pragma unroll
+        for (int t = 0; t < 5; ++t) { rd[t] = d0[t]; ri[t] = i0[t]; }
+      }
+    }
+    if (want1) {
+      float d1[5]; int i1[5];
+      group_knn5_cell(Ms, cfg.knn_gate_f, pw.x, pw.y, pw.z, active && w == 1, d1, i1);
+      if (active && w == 1) {
+#pragma unroll
+        for (int t = 0; t < 5; ++t) { rd[t] = d1[t]; ri[t] = i1[t]; }
+      }
+    }
+    if (active) {
+#pragma unroll
+      for (int t = 0; t < 5; ++t)
+        if (sl == t) {
+          L.nn_idx[w][k * 5 + t] = ri[t] == INT_MAX ? -1 : ri[t];
+          L.nn_d2[w][k * 5 + t] = rd[t];
+        }
+    }
+  }
+}
+
 
 __global__ void __launch_bounds__(KC_THREADS) k_knn_cell_assoc(LaneDev* lanes, int lane0, int cur, ConfigDev cfg, const double* pose_override) {
   const int ln = lane0 + blockIdx.y;
@@ -1117,7 +1327,9 @@ __global__ void __launch_bounds__(KC_THREADS) k_knn_cell_assoc(LaneDev* lanes, i
 
 void launch_knn_cell_fit(const Launch& L, LaneDev* lanes, int lane0, int nlanes, int cur, const ConfigDev& cfg, const double* pose_override) {
   dim3 g(KNN_G * 8, nlanes);
-  k_knn_cell_assoc<<<g, KC_THREADS, 0, L.st>>>(lanes, lane0, cur, cfg, pose_override);
+  static const bool warp_search = getenv("VILF_KNN_WARP") != nullptr;  // A/B: the warp-per-query search
+  if (warp_search) k_knn_cell_assoc<<<g, KC_THREADS, 0, L.st>>>(lanes, lane0, cur, cfg, pose_override);
+  else k_knn_cell8_assoc<<<g, KC_THREADS, 0, L.st>>>(lanes, lane0, cur, cfg, pose_override);
   L.tick(K_KNN_CELL);
   launch_fit(L, lanes, lane0, nlanes, cur, cfg);
 }
@@ -1151,9 +1363,39 @@ __global__ void __launch_bounds__(KC_THREADS) k_knn_cell_only(const float4* __re
       }
   }
 }
+__global__ void __launch_bounds__(KC_THREADS) k_knn_cell8_only(const float4* __restrict__ pts, const int* n_dev, const uint2* __restrict__ table, const int* meta,
+                                                                const uint32_t* __restrict__ orig, CellGeom g, const float4* __restrict__ q, const int* nq_dev,
+                                                                int* idx, float* d2, float gate_f) {
+  const int nq = *nq_dev;
+  const int sl = threadIdx.x & 7;
+  const int gpb = KC_THREADS / KG;
+  CellMapView M;
+  M.pts = pts; M.table = table; M.hmask = (uint32_t)meta[0]; M.orig = meta[1] ? orig : nullptr; M.g = g; M.n = *n_dev;
+  const bool empty = *n_dev == 0;
+  const int rounds = (nq + gridDim.x * gpb - 1) / (gridDim.x * gpb);
+  for (int it = 0; it < rounds; ++it) {  // whole warps stay in the loop: the search uses full-mask shuffles
+    const int i = (it * gridDim.x + blockIdx.x) * gpb + (threadIdx.x >> 3);
+    const bool active = i < nq && !empty;
+    const float4 p = i < nq ? q[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    float rd[5];
+    int ri[5];
+    group_knn5_cell(M, gate_f, p.x, p.y, p.z, active, rd, ri);
+    if (i < nq) {
+#pragma unroll
+      for (int j = 0; j < 5; ++j)
+        if (sl == j) {
+          const bool none = empty || ri[j] == INT_MAX;
+          idx[i * 5 + j] = none ? -1 : (M.orig ? (int)M.orig[ri[j]] : ri[j]);
+          d2[i * 5 + j] = none ? FLT_MAX : rd[j];
+        }
+    }
+  }
+}
 void launch_knn_cell_only(const Launch& L, const float4* pts, const int* n_dev, const uint2* table, const int* meta, const uint32_t* orig, CellGeom g,
                           const float4* q, const int* nq_dev, int* idx, float* d2, const ConfigDev& cfg) {
-  k_knn_cell_only<<<KNN_G * 8, KC_THREADS, 0, L.st>>>(pts, n_dev, table, meta, orig, g, q, nq_dev, idx, d2, cfg.knn_gate_f);
+  static const bool warp_search = getenv("VILF_KNN_WARP") != nullptr;  // A/B: the warp-per-query search
+  if (warp_search) k_knn_cell_only<<<KNN_G * 8, KC_THREADS, 0, L.st>>>(pts, n_dev, table, meta, orig, g, q, nq_dev, idx, d2, cfg.knn_gate_f);
+  else k_knn_cell8_only<<<KNN_G * 8, KC_THREADS, 0, L.st>>>(pts, n_dev, table, meta, orig, g, q, nq_dev, idx, d2, cfg.knn_gate_f);
   L.tick(K_KNN_CELL);
 }
 

@@ -182,13 +182,14 @@ void grid_geometry(const Ctx* C, double leaf, GridJob& G) {
 }
 
 // Search cells of a cell-ordered map: cubes of 2^shift voxels of the map's own voxel filter, walked shell by shell with early
-// exit.  Cell edge = the smallest power-of-two multiple of the leaf that is >= max(2 leaves, 0.4 x gate radius):
-//  - on a dense voxel-filtered surface the first shell (a box of three cells) then holds a few dozen candidates and the fifth
+// exit.  Cell edge = the smallest power-of-two multiple of the leaf that is >= max(2 leaves, 0.35 x gate radius):
+//  - on a dense voxel-filtered surface the first shell (a box of three cells) then holds a few dozen to ~150 candidates and the fifth
 //    neighbour (~1.3 leaves away) lies inside the distance that shell guarantees, so the walk stops after it;
 //  - in the sparse far field of a lidar map (point spacing set by the beams, not by the leaf) cells much finer than the gate make
-//    every query walk many shells of empty cells.  Measured on the configs[2] sequence (leaf 0.1 m, ~1e6 map points, 3.7e4 queries
-//    per sequence and iteration, 4 sequences): 229 us per search launch with 0.2 m cells, 95 us with 0.4 m, 180 us with 0.8 m
-//    (the hashed 0.25 m grid of the radix path: 247 us).
+//    every query walk many shells of empty cells.
+// Measured on the configs[2] sequence (one sequence, 3.9e4 queries per launch, warp-per-query search): leaf 0.1 m, ~1e6 map points:
+// 229 us per search launch with 0.2 m cells, 95 us with 0.4 m, 180 us with 0.8 m; leaf 0.09 m, 1.13e6 points
+// (gpurun_out/r2m_dense_shift*.json): 275 us with 0.18 m cells, 111 us with 0.36 m, 219 us with 0.72 m.
 // Leaves at or above the gate radius use one voxel per cell.
 CellGeom cell_geometry(const Ctx* C, double leaf) {
   CellGeom g;
@@ -197,7 +198,7 @@ CellGeom cell_geometry(const Ctx* C, double leaf) {
   const double reach = std::sqrt(C->ucfg.knn_gate) * 1.001;
   int shift = 0;
   if ((double)g.leaf < reach) {
-    const double target = std::max(2.0 * (double)g.leaf, 0.4 * reach);
+    const double target = std::max(2.0 * (double)g.leaf, 0.35 * reach);
     while ((double)(1 << shift) * (double)g.leaf < target * (1.0 - 1e-6) && shift < 12) ++shift;
   }
   if (const char* e = getenv("VILF_CELL_SHIFT")) shift = atoi(e);  // experiments only
