@@ -495,6 +495,7 @@ __global__ void __launch_bounds__(256) k_merge_partition(const MergeJob* __restr
     const int H = table_size(n_tot, J.hcap);
     V.hmask = H - 1;
     V.n_orph = 0;  // consumed by k_new_xform; the emitting pass appends the next ones
+    V.old_unique = J.meta[1] == 0 ? 1 : 0;  // (k_merge_scan clears meta[1] between the two merge passes: latch it here)
     if (n_tiles > J.max_tiles) atomicOr(J.status, ST_MAP_CAPACITY);
   }
 }
@@ -632,7 +633,27 @@ __global__ void __launch_bounds__(MERGE_THREADS, 4) k_merge(const MergeJob* __re
   float4 outp[MPER];
   unsigned long long outk[MPER];
   uint32_t hasm = 0;
-  {
+  // Fast path (most tiles of a big map): no new point falls into the tile and the old map has one point per voxel, so every live
+  // point is a complete voxel of its own: centroid = (0 + p) / 1.  A run is an old point followed by the new points of its voxel, so
+  // the only run that can leave such a tile is the one of its last point, when the next tile begins with new points of that voxel:
+  // then the general path below runs (the head of a run sums all of it, also what lies behind its tile).
+  bool fast = nb == 0 && nt > 0 && V.old_unique != 0;
+  if (fast && d1 < n_tot && b1 < n_new) fast = J.nkey[b1] != S.keys[nt - 1];
+  if (fast) {
+    const int r0 = tid * MPER;
+#pragma unroll
+    for (int it = 0; it < MPER; ++it) {
+      const int r = r0 + it;
+      outk[it] = 0;
+      outp[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < nt && S.live[r]) {
+        const float4 q = S.pts[r];
+        hasm |= 1u << it;
+        outp[it] = make_float4(fadd(0.f, q.x), fadd(0.f, q.y), fadd(0.f, q.z), fadd(0.f, q.w));
+        outk[it] = S.keys[r] >> s3;
+      }
+    }
+  } else {
     const int r0 = tid * MPER;
     unsigned long long pk = r0 == 0 ? prev_key : (r0 - 1 < nt ? S.keys[S.order[r0 - 1]] : 0ull);
 #pragma unroll
@@ -1066,15 +1087,17 @@ __device__ __forceinline__ void warp_knn5(const CellMapView& M, float gate_f, fl
 }
 
 // ------------------------------------------------------------------------------------------------
-// 5-NN: EIGHT lanes per query (the default; VILF_KNN_WARP=1 selects the warp-per-query search above for A/B runs)
+// 5-NN: EIGHT lanes per query — an A/B variant (VILF_KNN_GROUP8=1), NOT the default
 // ------------------------------------------------------------------------------------------------
-// The warp-per-query search costs ~1.3 k (sparse maps) to ~4 k (1e6-point maps) warp instructions per query and is issue bound
-// (profiles/r2_*): per 32 candidates it pays a 5-step owner search, three shuffles, a ballot and the pool bookkeeping, and the 27
-// table probes run on lanes that mostly find empty cells.  Here a query belongs to a group of eight lanes (four queries per warp),
-// as in the hashed-grid search of k_knn.cu: lane sl probes cells sl, sl + 8, ... of a shell and walks ITS cells' contiguous ranges
-// alone, keeping a private top five in registers (a candidate costs ~12 instructions: load, distance, compare); the eight lists
-// are merged at the end by five rounds of an 8-lane arg-min.  Early exit between shells as before (the smallest private fifth
-// distance bounds the group's fifth from above).  Same exact (d^2, PCL order) result, bit for bit.
+// The warp-per-query search above costs ~1.3 k (sparse maps) to ~3.3 k (1e6-point maps, 0.72 m cells) warp instructions per query and
+// is issue bound (profiles/r2m_dense_frame_S1.txt).  This variant gives a query to a group of eight lanes (four queries per warp), as
+// the hashed-grid search of k_knn.cu does: lane sl probes cells sl, sl + 8, ... of a shell and walks ITS cells' contiguous ranges
+// alone, keeping a private top five in registers; the eight lists are merged at the end by five rounds of an 8-lane arg-min.  It
+// executes far fewer instructions per query but was measured SLOWER on the 1e6-point maps (gpurun_out/r2n_dense*.json: 180 us per
+// search launch against 110 us; 0.32 G queries/s against 1.0 G on the synthetic 1e6 / 2.6e5 stage): every lane streams its own
+// 16-byte points (32 sectors per warp load instead of 4 for the coalesced batches of the warp search), the trip count of a warp is
+// the longest of its 32 per-lane walks, and 104 registers leave 16 warps per SM to hide the load latency.  Kept because it is exact
+// (bit-identical results, same tests) and documents the experiment.
 struct Top5C {
   float d[5];
   int id[5];
@@ -1327,9 +1350,9 @@ __global__ void __launch_bounds__(KC_THREADS) k_knn_cell_assoc(LaneDev* lanes, i
 
 void launch_knn_cell_fit(const Launch& L, LaneDev* lanes, int lane0, int nlanes, int cur, const ConfigDev& cfg, const double* pose_override) {
   dim3 g(KNN_G * 8, nlanes);
-  static const bool warp_search = getenv("VILF_KNN_WARP") != nullptr;  // A/B: the warp-per-query search
-  if (warp_search) k_knn_cell_assoc<<<g, KC_THREADS, 0, L.st>>>(lanes, lane0, cur, cfg, pose_override);
-  else k_knn_cell8_assoc<<<g, KC_THREADS, 0, L.st>>>(lanes, lane0, cur, cfg, pose_override);
+  static const bool group_search = getenv("VILF_KNN_GROUP8") != nullptr;  // A/B: eight lanes per query (measured slower, see above)
+  if (group_search) k_knn_cell8_assoc<<<g, KC_THREADS, 0, L.st>>>(lanes, lane0, cur, cfg, pose_override);
+  else k_knn_cell_assoc<<<g, KC_THREADS, 0, L.st>>>(lanes, lane0, cur, cfg, pose_override);
   L.tick(K_KNN_CELL);
   launch_fit(L, lanes, lane0, nlanes, cur, cfg);
 }
@@ -1393,9 +1416,9 @@ __global__ void __launch_bounds__(KC_THREADS) k_knn_cell8_only(const float4* __r
 }
 void launch_knn_cell_only(const Launch& L, const float4* pts, const int* n_dev, const uint2* table, const int* meta, const uint32_t* orig, CellGeom g,
                           const float4* q, const int* nq_dev, int* idx, float* d2, const ConfigDev& cfg) {
-  static const bool warp_search = getenv("VILF_KNN_WARP") != nullptr;  // A/B: the warp-per-query search
-  if (warp_search) k_knn_cell_only<<<KNN_G * 8, KC_THREADS, 0, L.st>>>(pts, n_dev, table, meta, orig, g, q, nq_dev, idx, d2, cfg.knn_gate_f);
-  else k_knn_cell8_only<<<KNN_G * 8, KC_THREADS, 0, L.st>>>(pts, n_dev, table, meta, orig, g, q, nq_dev, idx, d2, cfg.knn_gate_f);
+  static const bool group_search = getenv("VILF_KNN_GROUP8") != nullptr;  // A/B: eight lanes per query (measured slower)
+  if (group_search) k_knn_cell8_only<<<KNN_G * 8, KC_THREADS, 0, L.st>>>(pts, n_dev, table, meta, orig, g, q, nq_dev, idx, d2, cfg.knn_gate_f);
+  else k_knn_cell_only<<<KNN_G * 8, KC_THREADS, 0, L.st>>>(pts, n_dev, table, meta, orig, g, q, nq_dev, idx, d2, cfg.knn_gate_f);
   L.tick(K_KNN_CELL);
 }
 

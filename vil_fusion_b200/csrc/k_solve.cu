@@ -629,6 +629,9 @@ k_solve(LaneDev* lanes, int lane0, int outer, int finalize, ConfigDev cfg, int m
 }
 
 void launch_solve(const Launch& L, LaneDev* lanes, int lane0, int nlanes, int outer, int finalize, const ConfigDev& cfg, int max_iters) {
+#if VILF_LM_CLUSTER > 8
+  cudaFuncSetAttribute(k_solve, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);  // A/B builds only
+#endif
   dim3 grid(LM_CLUSTER, nlanes);
   k_solve<<<grid, LM_THREADS, 0, L.st>>>(lanes, lane0, outer, finalize, cfg, max_iters);
   L.tick(K_SOLVE);

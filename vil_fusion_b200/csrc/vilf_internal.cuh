@@ -181,7 +181,8 @@ struct MergeVars {
   int n_live_all;
   int n_orph;      // orphans waiting for the next update
   int hmask;       // cell table size - 1 of the map being written
-  int pad_[3];
+  int old_unique;  // the old map holds at most one point per voxel (it came out of an update; a first-frame / imported map does not)
+  int pad_[2];
 };
 struct TileAgg {   // per merge tile, written by the counting pass
   int count;             // voxels (map points) the tile emits
