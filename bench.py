@@ -42,7 +42,7 @@ WORKLOADS = {
     "beams128": dict(sensor="beams128", n_scan=0, n_rings=128, desc="synthetic 128x2048 sequence(s), explicit ring ids (configs[4] shape)"),
     # BASELINE.json configs[2]: dense world, 0.09 m voxels, ~1e6 points in the +-100 m crop once the maps have filled (vil_fusion_b200/synth.py DENSE)
     "hdl64_dense": dict(sensor="hdl64", n_scan=64, n_rings=64, seq_kw=dict(density=synth.DENSE["density"], speed=synth.DENSE["speed"], world_length=700.0),
-                        cfg_kw=dict(edge_leaf=synth.DENSE["edge_leaf"], surf_leaf=synth.DENSE["surf_leaf"]), map_cap=synth.DENSE["max_map_points"], seqs=4,
+                        cfg_kw=dict(edge_leaf=synth.DENSE["edge_leaf"], surf_leaf=synth.DENSE["surf_leaf"]), map_cap=synth.DENSE["max_map_points"], seqs=8,
                         preroll=320, cpu_frames=20,
                         desc="synthetic HDL-64E 64x1800 sequence(s) in a 3x denser world at 0.4 m/frame, leaf 0.09/0.09: >= 1e6 live map points per sequence (configs[2])"),
 }
@@ -468,21 +468,29 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         ach = (ab / dur_s / 1e9) if ab else None
         traffic = None
         traffic_src = None
-        try:  # DRAM bytes of the same kernel from a committed ncu --set full capture, scaled to this launch's sequence count
-            tt = json.load(open(os.path.join(ROOT, "profiles", "r1k_traffic.json")))["kernels"]
-            ent = tt.get(dk.replace("k_sector_select", "k_sector_warp<16>"))
+        issue = None
+        try:  # DRAM bytes / warp instructions of the same kernel from a committed ncu --set full capture, scaled to this launch's sequence count
+            tfile = "r2_traffic_dense.json" if args.workload == "hdl64_dense" else "r2_traffic.json"
+            tt = json.load(open(os.path.join(ROOT, "profiles", tfile)))["kernels"]
+            ent = tt.get({"k_sector_select": "k_sector_warp<16>", "k_new_xform": "k_new_cluster", "k_merge<count>": "k_merge<0>", "k_merge<emit>": "k_merge<1>"}.get(dk, dk))
             if ent:
                 per = ent["dram_bytes_per_launch"]
-                # k_voxel_cluster appears twice per frame: the scan job (~100 k points per sequence) is the larger one
-                one = (min(per) if dp == "map_update" else max(per)) if dk == "k_voxel_cluster" else per[0]
-                traffic = one * (bounds[1] - bounds[0]) / ent["sequences"]
-                traffic_src = "committed ncu --set full capture profiles/r1k_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum per launch), scaled to this launch's sequence count; NOT measured in this run"
+                # k_voxel_cluster appears twice per frame on the radix path (scan job first, then the map job); everything else: first launch
+                li = (1 if dp == "map_update" and len(per) > 1 else 0) if dk == "k_voxel_cluster" else 0
+                scale = (bounds[1] - bounds[0]) / ent["sequences"]
+                traffic = per[li] * scale
+                traffic_src = f"committed ncu --set full capture profiles/{tfile} (dram__bytes_read.sum + dram__bytes_write.sum per launch), scaled to this launch's sequence count; NOT measured in this run"
+                winst = ent["warp_instructions_per_launch"][li] * scale
+                sm_hz = float(clk.get("sm_mhz") or clk.get("sm_max_mhz") or 1965.0) * 1e6
+                issue_peak = 148 * 4 * sm_hz  # warp instructions per second: 148 SMs x 4 schedulers x 1 instruction per clock
+                issue = dict(warp_instructions_per_launch=winst, achieved_ginst_s=winst / dur_s / 1e9, peak_ginst_s=issue_peak / 1e9, frac=winst / dur_s / issue_peak,
+                             issue_active_pct_under_ncu=ent["issue_active_pct"][li], threads_per_warp_instruction=ent["threads_per_warp_instruction"][li],
+                             source=f"instruction count from profiles/{tfile} (same launch geometry), duration measured in this run",
+                             note="the instruction-issue roofline next to the HBM one: this kernel works on L2-resident data, so what bounds it is how many warp instructions the SMs it occupies can issue (and the latency between them), not DRAM bandwidth")
         except Exception:
             traffic = None
-        # instruction-issue roofline for kernels that are issue- rather than bandwidth-bound: warp instructions per launch from the
-        # committed ncu capture against the SMs' issue rate (4 schedulers x 1 instruction per clock)
         roof = dict(bound="hbm", kernel=f"{dp}/{dk}", achieved=ach, peak=peak, unit="GB/s", frac=(ach / peak) if ach else None, traffic=traffic,
-                    traffic_source=traffic_src,
+                    traffic_source=traffic_src, issue=issue,
                     peak_source="MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                     share_of_step=dms / tot, launches_timed=dn, avg_launch_us=dur_s * 1e6, algorithmic_bytes_per_launch=ab,
                     note="event-to-event interval (includes the launch gap) on steady-state frames; per-frame working set of this workload is L2-resident, so the path is latency- / issue-bound, not HBM-bound (DESIGN.md §6)")

@@ -1032,17 +1032,16 @@ __device__ __forceinline__ void warp_knn5(const CellMapView& M, float gate_f, fl
 #pragma unroll
       for (int off = 1; off < 32; off <<= 1) { const uint32_t u = __shfl_up_sync(FULL, inc, off); if (lane >= off) inc += u; }
       const uint32_t total = __shfl_sync(FULL, inc, 31);
+      const uint32_t rebase = s0 - (inc - cnt);  // map index of the range's first point minus its position in the concatenation
+      int own = 0;  // owner of this lane's candidate = first lane whose inclusive count exceeds c; it only moves forward with c
       for (uint32_t c0 = 0; c0 < total; c0 += 32) {
         const uint32_t c = c0 + lane;
-        int l = 0, h = 31;  // owner = first lane whose inclusive count exceeds c
-#pragma unroll
-        for (int it = 0; it < 5; ++it) {
-          const int m = (l + h) >> 1;
-          const uint32_t v = __shfl_sync(FULL, inc, m);
-          if (v > c) h = m; else l = m + 1;
-        }
-        const uint32_t so = __shfl_sync(FULL, s0, l), io = __shfl_sync(FULL, inc, l), co = __shfl_sync(FULL, cnt, l);
-        const int idx = (int)(so + (c - (io - co)));
+        bool adv;
+        do {  // a batch of 32 candidates spans a few ranges: a few rounds (the binary search it replaces cost five shuffles per batch)
+          adv = own < 31 && __shfl_sync(FULL, inc, own) <= c;
+          own += adv ? 1 : 0;
+        } while (__any_sync(FULL, adv));
+        const int idx = (int)(__shfl_sync(FULL, rebase, own) + c);
         bool cand = c < total;
         float cd = FLT_MAX;
         if (cand) {

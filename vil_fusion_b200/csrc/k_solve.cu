@@ -41,7 +41,7 @@ struct LmShared {
   double grad_spec;  // projected-gradient max-norm at the point just evaluated (adopted with the step)
   double H[21], g[6], cost;
   double acc[NACC];               // cluster-wide sums (leader only)
-  double parts[LM_CLUSTER][NACC];  // leader only: the partial sums every CTA of the cluster stores here over DSMEM
+  double parts[LM_CLUSTER_MAX][NACC];  // leader only: the partial sums every CTA of the cluster stores here over DSMEM
   double scale[6], diag[6];
   double radius, decrease_factor, minimum_cost, x_norm, grad_max, model_cost_change, candidate_cost;
   int iteration, step_successful, reuse_diagonal, num_invalid, done, need_eval, termination, n_edge, n_surf, n_rows;
@@ -200,11 +200,11 @@ struct Stage {
   int n_edge, n_surf, staged;
 };
 
-__device__ void stage_factors(const LaneDev& L, int ne, int ns, int rank, double* pool, int* wsum, Stage& st) {
+__device__ void stage_factors(const LaneDev& L, int ne, int ns, int rank, int ncl, double* pool, int* wsum, Stage& st) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int ce = 0, cs = 0;  // CTA-uniform running counts
   bool fits = true;
-  for (int base = rank * LM_THREADS; base < ne + ns; base += LM_CLUSTER * LM_THREADS) {
+  for (int base = rank * LM_THREADS; base < ne + ns; base += ncl * LM_THREADS) {
     const int i = base + tid;
     const bool is_e = i < ne, is_s = !is_e && i < ne + ns;
     double rec[9];
@@ -433,11 +433,13 @@ __device__ bool lm_step(const LmShared& S, double* step, double& model_cost_chan
 
 }  // namespace
 
-__global__ void __cluster_dims__(LM_CLUSTER, 1, 1) __launch_bounds__(LM_THREADS, LM_THREADS <= 256 ? 2 : 1)
+// Launched with a cluster of cfg.lm_cluster CTAs along x (8, or 16 for configurations with tens of thousands of factors per solve).
+__global__ void __launch_bounds__(LM_THREADS, LM_THREADS <= 256 ? 2 : 1)
 k_solve(LaneDev* lanes, int lane0, int outer, int finalize, ConfigDev cfg, int max_iters) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
+  const int ncl = (int)cluster.num_blocks();
   const LaneDev& L = lanes[lane0 + blockIdx.y];
   LaneVars& V = *L.v;
   __shared__ LmShared S;
@@ -454,13 +456,13 @@ k_solve(LaneDev* lanes, int lane0, int outer, int finalize, ConfigDev cfg, int m
 #endif
   const bool run = V.opt_ran != 0;  // EM:254 decided by the association kernel
   const int ne = V.n_ds[0], ns = V.n_ds[1];
-  const int first = rank * LM_THREADS + tid, stride = LM_CLUSTER * LM_THREADS;
+  const int first = rank * LM_THREADS + tid, stride = ncl * LM_THREADS;
   SolveTraceDev& T = L.trace[outer];
   // leader: add the 8 partials in rank order
   auto gather = [&]() {
     if (leader && tid < NACC) {
       double v = 0;
-      for (int r = 0; r < LM_CLUSTER; ++r) v += S.parts[r][tid];
+      for (int r = 0; r < ncl; ++r) v += S.parts[r][tid];
       S.acc[tid] = v;
     }
     if (leader) __syncthreads();
@@ -518,7 +520,7 @@ k_solve(LaneDev* lanes, int lane0, int outer, int finalize, ConfigDev cfg, int m
       S.n_rows = 0;
     }
     TS();
-    stage_factors(L, ne, ns, rank, pool, wsum, stage);
+    stage_factors(L, ne, ns, rank, ncl, pool, wsum, stage);
     TS();
     double xl[7];
 #pragma unroll
@@ -591,7 +593,7 @@ k_solve(LaneDev* lanes, int lane0, int outer, int finalize, ConfigDev cfg, int m
         }
         if (tid < 32) {
           __syncwarp();
-          if (tid >= 1 && tid < LM_CLUSTER) publish();
+          if (tid >= 1 && tid < ncl) publish();
         }
         TS();
       }
@@ -628,14 +630,23 @@ k_solve(LaneDev* lanes, int lane0, int outer, int finalize, ConfigDev cfg, int m
   cluster.sync();  // no CTA may exit while the leader can still read its shared memory
 }
 
+cudaError_t init_solve_kernels() {  // clusters of 16 CTAs are beyond the portable size
+  return cudaFuncSetAttribute(k_solve, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+}
+
 void launch_solve(const Launch& L, LaneDev* lanes, int lane0, int nlanes, int outer, int finalize, const ConfigDev& cfg, int max_iters) {
-#if VILF_LM_CLUSTER > 8
-  cudaFuncSetAttribute(k_solve, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);  // A/B builds only
-#endif
-  dim3 grid(LM_CLUSTER, nlanes);
-  k_solve<<<grid, LM_THREADS, 0, L.st>>>(lanes, lane0, outer, finalize, cfg, max_iters);
+  const int ncl = cfg.lm_cluster > 0 ? cfg.lm_cluster : LM_CLUSTER;
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3(ncl, nlanes);
+  lc.blockDim = dim3(LM_THREADS);
+  lc.dynamicSmemBytes = 0;
+  lc.stream = L.st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = ncl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  lc.attrs = at; lc.numAttrs = 1;
+  cudaLaunchKernelEx(&lc, k_solve, lanes, lane0, outer, finalize, cfg, max_iters);
   L.tick(K_SOLVE);
 }
 
 }  // namespace vilf
-

@@ -260,6 +260,11 @@ int build_ctx(Ctx* C) {
     while (c.sector_np < c.max_sector) c.sector_np <<= 1;
   }
   c.cap_scan = u.max_scan_points; c.cap_map = u.max_map_points;
+  // k_solve: one 8-CTA cluster per sequence; voxel leaves below 0.25 m mean tens of thousands of factors per solve (configs[2]: 3.7e4),
+  // where a 16-CTA cluster is faster (85 -> 59 us per solve, gpurun_out/r2o_dense*.json).  The choice depends on the configuration
+  // only, never on the batch size: the order of the partial sums, hence the last bits of the pose, must not change with it.
+  c.lm_cluster = std::min(u.edge_leaf, u.surf_leaf) < 0.25 ? 16 : 8;
+  if (const char* e = getenv("VILF_LM_CLUSTER")) { const int v = atoi(e); if (v >= 1 && v <= LM_CLUSTER_MAX) c.lm_cluster = v; }  // experiments only
   c.range_image = (u.flags & VILF_FLAG_RANGE_IMAGE) ? 1 : 0;
   c.horizon = u.horizon_scan; c.ri_down = u.downsample_rate > 0 ? u.downsample_rate : 1; c.ri_edge_thr = u.ri_edge_threshold; c.ri_surf_thr = u.ri_surf_threshold;
   const int NL = C->nlanes;
@@ -268,6 +273,7 @@ int build_ctx(Ctx* C) {
   CK(cudaSetDevice(C->device));
   CK(init_extract_kernels());
   CK(init_rangeimage_kernels());
+  CK(init_solve_kernels());
   CK(cudaStreamCreateWithFlags(&C->st, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&C->copy_st, cudaStreamNonBlocking));
   for (int i = 0; i < 2; ++i) {

@@ -34,7 +34,8 @@ constexpr int FIT_G = 148;           // CTAs (128 threads) of the fit kernel per
 #define VILF_LM_CLUSTER 8
 #endif
 constexpr int LM_THREADS = VILF_LM_THREADS;  // per CTA of the solve cluster
-constexpr int LM_CLUSTER = VILF_LM_CLUSTER;  // CTAs (SMs) per sequence in the solve kernel
+constexpr int LM_CLUSTER = VILF_LM_CLUSTER;  // CTAs (SMs) per sequence in the solve kernel (default; ConfigDev::lm_cluster selects 8 or 16 at run time)
+constexpr int LM_CLUSTER_MAX = 16;
 constexpr int MAX_TRACE_ROWS = 8;
 constexpr int MAX_OUTER = 4;
 
@@ -67,6 +68,7 @@ struct ConfigDev {
   int flags_no_cluster;  // VILF_FLAG_NO_CLUSTER: grid-wide multi-launch kernels everywhere
   CellGeom cg[2];        // cell-ordered edge / surf map geometry
   // ring-field / range-image extractor (k_rangeimage.cu), stage 1 when range_image != 0
+  int lm_cluster;  // CTAs per solve cluster: 8, or 16 when the leaves are fine enough for tens of thousands of factors per solve
   int range_image, horizon, ri_down;
   double ri_edge_thr, ri_surf_thr;
 };
@@ -411,6 +413,7 @@ void launch_sc_distance(const Launch& L, const double* sc1, const double* sc2, c
 void launch_sc_detect(const Launch& L, const float* keys, int n_snapshot, const float* cur_key, const double* descs, int cur_index, const ScParams& P, float* dist,
                       double* res);
 // k_solve.cu
+cudaError_t init_solve_kernels();
 void launch_solve(const Launch& L, LaneDev* lanes, int lane0, int nlanes, int outer, int finalize, const ConfigDev& cfg, int max_iters);
 
 }  // namespace vilf
