@@ -2,7 +2,7 @@
 // over the C ABI (vilf_sc_*): same method names, argument meaning and return values as the reference's user-side API
 // (makeAndSaveScancontextAndKeys SC:196-208, detectLoopClosureID SC:210-299, setSCdistThres SC:300, setMaximumRadius SC:305)
 // and its public parameter members.  Call sites in the reference: poseGraphOptimization.cpp:553 (every key frame) and
-// :585-600 (performSCLoopClosure).
+// :600-603 (performSCLoopClosure); setters :642-643.
 //
 // Differences a maintainer should know about:
 //  * descriptors live on the device; getScancontext(i) / distanceBtnScanContext(i, j) read them back on demand.  The Eigen

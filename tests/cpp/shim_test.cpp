@@ -187,7 +187,7 @@ int main(int argc, char** argv) {
       odomEstimation.pointAssociateToMap(&pi, &po);
       if (!(std::isfinite(po.x) && std::isfinite(po.y) && std::isfinite(po.z))) return 1;
     }
-    {  // D: the loop detector of global_fusion (poseGraphOptimization.cpp:553, :585-600) on the same scans, as key frames
+    {  // D: the loop detector of global_fusion (poseGraphOptimization.cpp:553, :600-603) on the same scans, as key frames
       vilf::SCManager scManager;
       scManager.NUM_EXCLUDE_RECENT = 2; scManager.TREE_MAKING_PERIOD_ = 1;
       scManager.setSCdistThres(0.3); scManager.setMaximumRadius(80.0);

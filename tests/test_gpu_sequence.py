@@ -64,8 +64,9 @@ def test_golden_sequence(cabi, golden):
 
 
 def test_teacher_forced(cabi, orc, synth):
-    """Every frame starts from the oracle's state (pose, previous pose, both maps): per-frame parity without feedback."""
-    frames = 25
+    """Every frame starts from the oracle's state (pose, previous pose, both maps): per-frame parity without feedback
+    (the teacher-forced gate on every frame of the configs[0] sequence)."""
+    frames = 100
     seq = synth.Sequence("hdl64", frames, seed=3)
     o = orc.Odometry(orc.config())
     g = cabi.Odometry(cabi.default_config(max_scan_points=116000, max_map_points=1 << 19))

@@ -226,6 +226,36 @@ def test_eig3_and_lstsq_vs_numpy(orc):
         assert np.allclose(n, nn, rtol=1e-9, atol=1e-12)
 
 
+def test_sensitivity_alternates_agree_with_the_oracle_proper(orc, golden):
+    """The switchable alternates of the third-party restatements (tools/sensitivity.py): Eigen 3.3.7's tridiagonal QR iteration
+    against the cyclic Jacobi solver and numpy, the unpivoted Householder plane fit against the column-pivoted one, and the
+    reciprocal / unstable-order voxel centroids against the canonical ones (equal to the last bit or two, same voxels)."""
+    rng = np.random.default_rng(8)
+    for t in range(300):
+        P = rng.normal(size=(5, 3)) * rng.uniform(0.01, 2.0, 3)
+        if t % 5 == 0:
+            P[:, 2] = 0.3 * P[:, 0]  # rank-deficient neighbourhoods (collinear / coplanar points are the common case)
+        Z = P - P.mean(0)
+        Cm = Z.T @ Z
+        w0, V0 = orc.eig3(Cm)
+        w1, V1 = orc.eig3(Cm, alt=True)
+        wn = np.linalg.eigvalsh(Cm)
+        sc = max(np.abs(wn).max(), 1e-300)
+        assert np.abs(w0 - w1).max() <= 1e-14 * sc and np.abs(w1 - wn).max() <= 1e-14 * sc
+        assert np.allclose(Cm @ V1, V1 * w1, atol=1e-13 * sc) and np.allclose(V1.T @ V1, np.eye(3), atol=1e-14)
+        if wn[2] > 1.5 * wn[1]:
+            assert 1 - abs(V0[:, 2] @ V1[:, 2]) < 1e-13
+        A = rng.normal(size=(5, 3)) * 0.2 + np.array([30.0, -12.0, 1.5])
+        assert np.allclose(orc.lstsq5x3(A, -np.ones(5)), orc.lstsq5x3(A, -np.ones(5), alt=True), rtol=1e-9, atol=1e-13)
+    pts = golden["voxel_in"] if "voxel_in" in golden.files else None
+    if pts is None:
+        pts = (rng.uniform(-20, 20, (20000, 4))).astype(np.float32)
+    a, _ = orc.voxel_grid(pts, 0.4, 0)
+    for mode in (1, 2, 3):  # unstable order, reciprocal centroid, both
+        b, _ = orc.voxel_grid(pts, 0.4, mode)
+        assert a.shape == b.shape and np.abs(a - b).max() <= 4e-6  # same voxels, centroids equal to a few ulp of ~20 m
+
+
 def test_se3_plus_and_jacobians(orc):
     rng = np.random.default_rng(4)
     x = np.array([0.1, -0.05, 0.02, 0.0, 1.0, 2.0, -0.5])

@@ -1038,7 +1038,8 @@ __device__ __forceinline__ void warp_knn5(const CellMapView& M, float gate_f, fl
         const uint32_t c = c0 + lane;
         bool adv;
         do {  // a batch of 32 candidates spans a few ranges: a few rounds (the binary search it replaces cost five shuffles per batch)
-          adv = own < 31 && __shfl_sync(FULL, inc, own) <= c;
+          const uint32_t vi = __shfl_sync(FULL, inc, own);  // (every lane takes part in the shuffle)
+          adv = own < 31 && vi <= c;
           own += adv ? 1 : 0;
         } while (__any_sync(FULL, adv));
         const int idx = (int)(__shfl_sync(FULL, rebase, own) + c);
