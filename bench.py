@@ -475,8 +475,9 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
             ent = tt.get({"k_sector_select": "k_sector_warp<16>", "k_new_xform": "k_new_cluster", "k_merge<count>": "k_merge<0>", "k_merge<emit>": "k_merge<1>"}.get(dk, dk))
             if ent:
                 per = ent["dram_bytes_per_launch"]
-                # k_voxel_cluster appears twice per frame on the radix path (scan job first, then the map job); everything else: first launch
-                li = (1 if dp == "map_update" and len(per) > 1 else 0) if dk == "k_voxel_cluster" else 0
+                # k_voxel_cluster appears twice per frame on the radix path: the scan job (~100 k points per sequence) is the one with the
+                # larger traffic, the map job the other; everything else: first launch
+                li = (int(np.argmin(per)) if dp == "map_update" else int(np.argmax(per))) if dk == "k_voxel_cluster" else 0
                 scale = (bounds[1] - bounds[0]) / ent["sequences"]
                 traffic = per[li] * scale
                 traffic_src = f"committed ncu --set full capture profiles/{tfile} (dram__bytes_read.sum + dram__bytes_write.sum per launch), scaled to this launch's sequence count; NOT measured in this run"
@@ -607,6 +608,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
                              "(H2D scan + stages + D2H pose through the C ABI) is e2e, which is the headline against the CPU arm"),
         e2e=dict(value=e2e_value, unit="scans/s", h2d_bytes_per_step=int(host_counts.mean() * 16 * S), d2h_bytes_per_step=int(S * 7 * 8),
                  ms_per_step=ms_host_max / K, h2d_gbs=h2d_gbs, h2d_copy_only_gbs=h2d_peak, e2e_efficiency=h2d_gbs / h2d_peak if h2d_peak else None,
+                 staging="write-combined pinned host memory (VILF_HOST_WC)" if os.environ.get("VILF_HOST_WC") else "pinned host memory",
                  host_placement=numa,
                  note="the step moves S packed scans (16 B per point, the payload of pcl::PointXYZI) over PCIe; h2d_copy_only_gbs is the same pinned buffers copied "
                       "with the GPU idle and e2e_efficiency = h2d_gbs / h2d_copy_only_gbs (1.0 = the run moves scans as fast as the link alone can)"),

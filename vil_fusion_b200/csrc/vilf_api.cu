@@ -720,7 +720,10 @@ int submit_common(Ctx* C, int lane0, int nl, const float* const* xyzi, const int
   S.profiled = C->profile;
   S.first = !C->have_map[lane0];
   int rc = enqueue_frame(C, lane0, nl, S.first, true, sel, &S);
-  if (rc) return rc;
+  if (rc) {  // nothing of this frame was launched: give the scan buffer back so that the buffer parity and the event chain stay in step
+    C->scan_sel--;
+    return rc;
+  }
   CK(cudaEventRecord(C->extract_done[sel], C->st));  // conservative: the whole frame (the scan is only read by stage 1)
   CK(cudaMemcpyAsync(S.vars_pin, C->vars_dev + lane0, sizeof(LaneVars) * nl, cudaMemcpyDeviceToHost, C->st));
   CK(cudaEventRecord(S.done, C->st));
@@ -960,7 +963,12 @@ int vilf_destroy(vilf_handle* h) {
 
 const char* vilf_last_error(const vilf_handle* h) { return (h && h->ctx) ? h->ctx->err : "invalid handle"; }
 
-int vilf_host_alloc(void** p, uint64_t bytes) { return cudaMallocHost(p, bytes) == cudaSuccess ? VILF_OK : VILF_ERR_CUDA; }
+int vilf_host_alloc(void** p, uint64_t bytes) {
+  // VILF_HOST_WC=1 (experiments): write-combined staging — the host only ever writes scans into these buffers, and the copy engine's
+  // reads then skip the CPU cache snoop; measured against plain pinned memory in the multi-GPU end-to-end runs
+  static const bool wc = getenv("VILF_HOST_WC") != nullptr;
+  return cudaHostAlloc(p, bytes, wc ? cudaHostAllocWriteCombined : cudaHostAllocDefault) == cudaSuccess ? VILF_OK : VILF_ERR_CUDA;
+}
 int vilf_memcpy_h2d_async(void* dst_dev, const void* src_host, uint64_t bytes, void* cuda_stream) {
   return cudaMemcpyAsync(dst_dev, src_host, (size_t)bytes, cudaMemcpyHostToDevice, (cudaStream_t)cuda_stream) == cudaSuccess ? VILF_OK : VILF_ERR_CUDA;
 }
