@@ -134,6 +134,48 @@ def test_batch_lockstep_equals_single(cabi, synth):
     batch.close()
 
 
+def test_batch_strided_host_array_equals_separate_scans(cabi, synth):
+    """Scans of a batch that lie in ONE host array with a row pitch of max_scan_points points are moved with one strided copy
+    (vilf_api.cu: submit_common); rows are ragged (every sequence has its own point count, one is empty in one frame).  Same poses
+    and maps as the same scans submitted from separate arrays; explicit ring ids take the same route."""
+    S, frames, cap = 5, 6, 58000
+    seqs = [synth.Sequence("vlp32", frames, seed=40 + s) for s in range(S)]
+    cfg = cabi.default_config(n_scan=32, n_rings=32, max_scan_points=cap, max_map_points=1 << 18)
+    a, b = cabi.Batch(cfg, S), cabi.Batch(cfg, S)
+    slab = cabi.host_alloc(frames * S * cap * 16).view(np.float32).reshape(frames, S, cap, 4)
+    slab[:] = np.nan  # what lies behind a scan's last point must never matter
+    for f in range(frames):
+        scans = [np.ascontiguousarray(seqs[s][f][0][: (None if s != 2 else 40000 + 1000 * f)]) for s in range(S)]
+        if f == 3:
+            scans[4] = scans[4][:0]
+        for s in range(S):
+            slab[f, s, : len(scans[s])] = scans[s]
+        pa = a.wait(a.submit([slab[f, s, : len(scans[s])] for s in range(S)]))
+        pb = b.wait(b.submit([scans[s].copy() for s in range(S)]))
+        assert np.array_equal(pa, pb), f
+    for s in range(S):
+        for which in (0, 1, 5):
+            assert np.array_equal(a.seqs[s].cloud(which), b.seqs[s].cloud(which))
+    a.close(); b.close()
+    # explicit rings (n_scan == 0): the ring ids travel as a second strided copy
+    seq = synth.Sequence("beams128", 3, seed=1)
+    cap = 263000
+    cfg = cabi.default_config(n_scan=0, n_rings=128, max_scan_points=cap, max_map_points=1 << 18, max_ring_points=2048 + 64)
+    a, b = cabi.Batch(cfg, 3), cabi.Batch(cfg, 3)
+    slab = cabi.host_alloc(3 * cap * 16).view(np.float32).reshape(3, cap, 4)
+    rslab = cabi.host_alloc(3 * cap * 2).view(np.uint16).reshape(3, cap)
+    for f in range(3):
+        x, r = seq[f]
+        ns = [len(x), len(x) - 5000, len(x) - 123]
+        for s in range(3):
+            slab[s, : ns[s]] = x[: ns[s]]; rslab[s, : ns[s]] = r[: ns[s]]
+        pa = a.wait(a.submit([slab[s, : ns[s]] for s in range(3)], [rslab[s, : ns[s]] for s in range(3)]))
+        pb = b.wait(b.submit([np.ascontiguousarray(x[: ns[s]]) for s in range(3)], [np.ascontiguousarray(r[: ns[s]]) for s in range(3)]))
+        assert np.array_equal(pa, pb), f
+    a.close(); b.close()
+    cabi.host_free(slab); cabi.host_free(rslab)
+
+
 def test_async_pipeline_equals_blocking(cabi, synth):
     frames = 12
     seq = synth.Sequence("vlp32", frames, seed=31)

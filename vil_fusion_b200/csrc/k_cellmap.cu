@@ -1234,6 +1234,11 @@ __device__ __forceinline__ void group_knn5_cell(const CellMapView& M, float gate
 }
 
 constexpr int KC_THREADS = 256;
+#ifndef VILF_KC_MINB
+#define VILF_KC_MINB 4
+#endif
+constexpr int KC_MINB = VILF_KC_MINB;  // resident CTAs per SM the warp search is compiled for: 4 caps it at 64 registers (16 B spilled) and was measured
+                                       // against 3 (80 registers): +12 % scans/s on the configs[2] workload with four stream groups (gpurun_out/r2t_dense*.json)
 
 __global__ void __launch_bounds__(KC_THREADS) k_knn_cell8_assoc(LaneDev* lanes, int lane0, int cur, ConfigDev cfg, const double* pose_override) {
   const int ln = lane0 + blockIdx.y;
@@ -1301,7 +1306,7 @@ __global__ void __launch_bounds__(KC_THREADS) k_knn_cell8_assoc(LaneDev* lanes, 
 }
 
 
-__global__ void __launch_bounds__(KC_THREADS) k_knn_cell_assoc(LaneDev* lanes, int lane0, int cur, ConfigDev cfg, const double* pose_override) {
+__global__ void __launch_bounds__(KC_THREADS, KC_MINB) k_knn_cell_assoc(LaneDev* lanes, int lane0, int cur, ConfigDev cfg, const double* pose_override) {
   const int ln = lane0 + blockIdx.y;
   const LaneDev& L = lanes[ln];
   LaneVars& V = *L.v;
@@ -1360,7 +1365,7 @@ void launch_knn_cell_fit(const Launch& L, LaneDev* lanes, int lane0, int nlanes,
 }
 
 // nearestKSearch alone against an explicit map (vilf_knn5); indices are reported in the caller's map order.
-__global__ void __launch_bounds__(KC_THREADS) k_knn_cell_only(const float4* __restrict__ pts, const int* n_dev, const uint2* __restrict__ table, const int* meta,
+__global__ void __launch_bounds__(KC_THREADS, KC_MINB) k_knn_cell_only(const float4* __restrict__ pts, const int* n_dev, const uint2* __restrict__ table, const int* meta,
                                                                const uint32_t* __restrict__ orig, CellGeom g, const float4* __restrict__ q, const int* nq_dev,
                                                                int* idx, float* d2, float gate_f) {
   const int nq = *nq_dev;

@@ -55,6 +55,7 @@ struct Ctx {
   std::vector<void*> pinned;
   std::vector<LaneDev> lanes_host;
   LaneDev* lanes_dev = nullptr;
+  float4* scan_all[2] = {nullptr, nullptr}; uint16_t* ring_all[2] = {nullptr, nullptr};  // [buffer][lane][cap_scan]
   LaneVars* vars_dev = nullptr;
   SolveTraceDev* trace_dev = nullptr;
   VoxVars* vv_dev = nullptr;  // [nlanes * 4 + 1] (last = aux)
@@ -315,15 +316,19 @@ int build_ctx(Ctx* C) {
   std::vector<SortJob> vox_scan_sort(NL * 2), vox_map_sort(NL * 2);
   std::vector<GridJob> grid[2] = {std::vector<GridJob>(NL * 2), std::vector<GridJob>(NL * 2)};
   std::vector<LaneVars> vars0(NL);
+  for (int b = 0; b < 2; ++b) {
+    CK(dalloc(C, &C->scan_all[b], (size_t)NL * capS));
+    CK(dalloc(C, &C->ring_all[b], (size_t)NL * capS));
+  }
   for (int l = 0; l < NL; ++l) {
     LaneDev& L = C->lanes_host[l];
     memset(&L, 0, sizeof(L));
     L.v = C->vars_dev + l;
     L.vv = C->vv_dev + (size_t)l * VV_PER_LANE;
     L.trace = C->trace_dev + (size_t)l * MAX_OUTER;
-    for (int b = 0; b < 2; ++b) {
-      CK(dalloc(C, &L.scan[b], (size_t)capS));
-      CK(dalloc(C, &L.ring_in[b], (size_t)capS));
+    for (int b = 0; b < 2; ++b) {  // the lanes' scan buffers are rows of ONE array (pitch = cap_scan points): a batch whose host scans have the same pitch moves with one strided copy
+      L.scan[b] = C->scan_all[b] + (size_t)l * capS;
+      L.ring_in[b] = C->ring_all[b] + (size_t)l * capS;
     }
     int rc = alloc_sort(C, L.ring_sort, &L.v->n_scan[0], nullptr, 8, 1, capS, true);
     if (rc) return rc;
@@ -705,12 +710,29 @@ int submit_common(Ctx* C, int lane0, int nl, const float* const* xyzi, const int
   C->scan_sel++;
   // H2D (or D2D) on the copy stream into scan buffer `sel`, which the extract kernels of two frames ago released
   CK(cudaStreamWaitEvent(C->copy_st, C->extract_done[sel], 0));
+  // Scans of a batch that lie in one array with a row pitch of max_scan_points points (how a driver that fills fixed slots, and
+  // bench.py, lay them out) move with ONE strided copy instead of one copy per scan: every cudaMemcpyAsync leaves the copy engine idle
+  // for ~4 us, which at 1.8 MB per scan is 10 % of the link (tools/h2d_probe.py: 49.6 GB/s with a copy per scan, 55.2 GB/s with a copy
+  // per 32 scans).  Rows are read up to the longest scan of the batch (inside the row's own pitch); the last row is copied with its
+  // own length, so nothing is read behind the end of the caller's array.
+  const cudaMemcpyKind kind = dev_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  const size_t pitch = (size_t)C->cfg.cap_scan * 16;
+  bool strided = nl > 2 && !dev_src, strided_ring = nl > 2 && !dev_src && ring != nullptr;  // (device-to-device: separate copies measured faster)
+  int maxn = 0;
+  for (int i = 0; i < nl; ++i) {
+    maxn = n[i] > maxn ? n[i] : maxn;
+    if ((const char*)xyzi[i] != (const char*)xyzi[0] + (size_t)i * pitch) strided = false;
+    if (strided_ring && (!ring[i] || (const char*)ring[i] != (const char*)ring[0] + (size_t)i * (pitch / 8))) strided_ring = false;
+    S.vars_pin[i].n_scan[sel] = n[i];
+  }
+  if (maxn == 0) strided = strided_ring = false;
+  const int rows2d = nl - 1;
+  if (strided) CK(cudaMemcpy2DAsync(C->lanes_host[lane0].scan[sel], pitch, xyzi[0], pitch, (size_t)maxn * 16, (size_t)rows2d, kind, C->copy_st));
+  if (strided_ring) CK(cudaMemcpy2DAsync(C->lanes_host[lane0].ring_in[sel], pitch / 8, ring[0], pitch / 8, (size_t)maxn * 2, (size_t)rows2d, kind, C->copy_st));
   for (int i = 0; i < nl; ++i) {
     LaneDev& L = C->lanes_host[lane0 + i];
-    const cudaMemcpyKind kind = dev_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    if (n[i] > 0) CK(cudaMemcpyAsync(L.scan[sel], xyzi[i], (size_t)n[i] * 16, kind, C->copy_st));
-    if (ring && ring[i] && n[i] > 0) CK(cudaMemcpyAsync(L.ring_in[sel], ring[i], (size_t)n[i] * 2, kind, C->copy_st));
-    S.vars_pin[i].n_scan[sel] = n[i];
+    if (n[i] > 0 && !(strided && i < rows2d)) CK(cudaMemcpyAsync(L.scan[sel], xyzi[i], (size_t)n[i] * 16, kind, C->copy_st));
+    if (ring && ring[i] && n[i] > 0 && !(strided_ring && i < rows2d)) CK(cudaMemcpyAsync(L.ring_in[sel], ring[i], (size_t)n[i] * 2, kind, C->copy_st));
   }
   // the point counts of all lanes in ONE strided copy (a 4-byte column of the pinned LaneVars array -> the same column on the device)
   CK(cudaMemcpy2DAsync(&C->vars_dev[lane0].n_scan[sel], sizeof(LaneVars), &S.vars_pin[0].n_scan[sel], sizeof(LaneVars), sizeof(int), (size_t)nl,
