@@ -1,5 +1,5 @@
 """The JSON lines bench.py prints: the reference arm is run here (it needs no GPU), the GPU arm is checked on the committed
-record of the final build (profiles/r1_bench_default.json)."""
+records of the final builds (profiles/r1_bench_default.json, profiles/r2_bench_default.json, profiles/r2_bench_dense.json)."""
 import json
 import os
 import subprocess
@@ -49,3 +49,21 @@ def test_committed_gpu_record():
     cl = d["clocks"]
     assert cl["sm_mhz"] > 0 and cl["sm_max_mhz"] >= cl["sm_mhz"] and not set(cl["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     assert set(d["stage_ms"]) == {"extract", "scan_ds", "assoc_solve", "map_update"}
+
+
+def test_committed_round2_records():
+    """Round 2 added: steady-state value after a preroll + the young-map value, the latency block, the copy-only ceilings, the
+    issue roofline; and the configs[2] workload as a second line."""
+    for name, min_map in (("r2_bench_default.json", 5e4), ("r2_bench_dense.json", 1e6)):
+        d = json.load(open(os.path.join(ROOT, "profiles", name)))
+        check_common(d)
+        assert d["config"]["preroll_frames"] >= 300 and d["config"]["mean_map_points"] >= min_map
+        assert d["young_map"]["value"] > 0 and d["latency"]["gpu_ms_per_frame"] > 0 and d["latency"]["cpu_one_core_ms_per_frame"] > d["latency"]["gpu_ms_per_frame"]
+        e = d["e2e"]
+        assert e["h2d_copy_only_per_scan_gbs"] > 0 and e["h2d_copy_only_per_group_gbs"] > 0 and 0 < e["e2e_efficiency"] <= 1.05
+        r = d["roofline"]
+        assert r["traffic"] is not None and "NOT measured in this run" in r["traffic_source"]
+        assert 0 < r["issue"]["frac"] < 1 and r["issue"]["warp_instructions_per_launch"] > 0
+        q = d["large_map"]["knn_query"]
+        assert q["queries_per_s"] > 9e8 and 0 < q["issue_roofline"]["frac"] < 1
+        assert d["gpu_launches"] > 0 and d["cpu_baseline"]["kind"] == "port"

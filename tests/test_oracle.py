@@ -25,6 +25,27 @@ def test_kdtree_matches_reference_nanoflann_live(orc, synth):
         assert np.array_equal(a[0][:, :k], b[0][:, :k]) and np.array_equal(a[1][:, :k], b[1][:, :k])
 
 
+def test_kdtree_matches_flann_single_index_of_opencv(orc, synth):
+    """PCL's KdTreeFLANN is FLANN's KDTreeSingleIndex (leaf 15, exact, sorted).  OpenCV vendors the FLANN sources
+    (cv2.flann_Index, algorithm 4 = FLANN_INDEX_KDTREE_SINGLE): the oracle's tree against that library on a real local map —
+    same squared fp32 distances bit for bit, same indices except on exact distance ties."""
+    cv2 = pytest.importorskip("cv2")
+    from conftest import check_knn
+    o = orc.Odometry(orc.config())
+    seq = synth.Sequence("hdl64", 4, seed=6)
+    for i in range(4):
+        o.process_scan(seq[i][0])
+    mp = o.cloud(orc.MAP_SURF)
+    q = o.cloud(orc.DS_SURF).copy()
+    q[:, :3] += np.float32(0.05)
+    index = cv2.flann_Index(np.ascontiguousarray(mp[:, :3]), dict(algorithm=4, leaf_max_size=15))
+    fi, fd = index.knnSearch(np.ascontiguousarray(q[:, :3]), 5, params=dict(checks=-1, eps=0.0, sorted=True))
+    oi, od = orc.knn(mp, q)
+    assert len(mp) > 5000 and len(q) > 2000
+    check_knn(fi.astype(np.int32), fd.astype(np.float32), oi, od, gate=np.float32(1e30))
+    assert (fi == oi).mean() > 0.9999
+
+
 def test_kdtree_is_exact_vs_bruteforce_and_scipy(orc):
     from scipy.spatial import cKDTree
     rng = np.random.default_rng(2)
