@@ -121,8 +121,6 @@ inline void ri_extract(const RIParams& P, const P4* pts, const uint16_t* ring, i
     }
   };
   for (int i = 0; i < R; ++i) {
-    const size_t surf_ring_begin = surf.size();
-    (void)surf_ring_begin;
     for (int j = 0; j < 6; ++j) {
       const int sp = (start[i] * (6 - j) + end[i] * j) / 6;
       const int ep = (start[i] * (5 - j) + end[i] * (j + 1)) / 6 - 1;

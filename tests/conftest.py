@@ -43,6 +43,12 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden2():
+    """Committed golden vectors of the round-2 stages (tests/golden/make_golden_r2.py)."""
+    return np.load(os.path.join(GOLDEN, "round2.npz"))
+
+
+@pytest.fixture(scope="session")
 def hdl64_frames(synth):
     seq = synth.Sequence("hdl64", 6, seed=0)
     return [seq[i] for i in range(6)]

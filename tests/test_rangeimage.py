@@ -129,6 +129,15 @@ def test_oracle_selection_invariants(orc, synth):
     assert np.array_equal(d2["col"], d["col"]) and np.array_equal(d2["ring_start_end"], se)
 
 
+def test_oracle_matches_committed_goldens(orc, golden2):
+    for i in (0, 3):
+        P = orc.ri_params(n_scan=16, horizon_scan=600)
+        e, es, s, ss, d = orc.ri_extract(P, golden2[f"ri{i}_scan"], golden2[f"ri{i}_ring"], debug=True)
+        assert np.array_equal(es, golden2[f"ri{i}_edge_src"]) and np.array_equal(ss, golden2[f"ri{i}_surf_src"])
+        assert np.array_equal(d["col"], golden2[f"ri{i}_col"]) and np.array_equal(d["curvature"], golden2[f"ri{i}_curvature"])
+        assert np.array_equal(d["picked"], golden2[f"ri{i}_picked"])
+
+
 def test_oracle_degenerate_inputs(orc):
     P = orc.ri_params(n_scan=16, horizon_scan=600)
     for x in (np.zeros((0, 4), np.float32), np.full((40, 4), np.nan, np.float32), np.array([[5, 0, 0, 1]] * 9, np.float32)):
@@ -178,6 +187,20 @@ def test_gpu_range_image_extract_bit_exact(cabi, orc, synth, scan16):
     g.close()
     with pytest.raises(cabi.VilfError):
         cabi.Odometry(cabi.default_config(n_scan=64, flags=cabi.FLAG_RANGE_IMAGE))  # needs explicit ring ids
+
+
+@pytest.mark.gpu
+def test_gpu_range_image_goldens(cabi, golden2):
+    """The CUDA path against the committed golden vectors (no oracle in the loop)."""
+    g = cabi.Odometry(gpu_cfg(cabi, 16, 600, 20000))
+    for i in (0, 3):
+        x, ring = golden2[f"ri{i}_scan"], golden2[f"ri{i}_ring"]
+        ne, ns = g.feature_extract(x, ring)
+        ge, ges = g.features(0)
+        gs, gss = g.features(1)
+        assert np.array_equal(ges, golden2[f"ri{i}_edge_src"]) and np.array_equal(gss, golden2[f"ri{i}_surf_src"])
+        assert np.array_equal(ge, x[ges]) and np.array_equal(gs, x[gss]) and (ne, ns) == (len(ges), len(gss))
+    g.close()
 
 
 @pytest.mark.gpu

@@ -107,6 +107,25 @@ def test_oracle_key_search_matches_the_reference_kdtree(orc, keyframes):
         assert np.array_equal(np.array([m[0] for m in mine], np.float32), d2)
 
 
+def test_oracle_matches_committed_goldens(orc, golden, golden2):
+    """Descriptors, keys and pairwise distances of the six golden scans; ring-key candidates equal to what the REFERENCE's kd-tree
+    returned in the build container (tests/golden/make_golden_r2.py)."""
+    descs = []
+    for i in range(6):
+        d, rk, sk = orc.sc_make(golden[f"scan{i}"])
+        assert np.array_equal(d, golden2[f"sc{i}_desc"]) and np.array_equal(rk, golden2[f"sc{i}_ringkey"]) and np.array_equal(sk, golden2[f"sc{i}_sectorkey"])
+        descs.append(d)
+    for i in range(6):
+        for j in range(6):
+            dist, sh = orc.sc_distance(descs[i], descs[j])
+            assert dist == golden2["sc_dist"][i, j] and sh == golden2["sc_shift"][i, j]
+    bank, q = golden2["sc_key_bank"], golden2["sc_key_q"]
+    for k in range(len(q)):
+        mine = sorted(((orc.sc_key_dist(q[k], bank[i]), i) for i in range(len(bank))))[:3]
+        assert [m[1] for m in mine] == list(golden2["ref_sc_key_idx"][k])
+        assert np.array_equal(np.array([m[0] for m in mine], np.float32), golden2["ref_sc_key_d2"][k])
+
+
 def test_oracle_loop_detection_sequence(orc, keyframes):
     """detectLoopClosureID: early return below 31 key frames, then a revisit of key frame 4 (rotated by 3 sectors) is found.
     (With the reference's TREE_MAKING_PERIOD_ = 30 the search set would still be the single key of the first rebuild, SC:227-238.)"""
@@ -141,6 +160,21 @@ def test_gpu_descriptor_keys_and_distance_bit_exact(cabi, orc, keyframes):
         assert g.distance_between(i, j) == orc.sc_distance(descs[i], descs[j]), (i, j)
         assert g.distance(descs[i], descs[j]) == orc.sc_distance(descs[i], descs[j])
     assert g.launch_count() > 0
+    g.close()
+
+
+@pytest.mark.gpu
+def test_gpu_scancontext_goldens(cabi, golden, golden2):
+    """The CUDA path against the committed golden vectors (no oracle in the loop)."""
+    g = cabi.SCManager()
+    for i in range(6):
+        g.add(golden[f"scan{i}"])
+        d, rk, sk = g.get(-1)
+        assert np.array_equal(d, golden2[f"sc{i}_desc"]) and np.array_equal(rk, golden2[f"sc{i}_ringkey"]) and np.array_equal(sk, golden2[f"sc{i}_sectorkey"])
+    for i in range(6):
+        for j in range(6):
+            dist, sh = g.distance_between(i, j)
+            assert dist == golden2["sc_dist"][i, j] and sh == golden2["sc_shift"][i, j]
     g.close()
 
 
