@@ -981,7 +981,9 @@ __device__ __forceinline__ int pool_reseed(uint2* pool, const float (&rd)[5], co
 // that fall inside the gate are appended to the pool (ballot + popc rank, one shared-memory store each); the pool is reduced to its
 // best five only when it would overflow, between shells (early exit) and at the end, and every reduction tightens the gate to
 // the fifth distance known so far.
-__device__ __forceinline__ void warp_knn5(const CellMapView& M, float gate_f, float qx, float qy, float qz, uint2* pool, float (&bd)[5], int (&bi)[5]) {
+template <bool SEEDED>
+__device__ __forceinline__ void warp_knn5(const CellMapView& M, float gate_f, float qx, float qy, float qz, uint2* pool, float (&bd)[5], int (&bi)[5],
+                                          const int* seed = nullptr) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
@@ -994,6 +996,26 @@ __device__ __forceinline__ void warp_knn5(const CellMapView& M, float gate_f, fl
   const int shells = M.g.shells;
   int npool = 0;
   float gate_dyn = gate_f;  // once five neighbours are known nothing farther than the fifth can matter (ties are kept: <=)
+  // the query's position inside its own cell, in voxels: [0, k)
+  const float kf = (float)(1 << s);
+  const float ux = fmul(qx, inv) - (float)(((qcx << s) - VOX_BIAS)), uy = fmul(qy, inv) - (float)(((qcy << s) - VOX_BIAS)),
+              uz = fmul(qz, inv) - (float)(((qcz << s) - VOX_BIAS));
+  const float leaf2 = M.g.leaf * M.g.leaf;
+  // Seeds: five map points known to be near the query (its neighbours of the previous outer iteration: the pose moved by millimetres,
+  // the map not at all).  Their largest distance bounds the fifth-nearest distance from above, so the search only has to look at the
+  // cells that intersect that ball — typically 1-4 of the 27 on a dense map.  The seeds themselves are found again in those cells.
+  if (SEEDED && seed) {
+    const int si = lane < 5 ? __ldg(seed + lane) : 0;
+    if (__all_sync(FULL, si >= 0 && si < M.n)) {
+      float sd = 0.f;
+      if (lane < 5) {
+        const float4 p = __ldg(M.pts + si);
+        const float ddx = fsub(qx, p.x), ddy = fsub(qy, p.y), ddz = fsub(qz, p.z);
+        sd = fadd(fadd(fmul(ddx, ddx), fmul(ddy, ddy)), fmul(ddz, ddz));
+      }
+      gate_dyn = fminf(gate_dyn, __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(sd))));
+    }
+  }
   for (int r = 1; r <= shells; ++r) {
     // cells of Chebyshev distance exactly r (r = 1: the whole 27-cell cube): the two z faces, then the square rings of the layers between
     const int side = 2 * r + 1, face = side * side, ring = 8 * r;
@@ -1015,7 +1037,14 @@ __device__ __forceinline__ void warp_knn5(const CellMapView& M, float gate_f, fl
           dy = sd == 0 ? -r : sd == 1 ? -r + off : sd == 2 ? r : r - off;
         }
         const int cx = qcx + dx, cy = qcy + dy, cz = qcz + dz;
-        if (cx >= 0 && cy >= 0 && cz >= 0 && cx <= ncmax && cy <= ncmax && cz <= ncmax) {
+        // squared distance from the query to the cell's box: a cell farther than the current bound holds nothing of interest (0.1 %
+        // margin for the rounding of the voxel coordinates; cells are skipped only when clearly outside)
+        const float gx = dx > 0 ? (float)dx * kf - ux : dx < 0 ? ux - (float)(dx + 1) * kf : 0.f;
+        const float gy = dy > 0 ? (float)dy * kf - uy : dy < 0 ? uy - (float)(dy + 1) * kf : 0.f;
+        const float gz = dz > 0 ? (float)dz * kf - uz : dz < 0 ? uz - (float)(dz + 1) * kf : 0.f;
+        const bool reachable = !SEEDED || (gx * gx + gy * gy + gz * gz) * leaf2 * 0.999f <= gate_dyn;  // (the unseeded search visits every cell of a shell:
+                                                                                                         // measured, the test costs it more than it saves)
+        if (reachable && cx >= 0 && cy >= 0 && cz >= 0 && cx <= ncmax && cy <= ncmax && cz <= ncmax) {
           const unsigned long long ck = cellkey_cells((uint32_t)cx, (uint32_t)cy, (uint32_t)cz, s);
           uint32_t h = cell_slot(ck) & M.hmask;
           for (;;) {
@@ -1060,7 +1089,7 @@ __device__ __forceinline__ void warp_knn5(const CellMapView& M, float gate_f, fl
           float rd[5]; int ri[5];
           pool_top5(M, pool, npool, rd, ri);
           npool = pool_reseed(pool, rd, ri);
-          gate_dyn = rd[4];  // FLT_MAX while fewer than five are known
+          gate_dyn = fminf(gate_dyn, rd[4]);  // (rd[4] is FLT_MAX while fewer than five are known)
         }
         if (cand) pool[npool + __popc(m & lt)] = make_uint2(__float_as_uint(cd), (uint32_t)idx);
         npool += cm;
@@ -1069,11 +1098,8 @@ __device__ __forceinline__ void warp_knn5(const CellMapView& M, float gate_f, fl
     if (r < shells) {  // after shell r every unseen point is farther than (r + f) cells: is the fifth best already closer?
       float rd[5]; int ri[5];
       pool_top5(M, pool, npool, rd, ri);
-      const float k = (float)(1 << s);
-      const float ux = fmul(qx, inv) - (float)(((qcx << s) - VOX_BIAS)), uy = fmul(qy, inv) - (float)(((qcy << s) - VOX_BIAS)),
-                  uz = fmul(qz, inv) - (float)(((qcz << s) - VOX_BIAS));
-      const float f = fminf(fminf(fminf(ux, k - ux), fminf(uy, k - uy)), fminf(uz, k - uz));  // voxels to the nearest face of the query's cell
-      const float fmin_cells = fmaxf(0.f, f / k - 1e-4f);
+      const float f = fminf(fminf(fminf(ux, kf - ux), fminf(uy, kf - uy)), fminf(uz, kf - uz));  // voxels to the nearest face of the query's cell
+      const float fmin_cells = fmaxf(0.f, f / kf - 1e-4f);
       const double cell = (double)M.g.leaf * (double)(1 << s) * (1.0 - 1e-5);  // a lower bound of the cell edge (inverse_leaf is rounded)
       const double reach = ((double)r + (double)fmin_cells) * cell;
       if ((double)rd[4] < reach * reach * (1.0 - 1e-5)) {
@@ -1082,7 +1108,7 @@ __device__ __forceinline__ void warp_knn5(const CellMapView& M, float gate_f, fl
         return;
       }
       npool = pool_reseed(pool, rd, ri);
-      gate_dyn = rd[4];
+      gate_dyn = fminf(gate_dyn, rd[4]);
     }
   }
   pool_top5(M, pool, npool, bd, bi);
@@ -1306,6 +1332,7 @@ __global__ void __launch_bounds__(KC_THREADS) k_knn_cell8_assoc(LaneDev* lanes, 
 }
 
 
+template <bool SEEDED>
 __global__ void __launch_bounds__(KC_THREADS, KC_MINB) k_knn_cell_assoc(LaneDev* lanes, int lane0, int cur, ConfigDev cfg, const double* pose_override) {
   const int ln = lane0 + blockIdx.y;
   const LaneDev& L = lanes[ln];
@@ -1344,7 +1371,8 @@ __global__ void __launch_bounds__(KC_THREADS, KC_MINB) k_knn_cell_assoc(LaneDev*
       float rd[5];
       int ri[5];
       const CellMapView M = w ? Ms : Me;
-      warp_knn5(M, cfg.knn_gate_f, pw.x, pw.y, pw.z, spool[threadIdx.x >> 5], rd, ri);
+      // seeded: the neighbours the previous outer iteration stored for this very feature bound the search (same map, pose moved by mm)
+      warp_knn5<SEEDED>(M, cfg.knn_gate_f, pw.x, pw.y, pw.z, spool[threadIdx.x >> 5], rd, ri, SEEDED ? L.nn_idx[w] + k * 5 : nullptr);
 #pragma unroll
       for (int t = 0; t < 5; ++t)
         if (lane == t) {
@@ -1355,11 +1383,12 @@ __global__ void __launch_bounds__(KC_THREADS, KC_MINB) k_knn_cell_assoc(LaneDev*
   }
 }
 
-void launch_knn_cell_fit(const Launch& L, LaneDev* lanes, int lane0, int nlanes, int cur, const ConfigDev& cfg, const double* pose_override) {
+void launch_knn_cell_fit(const Launch& L, LaneDev* lanes, int lane0, int nlanes, int cur, const ConfigDev& cfg, const double* pose_override, bool seeded) {
   dim3 g(KNN_G * 8, nlanes);
   static const bool group_search = getenv("VILF_KNN_GROUP8") != nullptr;  // A/B: eight lanes per query (measured slower, see above)
   if (group_search) k_knn_cell8_assoc<<<g, KC_THREADS, 0, L.st>>>(lanes, lane0, cur, cfg, pose_override);
-  else k_knn_cell_assoc<<<g, KC_THREADS, 0, L.st>>>(lanes, lane0, cur, cfg, pose_override);
+  else if (seeded) k_knn_cell_assoc<true><<<g, KC_THREADS, 0, L.st>>>(lanes, lane0, cur, cfg, pose_override);
+  else k_knn_cell_assoc<false><<<g, KC_THREADS, 0, L.st>>>(lanes, lane0, cur, cfg, pose_override);
   L.tick(K_KNN_CELL);
   launch_fit(L, lanes, lane0, nlanes, cur, cfg);
 }
@@ -1383,7 +1412,7 @@ __global__ void __launch_bounds__(KC_THREADS, KC_MINB) k_knn_cell_only(const flo
 #pragma unroll
       for (int j = 0; j < 5; ++j) { rd[j] = FLT_MAX; ri[j] = INT_MAX; }
     } else {
-      warp_knn5(M, gate_f, p.x, p.y, p.z, spool[threadIdx.x >> 5], rd, ri);
+      warp_knn5<false>(M, gate_f, p.x, p.y, p.z, spool[threadIdx.x >> 5], rd, ri);
     }
 #pragma unroll
     for (int j = 0; j < 5; ++j)

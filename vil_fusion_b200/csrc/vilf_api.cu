@@ -71,6 +71,7 @@ struct Ctx {
   bool cluster_scan = false, cluster_map = false;  // one-cluster-per-cloud path (k_cluster.cu) for scan / map clouds
   // cell-ordered maps (k_cellmap.cu): merge update + cell table; off with VILF_FLAG_LEGACY_MAP
   bool cellmap = true;
+  bool no_seed = false;  // VILF_KNN_NO_SEED=1 (A/B): the second outer iteration searches from scratch
   int max_tiles = 0;
   MergeJob* merge_dev[2] = {nullptr, nullptr}; SortJob* merge_sort_dev = nullptr;      // [cur][nlanes*2]
   CellBuildJob* build_dev[2] = {nullptr, nullptr}; SortJob* build_sort_dev = nullptr;  // [cur][nlanes*2]: first-frame map from the raw features
@@ -301,6 +302,7 @@ int build_ctx(Ctx* C) {
   C->cluster_scan = allow_cluster && capS <= CLUSTER_MAX_POINTS;
   C->cluster_map = allow_cluster && capM <= CLUSTER_MAX_POINTS;
   C->cellmap = (u.flags & VILF_FLAG_CELL_MAP) ? true : (u.flags & VILF_FLAG_LEGACY_MAP) ? false : capM > CLUSTER_MAX_POINTS;
+  C->no_seed = getenv("VILF_KNN_NO_SEED") != nullptr;
   c.cg[0] = cell_geometry(C, u.edge_leaf);
   c.cg[1] = cell_geometry(C, u.surf_leaf);
   CK(init_cellmap_kernels());
@@ -674,7 +676,7 @@ void issue_frame(Ctx* C, int lane0, int nl, bool first, bool with_extract, int s
     else launch_voxel(L, C->vox_scan_dev + lane0 * 2, nl * 2, C->vox_scan_sort_dev + lane0 * 2, with_extract);
     phase(2);
     for (int it = 0; it < cfg.outer_iters; ++it) {
-      if (C->cellmap) launch_knn_cell_fit(L, C->lanes_dev, lane0, nl, cur, cfg, nullptr);
+      if (C->cellmap) launch_knn_cell_fit(L, C->lanes_dev, lane0, nl, cur, cfg, nullptr, it > 0 && !C->no_seed);
       else launch_knn_fit(L, C->lanes_dev, C->grid_dev[cur], lane0, nl, cur, cfg, nullptr);
       launch_solve(L, C->lanes_dev, lane0, nl, it, it == cfg.outer_iters - 1 ? 1 : 0, cfg, cfg.lm_max_iters);
     }

@@ -390,7 +390,8 @@ void launch_knn_only(const Launch& L, const GridJob* job_dev, const float4* q, c
 cudaError_t init_cellmap_kernels();
 void launch_cell_update(const Launch& L, const MergeJob* jobs_dev, const SortJob* sort_jobs_dev, int njobs, int max_tiles, bool cluster_new);
 void launch_cell_build(const Launch& L, const CellBuildJob* jobs_dev, const SortJob* sort_jobs_dev, int njobs);
-void launch_knn_cell_fit(const Launch& L, LaneDev* lanes, int lane0, int nlanes, int cur, const ConfigDev& cfg, const double* pose_override);
+// seeded: the neighbour lists of the previous outer iteration of THIS frame are in nn_idx and bound the search
+void launch_knn_cell_fit(const Launch& L, LaneDev* lanes, int lane0, int nlanes, int cur, const ConfigDev& cfg, const double* pose_override, bool seeded = false);
 void launch_knn_cell_only(const Launch& L, const float4* pts, const int* n_dev, const uint2* table, const int* meta, const uint32_t* orig, CellGeom g,
                           const float4* q, const int* nq_dev, int* idx, float* d2, const ConfigDev& cfg);
 void launch_cell_unpermute(const Launch& L, const float4* pts, const uint32_t* orig, const int* n_dev, float4* out, int cap);
