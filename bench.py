@@ -489,13 +489,14 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
                 # larger traffic, the map job the other; everything else: first launch
                 li = (int(np.argmin(per)) if dp == "map_update" else int(np.argmax(per))) if dk == "k_voxel_cluster" else 0
                 scale = (bounds[1] - bounds[0]) / ent["sequences"]
-                traffic = per[li] * scale
+                pick = (lambda v: float(np.mean(v))) if dk == "k_knn_cell_assoc" else (lambda v: v[li])  # the search runs twice per frame (unseeded, seeded): the timing averages both
+                traffic = pick(per) * scale
                 traffic_src = f"committed ncu --set full capture profiles/{tfile} (dram__bytes_read.sum + dram__bytes_write.sum per launch), scaled to this launch's sequence count; NOT measured in this run"
-                winst = ent["warp_instructions_per_launch"][li] * scale
+                winst = pick(ent["warp_instructions_per_launch"]) * scale
                 sm_hz = float(clk.get("sm_mhz") or clk.get("sm_max_mhz") or 1965.0) * 1e6
                 issue_peak = 148 * 4 * sm_hz  # warp instructions per second: 148 SMs x 4 schedulers x 1 instruction per clock
                 issue = dict(warp_instructions_per_launch=winst, achieved_ginst_s=winst / dur_s / 1e9, peak_ginst_s=issue_peak / 1e9, frac=winst / dur_s / issue_peak,
-                             issue_active_pct_under_ncu=ent["issue_active_pct"][li], threads_per_warp_instruction=ent["threads_per_warp_instruction"][li],
+                             issue_active_pct_under_ncu=pick(ent["issue_active_pct"]), threads_per_warp_instruction=pick(ent["threads_per_warp_instruction"]),
                              source=f"instruction count from profiles/{tfile} (same launch geometry), duration measured in this run",
                              note="the instruction-issue roofline next to the HBM one: this kernel works on L2-resident data, so what bounds it is how many warp instructions the SMs it occupies can issue (and the latency between them), not DRAM bandwidth")
         except Exception:
