@@ -17,6 +17,8 @@
 // the first point of the range, which is a candidate anyway); the candidate ranges are concatenated with a warp scan and read
 // 32 at a time as coalesced float4; selection of the five best uses redux.sync min on the distance bits — no per-lane lists, no
 // merge tree.  Finer cells than the gate radius (dense maps) are walked shell by shell with the early exit of k_knn.cu.
+// The search of the second outer iteration of a frame is seeded with the first one's neighbours: they bound the fifth distance
+// before any cell is read, and cells whose box lies outside that ball are not probed (k_knn_cell_assoc<true>).
 //
 // The PCL order of the points (ascending voxel index) differs from the stored order; everything the reference's results depend
 // on is order independent or handled explicitly: voxel sums run in input order inside a voxel (= PCL's stable order), exact
