@@ -642,6 +642,15 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         for name, ms_k, _n in kern_table:  # event-to-event kernel intervals of one stream group, summed per stage, per frame
             per_stage[name.split("/")[0]] = per_stage.get(name.split("/")[0], 0.0) + ms_k / n_frames
         out["stage_ms"] = per_stage
+        try:  # 5-NN queries per second inside the frame = queries of the timed launches / their summed kernel intervals
+            for name, ms_k, n_l in kern_table:
+                if name.split("/")[-1] in ("k_knn_assoc", "k_knn_cell_assoc") and ms_k > 0:
+                    q_per_launch = mean_counts["n_ds"] * mean_counts["seqs"]
+                    out["knn_in_frame"] = dict(kernel=name, queries_per_launch=q_per_launch, launches=int(n_l), queries_per_s=q_per_launch * n_l / (ms_k * 1e-3),
+                                               map_points_per_sequence=mean_counts["n_map"],
+                                               note="voxel-filtered scan features searched against the live local maps, one stream group alone; the search structure is part of the map update (no separate build per frame)")
+        except Exception:
+            pass
     return out
 
 
