@@ -121,8 +121,8 @@ int vilf_process_scan(vilf_handle* h, const float* xyzi, int n, const uint16_t* 
 int vilf_submit_scan(vilf_handle* h, const float* xyzi, int n, const uint16_t* ring, int64_t* ticket);
 int vilf_wait(vilf_handle* h, int64_t ticket, double pose_out[7]);
 /* Lock-step over all sequences of a batch (hs = the array vilf_create_batch filled).  When the scans of the batch lie in one host
- * array with a row pitch of max_scan_points points (xyzi[i] == xyzi[0] + i * max_scan_points * 4 floats; ring ids likewise) they are
- * moved with one strided copy, rows being read up to the longest scan of the batch: 10 % more of the PCIe link than a copy per scan. */
+ * array from vilf_host_alloc with a row pitch of max_scan_points points (xyzi[i] == xyzi[0] + i * max_scan_points * 4 floats; ring ids
+ * likewise) they are moved with one strided copy, rows being read up to the longest scan of the batch: 10 % more of the PCIe link than a copy per scan. */
 int vilf_submit_scan_batch(vilf_handle* const* hs, int count, const float* const* xyzi, const int* n,
                            const uint16_t* const* ring, int64_t* ticket);
 int vilf_wait_batch(vilf_handle* const* hs, int count, int64_t ticket, double* poses_out /* [count][7] */);

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <new>
 #include <map>
+#include <mutex>
 #include <tuple>
 #include <vector>
 
@@ -685,6 +686,18 @@ void issue_frame(Ctx* C, int lane0, int nl, bool first, bool with_extract, int s
   }
 }
 
+// Pinned slabs handed out by vilf_host_alloc: the strided batch copy reads rows beyond a scan's last point (up to the longest scan of
+// the batch), which is only known to be mapped memory when the whole batch lies inside one such slab.
+std::mutex g_slab_mu;
+std::map<const char*, size_t> g_slabs;  // base -> bytes
+bool inside_one_slab(const void* first, const void* last_end) {
+  std::lock_guard<std::mutex> lk(g_slab_mu);
+  auto it = g_slabs.upper_bound((const char*)first);
+  if (it == g_slabs.begin()) return false;
+  --it;
+  return (const char*)first >= it->first && (const char*)last_end <= it->first + it->second;
+}
+
 bool lanes_uniform(Ctx* C, int lane0, int nl) {
   for (int l = lane0 + 1; l < lane0 + nl; ++l)
     if (C->cur[l] != C->cur[lane0] || C->have_map[l] != C->have_map[lane0]) return false;
@@ -715,8 +728,8 @@ int submit_common(Ctx* C, int lane0, int nl, const float* const* xyzi, const int
   // Scans of a batch that lie in one array with a row pitch of max_scan_points points (how a driver that fills fixed slots, and
   // bench.py, lay them out) move with ONE strided copy instead of one copy per scan: every cudaMemcpyAsync leaves the copy engine idle
   // for ~4 us, which at 1.8 MB per scan is 10 % of the link (tools/h2d_probe.py: 49.6 GB/s with a copy per scan, 55.2 GB/s with a copy
-  // per 32 scans).  Rows are read up to the longest scan of the batch (inside the row's own pitch); the last row is copied with its
-  // own length, so nothing is read behind the end of the caller's array.
+  // per 32 scans).  Rows are read up to the longest scan of the batch (inside the row's own pitch), so the path is taken only when the
+  // whole batch lies inside ONE slab from vilf_host_alloc; the last row is copied with its own length.
   const cudaMemcpyKind kind = dev_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   const size_t pitch = (size_t)C->cfg.cap_scan * 16;
   bool strided = nl > 2 && !dev_src, strided_ring = nl > 2 && !dev_src && ring != nullptr;  // (device-to-device: separate copies measured faster)
@@ -728,6 +741,8 @@ int submit_common(Ctx* C, int lane0, int nl, const float* const* xyzi, const int
     S.vars_pin[i].n_scan[sel] = n[i];
   }
   if (maxn == 0) strided = strided_ring = false;
+  if (strided && !inside_one_slab(xyzi[0], (const char*)xyzi[nl - 1] + (size_t)n[nl - 1] * 16)) strided = false;
+  if (strided_ring && !inside_one_slab(ring[0], (const char*)ring[nl - 1] + (size_t)n[nl - 1] * 2)) strided_ring = false;
   const int rows2d = nl - 1;
   if (strided) CK(cudaMemcpy2DAsync(C->lanes_host[lane0].scan[sel], pitch, xyzi[0], pitch, (size_t)maxn * 16, (size_t)rows2d, kind, C->copy_st));
   if (strided_ring) CK(cudaMemcpy2DAsync(C->lanes_host[lane0].ring_in[sel], pitch / 8, ring[0], pitch / 8, (size_t)maxn * 2, (size_t)rows2d, kind, C->copy_st));
@@ -991,7 +1006,11 @@ int vilf_host_alloc(void** p, uint64_t bytes) {
   // VILF_HOST_WC=1 (experiments): write-combined staging — the host only ever writes scans into these buffers, and the copy engine's
   // reads then skip the CPU cache snoop; measured against plain pinned memory in the multi-GPU end-to-end runs
   static const bool wc = getenv("VILF_HOST_WC") != nullptr;
-  return cudaHostAlloc(p, bytes, wc ? cudaHostAllocWriteCombined : cudaHostAllocDefault) == cudaSuccess ? VILF_OK : VILF_ERR_CUDA;
+  if (!p) return VILF_ERR_INVALID;
+  if (cudaHostAlloc(p, bytes, wc ? cudaHostAllocWriteCombined : cudaHostAllocDefault) != cudaSuccess) return VILF_ERR_CUDA;
+  std::lock_guard<std::mutex> lk(g_slab_mu);
+  g_slabs[(const char*)*p] = (size_t)bytes;
+  return VILF_OK;
 }
 int vilf_memcpy_h2d_async(void* dst_dev, const void* src_host, uint64_t bytes, void* cuda_stream) {
   return cudaMemcpyAsync(dst_dev, src_host, (size_t)bytes, cudaMemcpyHostToDevice, (cudaStream_t)cuda_stream) == cudaSuccess ? VILF_OK : VILF_ERR_CUDA;
@@ -1078,7 +1097,13 @@ int vilf_node_outputs(const double rt12[12], double last[7], double relative_out
   for (int c = 0; c < 3; ++c) last[4 + c] = tt[c];
   return VILF_OK;
 }
-int vilf_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? VILF_OK : VILF_ERR_CUDA; }
+int vilf_host_free(void* p) {
+  {
+    std::lock_guard<std::mutex> lk(g_slab_mu);
+    g_slabs.erase((const char*)p);
+  }
+  return cudaFreeHost(p) == cudaSuccess ? VILF_OK : VILF_ERR_CUDA;
+}
 
 int vilf_submit_scan(vilf_handle* h, const float* xyzi, int n, const uint16_t* ring, int64_t* ticket) {
   HCHECK(h);
