@@ -65,6 +65,36 @@ def test_oracle_descriptor_matches_numpy_restatement(orc, keyframes):
     assert d[2, 0] == 5.0 and d[5, 30] == 1.0 and np.count_nonzero(d) == 2
 
 
+def numpy_sc_distance(a, b, search_ratio=0.1):
+    """distanceBtnScanContext (SC:163-193) written independently with numpy reductions (as Eigen would vectorise them)."""
+    S = a.shape[1]
+    v1, v2 = a.mean(axis=0), b.mean(axis=0)
+    norms = [np.linalg.norm(v1 - np.roll(v2, sh)) for sh in range(S)]
+    arg = int(np.argmin(norms))
+    radius = int(np.floor(0.5 * search_ratio * S + 0.5))
+    space = sorted({arg} | {(arg + i + S) % S for i in range(1, radius + 1)} | {(arg - i + S) % S for i in range(1, radius + 1)})
+    best, best_sh = 10000000.0, 0
+    for sh in space:
+        bs = np.roll(b, sh, axis=1)
+        n1, n2 = np.linalg.norm(a, axis=0), np.linalg.norm(bs, axis=0)
+        ok = (n1 != 0) & (n2 != 0)
+        if not ok.any():
+            continue
+        sim = ((a * bs).sum(axis=0)[ok] / (n1[ok] * n2[ok])).sum() / ok.sum()
+        if 1.0 - sim < best:
+            best, best_sh = 1.0 - sim, sh
+    return best, best_sh
+
+
+def test_oracle_distance_matches_numpy_restatement(orc, keyframes):
+    descs = [orc.sc_make(p)[0] for p in keyframes[:10]] + [orc.sc_make(rotz(keyframes[2], 33.0))[0]]
+    for i in range(len(descs)):
+        for j in range(len(descs)):
+            do, so = orc.sc_distance(descs[i], descs[j])
+            dn, sn = numpy_sc_distance(descs[i], descs[j])
+            assert so == sn and abs(do - dn) < 1e-12, (i, j, do, dn, so, sn)
+
+
 def test_oracle_empty_and_degenerate_clouds(orc):
     d, rk, sk = orc.sc_make(np.zeros((0, 4), np.float32))
     assert not d.any() and not rk.any() and not sk.any()
