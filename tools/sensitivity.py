@@ -18,7 +18,7 @@ Alternates (reference call site):
   knn_canonical EM:128, :185   (d^2, index) tie order instead of FLANN's visiting order (the CUDA path's choice)
   all           every switch at once
 
-    python tools/sensitivity.py [frames] > profiles/r2_sensitivity.json       (CPU only, ~10 min on 8 cores)
+    python tools/sensitivity.py [frames] [hdl64|vlp32] > profiles/r2_sensitivity.json       (CPU only, ~7 min on 8 cores)
 """
 import json
 import multiprocessing as mp
@@ -41,6 +41,7 @@ ALTS = {
 }
 TOL = dict(rot_rad=1e-4, trans_m=1e-3, map_m=1e-5)
 SENSOR, SEED = "hdl64", 21
+N_SCAN = {"hdl64": 64, "vlp32": 32}
 
 
 def pose_err(a, b):
@@ -65,7 +66,7 @@ def features(frames):
     from oracle import orc
     from vil_fusion_b200 import synth
     seq = synth.Sequence(SENSOR, frames, seed=SEED)
-    cfg = orc.config()
+    cfg = orc.config(n_scan=N_SCAN[SENSOR], n_rings=N_SCAN[SENSOR])
     out, gt = [], []
     for i in range(frames):
         e, _, s, _ = orc.extract(cfg, np.ascontiguousarray(seq[i][0]))
@@ -78,7 +79,7 @@ def run_free(args):
     name, frames = args
     from oracle import orc
     feats = FEATS
-    o = orc.Odometry(orc.config(**ALTS.get(name, {})))
+    o = orc.Odometry(orc.config(n_scan=N_SCAN[SENSOR], n_rings=N_SCAN[SENSOR], **ALTS.get(name, {})))
     poses = np.zeros((frames, 7))
     solves = []
     for i, (e, s) in enumerate(feats[:frames]):
@@ -95,7 +96,7 @@ def run_forced(args):
     name, frames = args
     from oracle import orc
     feats = FEATS
-    cb, ca = orc.config(), orc.config(**ALTS[name])
+    cb, ca = orc.config(n_scan=N_SCAN[SENSOR], n_rings=N_SCAN[SENSOR]), orc.config(n_scan=N_SCAN[SENSOR], n_rings=N_SCAN[SENSOR], **ALTS[name])
     B, A = orc.Odometry(cb), orc.Odometry(ca)
     r = dict(frames=0, edge_decisions=0, surf_decisions=0, edge_flips=0, surf_flips=0, knn_sets_differ=0, solve_summaries_differ=0, frames_with_any_flip=0,
              max_rot_rad=0.0, max_trans_m=0.0, map_points_not_identical=0, max_map_dist_m=0.0, frames_map_size_differs=0)
@@ -138,8 +139,10 @@ FEATS = None
 
 
 def main():
-    global FEATS
+    global FEATS, SENSOR
     frames = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
+    if len(sys.argv) > 2:
+        SENSOR = sys.argv[2]
     t0 = time.time()
     FEATS, gt = features(frames)  # forked workers inherit FEATS
     ctx = mp.get_context("fork")
