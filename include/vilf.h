@@ -7,7 +7,8 @@
  * cites the reference member it stands in for.  Abbreviations (all under
  * src/visual_inertial_lidar/feature_tracker/include/):
  *   FE = featureExtraction.hpp   EM = EstimationMapping.hpp   LF = lidarFactor.hpp   CM = common.h
- *   NODE = ../feature_tracker_node.cpp
+ *   NODE = ../feature_tracker_node.cpp   FX = featureExtract.hpp (the ring-field / range-image extractor)
+ *   SC = src/global_fusion/include/Scancontext/Scancontext.h (SCManager)
  *
  * Conventions: plain pointers and sizes only; every function returns a vilf_status (0 = OK); point
  * clouds are packed float[n][4] = x, y, z, intensity (the payload of pcl::PointXYZI, CM:25); poses are
